@@ -1,0 +1,120 @@
+"""Seeded synthetic EuRoC-style stereo+IMU streams (host build of synth/scene.h).
+
+Makes the inputs of BASELINE.json config 1 ("60 s textured room, 752x480 stereo @20 Hz,
+IMU @200 Hz").  Input generation only: nothing here is on the hot path.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    d = os.path.join(_HERE, "synth")
+    so = os.path.join(d, "libmskf_synth.so")
+    if force or not os.path.exists(so):
+        subprocess.check_call(["make", "-s", "-C", d])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.synth_create.restype = C.c_void_p
+        L.synth_create.argtypes = [C.POINTER(abi.Config), C.c_uint32, C.c_double]
+        L.synth_destroy.argtypes = [C.c_void_p]
+        L.synth_get_pose.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        L.synth_get_imu.argtypes = [C.c_void_p, C.c_double, C.c_uint32, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        L.synth_render.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int]
+        L.synth_rays.restype = C.c_void_p
+        L.synth_rays.argtypes = [C.c_void_p, C.c_int]
+        L.synth_traj.restype = C.c_void_p
+        L.synth_traj.argtypes = [C.c_void_p]
+        L.synth_cam.restype = C.c_void_p
+        L.synth_cam.argtypes = [C.c_void_p, C.c_int]
+        L.synth_default_config.argtypes = [C.POINTER(abi.Config), C.c_char_p]
+        _LIB = L
+    return _LIB
+
+
+def default_config(preset="ref"):
+    cfg = abi.Config()
+    rc = lib().synth_default_config(C.byref(cfg), preset.encode())
+    if rc != 0:
+        raise ValueError(f"unknown preset {preset!r}")
+    return cfg
+
+
+class Stream:
+    """One synthetic stereo+IMU stream: images at `frame_rate`, IMU at `imu_rate`."""
+
+    def __init__(self, cfg, seed=0, t0=1000.0, frame_rate=20.0, imu_rate=200.0, imu_noise=True, threads=8):
+        self.cfg, self.seed, self.t0 = cfg, seed, t0
+        self.frame_dt, self.imu_dt = 1.0 / frame_rate, 1.0 / imu_rate
+        self.threads = threads
+        self.h = lib().synth_create(C.byref(cfg), seed, t0)
+        # discrete-time sigma of the continuous noise densities the filter is configured with
+        self.ng = cfg.noise_gyro * np.sqrt(imu_rate) if imu_noise else 0.0
+        self.na = cfg.noise_acc * np.sqrt(imu_rate) if imu_noise else 0.0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().synth_destroy(self.h)
+            self.h = None
+
+    def frame_time(self, k):
+        # images lag the IMU clock start by 1/4 IMU period so stamps never coincide exactly
+        return self.t0 + k * self.frame_dt + 0.25 * self.imu_dt
+
+    def imu_time(self, j):
+        return self.t0 + j * self.imu_dt
+
+    def imu(self, j):
+        w = np.zeros(3)
+        a = np.zeros(3)
+        lib().synth_get_imu(self.h, self.imu_time(j), j, self.ng, self.na, w.ctypes.data, a.ctypes.data)
+        return self.imu_time(j), w, a
+
+    def pose(self, t):
+        R = np.zeros(9)
+        p = np.zeros(3)
+        lib().synth_get_pose(self.h, t, R.ctypes.data, p.ctypes.data)
+        return R.reshape(3, 3), p
+
+    def render(self, k):
+        t = self.frame_time(k)
+        out = []
+        for cam in (0, 1):
+            img = np.empty((self.cfg.img_rows, self.cfg.img_cols), np.uint8)
+            lib().synth_render(self.h, t, cam, img.ctypes.data, self.threads)
+            out.append(img)
+        return t, out[0], out[1]
+
+    def rays(self, cam):
+        n = self.cfg.img_rows * self.cfg.img_cols * 8
+        p = lib().synth_rays(self.h, cam)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n,)).copy()
+
+
+def feed(stream, n_frames, sink):
+    """EuRoC runner feed order (apps/run_euroc_single_thread.cpp:209-254): before image k,
+    push IMU rows until one has t > t_img (the overshoot row is pushed too)."""
+    j = 0
+    for k in range(n_frames):
+        t_img, im0, im1 = stream.render(k)
+        while True:
+            t, w, a = stream.imu(j)
+            j += 1
+            sink.imu(t, w, a)
+            if not (t <= t_img):
+                break
+        sink.stereo(t_img, im0, im1)
+        sink.backend()
+        yield k, t_img

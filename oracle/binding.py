@@ -1,0 +1,178 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY: ctypes binding of oracle/liboracle.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+from msckf_stereo_c_b200 import abi  # noqa: E402
+
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    if force or not os.path.exists(so):
+        subprocess.check_call(["make", "-s", "-C", _HERE])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.POINTER(abi.Config)]
+        for name in ("orc_destroy", "orc_backend", "orc_reset"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.orc_imu.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        L.orc_stereo.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        L.orc_backend_features.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int]
+        L.orc_get_features.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.orc_get_n_published.argtypes = [C.c_void_p]
+        L.orc_get_tracking_info.argtypes = [C.c_void_p, C.POINTER(abi.TrackingInfo)]
+        L.orc_get_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_get_pyramid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_get_state.argtypes = [C.c_void_p, C.POINTER(abi.State)]
+        L.orc_get_cam_states.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_get_cov.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_pyr_down.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_detect.argtypes = [C.POINTER(abi.Config), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_klt.argtypes = [C.POINTER(abi.Config), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_undistort.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_distort.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+GRID_DT = np.dtype([("id", "<u8"), ("response", "<f4"), ("lifetime", "<i4"), ("cam0", "<f4", 2), ("cam1", "<f4", 2),
+                    ("cell", "<i4"), ("pad", "<i4")])
+FEAT_DT = np.dtype([("id", "<u4"), ("pad", "<u4"), ("u0", "<f8"), ("v0", "<f8"), ("u1", "<f8"), ("v1", "<f8")])
+CAM_DT = np.dtype([("id", "<i8"), ("time", "<f8"), ("orientation", "<f8", 4), ("position", "<f8", 3)])
+
+
+class Oracle:
+    """System re-host (system.cpp:12-54) over the CPU restatement."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.h = lib().orc_create(C.byref(cfg))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_destroy(self.h)
+            self.h = None
+
+    def imu(self, t, w, a):
+        w = np.ascontiguousarray(w, np.float64)
+        a = np.ascontiguousarray(a, np.float64)
+        lib().orc_imu(self.h, t, w.ctypes.data, a.ctypes.data)
+
+    def stereo(self, t, im0, im1):
+        im0 = np.ascontiguousarray(im0, np.uint8)
+        im1 = np.ascontiguousarray(im1, np.uint8)
+        lib().orc_stereo(self.h, t, im0.ctypes.data, im1.ctypes.data)
+
+    def backend(self):
+        lib().orc_backend(self.h)
+
+    def backend_features(self, t, feats):
+        feats = np.ascontiguousarray(feats, FEAT_DT)
+        lib().orc_backend_features(self.h, t, feats.ctypes.data, len(feats))
+
+    def features(self):
+        t = C.c_double()
+        n = lib().orc_get_features(self.h, None, 0, C.byref(t))
+        out = np.zeros(n, FEAT_DT)
+        lib().orc_get_features(self.h, out.ctypes.data, n, C.byref(t))
+        return t.value, out, lib().orc_get_n_published(self.h)
+
+    def tracking_info(self):
+        ti = abi.TrackingInfo()
+        lib().orc_get_tracking_info(self.h, C.byref(ti))
+        return ti
+
+    def grid(self):
+        n = lib().orc_get_grid(self.h, None, 0)
+        out = np.zeros(n, GRID_DT)
+        lib().orc_get_grid(self.h, out.ctypes.data, n)
+        return out
+
+    def pyramid(self, cam, level):
+        r, c = C.c_int(), C.c_int()
+        buf = np.zeros(self.cfg.img_rows * self.cfg.img_cols, np.uint8)
+        rc = lib().orc_get_pyramid(self.h, cam, level, buf.ctypes.data, buf.size, C.byref(r), C.byref(c))
+        assert rc == 0
+        return buf[: r.value * c.value].reshape(r.value, c.value).copy()
+
+    def state(self):
+        s = abi.State()
+        lib().orc_get_state(self.h, C.byref(s))
+        return s
+
+    def cam_states(self):
+        n = lib().orc_get_cam_states(self.h, None, 0)
+        out = np.zeros(n, CAM_DT)
+        lib().orc_get_cam_states(self.h, out.ctypes.data, n)
+        return out
+
+    def cov(self):
+        n = lib().orc_get_cov(self.h, None, 0)
+        out = np.zeros((n, n))
+        lib().orc_get_cov(self.h, out.ctypes.data, n * n)
+        return out
+
+
+def pyr_down(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty(((img.shape[0] + 1) // 2, (img.shape[1] + 1) // 2), np.uint8)
+    lib().orc_pyr_down(img.ctypes.data, img.shape[0], img.shape[1], out.ctypes.data)
+    return out
+
+
+def detect(cfg, img, occupied=None, want_scores=False):
+    img = np.ascontiguousarray(img, np.uint8)
+    occ = np.ascontiguousarray(occupied if occupied is not None else np.zeros((0, 2)), np.float32)
+    cap = cfg.det_rows * cfg.det_cols
+    xy = np.zeros((cap, 2), np.float32)
+    resp = np.zeros(cap)
+    sm = np.zeros(img.shape, np.uint8) if want_scores else None
+    n = lib().orc_detect(C.byref(cfg), img.ctypes.data, occ.ctypes.data, len(occ), xy.ctypes.data, resp.ctypes.data, cap,
+                         sm.ctypes.data if want_scores else None)
+    return (xy[:n], resp[:n], sm) if want_scores else (xy[:n], resp[:n])
+
+
+def klt(cfg, a, b, pts_a, pts_b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    pa = np.ascontiguousarray(pts_a, np.float32)
+    pb = np.array(pts_b, np.float32, copy=True)
+    st = np.zeros(len(pa), np.uint8)
+    lib().orc_klt(C.byref(cfg), a.ctypes.data, b.ctypes.data, pa.ctypes.data, pb.ctypes.data, st.ctypes.data, len(pa))
+    return pb, st
+
+
+def undistort(pts, K, model, D, R=None, Kn=(1, 1, 0, 0)):
+    pts = np.ascontiguousarray(pts, np.float32)
+    K = np.ascontiguousarray(K, np.float64)
+    D = np.ascontiguousarray(D, np.float64)
+    R = np.ascontiguousarray(np.eye(3) if R is None else R, np.float64)
+    Kn = np.ascontiguousarray(Kn, np.float64)
+    out = np.zeros_like(pts)
+    lib().orc_undistort(pts.ctypes.data, len(pts), K.ctypes.data, model, D.ctypes.data, R.ctypes.data, Kn.ctypes.data, out.ctypes.data)
+    return out
+
+
+def distort(pts, K, model, D):
+    pts = np.ascontiguousarray(pts, np.float32)
+    K = np.ascontiguousarray(K, np.float64)
+    D = np.ascontiguousarray(D, np.float64)
+    out = np.zeros_like(pts)
+    lib().orc_distort(pts.ctypes.data, len(pts), K.ctypes.data, model, D.ctypes.data, out.ctypes.data)
+    return out

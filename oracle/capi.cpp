@@ -1,0 +1,221 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see linalg.h).
+//
+// capi.cpp: C entry points for ctypes (tests/, smoke(), bench.py's CPU legs).  `Oracle`
+// re-hosts System (msckf_core/src/system.cpp:12-54): one ImageProcessor + one MsckfVio and
+// the three forwarders; the feed order (IMU rows with t <= t_img plus one overshoot, then
+// stereo_callback, then backend_callback; apps/run_euroc_single_thread.cpp:209-254) is
+// driven by the caller.
+#include "backend.h"
+
+using namespace orc;
+
+struct Oracle {
+    ImageProcessor fe;
+    MsckfVio be;
+    explicit Oracle(const mskf_config &c) : fe(c), be(c) {}
+};
+
+extern "C" {
+
+void *orc_create(const mskf_config *cfg) { return new Oracle(*cfg); }
+void orc_destroy(void *h) { delete (Oracle *)h; }
+
+// System::imu_callback, system.cpp:45-48
+void orc_imu(void *h, double t, const double w[3], const double a[3]) {
+    Oracle *o = (Oracle *)h;
+    ImuMsg m{t, V3(w[0], w[1], w[2]), V3(a[0], a[1], a[2])};
+    o->fe.imuCallback(m);
+    o->be.imuCallback(m);
+}
+// System::stereo_callback, system.cpp:40-43
+void orc_stereo(void *h, double t, const uint8_t *cam0, const uint8_t *cam1) { ((Oracle *)h)->fe.stereoCallback(t, cam0, cam1); }
+// System::backend_callback, system.cpp:50-54
+void orc_backend(void *h) {
+    Oracle *o = (Oracle *)h;
+    o->be.featureCallback(*o->fe.feature_msg);
+}
+void orc_backend_features(void *h, double t, const mskf_feature *f, int n) {
+    Oracle *o = (Oracle *)h;
+    CameraMeasurement msg;
+    msg.time_stamp = t;
+    msg.features.resize(n);
+    for (int i = 0; i < n; ++i) {
+        msg.features[i].id = f[i].id;
+        msg.features[i].u0 = f[i].u0;
+        msg.features[i].v0 = f[i].v0;
+        msg.features[i].u1 = f[i].u1;
+        msg.features[i].v1 = f[i].v1;
+    }
+    o->be.featureCallback(msg);
+}
+void orc_reset(void *h) { ((Oracle *)h)->be.resetCallback(); }
+
+int orc_get_features(void *h, mskf_feature *out, int cap, double *t) {
+    Oracle *o = (Oracle *)h;
+    const auto &v = o->fe.feature_msg->features;
+    if (t) *t = o->fe.feature_msg->time_stamp;
+    for (int i = 0; i < (int)v.size() && i < cap; ++i) {
+        out[i].id = v[i].id;
+        out[i].pad = 0;
+        out[i].u0 = v[i].u0; out[i].v0 = v[i].v0; out[i].u1 = v[i].u1; out[i].v1 = v[i].v1;
+    }
+    return (int)v.size();
+}
+int orc_get_n_published(void *h) { return ((Oracle *)h)->fe.n_published; }
+void orc_get_tracking_info(void *h, mskf_tracking_info *ti) {
+    Oracle *o = (Oracle *)h;
+    ti->time_stamp = o->fe.feature_msg->time_stamp;
+    ti->before_tracking = o->fe.before_tracking;
+    ti->after_tracking = o->fe.after_tracking;
+    ti->after_matching = o->fe.after_matching;
+    ti->after_ransac = o->fe.after_ransac;
+}
+int orc_get_grid(void *h, mskf_grid_feature *out, int cap) {
+    Oracle *o = (Oracle *)h;
+    int n = 0;
+    for (const auto &cell : *o->fe.prev_features)
+        for (const auto &f : cell.second) {
+            if (n < cap) {
+                out[n].id = f.id; out[n].response = f.response; out[n].lifetime = f.lifetime;
+                out[n].cam0_x = f.cam0_point.x; out[n].cam0_y = f.cam0_point.y;
+                out[n].cam1_x = f.cam1_point.x; out[n].cam1_y = f.cam1_point.y;
+                out[n].cell = cell.first; out[n].pad = 0;
+            }
+            ++n;
+        }
+    return n;
+}
+int orc_get_pyramid(void *h, int cam, int level, uint8_t *out, int cap, int *rows, int *cols) {
+    Oracle *o = (Oracle *)h;
+    const std::vector<Img> &p = cam == 0 ? o->fe.prev_cam0_pyramid : o->fe.curr_cam1_pyramid;
+    if (level < 0 || level >= (int)p.size()) return -1;
+    *rows = p[level].rows; *cols = p[level].cols;
+    if ((int)p[level].d.size() > cap) return -3;
+    std::memcpy(out, p[level].d.data(), p[level].d.size());
+    return 0;
+}
+void orc_get_state(void *h, mskf_state *s) {
+    Oracle *o = (Oracle *)h;
+    const MsckfVio &b = o->be;
+    std::memset(s, 0, sizeof(*s));
+    s->time = b.imu_state.time; s->id = b.imu_state.id;
+    s->orientation[0] = b.imu_state.orientation.x; s->orientation[1] = b.imu_state.orientation.y;
+    s->orientation[2] = b.imu_state.orientation.z; s->orientation[3] = b.imu_state.orientation.w;
+    for (int i = 0; i < 3; ++i) {
+        s->position[i] = b.imu_state.position[i]; s->velocity[i] = b.imu_state.velocity[i];
+        s->gyro_bias[i] = b.imu_state.gyro_bias[i]; s->acc_bias[i] = b.imu_state.acc_bias[i];
+        s->t_cam0_imu[i] = b.imu_state.t_cam0_imu[i]; s->gravity[i] = b.gravity[i];
+    }
+    for (int i = 0; i < 9; ++i) s->R_imu_cam0[i] = b.imu_state.R_imu_cam0.m[i];
+    s->n_cam_states = (int)b.cam_states.size(); s->cov_dim = b.state_cov.r;
+    s->is_gravity_set = b.is_gravity_set; s->n_map_features = (int)b.map_server.size();
+    s->tracking_rate = b.tracking_rate;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) s->T_b_w[i * 4 + j] = b.T_b_w.R(i, j);
+        s->T_b_w[i * 4 + 3] = b.T_b_w.t[i];
+    }
+    s->T_b_w[15] = 1.0;
+    s->n_updates = b.n_updates; s->n_resets = b.n_resets;
+}
+int orc_get_cam_states(void *h, mskf_cam_state *out, int cap) {
+    Oracle *o = (Oracle *)h;
+    int n = 0;
+    for (const auto &kv : o->be.cam_states) {
+        if (n < cap) {
+            out[n].id = kv.first; out[n].time = kv.second.time;
+            out[n].orientation[0] = kv.second.orientation.x; out[n].orientation[1] = kv.second.orientation.y;
+            out[n].orientation[2] = kv.second.orientation.z; out[n].orientation[3] = kv.second.orientation.w;
+            for (int i = 0; i < 3; ++i) out[n].position[i] = kv.second.position[i];
+        }
+        ++n;
+    }
+    return n;
+}
+int orc_get_cov(void *h, double *out, int cap) {
+    Oracle *o = (Oracle *)h;
+    const Mat &P = o->be.state_cov;
+    if ((int)P.d.size() <= cap) std::memcpy(out, P.d.data(), P.d.size() * sizeof(double));
+    return P.r;
+}
+
+// ---- stand-alone primitives -------------------------------------------------------------
+void orc_pyr_down(const uint8_t *in, int rows, int cols, uint8_t *out) {
+    Img a(rows, cols), b;
+    std::memcpy(a.d.data(), in, a.d.size());
+    pyr_down(a, b);
+    std::memcpy(out, b.d.data(), b.d.size());
+}
+static void build_pyr(const uint8_t *img, int rows, int cols, int levels, std::vector<Img> &p) {
+    p.clear();
+    Img a(rows, cols);
+    std::memcpy(a.d.data(), img, a.d.size());
+    p.push_back(a);
+    for (int i = 1; i < levels; ++i) {
+        Img t;
+        pyr_down(p[i - 1], t);
+        p.push_back(t);
+    }
+}
+int orc_detect(const mskf_config *cfg, const uint8_t *img, const float *occ_xy, int n_occ, float *out_xy,
+               double *out_resp, int cap, uint8_t *score_map) {
+    CornerDetector d;
+    d.n_rows = cfg->det_rows; d.n_cols = cfg->det_cols;
+    d.fast_threshold = cfg->fast_threshold; d.detection_threshold = cfg->detection_threshold;
+    d.configure(cfg->img_rows, cfg->img_cols);
+    Img a(cfg->img_rows, cfg->img_cols);
+    std::memcpy(a.d.data(), img, a.d.size());
+    for (int i = 0; i < n_occ; ++i) d.set_grid_position(Pt((float)(int)occ_xy[2 * i], (float)(int)occ_xy[2 * i + 1]));
+    std::vector<Pt> pts;
+    std::vector<double> resp;
+    std::vector<uint8_t> sm;
+    d.detect_features(a, pts, resp, score_map ? &sm : nullptr);
+    if (score_map) std::memcpy(score_map, sm.data(), sm.size());
+    for (int i = 0; i < (int)pts.size() && i < cap; ++i) {
+        out_xy[2 * i] = pts[i].x; out_xy[2 * i + 1] = pts[i].y;
+        out_resp[i] = resp[i];
+    }
+    return (int)pts.size();
+}
+void orc_klt(const mskf_config *cfg, const uint8_t *a, const uint8_t *b, const float *pts_a, float *pts_b,
+             uint8_t *status, int n) {
+    std::vector<Img> pa, pb;
+    build_pyr(a, cfg->img_rows, cfg->img_cols, cfg->pyramid_levels, pa);
+    build_pyr(b, cfg->img_rows, cfg->img_cols, cfg->pyramid_levels, pb);
+    KltParams kp;
+    kp.win = cfg->klt_win; kp.max_iters = cfg->klt_max_iters; kp.eps = cfg->klt_eps; kp.min_eig = cfg->klt_min_eig;
+    std::vector<Pt> A(n), B(n);
+    for (int i = 0; i < n; ++i) {
+        A[i] = Pt(pts_a[2 * i], pts_a[2 * i + 1]);
+        B[i] = Pt(pts_b[2 * i], pts_b[2 * i + 1]);
+    }
+    std::vector<uint8_t> st;
+    optical_flow_multi_level(pa, pb, A, B, st, kp);
+    for (int i = 0; i < n; ++i) {
+        pts_b[2 * i] = B[i].x; pts_b[2 * i + 1] = B[i].y;
+        status[i] = st[i];
+    }
+}
+void orc_undistort(const float *in, int n, const double K[4], int model, const double D[4], const double R[9],
+                   const double Kn[4], float *out) {
+    std::vector<Pt> a(n), b;
+    for (int i = 0; i < n; ++i) a[i] = Pt(in[2 * i], in[2 * i + 1]);
+    M3 Rm;
+    for (int i = 0; i < 9; ++i) Rm.m[i] = R[i];
+    undistort_points(a, b, K, model, D, Rm, Kn);
+    for (int i = 0; i < n; ++i) { out[2 * i] = b[i].x; out[2 * i + 1] = b[i].y; }
+}
+void orc_distort(const float *in, int n, const double K[4], int model, const double D[4], float *out) {
+    std::vector<Pt> a(n), b;
+    for (int i = 0; i < n; ++i) a[i] = Pt(in[2 * i], in[2 * i + 1]);
+    distort_points(a, b, K, model, D);
+    for (int i = 0; i < n; ++i) { out[2 * i] = b[i].x; out[2 * i + 1] = b[i].y; }
+}
+// null-space projection + gating ingredients of one feature, for the basis-invariance test
+void orc_last_update_debug(void *h, double *delta_x, int cap, int *n, double *gamma) {
+    Oracle *o = (Oracle *)h;
+    *n = o->be.last_delta_x.r;
+    for (int i = 0; i < *n && i < cap; ++i) delta_x[i] = o->be.last_delta_x(i, 0);
+    *gamma = o->be.last_gamma;
+}
+
+}  // extern "C"
