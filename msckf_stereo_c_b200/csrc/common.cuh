@@ -1,0 +1,177 @@
+// common.cuh — shared declarations of the sm_100a engine behind include/msckf_b200.h.
+//
+// Memory layout in HBM (per handle, S = n_streams):
+//   pyramids   3 sets [S][pyr_bytes]  (cam0 ping, cam0 pong, cam1); level l of a stream
+//              starts at lvl_off[l], rows tightly packed (cols bytes per row)
+//   staging    [S][2][rows*cols]      level-0 landing area for host uploads
+//   front end  per-stream grids, KLT work lists, detector tables (struct FeBuffers)
+//   back end   per-stream filter state, covariance [S][LD*LD] fp64, feature map,
+//              Jacobian scratch (struct BeBuffers)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/msckf_b200.h"
+
+#define MSKF_CUDA_CHECK(h, expr)                                                            \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                  \
+            return MSKF_ERR_CUDA;                                                           \
+        }                                                                                   \
+    } while (0)
+
+namespace mskf {
+
+// ---- constants handed to the front-end kernels by value -------------------------------
+struct FeConst {
+    int rows, cols, levels;
+    int lvl_rows[MSKF_MAX_LEVELS], lvl_cols[MSKF_MAX_LEVELS];
+    unsigned lvl_off[MSKF_MAX_LEVELS];
+    unsigned pyr_bytes;  // per image, all levels
+    int klt_win, klt_max_iters;
+    double klt_eps2, klt_min_eig;
+    int grid_row, grid_col, grid_min, grid_max, grid_h, grid_w, n_cells, n_cells_all;
+    int det_rows, det_cols, det_cell_h, det_cell_w, det_cells;
+    int fast_threshold;
+    double detection_threshold;
+    int max_f;    // capacity of a grid / tracked list
+    int cap_k;    // capacity of a KLT work list (>= det_cells)
+    int cam_model[2];
+    double K[2][4], D[2][4];
+    double R01[9];      // R_cam0_cam1 = R_cam1_imu^T R_cam0_imu (image_processor.cpp:544)
+    double E[9];        // essential matrix (image_processor.cpp:591)
+    double stereo_gate; // stereo_threshold * norm_pixel_unit (image_processor.cpp:606,615)
+    int compat_stale;
+};
+
+// per-stream, per-step descriptor written by the host before each front-end step
+struct FeStep {
+    int active, is_first, slot, pad;
+    double t;
+    double H0[9];  // K R_p_c K^-1 for cam0 (image_processor.cpp:340)
+};
+
+struct GridSoA {            // one grid of one stream, publish order (cell asc, insertion order)
+    unsigned long long *id;
+    float *response;
+    int *lifetime;
+    float2 *cam0, *cam1;
+    int *cell;
+};
+
+struct FeBuffers {
+    uint8_t *pyr[3];        // [S][pyr_bytes] x3 : cam0 slot0, cam0 slot1, cam1
+    uint8_t *staging;       // [S][2][rows*cols]
+    const uint8_t **src0, **src1;  // [S] device pointers to this step's level-0 sources
+    FeStep *step;           // [S]
+    // grids: prev and curr (index by ping-pong flag gslot[s])
+    unsigned long long *g_id[2];
+    float *g_resp[2];
+    int *g_life[2];
+    float2 *g_cam0[2], *g_cam1[2];
+    int *g_cell[2];
+    int *g_n[2];            // [S]
+    int *gslot;             // [S] which grid buffer is "prev"
+    unsigned long long *next_id;  // [S]
+    // KLT work lists
+    float2 *k_a, *k_b;      // [S][cap_k]
+    uint8_t *k_status;      // [S][cap_k]
+    int *k_n;               // [S]
+    // tracked meta carried through the temporal track
+    unsigned long long *t_id;  // [S][max_f]
+    int *t_life;               // [S][max_f]
+    // detector
+    unsigned long long *det_best;  // [S][det_cells] packed (score bits << 32 | ~raster)
+    uint8_t *det_occ;              // [S][det_cells]
+    float *nf_resp;                // [S][det_cells] responses in detect order
+    float *in_resp;                // [S][cap_k] responses of the stereo inliers (fe_finish)
+    int *nf_n;                     // [S] number detected
+    // outputs
+    mskf_feature *msg;      // [S][max_f] current frame measurements
+    int *msg_n;             // [S]
+    mskf_feature *stale;    // [S][max_f] high-water copy emulating the never-cleared vector (F4)
+    int *stale_hw;          // [S] high-water mark
+    long long *msg_total;   // [S] total length of the reference's growing vector
+    mskf_tracking_info *info;  // [S]
+    uint8_t *dbg_score;     // optional [rows*cols] FAST score map of stream 0 (tests only)
+};
+
+}  // namespace mskf
+
+struct BeBuffers;  // backend.cu
+
+struct HostImu {
+    double t, w[3], a[3];
+};
+
+struct HostStream {
+    // front end (image_processor.cpp:205-211, 850-889)
+    bool fe_first = true;
+    std::vector<HostImu> fe_imu;
+    double fe_prev_t = 0, fe_curr_t = 0;
+    int slot = 0;
+    bool pending = false;      // a stereo pair is staged
+    bool published = false;    // front end produced a message not yet consumed by the back end
+    double pending_t = 0;
+    const uint8_t *src0 = nullptr, *src1 = nullptr;
+    // back end (msckf_vio.cpp:190-241, 377-407)
+    std::vector<HostImu> be_imu;
+    bool gravity_set = false, be_first = true;
+    double be_time = 0;        // mirror of imu_state.time
+    double msg_t = 0;
+};
+
+struct mskf_handle {
+    mskf_config cfg;
+    int S = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    mskf::FeConst fc;
+    mskf::FeBuffers fb;
+    BeBuffers *bb = nullptr;
+    std::vector<HostStream> hs;
+    // pinned staging
+    uint8_t *h_stage = nullptr;        // [S][2][rows*cols]
+    mskf::FeStep *h_step = nullptr;    // [S]
+    const uint8_t **h_src = nullptr;   // [2][S]
+    void *h_be_step = nullptr;         // backend step descriptors (pinned)
+    std::vector<void *> allocs;
+    long long launches = 0;            // kernels launched so far (bench: gpu_launches)
+};
+
+// frontend.cu
+int fe_create(mskf_handle *h);
+int fe_step(mskf_handle *h, bool any_first, int max_prev);
+int fe_op_detect(mskf_handle *t, const float *occ, int n_occ, float *out_xy, double *out_resp, int cap, int *n,
+                 uint8_t *score_map);
+int fe_op_klt(mskf_handle *t, const float *pts_a, float *pts_b, uint8_t *status, int n);
+// backend.cu
+int be_create(mskf_handle *h);
+void be_destroy(mskf_handle *h);
+int be_step(mskf_handle *h, const std::vector<int> &streams, const mskf_feature *inject, int n_inject,
+            int inject_stream, double inject_t);
+int be_init_gravity(mskf_handle *h, int s);
+int be_get_state(mskf_handle *h, int s, mskf_state *out);
+int be_get_cam_states(mskf_handle *h, int s, mskf_cam_state *out, int cap, int *n);
+int be_get_cov(mskf_handle *h, int s, double *out, int cap, int *dim);
+int be_reset(mskf_handle *h, int s);
+
+template <typename T>
+int dev_alloc(mskf_handle *h, T **p, size_t n) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess) {
+        h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        return MSKF_ERR_CUDA;
+    }
+    cudaMemset(q, 0, n * sizeof(T));
+    h->allocs.push_back(q);
+    *p = (T *)q;
+    return MSKF_OK;
+}

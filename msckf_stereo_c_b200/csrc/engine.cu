@@ -1,0 +1,508 @@
+// engine.cu — the C ABI of include/msckf_b200.h: handle life cycle, host-side IMU
+// buffering (the strictly sequential, negligible parts of the path: SURVEY a8, a14's
+// bookkeeping) and step orchestration.  All image and filter arithmetic runs in the CUDA
+// kernels of frontend.cu / backend.cu; there is no CPU fallback.
+#include <math.h>
+#include <string.h>
+
+#include "../../include/msckf_b200_presets.h"
+#include "common.cuh"
+
+using namespace mskf;
+
+#define STEP_RING 4
+
+struct EngineExtra {
+    cudaEvent_t ring_ev[STEP_RING];
+    bool ring_used[STEP_RING];
+    int ring_pos = 0;
+    FeStep *h_step_ring[STEP_RING];
+    const uint8_t **h_src_ring[STEP_RING];
+    std::vector<mskf_feature> scratch;
+};
+static EngineExtra *extra(mskf_handle *h) { return (EngineExtra *)h->h_be_step; }
+
+// ---- small host math, written to evaluate exactly like the reference's cg::Matrix code
+// paths restated in the oracle (same operation order => same bits) ------------------------
+static void m3_mul(const double *a, const double *b, double *c) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += a[i * 3 + k] * b[k * 3 + j];
+            c[i * 3 + j] = s;
+        }
+}
+static void m3_inv(const double *a, double *r) {
+    double c00 = a[4] * a[8] - a[5] * a[7];
+    double c01 = a[5] * a[6] - a[3] * a[8];
+    double c02 = a[3] * a[7] - a[4] * a[6];
+    double det = a[0] * c00 + a[1] * c01 + a[2] * c02;
+    double id = 1.0 / det;
+    r[0] = c00 * id;
+    r[1] = (a[2] * a[7] - a[1] * a[8]) * id;
+    r[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+    r[3] = c01 * id;
+    r[4] = (a[0] * a[8] - a[2] * a[6]) * id;
+    r[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+    r[6] = c02 * id;
+    r[7] = (a[1] * a[6] - a[0] * a[7]) * id;
+    r[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+}
+// cv::Rodrigues semantics, transposed result (image_processor.cpp:882)
+static void rodrigues_t(const double v[3], double Rt[9]) {
+    double th = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    double R[9];
+    const double sk[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
+    if (th < 1e-12) {
+        for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0 ? 1.0 : 0.0) + sk[i];
+    } else {
+        double k[3] = {v[0] / th, v[1] / th, v[2] / th};
+        double c = cos(th), s = sin(th);
+        const double skk[9] = {0, -k[2], k[1], k[2], 0, -k[0], -k[1], k[0], 0};
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                R[i * 3 + j] = (i == j ? 1.0 : 0.0) * c + (k[i] * k[j]) * (1 - c) + skk[i * 3 + j] * s;
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Rt[j * 3 + i] = R[i * 3 + j];
+}
+
+// ImageProcessor::integrateImuData (image_processor.cpp:850-889) + the homography of
+// predictFeatureTracking (:335-340) for cam0.
+static void host_predict_homography(mskf_handle *h, HostStream &hs, double H0[9]) {
+    const mskf_config &c = h->cfg;
+    const double prev_t = c.fix_prev_image_alias ? hs.fe_prev_t : hs.fe_curr_t;  // defect F6
+    size_t begin = 0;
+    while (begin < hs.fe_imu.size()) {
+        if (hs.fe_imu[begin].t - prev_t < -0.01) ++begin;
+        else break;
+    }
+    size_t end = begin;
+    while (end < hs.fe_imu.size()) {
+        if (hs.fe_imu[end].t - hs.fe_curr_t < 0.005) ++end;
+        else break;
+    }
+    double mean[3] = {0, 0, 0};
+    for (size_t i = begin; i < end; ++i)
+        for (int k = 0; k < 3; ++k) mean[k] = mean[k] + hs.fe_imu[i].w[k];
+    if (end > begin) {
+        double sc = (double)(1.0f / (float)(end - begin));
+        for (int k = 0; k < 3; ++k) mean[k] = mean[k] * sc;
+    }
+    // cam0_mean_ang_vel = R_cam0_imu^T * mean ; R_cam0_imu = rot(T_cam0_imu)^T  => rot(T) * mean
+    double cam0_w[3];
+    for (int i = 0; i < 3; ++i)
+        cam0_w[i] = c.T_cam0_imu[i * 4 + 0] * mean[0] + c.T_cam0_imu[i * 4 + 1] * mean[1] + c.T_cam0_imu[i * 4 + 2] * mean[2];
+    double dtime = hs.fe_curr_t - prev_t;
+    double v[3] = {cam0_w[0] * dtime, cam0_w[1] * dtime, cam0_w[2] * dtime};
+    double Rpc[9];
+    rodrigues_t(v, Rpc);
+    hs.fe_imu.erase(hs.fe_imu.begin(), hs.fe_imu.begin() + end);
+    double K[9] = {c.cam0_intrinsics[0], 0, c.cam0_intrinsics[2], 0, c.cam0_intrinsics[1], c.cam0_intrinsics[3], 0, 0, 1.0};
+    double KR[9], Ki[9];
+    m3_mul(K, Rpc, KR);
+    m3_inv(K, Ki);
+    m3_mul(KR, Ki, H0);
+}
+
+extern "C" {
+
+int mskf_default_config(mskf_config *cfg, const char *preset) { return mskf_fill_preset(cfg, preset); }
+
+int mskf_create(const mskf_config *cfg, int n_streams, int device, mskf_handle **out) {
+    if (!cfg || !out || n_streams < 1) return MSKF_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return MSKF_ERR_CUDA;
+    mskf_handle *h = new mskf_handle;
+    h->cfg = *cfg;
+    h->S = n_streams;
+    h->device = device;
+    h->hs.resize(n_streams);
+    *out = h;  // returned even on failure so that mskf_last_error can be read
+    MSKF_CUDA_CHECK(h, cudaSetDevice(device));
+    MSKF_CUDA_CHECK(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+    int rc = fe_create(h);
+    if (rc != MSKF_OK) return rc;
+    rc = be_create(h);
+    if (rc != MSKF_OK) return rc;
+    EngineExtra *ex = new EngineExtra;
+    h->h_be_step = ex;
+    for (int i = 0; i < STEP_RING; ++i) {
+        MSKF_CUDA_CHECK(h, cudaEventCreateWithFlags(&ex->ring_ev[i], cudaEventDisableTiming));
+        ex->ring_used[i] = false;
+        MSKF_CUDA_CHECK(h, cudaMallocHost((void **)&ex->h_step_ring[i], sizeof(FeStep) * n_streams));
+        MSKF_CUDA_CHECK(h, cudaMallocHost((void **)&ex->h_src_ring[i], sizeof(uint8_t *) * 2 * n_streams));
+    }
+    MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    return MSKF_OK;
+}
+
+void mskf_destroy(mskf_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    be_destroy(h);
+    EngineExtra *ex = extra(h);
+    if (ex) {
+        for (int i = 0; i < STEP_RING; ++i) {
+            cudaEventDestroy(ex->ring_ev[i]);
+            cudaFreeHost(ex->h_step_ring[i]);
+            cudaFreeHost((void *)ex->h_src_ring[i]);
+        }
+        delete ex;
+    }
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char *mskf_last_error(const mskf_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+int mskf_set_cuda_stream(mskf_handle *h, void *cuda_stream) {
+    if (!h) return MSKF_ERR_ARG;
+    cudaStreamSynchronize(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)cuda_stream;
+    h->own_stream = false;
+    return MSKF_OK;
+}
+
+long long mskf_launch_count(const mskf_handle *h) { return h ? h->launches : 0; }
+
+int mskf_push_imu(mskf_handle *h, int s, double t, const double w[3], const double a[3]) {
+    if (!h || s < 0 || s >= h->S) return MSKF_ERR_ARG;
+    HostStream &hs = h->hs[s];
+    HostImu m;
+    m.t = t;
+    for (int i = 0; i < 3; ++i) { m.w[i] = w[i]; m.a[i] = a[i]; }
+    if (!hs.fe_first) hs.fe_imu.push_back(m);  // image_processor.cpp:205-211
+    hs.be_imu.push_back(m);                     // msckf_vio.cpp:190-207
+    if (!hs.gravity_set && hs.be_imu.size() >= 200) {
+        int rc = be_init_gravity(h, s);
+        if (rc != MSKF_OK) return rc;
+        hs.gravity_set = true;
+    }
+    return MSKF_OK;
+}
+
+int mskf_push_stereo(mskf_handle *h, int s, double t, const uint8_t *cam0, const uint8_t *cam1, int rows, int cols,
+                     int stride) {
+    if (!h || s < 0 || s >= h->S || !cam0 || !cam1) return MSKF_ERR_ARG;
+    if (rows != h->cfg.img_rows || cols != h->cfg.img_cols || stride < cols) {
+        h->err = "image geometry does not match the configuration";
+        return MSKF_ERR_ARG;
+    }
+    MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
+    const size_t img = (size_t)rows * cols;
+    uint8_t *d0 = h->fb.staging + ((size_t)s * 2 + 0) * img, *d1 = h->fb.staging + ((size_t)s * 2 + 1) * img;
+    // pageable sources are staged by the runtime before the call returns; page-locked
+    // sources are read asynchronously and must stay unchanged until the next mskf_sync()
+    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(d0, cols, cam0, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(d1, cols, cam1, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+    HostStream &hs = h->hs[s];
+    hs.pending = true;
+    hs.pending_t = t;
+    hs.src0 = d0;
+    hs.src1 = d1;
+    return MSKF_OK;
+}
+
+int mskf_push_stereo_device(mskf_handle *h, int s, double t, const uint8_t *d_cam0, const uint8_t *d_cam1) {
+    if (!h || s < 0 || s >= h->S || !d_cam0 || !d_cam1) return MSKF_ERR_ARG;
+    HostStream &hs = h->hs[s];
+    hs.pending = true;
+    hs.pending_t = t;
+    hs.src0 = d_cam0;
+    hs.src1 = d_cam1;
+    return MSKF_OK;
+}
+
+int mskf_frontend_step(mskf_handle *h) {
+    if (!h) return MSKF_ERR_ARG;
+    MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
+    EngineExtra *ex = extra(h);
+    const int S = h->S;
+    int slot = ex->ring_pos;
+    ex->ring_pos = (ex->ring_pos + 1) % STEP_RING;
+    if (ex->ring_used[slot]) MSKF_CUDA_CHECK(h, cudaEventSynchronize(ex->ring_ev[slot]));
+    FeStep *hstep = ex->h_step_ring[slot];
+    const uint8_t **hsrc = ex->h_src_ring[slot];
+    bool any = false, any_first = false;
+    int max_prev = 0;
+    for (int s = 0; s < S; ++s) {
+        HostStream &hs = h->hs[s];
+        FeStep &st = hstep[s];
+        memset(&st, 0, sizeof(st));
+        hsrc[s] = hs.src0;
+        hsrc[S + s] = hs.src1;
+        if (!hs.pending) continue;
+        any = true;
+        st.active = 1;
+        st.is_first = hs.fe_first ? 1 : 0;
+        hs.fe_curr_t = hs.pending_t;
+        st.t = hs.pending_t;
+        if (hs.fe_first) {
+            any_first = true;
+            hs.slot = 0;
+        } else {
+            hs.slot ^= 1;  // std::swap(prev_cam0_pyramid_, curr_cam0_pyramid_), image_processor.cpp:194
+            host_predict_homography(h, hs, st.H0);
+            max_prev = h->fc.max_f;
+        }
+        st.slot = hs.slot;
+        hs.fe_prev_t = hs.fe_curr_t;
+        hs.fe_first = false;
+        hs.pending = false;
+        hs.published = true;
+        hs.msg_t = st.t;
+    }
+    if (!any) return MSKF_OK;
+    MSKF_CUDA_CHECK(h, cudaMemcpyAsync(h->fb.step, hstep, sizeof(FeStep) * S, cudaMemcpyHostToDevice, h->stream));
+    MSKF_CUDA_CHECK(h, cudaMemcpyAsync(h->fb.src0, hsrc, sizeof(uint8_t *) * S, cudaMemcpyHostToDevice, h->stream));
+    MSKF_CUDA_CHECK(h, cudaMemcpyAsync(h->fb.src1, hsrc + S, sizeof(uint8_t *) * S, cudaMemcpyHostToDevice, h->stream));
+    MSKF_CUDA_CHECK(h, cudaEventRecord(ex->ring_ev[slot], h->stream));
+    ex->ring_used[slot] = true;
+    return fe_step(h, any_first, max_prev);
+}
+
+int mskf_backend_step(mskf_handle *h) {
+    if (!h) return MSKF_ERR_ARG;
+    MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
+    std::vector<int> streams;
+    for (int s = 0; s < h->S; ++s) {
+        HostStream &hs = h->hs[s];
+        if (!hs.published) continue;
+        hs.published = false;
+        if (!hs.gravity_set) continue;  // msckf_vio.cpp:308
+        streams.push_back(s);
+    }
+    if (streams.empty()) return MSKF_OK;
+    return be_step(h, streams, nullptr, 0, -1, 0.0);
+}
+
+int mskf_step(mskf_handle *h) {
+    int rc = mskf_frontend_step(h);
+    if (rc != MSKF_OK) return rc;
+    return mskf_backend_step(h);
+}
+
+int mskf_sync(mskf_handle *h) {
+    if (!h) return MSKF_ERR_ARG;
+    MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
+    MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    return MSKF_OK;
+}
+
+int mskf_backend_step_features(mskf_handle *h, int s, double t, const mskf_feature *f, int n) {
+    if (!h || s < 0 || s >= h->S || n < 0 || (n > 0 && !f)) return MSKF_ERR_ARG;
+    MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
+    HostStream &hs = h->hs[s];
+    hs.published = false;
+    if (!hs.gravity_set) return MSKF_OK;
+    std::vector<int> streams(1, s);
+    return be_step(h, streams, f, n, s, t);
+}
+
+int mskf_get_features(mskf_handle *h, int s, mskf_feature *out, int cap, int *n, double *t) {
+    if (!h || s < 0 || s >= h->S || !n) return MSKF_ERR_ARG;
+    int rc = mskf_sync(h);
+    if (rc != MSKF_OK) return rc;
+    const FeConst &fc = h->fc;
+    int cur = 0, hw = 0;
+    long long total = 0;
+    MSKF_CUDA_CHECK(h, cudaMemcpy(&cur, h->fb.msg_n + s, sizeof(int), cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(h, cudaMemcpy(&hw, h->fb.stale_hw + s, sizeof(int), cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(h, cudaMemcpy(&total, h->fb.msg_total + s, sizeof(long long), cudaMemcpyDeviceToHost));
+    *n = (int)total;
+    if (t) *t = h->hs[s].msg_t;
+    if (!out || cap <= 0) return MSKF_OK;
+    std::vector<mskf_feature> buf(fc.max_f);
+    // entries [0, cur) are this frame's; [cur, hw) are stale leftovers; the rest are value-initialised
+    MSKF_CUDA_CHECK(h, cudaMemcpy(buf.data(), h->fb.stale + (size_t)s * fc.max_f, sizeof(mskf_feature) * (size_t)hw, cudaMemcpyDeviceToHost));
+    (void)cur;
+    for (long long i = 0; i < total && i < cap; ++i) {
+        if (i < hw) out[i] = buf[(size_t)i];
+        else memset(&out[i], 0, sizeof(mskf_feature));
+    }
+    return MSKF_OK;
+}
+
+int mskf_get_n_published(mskf_handle *h, int s, int *n) {
+    if (!h || s < 0 || s >= h->S || !n) return MSKF_ERR_ARG;
+    int rc = mskf_sync(h);
+    if (rc != MSKF_OK) return rc;
+    MSKF_CUDA_CHECK(h, cudaMemcpy(n, h->fb.msg_n + s, sizeof(int), cudaMemcpyDeviceToHost));
+    return MSKF_OK;
+}
+
+int mskf_get_tracking_info(mskf_handle *h, int s, mskf_tracking_info *out) {
+    if (!h || s < 0 || s >= h->S || !out) return MSKF_ERR_ARG;
+    int rc = mskf_sync(h);
+    if (rc != MSKF_OK) return rc;
+    MSKF_CUDA_CHECK(h, cudaMemcpy(out, h->fb.info + s, sizeof(*out), cudaMemcpyDeviceToHost));
+    return MSKF_OK;
+}
+
+int mskf_get_grid(mskf_handle *h, int s, mskf_grid_feature *out, int cap, int *n) {
+    if (!h || s < 0 || s >= h->S || !n) return MSKF_ERR_ARG;
+    int rc = mskf_sync(h);
+    if (rc != MSKF_OK) return rc;
+    const FeConst &fc = h->fc;
+    int gp = 0, cnt = 0;
+    MSKF_CUDA_CHECK(h, cudaMemcpy(&gp, h->fb.gslot + s, sizeof(int), cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(h, cudaMemcpy(&cnt, h->fb.g_n[gp] + s, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = cnt;
+    if (!out || cap <= 0 || cnt == 0) return MSKF_OK;
+    std::vector<unsigned long long> id(cnt);
+    std::vector<float> resp(cnt);
+    std::vector<int> life(cnt), cell(cnt);
+    std::vector<float2> c0(cnt), c1(cnt);
+    const size_t go = (size_t)s * fc.max_f;
+    MSKF_CUDA_CHECK(h, cudaMemcpy(id.data(), h->fb.g_id[gp] + go, sizeof(unsigned long long) * cnt, cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(h, cudaMemcpy(resp.data(), h->fb.g_resp[gp] + go, sizeof(float) * cnt, cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(h, cudaMemcpy(life.data(), h->fb.g_life[gp] + go, sizeof(int) * cnt, cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(h, cudaMemcpy(cell.data(), h->fb.g_cell[gp] + go, sizeof(int) * cnt, cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(h, cudaMemcpy(c0.data(), h->fb.g_cam0[gp] + go, sizeof(float2) * cnt, cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(h, cudaMemcpy(c1.data(), h->fb.g_cam1[gp] + go, sizeof(float2) * cnt, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < cnt && i < cap; ++i) {
+        out[i].id = id[i]; out[i].response = resp[i]; out[i].lifetime = life[i];
+        out[i].cam0_x = c0[i].x; out[i].cam0_y = c0[i].y; out[i].cam1_x = c1[i].x; out[i].cam1_y = c1[i].y;
+        out[i].cell = cell[i]; out[i].pad = 0;
+    }
+    return MSKF_OK;
+}
+
+int mskf_get_pyramid(mskf_handle *h, int s, int cam, int level, uint8_t *out, int cap, int *rows, int *cols) {
+    if (!h || s < 0 || s >= h->S || cam < 0 || cam > 1 || level < 0 || level >= h->fc.levels || !rows || !cols)
+        return MSKF_ERR_ARG;
+    int rc = mskf_sync(h);
+    if (rc != MSKF_OK) return rc;
+    const FeConst &fc = h->fc;
+    *rows = fc.lvl_rows[level];
+    *cols = fc.lvl_cols[level];
+    size_t bytes = (size_t)(*rows) * (*cols);
+    if (!out) return MSKF_OK;
+    if ((size_t)cap < bytes) return MSKF_ERR_CAPACITY;
+    const uint8_t *p = (cam == 0 ? h->fb.pyr[h->hs[s].slot] : h->fb.pyr[2]) + (size_t)s * fc.pyr_bytes + fc.lvl_off[level];
+    MSKF_CUDA_CHECK(h, cudaMemcpy(out, p, bytes, cudaMemcpyDeviceToHost));
+    return MSKF_OK;
+}
+
+int mskf_get_state(mskf_handle *h, int s, mskf_state *out) {
+    if (!h || s < 0 || s >= h->S || !out) return MSKF_ERR_ARG;
+    int rc = mskf_sync(h);
+    if (rc != MSKF_OK) return rc;
+    return be_get_state(h, s, out);
+}
+int mskf_get_cam_states(mskf_handle *h, int s, mskf_cam_state *out, int cap, int *n) {
+    if (!h || s < 0 || s >= h->S || !n) return MSKF_ERR_ARG;
+    int rc = mskf_sync(h);
+    if (rc != MSKF_OK) return rc;
+    return be_get_cam_states(h, s, out, cap, n);
+}
+int mskf_get_covariance(mskf_handle *h, int s, double *out, int cap, int *dim) {
+    if (!h || s < 0 || s >= h->S || !dim) return MSKF_ERR_ARG;
+    int rc = mskf_sync(h);
+    if (rc != MSKF_OK) return rc;
+    return be_get_cov(h, s, out, cap, dim);
+}
+int mskf_reset(mskf_handle *h, int s) {
+    if (!h || s < 0 || s >= h->S) return MSKF_ERR_ARG;
+    int rc = mskf_sync(h);
+    if (rc != MSKF_OK) return rc;
+    HostStream &hs = h->hs[s];
+    hs.be_imu.clear();
+    hs.gravity_set = false;
+    hs.be_first = true;
+    hs.be_time = 0;
+    return be_reset(h, s);
+}
+
+// ---- stand-alone operators: a private one-stream (or n-stream) engine runs the same kernels
+static int op_make(mskf_handle *h, int rows, int cols, int levels, int n_streams, mskf_handle **tmp) {
+    mskf_config c = h->cfg;
+    c.img_rows = rows;
+    c.img_cols = cols;
+    if (levels > 0) c.pyramid_levels = levels;
+    int rc = mskf_create(&c, n_streams, h->device, tmp);
+    if (rc != MSKF_OK && *tmp) {
+        h->err = (*tmp)->err;
+        mskf_destroy(*tmp);
+        *tmp = nullptr;
+    }
+    return rc;
+}
+
+int mskf_op_pyramid(mskf_handle *h, const uint8_t *img, int n_images, int rows, int cols, int levels, uint8_t *out) {
+    if (!h || !img || !out || n_images < 1 || levels < 2) return MSKF_ERR_ARG;
+    mskf_handle *t = nullptr;
+    int S = (n_images + 1) / 2;
+    int rc = op_make(h, rows, cols, levels, S, &t);
+    if (rc != MSKF_OK) return rc;
+    const size_t isz = (size_t)rows * cols;
+    for (int s = 0; s < S && rc == MSKF_OK; ++s) {
+        const uint8_t *a = img + (size_t)(2 * s) * isz;
+        const uint8_t *b = (2 * s + 1 < n_images) ? img + (size_t)(2 * s + 1) * isz : a;
+        rc = mskf_push_stereo(t, s, 0.0, a, b, rows, cols, cols);
+    }
+    if (rc == MSKF_OK) rc = mskf_frontend_step(t);
+    size_t per = 0;
+    for (int l = 1; l < levels; ++l) per += (size_t)t->fc.lvl_rows[l] * t->fc.lvl_cols[l];
+    for (int i = 0; i < n_images && rc == MSKF_OK; ++i) {
+        uint8_t *o = out + (size_t)i * per;
+        for (int l = 1; l < levels && rc == MSKF_OK; ++l) {
+            int r, q;
+            rc = mskf_get_pyramid(t, i / 2, i & 1, l, o, (int)((size_t)t->fc.lvl_rows[l] * t->fc.lvl_cols[l]), &r, &q);
+            o += (size_t)r * q;
+        }
+    }
+    if (rc != MSKF_OK) h->err = t->err;
+    mskf_destroy(t);
+    return rc;
+}
+
+
+static int op_detect_impl(mskf_handle *h, const uint8_t *img, int rows, int cols, const float *occupied_xy,
+                          int n_occupied, float *out_xy, double *out_response, int cap, int *n, uint8_t *score_map) {
+    if (!h || !img || !n) return MSKF_ERR_ARG;
+    mskf_handle *t = nullptr;
+    int rc = op_make(h, rows, cols, 0, 1, &t);
+    if (rc != MSKF_OK) return rc;
+    rc = mskf_push_stereo(t, 0, 0.0, img, img, rows, cols, cols);
+    if (rc == MSKF_OK) rc = fe_op_detect(t, occupied_xy, n_occupied, out_xy, out_response, cap, n, score_map);
+    if (rc != MSKF_OK) h->err = t->err;
+    mskf_destroy(t);
+    return rc;
+}
+int mskf_op_detect(mskf_handle *h, const uint8_t *img, int rows, int cols, const float *occupied_xy, int n_occupied,
+                   float *out_xy, double *out_response, int cap, int *n) {
+    return op_detect_impl(h, img, rows, cols, occupied_xy, n_occupied, out_xy, out_response, cap, n, nullptr);
+}
+// test hook: also returns the per-pixel FAST score map (0 = not a corner)
+int mskf_debug_detect_scores(mskf_handle *h, const uint8_t *img, int rows, int cols, float *out_xy,
+                             double *out_response, int cap, int *n, uint8_t *score_map) {
+    return op_detect_impl(h, img, rows, cols, nullptr, 0, out_xy, out_response, cap, n, score_map);
+}
+
+int mskf_op_klt(mskf_handle *h, const uint8_t *img_a, const uint8_t *img_b, int rows, int cols, const float *pts_a,
+                float *pts_b, uint8_t *status, int n) {
+    if (!h || !img_a || !img_b || n < 0) return MSKF_ERR_ARG;
+    if (n == 0) return MSKF_OK;
+    mskf_handle *t = nullptr;
+    int rc = op_make(h, rows, cols, 0, 1, &t);
+    if (rc != MSKF_OK) return rc;
+    if (n > t->fc.cap_k) {
+        h->err = "mskf_op_klt: too many points for one call";
+        mskf_destroy(t);
+        return MSKF_ERR_CAPACITY;
+    }
+    rc = mskf_push_stereo(t, 0, 0.0, img_a, img_b, rows, cols, cols);
+    if (rc == MSKF_OK) rc = fe_op_klt(t, pts_a, pts_b, status, n);
+    if (rc != MSKF_OK) h->err = t->err;
+    mskf_destroy(t);
+    return rc;
+}
+
+}  // extern "C"

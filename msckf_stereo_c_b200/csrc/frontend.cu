@@ -1,0 +1,1119 @@
+// frontend.cu — ImageProcessor hot path on sm_100a, batched over streams.
+//
+// Compiled with -fmad=false: every floating-point expression below is evaluated with the
+// same IEEE operations, in the same order, as the CPU oracle built with -ffp-contract=off,
+// and all pixel sums are integers, so pyramids, corners, KLT tracks and the published
+// measurements are bit-identical to the oracle (SPEC.md).
+//
+// Reference call sites replaced (msckf_core/src/image_processor.cpp):
+//   pyr_down_kernel      createImagePyramids :213-245  (cg::pyr_down :239,242)
+//   klt_kernel           cg::optical_flow_multi_level :410 (temporal), :569 (stereo)
+//   detect_kernel        CornerDetector::detect_features :259,657, set_grid_position :647
+//   fe_prep_track        trackFeatures :362-389, predictFeatureTracking :321-350
+//   fe_after_track       trackFeatures :415-440, stereoMatch :542-548
+//   fe_after_stereo      stereoMatch :574-617, trackFeatures :465-513, addNewFeatures :632-649
+//   fe_sieve             addNewFeatures :659-688 / initializeFirstFrame :261-268
+//   fe_finish            addNewFeatures :690-750, initializeFirstFrame :270-316,
+//                        pruneGridFeatures :758-768, publish :1137-1182, stereoCallback :192-200
+#include "common.cuh"
+
+namespace mskf {
+
+// ======================================================================================
+// Pyramid: 5x5 Gaussian [1 4 6 4 1]^2 / 256, round half up, BORDER_REFLECT_101, decimate.
+// One CTA produces a 64x16 output tile from a 132x36 input tile staged in shared memory;
+// the level-1 launch also lands level 0 in the stream's pyramid (the copy the reference
+// makes at image_processor.cpp:144-145,234-235).
+// ======================================================================================
+#define PD_TW 64
+#define PD_TH 16
+#define PD_IW (2 * PD_TW + 4)
+#define PD_IH (2 * PD_TH + 4)
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i;
+}
+
+template <bool COPY_SRC>
+__global__ void __launch_bounds__(256) pyr_down_kernel(FeConst fc, FeBuffers fb, int level) {
+    const int s = blockIdx.z >> 1, cam = blockIdx.z & 1;
+    const FeStep st = fb.step[s];
+    if (!st.active) return;
+    uint8_t *pyr = (cam == 0 ? fb.pyr[st.slot] : fb.pyr[2]) + (size_t)s * fc.pyr_bytes;
+    const int irows = fc.lvl_rows[level - 1], icols = fc.lvl_cols[level - 1];
+    const int orows = fc.lvl_rows[level], ocols = fc.lvl_cols[level];
+    const uint8_t *src = COPY_SRC ? (cam == 0 ? fb.src0[s] : fb.src1[s]) : pyr + fc.lvl_off[level - 1];
+    uint8_t *dst = pyr + fc.lvl_off[level];
+
+    __shared__ uint8_t tin[PD_IH][PD_IW + 4];
+    __shared__ unsigned short hrow[PD_IH][PD_TW];
+
+    const int ox0 = blockIdx.x * PD_TW, oy0 = blockIdx.y * PD_TH;
+    const int ix0 = 2 * ox0 - 2, iy0 = 2 * oy0 - 2;
+    for (int idx = threadIdx.x; idx < PD_IH * PD_IW; idx += 256) {
+        int r = idx / PD_IW, c = idx - r * PD_IW;
+        int gy = reflect101(iy0 + r, irows), gx = reflect101(ix0 + c, icols);
+        uint8_t v = src[(size_t)gy * icols + gx];
+        tin[r][c] = v;
+        if (COPY_SRC) {
+            // interior of the tile = this CTA's share of the level-0 landing copy
+            int yy = iy0 + r, xx = ix0 + c;
+            if (r >= 2 && r < PD_IH - 2 && c >= 2 && c < PD_IW - 2 && yy < irows && xx < icols)
+                pyr[(size_t)yy * icols + xx] = v;
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < PD_IH * PD_TW; idx += 256) {
+        int r = idx / PD_TW, c = idx - r * PD_TW;
+        const uint8_t *p = &tin[r][2 * c];
+        hrow[r][c] = (unsigned short)(p[0] + 4 * p[1] + 6 * p[2] + 4 * p[3] + p[4]);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < PD_TH * PD_TW; idx += 256) {
+        int r = idx / PD_TW, c = idx - r * PD_TW;
+        int oy = oy0 + r, ox = ox0 + c;
+        if (oy < orows && ox < ocols) {
+            int v = hrow[2 * r][c] + 4 * hrow[2 * r + 1][c] + 6 * hrow[2 * r + 2][c] + 4 * hrow[2 * r + 3][c] +
+                    hrow[2 * r + 4][c];
+            dst[(size_t)oy * ocols + ox] = (uint8_t)((v + 128) >> 8);
+        }
+    }
+}
+
+// ======================================================================================
+// Pyramidal Lucas-Kanade, one warp per feature, all levels in one launch.
+// Integer fixed point (14-bit bilinear weights, 5 fractional sample bits), warp-shuffle
+// reductions of the 2x2 structure tensor and the mismatch vector, fp64 2x2 solve.
+// ======================================================================================
+struct BilinW { int ix, iy, w00, w01, w10, w11; };
+
+__device__ __forceinline__ BilinW bilin_weights(float x, float y) {
+    BilinW b;
+    float fx = floorf(x), fy = floorf(y);
+    b.ix = (int)fx; b.iy = (int)fy;
+    float a = x - fx, c = y - fy;
+    b.w00 = __float2int_rn((1.f - a) * (1.f - c) * 16384.f);
+    b.w01 = __float2int_rn(a * (1.f - c) * 16384.f);
+    b.w10 = __float2int_rn((1.f - a) * c * 16384.f);
+    b.w11 = 16384 - b.w00 - b.w01 - b.w10;
+    return b;
+}
+__device__ __forceinline__ int sample_fx(const uint8_t *__restrict__ im, int rows, int cols, const BilinW &b, int i, int j) {
+    int x0 = b.ix + i, y0 = b.iy + j;
+    int x1 = x0 + 1, y1 = y0 + 1;
+    x0 = min(max(x0, 0), cols - 1); x1 = min(max(x1, 0), cols - 1);
+    y0 = min(max(y0, 0), rows - 1); y1 = min(max(y1, 0), rows - 1);
+    const uint8_t *r0 = im + (size_t)y0 * cols, *r1 = im + (size_t)y1 * cols;
+    int sum = b.w00 * __ldg(r0 + x0) + b.w01 * __ldg(r0 + x1) + b.w10 * __ldg(r1 + x0) + b.w11 * __ldg(r1 + x1);
+    return (sum + 256) >> 9;
+}
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+#define KLT_WARPS 4
+// mode 0: temporal (A = previous cam0 pyramid, B = current cam0 pyramid)
+// mode 1: stereo   (A = current cam0 pyramid,  B = current cam1 pyramid)
+__global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffers fb, int mode) {
+    const int s = blockIdx.y;
+    const FeStep st = fb.step[s];
+    if (!st.active) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * KLT_WARPS + warp;
+    if (f >= fb.k_n[s]) return;
+    const uint8_t *pa = (mode == 0 ? fb.pyr[st.slot ^ 1] : fb.pyr[st.slot]) + (size_t)s * fc.pyr_bytes;
+    const uint8_t *pb = (mode == 0 ? fb.pyr[st.slot] : fb.pyr[2]) + (size_t)s * fc.pyr_bytes;
+
+    const int win = fc.klt_win, half = win >> 1, tw = win + 2;
+    extern __shared__ short klt_smem[];
+    short *T = klt_smem + (size_t)warp * (tw * tw + 2 * win * win);
+    short *Ix = T + tw * tw, *Iy = Ix + win * win;
+
+    const float2 p0 = fb.k_a[(size_t)s * fc.cap_k + f];
+    float2 q0 = fb.k_b[(size_t)s * fc.cap_k + f];
+    int status = 1;
+    const int L = fc.levels;
+    const float top = 1.0f / (float)(1 << (L - 1));
+    float qx = q0.x * top, qy = q0.y * top;
+    for (int l = L - 1; l >= 0; --l) {
+        const int rows = fc.lvl_rows[l], cols = fc.lvl_cols[l];
+        const uint8_t *A = pa + fc.lvl_off[l], *B = pb + fc.lvl_off[l];
+        const float sc = 1.0f / (float)(1 << l);
+        const float px = p0.x * sc, py = p0.y * sc;
+        const BilinW wa = bilin_weights(px, py);
+        __syncwarp();
+        for (int idx = lane; idx < tw * tw; idx += 32) {
+            int j = idx / tw, i = idx - j * tw;
+            T[idx] = (short)sample_fx(A, rows, cols, wa, i - half - 1, j - half - 1);
+        }
+        __syncwarp();
+        long long A11 = 0, A12 = 0, A22 = 0;
+        for (int idx = lane; idx < win * win; idx += 32) {
+            int j = idx / win, i = idx - j * win;
+            int gx = (int)T[(j + 1) * tw + i + 2] - (int)T[(j + 1) * tw + i];
+            int gy = (int)T[(j + 2) * tw + i + 1] - (int)T[j * tw + i + 1];
+            Ix[idx] = (short)gx;
+            Iy[idx] = (short)gy;
+            A11 += (long long)(gx * gx);
+            A12 += (long long)(gx * gy);
+            A22 += (long long)(gy * gy);
+        }
+        A11 = warp_sum(A11); A12 = warp_sum(A12); A22 = warp_sum(A22);
+        __syncwarp();
+        const double a11 = (double)A11, a12 = (double)A12, a22 = (double)A22;
+        const double m1 = a11 * a22, m2 = a12 * a12;
+        const double D = m1 - m2;
+        const double df = a11 - a22;
+        const double disc = df * df + 4.0 * m2;
+        const double lam = (a11 + a22 - sqrt(disc)) * 0.5;
+        const double min_eig = lam / (4194304.0 * (double)(win * win));
+        const bool ok = !(min_eig < fc.klt_min_eig || D < 1.1920929e-07);
+        if (!ok) {
+            if (l == 0) status = 0;
+        } else {
+            const double Dinv = 1.0 / D;
+            double pdx = 0, pdy = 0;
+            for (int it = 0; it < fc.klt_max_iters; ++it) {
+                if (qx < 0.f || qy < 0.f || qx > (float)(cols - 1) || qy > (float)(rows - 1)) {
+                    if (l == 0) status = 0;
+                    break;
+                }
+                const BilinW wb = bilin_weights(qx, qy);
+                long long b1 = 0, b2 = 0;
+                for (int idx = lane; idx < win * win; idx += 32) {
+                    int j = idx / win, i = idx - j * win;
+                    int diff = sample_fx(B, rows, cols, wb, i - half, j - half) - (int)T[(j + 1) * tw + i + 1];
+                    b1 += (long long)(diff * (int)Ix[idx]);
+                    b2 += (long long)(diff * (int)Iy[idx]);
+                }
+                b1 = warp_sum(b1); b2 = warp_sum(b2);
+                const double fb1 = (double)b1, fb2 = (double)b2;
+                const double dx = (a12 * fb2 - a22 * fb1) * Dinv * 2.0;
+                const double dy = (a12 * fb1 - a11 * fb2) * Dinv * 2.0;
+                const float fdx = (float)dx, fdy = (float)dy;
+                qx += fdx;
+                qy += fdy;
+                if (dx * dx + dy * dy <= fc.klt_eps2) break;
+                if (it > 0 && fabs(dx + pdx) < 0.01 && fabs(dy + pdy) < 0.01) {
+                    qx -= fdx * 0.5f;
+                    qy -= fdy * 0.5f;
+                    break;
+                }
+                pdx = dx;
+                pdy = dy;
+            }
+        }
+        if (l > 0) { qx *= 2.0f; qy *= 2.0f; }
+    }
+    if (lane == 0) {
+        fb.k_b[(size_t)s * fc.cap_k + f] = make_float2(qx, qy);
+        fb.k_status[(size_t)s * fc.cap_k + f] = (uint8_t)status;
+    }
+}
+
+// ======================================================================================
+// FAST-9/16 + score + 3x3 NMS + Shi-Tomasi response + best-per-fine-cell (atomicMax).
+// Shared-memory tile with a 5-pixel halo; the 16-bit brighter/darker ring masks decide
+// cornerness, the arc score is the sliding minimum over 9 contiguous ring differences.
+// ======================================================================================
+#define DT_W 64
+#define DT_H 16
+#define DT_HALO 5
+__constant__ int c_fdx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+__constant__ int c_fdy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+
+__device__ __forceinline__ bool has_arc9(unsigned m) {  // 9 contiguous set bits in a 16-bit ring
+    m |= m << 16;
+    unsigned a = m & (m >> 1);
+    a &= a >> 2;
+    a &= a >> 4;          // 8 contiguous
+    a &= m >> 8;          // 9 contiguous
+    return (a & 0xffffu) != 0;
+}
+
+__global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
+    const int s = blockIdx.z;
+    const FeStep st = fb.step[s];
+    if (!st.active) return;
+    const uint8_t *img = fb.pyr[st.slot] + (size_t)s * fc.pyr_bytes;  // level 0 of current cam0
+    const int rows = fc.rows, cols = fc.cols;
+    __shared__ uint8_t tile[DT_H + 2 * DT_HALO][DT_W + 2 * DT_HALO + 2];
+    __shared__ uint8_t score[DT_H + 2][DT_W + 2];
+    const int x0 = blockIdx.x * DT_W, y0 = blockIdx.y * DT_H;
+    for (int idx = threadIdx.x; idx < (DT_H + 2 * DT_HALO) * (DT_W + 2 * DT_HALO); idx += 256) {
+        int r = idx / (DT_W + 2 * DT_HALO), c = idx - r * (DT_W + 2 * DT_HALO);
+        int gy = y0 - DT_HALO + r, gx = x0 - DT_HALO + c;
+        uint8_t v = 0;
+        if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) v = img[(size_t)gy * cols + gx];
+        tile[r][c] = v;
+    }
+    __syncthreads();
+    const int t = fc.fast_threshold;
+    for (int idx = threadIdx.x; idx < (DT_H + 2) * (DT_W + 2); idx += 256) {
+        int r = idx / (DT_W + 2), c = idx - r * (DT_W + 2);
+        int gy = y0 - 1 + r, gx = x0 - 1 + c;
+        uint8_t sc = 0;
+        if (gy >= 3 && gy < rows - 3 && gx >= 3 && gx < cols - 3) {
+            const int tr = r + DT_HALO - 1, tc = c + DT_HALO - 1;
+            const int v = tile[tr][tc];
+            int d[16];
+            unsigned dark = 0, bright = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                d[k] = v - (int)tile[tr + c_fdy[k]][tc + c_fdx[k]];
+                dark |= (unsigned)(d[k] > t) << k;
+                bright |= (unsigned)(d[k] < -t) << k;
+            }
+            if (has_arc9(dark) || has_arc9(bright)) {
+                // S = max over the 16 arcs of min(d) and of min(-d): sliding minimum of width 9 by
+                // doubling (2, 4, 8, +1).  Only `min` chains are used on purpose: ptxas 12.9 for
+                // sm_100a miscompiles interleaved min/max chains when it fuses them into VIMNMX3
+                // (tools/scratch/t2.cu reproduces it), so the "brighter" side runs on n = -d.
+                int n[16], a2[16], b2[16], a4[16], b4[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) n[k] = -d[k];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    a2[k] = min(d[k], d[(k + 1) & 15]);
+                    b2[k] = min(n[k], n[(k + 1) & 15]);
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    a4[k] = min(a2[k], a2[(k + 2) & 15]);
+                    b4[k] = min(b2[k], b2[(k + 2) & 15]);
+                }
+                int best = -255;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    int a9 = min(min(a4[k], a4[(k + 4) & 15]), d[(k + 8) & 15]);
+                    int b9 = min(min(b4[k], b4[(k + 4) & 15]), n[(k + 8) & 15]);
+                    best = max(best, max(a9, b9));
+                }
+                sc = (uint8_t)(best - 1);
+            }
+        }
+        score[r][c] = sc;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < DT_H * DT_W; idx += 256) {
+        int r = idx / DT_W, c = idx - r * DT_W;
+        int gy = y0 + r, gx = x0 + c;
+        int sc = score[r + 1][c + 1];
+        if (fb.dbg_score && s == 0 && gy < rows && gx < cols) fb.dbg_score[(size_t)gy * cols + gx] = (uint8_t)sc;
+        if (sc == 0) continue;
+        bool is_max = sc > score[r][c] && sc > score[r][c + 1] && sc > score[r][c + 2] && sc > score[r + 1][c] &&
+                      sc > score[r + 1][c + 2] && sc > score[r + 2][c] && sc > score[r + 2][c + 1] &&
+                      sc > score[r + 2][c + 2];
+        if (!is_max) continue;
+        int k = (gy / fc.det_cell_h) * fc.det_cols + (gx / fc.det_cell_w);
+        if (fb.det_occ[(size_t)s * fc.det_cells + k]) continue;
+        float resp = 0.0f;
+        if (!(gx < 5 || gy < 5 || gx > cols - 6 || gy > rows - 6)) {
+            int dXX = 0, dYY = 0, dXY = 0;
+            const int tr = r + DT_HALO, tc = c + DT_HALO;
+            for (int yy = -4; yy < 4; ++yy)
+                for (int xx = -4; xx < 4; ++xx) {
+                    int dx = (int)tile[tr + yy][tc + xx + 1] - (int)tile[tr + yy][tc + xx - 1];
+                    int dy = (int)tile[tr + yy + 1][tc + xx] - (int)tile[tr + yy - 1][tc + xx];
+                    dXX += dx * dx;
+                    dYY += dy * dy;
+                    dXY += dx * dy;
+                }
+            float fXX = (float)dXX / 128.0f, fYY = (float)dYY / 128.0f, fXY = (float)dXY / 128.0f;
+            float trc = fXX + fYY;
+            float d1 = fXX - fYY;
+            float xy2 = fXY * fXY;
+            float disc = d1 * d1 + 4.0f * xy2;
+            resp = 0.5f * (trc - sqrtf(disc));
+        }
+        if (resp > 0.0f) {
+            unsigned long long key = ((unsigned long long)__float_as_uint(resp) << 32) |
+                                     (unsigned long long)(0xffffffffu - (unsigned)(gy * cols + gx));
+            atomicMax(&fb.det_best[(size_t)s * fc.det_cells + k], key);
+        }
+    }
+}
+
+// ======================================================================================
+// Point maps (cg::undistort_points / project_points, SPEC = cv::undistortPoints 5 iters)
+// ======================================================================================
+__device__ __forceinline__ float2 undistort_pt(const FeConst &fc, int cam, float2 p, const double *R) {
+    const double *K = fc.K[cam], *D = fc.D[cam];
+    double x = ((double)p.x - K[2]) / K[0], y = ((double)p.y - K[3]) / K[1];
+    if (fc.cam_model[cam] == 0) {
+        double x0 = x, y0 = y;
+        for (int it = 0; it < 5; ++it) {
+            double r2 = x * x + y * y;
+            double icd = 1.0 / (1.0 + (D[1] * r2 + D[0]) * r2);
+            double dx = 2.0 * D[2] * x * y + D[3] * (r2 + 2.0 * x * x);
+            double dy = D[2] * (r2 + 2.0 * y * y) + 2.0 * D[3] * x * y;
+            x = (x0 - dx) * icd;
+            y = (y0 - dy) * icd;
+        }
+    } else {
+        double thd = sqrt(x * x + y * y);
+        thd = fmin(fmax(-1.5707963267948966, thd), 1.5707963267948966);
+        double scale = 1.0;
+        if (thd > 1e-8) {
+            double th = thd;
+            for (int it = 0; it < 10; ++it) {
+                double t2 = th * th, t4 = t2 * t2, t6 = t4 * t2, t8 = t6 * t2;
+                double k0t2 = D[0] * t2, k1t4 = D[1] * t4, k2t6 = D[2] * t6, k3t8 = D[3] * t8;
+                double fix = (th * (1 + k0t2 + k1t4 + k2t6 + k3t8) - thd) / (1 + 3 * k0t2 + 5 * k1t4 + 7 * k2t6 + 9 * k3t8);
+                th = th - fix;
+                if (fabs(fix) < 1e-10) break;
+            }
+            scale = tan(th) / thd;
+        }
+        x *= scale;
+        y *= scale;
+    }
+    if (R) {
+        double X = R[0] * x + R[1] * y + R[2];
+        double Y = R[3] * x + R[4] * y + R[5];
+        double W = R[6] * x + R[7] * y + R[8];
+        x = X / W;
+        y = Y / W;
+    } else {
+        // identity rectification, evaluated with the same operations as the general case
+        double X = 1.0 * x + 0.0 * y + 0.0;
+        double Y = 0.0 * x + 1.0 * y + 0.0;
+        double W = 0.0 * x + 0.0 * y + 1.0;
+        x = X / W;
+        y = Y / W;
+    }
+    return make_float2((float)(x * 1.0 + 0.0), (float)(y * 1.0 + 0.0));
+}
+__device__ __forceinline__ float2 distort_pt(const FeConst &fc, int cam, float2 p) {
+    const double *K = fc.K[cam], *D = fc.D[cam];
+    double x = (double)p.x, y = (double)p.y, xd, yd;
+    if (fc.cam_model[cam] == 0) {
+        double r2 = x * x + y * y;
+        double cd = 1.0 + (D[1] * r2 + D[0]) * r2;
+        xd = x * cd + 2.0 * D[2] * x * y + D[3] * (r2 + 2.0 * x * x);
+        yd = y * cd + D[2] * (r2 + 2.0 * y * y) + 2.0 * D[3] * x * y;
+    } else {
+        double r = sqrt(x * x + y * y);
+        double th = atan(r);
+        double t2 = th * th, t4 = t2 * t2, t6 = t4 * t2, t8 = t4 * t4;
+        double thd = th * (1 + D[0] * t2 + D[1] * t4 + D[2] * t6 + D[3] * t8);
+        double sc = r > 1e-8 ? thd / r : 1.0;
+        xd = x * sc;
+        yd = y * sc;
+    }
+    return make_float2((float)(xd * K[0] + K[2]), (float)(yd * K[1] + K[3]));
+}
+// stereoMatch epipolar gate, image_processor.cpp:587-617
+__device__ __forceinline__ bool epipolar_ok(const FeConst &fc, float2 c0, float2 c1) {
+    float2 u0 = undistort_pt(fc, 0, c0, nullptr), u1 = undistort_pt(fc, 1, c1, nullptr);
+    double p0x = (double)u0.x, p0y = (double)u0.y, p1x = (double)u1.x, p1y = (double)u1.y;
+    const double *E = fc.E;
+    double l0 = E[0] * p0x + E[1] * p0y + E[2] * 1.0;
+    double l1 = E[3] * p0x + E[4] * p0y + E[5] * 1.0;
+    double l2 = E[6] * p0x + E[7] * p0y + E[8] * 1.0;
+    double error = fabs(p1x * l0 + p1y * l1 + 1.0 * l2) / sqrt(l0 * l0 + l1 * l1);
+    return !(error > fc.stereo_gate);
+}
+__device__ __forceinline__ bool in_image(const FeConst &fc, float2 p) {
+    return !(p.y < 0 || p.y > (float)(fc.rows - 1) || p.x < 0 || p.x > (float)(fc.cols - 1));
+}
+__device__ __forceinline__ int grid_code(const FeConst &fc, float2 p) {
+    int row = (int)(p.y / (float)fc.grid_h);
+    int col = (int)(p.x / (float)fc.grid_w);
+    return row * fc.grid_col + col;
+}
+
+#define FE_THREADS 128
+
+// Order-preserving block compaction: returns the number kept; dst index of element i
+// (when flag) is written to pos[i].  Executed by all FE_THREADS threads.
+__device__ int block_compact_positions(const uint8_t *flag, int n, int *pos, int *s_warp) {
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int start = 0; start < n; start += FE_THREADS) {
+        int i = start + threadIdx.x;
+        int f = (i < n) ? (flag[i] != 0) : 0;
+        unsigned bal = __ballot_sync(0xffffffffu, f);
+        int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        if (f) pos[i] = off + __popc(bal & ((1u << lane) - 1));
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < FE_THREADS / 32; ++w) tot += s_warp[w];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+    return s_base;
+}
+
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FE_THREADS) fe_prep_track(FeConst fc, FeBuffers fb) {
+    const int s = blockIdx.x;
+    const FeStep st = fb.step[s];
+    if (!st.active) return;
+    if (st.is_first) {
+        if (threadIdx.x == 0) fb.k_n[s] = 0;
+        return;
+    }
+    const int gp = fb.gslot[s];  // prev grid buffer
+    const int n = fb.g_n[gp][s];
+    const size_t go = (size_t)s * fc.max_f, ko = (size_t)s * fc.cap_k;
+    for (int i = threadIdx.x; i < n; i += FE_THREADS) {
+        float2 p = fb.g_cam0[gp][go + i];
+        fb.k_a[ko + i] = p;
+        double x = (double)p.x, y = (double)p.y;
+        const double *H = st.H0;
+        double p20 = H[0] * x + H[1] * y + H[2] * 1.0;
+        double p21 = H[3] * x + H[4] * y + H[5] * 1.0;
+        double p22 = H[6] * x + H[7] * y + H[8] * 1.0;
+        fb.k_b[ko + i] = make_float2((float)(p20 / p22), (float)(p21 / p22));
+        fb.t_id[go + i] = fb.g_id[gp][go + i];
+        fb.t_life[go + i] = fb.g_life[gp][go + i];
+    }
+    if (threadIdx.x == 0) {
+        fb.k_n[s] = n;
+        fb.info[s].before_tracking = n;
+    }
+}
+
+// after the temporal track: bounds check, compaction, stereo initial guess
+__global__ void __launch_bounds__(FE_THREADS) fe_after_track(FeConst fc, FeBuffers fb) {
+    const int s = blockIdx.x;
+    const FeStep st = fb.step[s];
+    if (!st.active || st.is_first) return;
+    __shared__ int s_warp[FE_THREADS / 32];
+    extern __shared__ int s_pos[];  // [max_f]
+    const int n = fb.k_n[s];
+    if (n == 0) return;  // trackFeatures returns early (:383); counters keep their old values
+    const size_t go = (size_t)s * fc.max_f, ko = (size_t)s * fc.cap_k;
+    uint8_t *flag = fb.k_status + ko;
+    for (int i = threadIdx.x; i < n; i += FE_THREADS)
+        if (flag[i] && !in_image(fc, fb.k_b[ko + i])) flag[i] = 0;
+    __syncthreads();
+    int m = block_compact_positions(flag, n, s_pos, s_warp);
+    // gather into registers, then scatter (positions are <= source index; two-phase keeps it race free)
+    for (int start = 0; start < n; start += FE_THREADS) {
+        int i = start + threadIdx.x;
+        bool keep = i < n && flag[i];
+        float2 c0 = make_float2(0, 0);
+        unsigned long long id = 0;
+        int life = 0;
+        if (keep) {
+            c0 = fb.k_b[ko + i];
+            id = fb.t_id[go + i];
+            life = fb.t_life[go + i];
+        }
+        __syncthreads();
+        if (keep) {
+            int d = s_pos[i];
+            fb.k_a[ko + d] = c0;  // current cam0 point becomes the stereo template point
+            fb.t_id[go + d] = id;
+            fb.t_life[go + d] = life;
+            float2 u = undistort_pt(fc, 0, c0, fc.R01);
+            fb.k_b[ko + d] = distort_pt(fc, 1, u);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        fb.k_n[s] = m;
+        fb.info[s].after_tracking = m;
+    }
+}
+
+// after the stereo match of tracked features: gates, compaction, re-bucket into the grid
+__global__ void __launch_bounds__(FE_THREADS) fe_after_stereo(FeConst fc, FeBuffers fb) {
+    const int s = blockIdx.x;
+    const FeStep st = fb.step[s];
+    if (!st.active) return;
+    __shared__ int s_warp[FE_THREADS / 32];
+    __shared__ int s_cnt[64], s_start[65];
+    extern __shared__ int s_pos[];
+    const size_t go = (size_t)s * fc.max_f, ko = (size_t)s * fc.cap_k;
+    const int gc = fb.gslot[s] ^ 1;  // curr grid buffer
+    // reset the detector tables of this stream
+    for (int k = threadIdx.x; k < fc.det_cells; k += FE_THREADS) {
+        fb.det_best[(size_t)s * fc.det_cells + k] = 0ull;
+        fb.det_occ[(size_t)s * fc.det_cells + k] = 0;
+    }
+    const int n = st.is_first ? 0 : fb.k_n[s];
+    const bool tracked_any = !st.is_first && fb.info[s].before_tracking > 0;
+    uint8_t *flag = fb.k_status + ko;
+    for (int i = threadIdx.x; i < n; i += FE_THREADS) {
+        if (flag[i]) {
+            float2 c1 = fb.k_b[ko + i];
+            if (!in_image(fc, c1) || !epipolar_ok(fc, fb.k_a[ko + i], c1)) flag[i] = 0;
+        }
+    }
+    __syncthreads();
+    int m = block_compact_positions(flag, n, s_pos, s_warp);
+    // stable counting sort of the survivors by grid cell = publish order of the std::map
+    for (int c = threadIdx.x; c < fc.n_cells_all; c += FE_THREADS) s_cnt[c] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < n; ++i)
+            if (flag[i]) s_cnt[grid_code(fc, fb.k_a[ko + i])]++;
+        int acc = 0;
+        for (int c = 0; c < fc.n_cells_all; ++c) {
+            s_start[c] = acc;
+            acc += s_cnt[c];
+            s_cnt[c] = 0;
+        }
+        s_start[fc.n_cells_all] = acc;
+        for (int i = 0; i < n; ++i) {
+            if (!flag[i]) continue;
+            float2 c0 = fb.k_a[ko + i];
+            int code = grid_code(fc, c0);
+            int d = s_start[code] + s_cnt[code]++;
+            fb.g_id[gc][go + d] = fb.t_id[go + i];
+            fb.g_life[gc][go + d] = fb.t_life[go + i] + 1;
+            fb.g_resp[gc][go + d] = 0.0f;
+            fb.g_cam0[gc][go + d] = c0;
+            fb.g_cam1[gc][go + d] = fb.k_b[ko + i];
+            fb.g_cell[gc][go + d] = code;
+            // CornerDetector::set_grid_position on the truncated position (:634-647)
+            int x = (int)c0.x, y = (int)c0.y;
+            if (x >= 0 && y >= 0 && x < fc.cols && y < fc.rows)
+                fb.det_occ[(size_t)s * fc.det_cells + (y / fc.det_cell_h) * fc.det_cols + (x / fc.det_cell_w)] = 1;
+        }
+        fb.g_n[gc][s] = m;
+        if (tracked_any) {
+            fb.info[s].after_matching = m;
+            fb.info[s].after_ransac = m;
+        }
+    }
+}
+
+// detector output -> candidate list for the stereo match of new features
+__global__ void __launch_bounds__(FE_THREADS) fe_sieve(FeConst fc, FeBuffers fb) {
+    const int s = blockIdx.x;
+    const FeStep st = fb.step[s];
+    if (!st.active) return;
+    __shared__ int s_n, s_cell_n[64], s_cell_off[65];
+    extern __shared__ int s_sel[];  // [n_cells][grid_max] selected detect indices
+    const size_t ko = (size_t)s * fc.cap_k, dofs = (size_t)s * fc.det_cells;
+    // gather detections in fine-cell order (thread 0: <= det_cells entries)
+    // k_a temporarily holds the detect-order points in its upper half is not possible
+    // (cap_k = det_cells), so detections are decoded on the fly from det_best.
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int k = 0; k < fc.det_cells; ++k) {
+            unsigned long long key = fb.det_best[dofs + k];
+            float resp = __uint_as_float((unsigned)(key >> 32));
+            if (key != 0ull && (double)resp > fc.detection_threshold) {
+                fb.nf_resp[dofs + n] = resp;
+                // compact the keys in place so that entry n describes detection n
+                fb.det_best[dofs + n] = key;
+                ++n;
+            }
+        }
+        s_n = n;
+        fb.nf_n[s] = n;
+    }
+    __syncthreads();
+    const int n = s_n;
+    auto det_pt = [&](int i) {
+        unsigned ridx = 0xffffffffu - (unsigned)(fb.det_best[dofs + i] & 0xffffffffull);
+        return make_float2((float)(ridx % (unsigned)fc.cols), (float)(ridx / (unsigned)fc.cols));
+    };
+    if (st.is_first) {
+        for (int i = threadIdx.x; i < n; i += FE_THREADS) {
+            float2 p = det_pt(i);
+            fb.k_a[ko + i] = p;
+            fb.k_b[ko + i] = distort_pt(fc, 1, undistort_pt(fc, 0, p, fc.R01));
+        }
+        if (threadIdx.x == 0) fb.k_n[s] = n;
+        return;
+    }
+    // one thread per coarse cell: members in detect order, keep the grid_max best (stable)
+    for (int c = threadIdx.x; c < fc.n_cells; c += FE_THREADS) {
+        int cnt = 0;
+        for (int i = 0; i < n; ++i)
+            if (grid_code(fc, det_pt(i)) == c) ++cnt;
+        int *sel = s_sel + c * fc.grid_max;
+        int kept = 0;
+        if (cnt <= fc.grid_max) {
+            for (int i = 0; i < n; ++i)
+                if (grid_code(fc, det_pt(i)) == c) sel[kept++] = i;
+        } else {
+            // stable sort by response desc, truncated: repeated selection of the best not yet taken
+            float last_r = 3.0e38f;
+            int last_i = -1;
+            for (int k = 0; k < fc.grid_max; ++k) {
+                int bi = -1;
+                float br = -1.0f;
+                for (int i = 0; i < n; ++i) {
+                    if (grid_code(fc, det_pt(i)) != c) continue;
+                    float r = fb.nf_resp[dofs + i];
+                    bool after_last = (r < last_r) || (r == last_r && i > last_i);
+                    if (!after_last) continue;
+                    if (bi < 0 || r > br) { bi = i; br = r; }
+                }
+                sel[kept++] = bi;
+                last_r = br;
+                last_i = bi;
+            }
+        }
+        s_cell_n[c] = kept;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int c = 0; c < fc.n_cells; ++c) {
+            s_cell_off[c] = acc;
+            acc += s_cell_n[c];
+        }
+        s_cell_off[fc.n_cells] = acc;
+        fb.k_n[s] = acc;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < fc.n_cells; c += FE_THREADS) {
+        for (int k = 0; k < s_cell_n[c]; ++k) {
+            float2 p = det_pt(s_sel[c * fc.grid_max + k]);
+            int d = s_cell_off[c] + k;
+            fb.k_a[ko + d] = p;
+            fb.k_b[ko + d] = distort_pt(fc, 1, undistort_pt(fc, 0, p, fc.R01));
+        }
+    }
+}
+
+// stereo-matched new features -> grid, prune, publish, rotate prev/curr
+__global__ void __launch_bounds__(FE_THREADS) fe_finish(FeConst fc, FeBuffers fb) {
+    const int s = blockIdx.x;
+    const FeStep st = fb.step[s];
+    if (!st.active) return;
+    __shared__ int s_warp[FE_THREADS / 32];
+    __shared__ int s_m, s_add[64], s_keep[64], s_idbase[65], s_outoff[65];
+    extern __shared__ int s_dyn[];
+    const size_t go = (size_t)s * fc.max_f, ko = (size_t)s * fc.cap_k, dofs = (size_t)s * fc.det_cells;
+    const int gc = fb.gslot[s] ^ 1, gp = fb.gslot[s];
+    const int n = fb.k_n[s];
+    int *s_pos = s_dyn;                                  // [cap_k]
+    int *s_addsel = s_dyn + fc.cap_k;                    // [n_cells][grid_min] inlier indices to add
+    int *s_final = s_addsel + fc.n_cells * fc.grid_min;  // [n_cells_all][grid_max] encoded final members
+    uint8_t *flag = fb.k_status + ko;
+    for (int i = threadIdx.x; i < n; i += FE_THREADS) {
+        if (flag[i]) {
+            float2 c1 = fb.k_b[ko + i];
+            if (!in_image(fc, c1) || !epipolar_ok(fc, fb.k_a[ko + i], c1)) flag[i] = 0;
+        }
+    }
+    __syncthreads();
+    int m = block_compact_positions(flag, n, s_pos, s_warp);
+    // compact inliers in place (dst <= src): cam0 -> k_a, cam1 -> k_b, response -> nf_resp'
+    // response_inliers[j] = new_features_responses[i] with i the POST-sieve index (:698)
+    float *resp_in = fb.in_resp + ko;
+    for (int start = 0; start < n; start += FE_THREADS) {
+        int i = start + threadIdx.x;
+        bool keep = i < n && flag[i];
+        float2 a, b;
+        float r = 0;
+        if (keep) {
+            a = fb.k_a[ko + i];
+            b = fb.k_b[ko + i];
+            r = fb.nf_resp[dofs + i];
+        }
+        __syncthreads();
+        if (keep) {
+            int d = s_pos[i];
+            fb.k_a[ko + d] = a;
+            fb.k_b[ko + d] = b;
+            resp_in[d] = r;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) s_m = m;
+    __syncthreads();
+    const int ncur = st.is_first ? 0 : fb.g_n[gc][s];
+    // one thread per cell: choose the new features to add (best responses, stable)
+    for (int c = threadIdx.x; c < fc.n_cells_all; c += FE_THREADS) {
+        int cur = 0;
+        for (int i = 0; i < ncur; ++i)
+            if (fb.g_cell[gc][go + i] == c) ++cur;
+        int add = 0;
+        if (c < fc.n_cells && cur < fc.grid_min) {
+            int vacancy = fc.grid_min - cur;
+            float last_r = 3.0e38f;
+            int last_i = -1;
+            for (int k = 0; k < vacancy; ++k) {
+                int bi = -1;
+                float br = -1.0f;
+                for (int i = 0; i < m; ++i) {
+                    if (grid_code(fc, fb.k_a[ko + i]) != c) continue;
+                    float r = resp_in[i];
+                    bool after_last = (r < last_r) || (r == last_r && i > last_i);
+                    if (!after_last) continue;
+                    if (bi < 0 || r > br) { bi = i; br = r; }
+                }
+                if (bi < 0) break;
+                s_addsel[c * fc.grid_min + add++] = bi;
+                last_r = br;
+                last_i = bi;
+            }
+        }
+        s_add[c] = add;
+        // members after the additions: tracked entries (index i, lifetime from the grid) then
+        // new ones (lifetime 1); pruneGridFeatures keeps the grid_max longest-lived (stable)
+        int total = cur + add;
+        int keep = 0;
+        int *fin = s_final + c * fc.grid_max;
+        if (total <= fc.grid_max) {
+            for (int i = 0; i < ncur; ++i)
+                if (fb.g_cell[gc][go + i] == c) fin[keep++] = i;
+            for (int k = 0; k < add; ++k) fin[keep++] = -1 - k;
+        } else {
+            int last_l = 0x7fffffff, last_o = -1;
+            for (int k = 0; k < fc.grid_max; ++k) {
+                int bo = -1, bl = -1, benc = 0, o = 0;
+                for (int i = 0; i < ncur; ++i) {
+                    if (fb.g_cell[gc][go + i] != c) continue;
+                    int l = fb.g_life[gc][go + i];
+                    bool after_last = (l < last_l) || (l == last_l && o > last_o);
+                    if (after_last && (bo < 0 || l > bl)) { bo = o; bl = l; benc = i; }
+                    ++o;
+                }
+                for (int a = 0; a < add; ++a, ++o) {
+                    int l = 1;
+                    bool after_last = (l < last_l) || (l == last_l && o > last_o);
+                    if (after_last && (bo < 0 || l > bl)) { bo = o; bl = l; benc = -1 - a; }
+                }
+                fin[keep++] = benc;
+                last_l = bl;
+                last_o = bo;
+            }
+        }
+        s_keep[c] = keep;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long base = fb.next_id[s];
+        int acc_id = 0, acc_out = 0;
+        for (int c = 0; c < fc.n_cells_all; ++c) {
+            s_idbase[c] = acc_id;
+            s_outoff[c] = acc_out;
+            acc_id += s_add[c];
+            acc_out += s_keep[c];
+        }
+        s_outoff[fc.n_cells_all] = acc_out;
+        fb.next_id[s] = base + (unsigned long long)acc_id;
+        s_idbase[fc.n_cells_all] = (int)0;
+        fb.g_n[gp][s] = acc_out;  // the finished grid goes to the buffer that was "prev"
+        fb.msg_n[s] = acc_out;
+        s_m = acc_out;
+    }
+    __syncthreads();
+    const unsigned long long id0 = fb.next_id[s];  // already advanced; recompute base below
+    // write the finished grid (publish order) into buffer gp and the measurement message
+    for (int c = threadIdx.x; c < fc.n_cells_all; c += FE_THREADS) {
+        unsigned long long total_added = 0;
+        for (int cc = 0; cc < fc.n_cells_all; ++cc) total_added += (unsigned long long)s_add[cc];
+        const unsigned long long base = id0 - total_added;
+        for (int k = 0; k < s_keep[c]; ++k) {
+            int enc = s_final[c * fc.grid_max + k];
+            int d = s_outoff[c] + k;
+            unsigned long long id;
+            float resp;
+            int life;
+            float2 c0, c1;
+            if (enc >= 0) {
+                id = fb.g_id[gc][go + enc];
+                resp = fb.g_resp[gc][go + enc];
+                life = fb.g_life[gc][go + enc];
+                c0 = fb.g_cam0[gc][go + enc];
+                c1 = fb.g_cam1[gc][go + enc];
+            } else {
+                int a = -1 - enc;
+                int src = s_addsel[c * fc.grid_min + a];
+                id = base + (unsigned long long)(s_idbase[c] + a);
+                resp = resp_in[src];
+                life = 1;
+                c0 = fb.k_a[ko + src];
+                c1 = fb.k_b[ko + src];
+            }
+            fb.g_id[gp][go + d] = id;
+            fb.g_resp[gp][go + d] = resp;
+            fb.g_life[gp][go + d] = life;
+            fb.g_cam0[gp][go + d] = c0;
+            fb.g_cam1[gp][go + d] = c1;
+            fb.g_cell[gp][go + d] = c;
+            float2 u0 = undistort_pt(fc, 0, c0, nullptr), u1 = undistort_pt(fc, 1, c1, nullptr);
+            mskf_feature f;
+            f.id = (uint32_t)id;
+            f.pad = 0;
+            f.u0 = (double)u0.x; f.v0 = (double)u0.y; f.u1 = (double)u1.x; f.v1 = (double)u1.y;
+            fb.msg[go + d] = f;
+            fb.stale[go + d] = f;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nout = s_m;
+        if (fc.compat_stale) {
+            if (nout > fb.stale_hw[s]) fb.stale_hw[s] = nout;
+            fb.msg_total[s] += nout;
+        } else {
+            fb.stale_hw[s] = nout;
+            fb.msg_total[s] = nout;
+        }
+        fb.info[s].time_stamp = st.t;
+        // rotate prev/curr: the finished grid already sits in buffer gp, so "prev" stays gp
+    }
+}
+
+}  // namespace mskf
+
+using namespace mskf;
+
+int fe_create(mskf_handle *h) {
+    const mskf_config &c = h->cfg;
+    FeConst &fc = h->fc;
+    memset(&fc, 0, sizeof(fc));
+    if (c.pyramid_levels < 1 || c.pyramid_levels > MSKF_MAX_LEVELS || (c.klt_win & 1) == 0 || c.klt_win < 3 ||
+        c.klt_win > 31) {
+        h->err = "bad pyramid_levels / klt_win";
+        return MSKF_ERR_ARG;
+    }
+    fc.rows = c.img_rows; fc.cols = c.img_cols; fc.levels = c.pyramid_levels;
+    unsigned off = 0;
+    int r = c.img_rows, q = c.img_cols;
+    for (int l = 0; l < fc.levels; ++l) {
+        fc.lvl_rows[l] = r; fc.lvl_cols[l] = q; fc.lvl_off[l] = off;
+        off += (unsigned)(r * q);
+        off = (off + 255u) & ~255u;
+        r = (r + 1) / 2; q = (q + 1) / 2;
+    }
+    fc.pyr_bytes = off;
+    fc.klt_win = c.klt_win; fc.klt_max_iters = c.klt_max_iters;
+    fc.klt_eps2 = c.klt_eps * c.klt_eps; fc.klt_min_eig = c.klt_min_eig;
+    fc.grid_row = c.grid_row; fc.grid_col = c.grid_col; fc.grid_min = c.grid_min_feature_num;
+    fc.grid_max = c.grid_max_feature_num;
+    fc.grid_h = c.img_rows / c.grid_row; fc.grid_w = c.img_cols / c.grid_col;
+    fc.n_cells = c.grid_row * c.grid_col;
+    fc.n_cells_all = ((c.img_rows - 1) / fc.grid_h) * c.grid_col + (c.img_cols - 1) / fc.grid_w + 1;
+    if (fc.n_cells_all < fc.n_cells) fc.n_cells_all = fc.n_cells;
+    if (fc.n_cells_all > 64 || fc.grid_min > fc.grid_max) {
+        h->err = "grid too large (max 64 cells incl. overflow) or grid_min > grid_max";
+        return MSKF_ERR_ARG;
+    }
+    fc.det_rows = c.det_rows; fc.det_cols = c.det_cols;
+    fc.det_cell_h = c.img_rows / c.det_rows + 1; fc.det_cell_w = c.img_cols / c.det_cols + 1;
+    fc.det_cells = c.det_rows * c.det_cols;
+    fc.fast_threshold = c.fast_threshold;
+    fc.detection_threshold = c.detection_threshold;
+    fc.max_f = ((fc.n_cells_all * (fc.grid_max + fc.grid_min) + 31) / 32) * 32;
+    fc.cap_k = fc.det_cells > fc.max_f ? fc.det_cells : fc.max_f;
+    fc.cam_model[0] = c.cam0_model; fc.cam_model[1] = c.cam1_model;
+    for (int i = 0; i < 4; ++i) {
+        fc.K[0][i] = c.cam0_intrinsics[i]; fc.D[0][i] = c.cam0_distortion[i];
+        fc.K[1][i] = c.cam1_intrinsics[i]; fc.D[1][i] = c.cam1_distortion[i];
+    }
+    fc.compat_stale = c.compat_stale_features;
+    // extrinsics as ImageProcessor::loadParameters derives them (image_processor.cpp:63-72)
+    auto R = [](const double *T, int i, int j) { return T[i * 4 + j]; };
+    double R_c0_imu[9], t_c0_imu[3], T1[16], R_c1_imu[9], t_c1_imu[3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R_c0_imu[i * 3 + j] = R(c.T_cam0_imu, j, i);
+    for (int i = 0; i < 3; ++i) {
+        double sacc = R_c0_imu[i * 3 + 0] * c.T_cam0_imu[3] + R_c0_imu[i * 3 + 1] * c.T_cam0_imu[7] + R_c0_imu[i * 3 + 2] * c.T_cam0_imu[11];
+        t_c0_imu[i] = -sacc;
+    }
+    // T_cam1_imu = T_cn_cnm1 * T_cam0_imu  (R = Ra Rb, t = Ra tb + ta)
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            double sacc = 0;
+            for (int k = 0; k < 3; ++k) sacc += R(c.T_cn_cnm1, i, k) * R(c.T_cam0_imu, k, j);
+            T1[i * 4 + j] = sacc;
+        }
+        double sacc = R(c.T_cn_cnm1, i, 0) * c.T_cam0_imu[3] + R(c.T_cn_cnm1, i, 1) * c.T_cam0_imu[7] + R(c.T_cn_cnm1, i, 2) * c.T_cam0_imu[11];
+        T1[i * 4 + 3] = sacc + c.T_cn_cnm1[i * 4 + 3];
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R_c1_imu[i * 3 + j] = T1[j * 4 + i];
+    for (int i = 0; i < 3; ++i) {
+        double sacc = R_c1_imu[i * 3 + 0] * T1[3] + R_c1_imu[i * 3 + 1] * T1[7] + R_c1_imu[i * 3 + 2] * T1[11];
+        t_c1_imu[i] = -sacc;
+    }
+    // R_cam0_cam1 = R_cam1_imu^T * R_cam0_imu ; t_cam0_cam1 = R_cam1_imu^T (t_cam0_imu - t_cam1_imu)
+    double tdiff[3] = {t_c0_imu[0] - t_c1_imu[0], t_c0_imu[1] - t_c1_imu[1], t_c0_imu[2] - t_c1_imu[2]};
+    double t01[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            double sacc = 0;
+            for (int k = 0; k < 3; ++k) sacc += R_c1_imu[k * 3 + i] * R_c0_imu[k * 3 + j];
+            fc.R01[i * 3 + j] = sacc;
+        }
+        t01[i] = R_c1_imu[0 * 3 + i] * tdiff[0] + R_c1_imu[1 * 3 + i] * tdiff[1] + R_c1_imu[2 * 3 + i] * tdiff[2];
+    }
+    double sk[9] = {0, -t01[2], t01[1], t01[2], 0, -t01[0], -t01[1], t01[0], 0};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double sacc = 0;
+            for (int k = 0; k < 3; ++k) sacc += sk[i * 3 + k] * fc.R01[k * 3 + j];
+            fc.E[i * 3 + j] = sacc;
+        }
+    double npu = 4.0 / (c.cam0_intrinsics[0] + c.cam0_intrinsics[1] + c.cam1_intrinsics[0] + c.cam1_intrinsics[1]);
+    fc.stereo_gate = c.stereo_threshold * npu;
+
+    FeBuffers &fb = h->fb;
+    memset(&fb, 0, sizeof(fb));
+    const size_t S = h->S;
+    int rc;
+#define A(p, n) if ((rc = dev_alloc(h, &(p), (n))) != MSKF_OK) return rc
+    for (int i = 0; i < 3; ++i) A(fb.pyr[i], S * fc.pyr_bytes);
+    A(fb.staging, S * 2 * (size_t)fc.rows * fc.cols);
+    A(fb.src0, S); A(fb.src1, S);
+    A(fb.step, S);
+    for (int g = 0; g < 2; ++g) {
+        A(fb.g_id[g], S * fc.max_f); A(fb.g_resp[g], S * fc.max_f); A(fb.g_life[g], S * fc.max_f);
+        A(fb.g_cam0[g], S * fc.max_f); A(fb.g_cam1[g], S * fc.max_f); A(fb.g_cell[g], S * fc.max_f);
+        A(fb.g_n[g], S);
+    }
+    A(fb.gslot, S); A(fb.next_id, S);
+    A(fb.k_a, S * fc.cap_k); A(fb.k_b, S * fc.cap_k); A(fb.k_status, S * fc.cap_k); A(fb.k_n, S);
+    A(fb.t_id, S * fc.max_f); A(fb.t_life, S * fc.max_f);
+    A(fb.det_best, S * fc.det_cells); A(fb.det_occ, S * fc.det_cells);
+    A(fb.nf_resp, S * fc.det_cells); A(fb.nf_n, S); A(fb.in_resp, S * fc.cap_k);
+    A(fb.msg, S * fc.max_f); A(fb.msg_n, S); A(fb.stale, S * fc.max_f); A(fb.stale_hw, S); A(fb.msg_total, S);
+    A(fb.info, S);
+#undef A
+    return MSKF_OK;
+}
+
+int fe_step(mskf_handle *h, bool any_first, int max_prev) {
+    const FeConst &fc = h->fc;
+    const FeBuffers &fb = h->fb;
+    cudaStream_t q = h->stream;
+    const int S = h->S;
+    // pyramids
+    for (int l = 1; l < fc.levels; ++l) {
+        dim3 g((fc.lvl_cols[l] + PD_TW - 1) / PD_TW, (fc.lvl_rows[l] + PD_TH - 1) / PD_TH, S * 2);
+        if (l == 1) pyr_down_kernel<true><<<g, 256, 0, q>>>(fc, fb, l);
+        else pyr_down_kernel<false><<<g, 256, 0, q>>>(fc, fb, l);
+        h->launches++;
+    }
+    if (fc.levels == 1) {
+        h->err = "pyramid_levels must be >= 2";
+        return MSKF_ERR_ARG;
+    }
+    const size_t klt_smem = (size_t)KLT_WARPS * ((fc.klt_win + 2) * (fc.klt_win + 2) + 2 * fc.klt_win * fc.klt_win) * sizeof(short);
+    const size_t pos_smem = (size_t)fc.cap_k * sizeof(int);
+    fe_prep_track<<<S, FE_THREADS, 0, q>>>(fc, fb);
+    h->launches++;
+    if (max_prev > 0) {
+        dim3 g((max_prev + KLT_WARPS - 1) / KLT_WARPS, S);
+        klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 0);
+        fe_after_track<<<S, FE_THREADS, pos_smem, q>>>(fc, fb);
+        klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 1);
+        h->launches += 3;
+    }
+    fe_after_stereo<<<S, FE_THREADS, pos_smem, q>>>(fc, fb);
+    {
+        dim3 g((fc.cols + DT_W - 1) / DT_W, (fc.rows + DT_H - 1) / DT_H, S);
+        detect_kernel<<<g, 256, 0, q>>>(fc, fb);
+    }
+    fe_sieve<<<S, FE_THREADS, (size_t)fc.n_cells * fc.grid_max * sizeof(int), q>>>(fc, fb);
+    {
+        int cap = any_first ? fc.det_cells : fc.n_cells * fc.grid_max;
+        dim3 g((cap + KLT_WARPS - 1) / KLT_WARPS, S);
+        klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 1);
+    }
+    size_t fin_smem = ((size_t)fc.cap_k + (size_t)fc.n_cells * fc.grid_min + (size_t)fc.n_cells_all * fc.grid_max) * sizeof(int);
+    fe_finish<<<S, FE_THREADS, fin_smem, q>>>(fc, fb);
+    h->launches += 5;
+    MSKF_CUDA_CHECK(h, cudaGetLastError());
+    return MSKF_OK;
+}
+
+// ---- stand-alone operator helpers (mskf_op_detect / mskf_op_klt), one-stream handle ----
+static int op_prepare(mskf_handle *t) {
+    FeStep st;
+    memset(&st, 0, sizeof(st));
+    st.active = 1;
+    st.is_first = 1;
+    st.slot = 0;
+    HostStream &hs = t->hs[0];
+    MSKF_CUDA_CHECK(t, cudaMemcpyAsync(t->fb.step, &st, sizeof(st), cudaMemcpyHostToDevice, t->stream));
+    MSKF_CUDA_CHECK(t, cudaMemcpyAsync(t->fb.src0, &hs.src0, sizeof(uint8_t *), cudaMemcpyHostToDevice, t->stream));
+    MSKF_CUDA_CHECK(t, cudaMemcpyAsync(t->fb.src1, &hs.src1, sizeof(uint8_t *), cudaMemcpyHostToDevice, t->stream));
+    MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->stream));
+    const FeConst &fc = t->fc;
+    for (int l = 1; l < fc.levels; ++l) {
+        dim3 g((fc.lvl_cols[l] + PD_TW - 1) / PD_TW, (fc.lvl_rows[l] + PD_TH - 1) / PD_TH, 2);
+        if (l == 1) pyr_down_kernel<true><<<g, 256, 0, t->stream>>>(fc, t->fb, l);
+        else pyr_down_kernel<false><<<g, 256, 0, t->stream>>>(fc, t->fb, l);
+    }
+    MSKF_CUDA_CHECK(t, cudaGetLastError());
+    hs.slot = 0;
+    hs.pending = false;
+    return MSKF_OK;
+}
+
+int fe_op_detect(mskf_handle *t, const float *occ, int n_occ, float *out_xy, double *out_resp, int cap, int *n,
+                 uint8_t *score_map) {
+    int rc = op_prepare(t);
+    if (rc != MSKF_OK) return rc;
+    const FeConst &fc = t->fc;
+    if (score_map) {
+        rc = dev_alloc(t, &t->fb.dbg_score, (size_t)fc.rows * fc.cols);
+        if (rc != MSKF_OK) return rc;
+    }
+    std::vector<uint8_t> occv(fc.det_cells, 0);
+    for (int i = 0; i < n_occ; ++i) {
+        int x = (int)occ[2 * i], y = (int)occ[2 * i + 1];
+        if (x < 0 || y < 0 || x >= fc.cols || y >= fc.rows) continue;
+        occv[(y / fc.det_cell_h) * fc.det_cols + (x / fc.det_cell_w)] = 1;
+    }
+    MSKF_CUDA_CHECK(t, cudaMemcpyAsync(t->fb.det_occ, occv.data(), occv.size(), cudaMemcpyHostToDevice, t->stream));
+    MSKF_CUDA_CHECK(t, cudaMemsetAsync(t->fb.det_best, 0, sizeof(unsigned long long) * fc.det_cells, t->stream));
+    dim3 g((fc.cols + DT_W - 1) / DT_W, (fc.rows + DT_H - 1) / DT_H, 1);
+    detect_kernel<<<g, 256, 0, t->stream>>>(fc, t->fb);
+    MSKF_CUDA_CHECK(t, cudaGetLastError());
+    std::vector<unsigned long long> keys(fc.det_cells);
+    MSKF_CUDA_CHECK(t, cudaMemcpyAsync(keys.data(), t->fb.det_best, sizeof(unsigned long long) * fc.det_cells, cudaMemcpyDeviceToHost, t->stream));
+    if (score_map)
+        MSKF_CUDA_CHECK(t, cudaMemcpyAsync(score_map, t->fb.dbg_score, (size_t)fc.rows * fc.cols, cudaMemcpyDeviceToHost, t->stream));
+    MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->stream));
+    int cnt = 0;
+    for (int k = 0; k < fc.det_cells; ++k) {
+        if (!keys[k]) continue;
+        unsigned bits = (unsigned)(keys[k] >> 32);
+        float resp;
+        memcpy(&resp, &bits, 4);
+        if (!((double)resp > fc.detection_threshold)) continue;
+        unsigned ridx = 0xffffffffu - (unsigned)(keys[k] & 0xffffffffull);
+        if (cnt < cap) {
+            out_xy[2 * cnt] = (float)(ridx % (unsigned)fc.cols);
+            out_xy[2 * cnt + 1] = (float)(ridx / (unsigned)fc.cols);
+            out_resp[cnt] = (double)resp;
+        }
+        ++cnt;
+    }
+    *n = cnt;
+    return MSKF_OK;
+}
+
+int fe_op_klt(mskf_handle *t, const float *pts_a, float *pts_b, uint8_t *status, int n) {
+    int rc = op_prepare(t);
+    if (rc != MSKF_OK) return rc;
+    const FeConst &fc = t->fc;
+    MSKF_CUDA_CHECK(t, cudaMemcpyAsync(t->fb.k_a, pts_a, sizeof(float2) * n, cudaMemcpyHostToDevice, t->stream));
+    MSKF_CUDA_CHECK(t, cudaMemcpyAsync(t->fb.k_b, pts_b, sizeof(float2) * n, cudaMemcpyHostToDevice, t->stream));
+    MSKF_CUDA_CHECK(t, cudaMemcpyAsync(t->fb.k_n, &n, sizeof(int), cudaMemcpyHostToDevice, t->stream));
+    const size_t klt_smem = (size_t)KLT_WARPS * ((fc.klt_win + 2) * (fc.klt_win + 2) + 2 * fc.klt_win * fc.klt_win) * sizeof(short);
+    dim3 g((n + KLT_WARPS - 1) / KLT_WARPS, 1);
+    klt_kernel<<<g, KLT_WARPS * 32, klt_smem, t->stream>>>(fc, t->fb, 1);
+    MSKF_CUDA_CHECK(t, cudaGetLastError());
+    MSKF_CUDA_CHECK(t, cudaMemcpyAsync(pts_b, t->fb.k_b, sizeof(float2) * n, cudaMemcpyDeviceToHost, t->stream));
+    MSKF_CUDA_CHECK(t, cudaMemcpyAsync(status, t->fb.k_status, n, cudaMemcpyDeviceToHost, t->stream));
+    MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->stream));
+    return MSKF_OK;
+}

@@ -1,0 +1,266 @@
+"""Host-side mirror of the reference's System / ImageProcessor / MsckfVio callback API over
+the C ABI of include/msckf_b200.h (libmsckf_b200.so, hand-written sm_100a kernels).
+
+There is no CPU fallback: importing works anywhere (so the ABI can be inspected), but
+creating an engine without the built library or without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmsckf_b200.so")
+_LIB = None
+
+GRID_DT = np.dtype([("id", "<u8"), ("response", "<f4"), ("lifetime", "<i4"), ("cam0", "<f4", 2), ("cam1", "<f4", 2),
+                    ("cell", "<i4"), ("pad", "<i4")])
+FEAT_DT = np.dtype([("id", "<u4"), ("pad", "<u4"), ("u0", "<f8"), ("v0", "<f8"), ("u1", "<f8"), ("v1", "<f8")])
+CAM_DT = np.dtype([("id", "<i8"), ("time", "<f8"), ("orientation", "<f8", 4), ("position", "<f8", 3)])
+
+# every symbol include/msckf_b200.h declares
+ABI_SYMBOLS = [
+    "mskf_default_config", "mskf_create", "mskf_destroy", "mskf_last_error", "mskf_set_cuda_stream",
+    "mskf_push_imu", "mskf_push_stereo", "mskf_push_stereo_device", "mskf_frontend_step", "mskf_backend_step",
+    "mskf_step", "mskf_sync", "mskf_backend_step_features", "mskf_get_features", "mskf_get_tracking_info",
+    "mskf_get_grid", "mskf_get_pyramid", "mskf_get_state", "mskf_get_cam_states", "mskf_get_covariance",
+    "mskf_reset", "mskf_op_pyramid", "mskf_op_detect", "mskf_op_klt",
+]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(f"{LIB_PATH} is missing: run __graft_entry__.build() (no CPU fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        P, I, D = C.c_void_p, C.c_int, C.c_double
+        L.mskf_default_config.argtypes = [C.POINTER(abi.Config), C.c_char_p]
+        L.mskf_create.argtypes = [C.POINTER(abi.Config), I, I, C.POINTER(P)]
+        L.mskf_destroy.argtypes = [P]
+        L.mskf_destroy.restype = None
+        L.mskf_last_error.argtypes = [P]
+        L.mskf_last_error.restype = C.c_char_p
+        L.mskf_set_cuda_stream.argtypes = [P, P]
+        L.mskf_launch_count.argtypes = [P]
+        L.mskf_launch_count.restype = C.c_longlong
+        L.mskf_push_imu.argtypes = [P, I, D, P, P]
+        L.mskf_push_stereo.argtypes = [P, I, D, P, P, I, I, I]
+        L.mskf_push_stereo_device.argtypes = [P, I, D, P, P]
+        for n in ("mskf_frontend_step", "mskf_backend_step", "mskf_step", "mskf_sync"):
+            getattr(L, n).argtypes = [P]
+        L.mskf_backend_step_features.argtypes = [P, I, D, P, I]
+        L.mskf_get_features.argtypes = [P, I, P, I, C.POINTER(I), C.POINTER(D)]
+        L.mskf_get_n_published.argtypes = [P, I, C.POINTER(I)]
+        L.mskf_get_tracking_info.argtypes = [P, I, C.POINTER(abi.TrackingInfo)]
+        L.mskf_get_grid.argtypes = [P, I, P, I, C.POINTER(I)]
+        L.mskf_get_pyramid.argtypes = [P, I, I, I, P, I, C.POINTER(I), C.POINTER(I)]
+        L.mskf_get_state.argtypes = [P, I, C.POINTER(abi.State)]
+        L.mskf_get_cam_states.argtypes = [P, I, P, I, C.POINTER(I)]
+        L.mskf_get_covariance.argtypes = [P, I, P, I, C.POINTER(I)]
+        L.mskf_reset.argtypes = [P, I]
+        L.mskf_op_pyramid.argtypes = [P, P, I, I, I, I, P]
+        L.mskf_op_detect.argtypes = [P, P, I, I, P, I, P, P, I, C.POINTER(I)]
+        L.mskf_op_klt.argtypes = [P, P, P, I, I, P, P, P, I]
+        L.mskf_debug_detect_scores.argtypes = [P, P, I, I, P, P, I, C.POINTER(I), P]
+        L.mskf_synth_render_device.argtypes = [P, P, P, P, P, P, I, I, I, P]
+        _LIB = L
+    return _LIB
+
+
+def default_config(preset="ref"):
+    cfg = abi.Config()
+    if lib().mskf_default_config(C.byref(cfg), preset.encode()) != 0:
+        raise ValueError(f"unknown preset {preset!r}")
+    return cfg
+
+
+class Engine:
+    """`n_streams` independent System instances (system.cpp:12-54) advanced together on one GPU."""
+
+    def __init__(self, cfg, n_streams=1, device=0, cuda_stream=None):
+        self.cfg, self.n_streams = cfg, n_streams
+        self.h = C.c_void_p()
+        rc = lib().mskf_create(C.byref(cfg), n_streams, device, C.byref(self.h))
+        if rc != 0:
+            msg = lib().mskf_last_error(self.h).decode() if self.h else "no CUDA device"
+            if self.h:
+                lib().mskf_destroy(self.h)
+                self.h = None
+            raise EngineError(f"mskf_create failed ({rc}): {msg}")
+        if cuda_stream is not None:
+            self._ck(lib().mskf_set_cuda_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mskf_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError(f"msckf_b200 error {rc}: {lib().mskf_last_error(self.h).decode()}")
+
+    # ---- System::imu_callback / stereo_callback / backend_callback ---------------------
+    def imu_callback(self, t, w, a, stream=0):
+        w = np.ascontiguousarray(w, np.float64)
+        a = np.ascontiguousarray(a, np.float64)
+        self._ck(lib().mskf_push_imu(self.h, stream, t, w.ctypes.data, a.ctypes.data))
+
+    def push_stereo(self, t, cam0, cam1, stream=0):
+        cam0 = np.ascontiguousarray(cam0, np.uint8)
+        cam1 = np.ascontiguousarray(cam1, np.uint8)
+        r, c = cam0.shape
+        self._ck(lib().mskf_push_stereo(self.h, stream, t, cam0.ctypes.data, cam1.ctypes.data, r, c, c))
+
+    def push_stereo_ptr(self, t, p0, p1, stream=0, device=False):
+        if device:
+            self._ck(lib().mskf_push_stereo_device(self.h, stream, t, C.c_void_p(p0), C.c_void_p(p1)))
+        else:
+            self._ck(lib().mskf_push_stereo(self.h, stream, t, C.c_void_p(p0), C.c_void_p(p1), self.cfg.img_rows,
+                                            self.cfg.img_cols, self.cfg.img_cols))
+
+    def stereo_callback(self, t, cam0, cam1, stream=0):
+        self.push_stereo(t, cam0, cam1, stream)
+        self.frontend_step()
+
+    def frontend_step(self):
+        self._ck(lib().mskf_frontend_step(self.h))
+
+    def backend_callback(self):
+        self._ck(lib().mskf_backend_step(self.h))
+
+    def step(self):
+        self._ck(lib().mskf_step(self.h))
+
+    def sync(self):
+        self._ck(lib().mskf_sync(self.h))
+
+    def backend_features(self, t, feats, stream=0):
+        feats = np.ascontiguousarray(feats, FEAT_DT)
+        self._ck(lib().mskf_backend_step_features(self.h, stream, t, feats.ctypes.data, len(feats)))
+
+    # sink protocol shared with the oracle (synth.feed)
+    def imu(self, t, w, a):
+        self.imu_callback(t, w, a, 0)
+
+    def stereo(self, t, im0, im1):
+        self.stereo_callback(t, im0, im1, 0)
+
+    def backend(self):
+        self.backend_callback()
+
+    # ---- outputs -----------------------------------------------------------------------
+    def launch_count(self):
+        return int(lib().mskf_launch_count(self.h))
+
+    def features(self, stream=0):
+        n, t = C.c_int(), C.c_double()
+        self._ck(lib().mskf_get_features(self.h, stream, None, 0, C.byref(n), C.byref(t)))
+        out = np.zeros(n.value, FEAT_DT)
+        self._ck(lib().mskf_get_features(self.h, stream, out.ctypes.data, n.value, C.byref(n), C.byref(t)))
+        npub = C.c_int()
+        self._ck(lib().mskf_get_n_published(self.h, stream, C.byref(npub)))
+        return t.value, out, npub.value
+
+    def tracking_info(self, stream=0):
+        ti = abi.TrackingInfo()
+        self._ck(lib().mskf_get_tracking_info(self.h, stream, C.byref(ti)))
+        return ti
+
+    def grid(self, stream=0):
+        n = C.c_int()
+        self._ck(lib().mskf_get_grid(self.h, stream, None, 0, C.byref(n)))
+        out = np.zeros(n.value, GRID_DT)
+        if n.value:
+            self._ck(lib().mskf_get_grid(self.h, stream, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def pyramid(self, cam, level, stream=0):
+        r, c = C.c_int(), C.c_int()
+        self._ck(lib().mskf_get_pyramid(self.h, stream, cam, level, None, 0, C.byref(r), C.byref(c)))
+        out = np.empty((r.value, c.value), np.uint8)
+        self._ck(lib().mskf_get_pyramid(self.h, stream, cam, level, out.ctypes.data, out.size, C.byref(r), C.byref(c)))
+        return out
+
+    def state(self, stream=0):
+        s = abi.State()
+        self._ck(lib().mskf_get_state(self.h, stream, C.byref(s)))
+        return s
+
+    def cam_states(self, stream=0):
+        n = C.c_int()
+        self._ck(lib().mskf_get_cam_states(self.h, stream, None, 0, C.byref(n)))
+        out = np.zeros(n.value, CAM_DT)
+        if n.value:
+            self._ck(lib().mskf_get_cam_states(self.h, stream, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def cov(self, stream=0):
+        d = C.c_int()
+        self._ck(lib().mskf_get_covariance(self.h, stream, None, 0, C.byref(d)))
+        out = np.zeros((d.value, d.value))
+        self._ck(lib().mskf_get_covariance(self.h, stream, out.ctypes.data, out.size, C.byref(d)))
+        return out
+
+    def reset(self, stream=0):
+        self._ck(lib().mskf_reset(self.h, stream))
+
+    # ---- stand-alone operators ---------------------------------------------------------
+    def op_pyramid(self, imgs, levels):
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        n, r, c = imgs.shape
+        sizes, rr, cc = [], r, c
+        for _ in range(1, levels):
+            rr, cc = (rr + 1) // 2, (cc + 1) // 2
+            sizes.append((rr, cc))
+        per = sum(a * b for a, b in sizes)
+        out = np.empty((n, per), np.uint8)
+        self._ck(lib().mskf_op_pyramid(self.h, imgs.ctypes.data, n, r, c, levels, out.ctypes.data))
+        res = []
+        for i in range(n):
+            o, lv = 0, []
+            for a, b in sizes:
+                lv.append(out[i, o:o + a * b].reshape(a, b))
+                o += a * b
+            res.append(lv)
+        return res
+
+    def op_detect(self, img, occupied=None):
+        img = np.ascontiguousarray(img, np.uint8)
+        occ = np.ascontiguousarray(occupied if occupied is not None else np.zeros((0, 2)), np.float32)
+        cap = self.cfg.det_rows * self.cfg.det_cols
+        xy = np.zeros((cap, 2), np.float32)
+        resp = np.zeros(cap)
+        n = C.c_int()
+        self._ck(lib().mskf_op_detect(self.h, img.ctypes.data, img.shape[0], img.shape[1], occ.ctypes.data, len(occ),
+                                      xy.ctypes.data, resp.ctypes.data, cap, C.byref(n)))
+        return xy[:n.value], resp[:n.value]
+
+    def debug_detect_scores(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = self.cfg.det_rows * self.cfg.det_cols
+        xy = np.zeros((cap, 2), np.float32)
+        resp = np.zeros(cap)
+        sm = np.zeros(img.shape, np.uint8)
+        n = C.c_int()
+        self._ck(lib().mskf_debug_detect_scores(self.h, img.ctypes.data, img.shape[0], img.shape[1], xy.ctypes.data,
+                                                resp.ctypes.data, cap, C.byref(n), sm.ctypes.data))
+        return xy[:n.value], resp[:n.value], sm
+
+    def op_klt(self, a, b, pts_a, pts_b):
+        a = np.ascontiguousarray(a, np.uint8)
+        b = np.ascontiguousarray(b, np.uint8)
+        pa = np.ascontiguousarray(pts_a, np.float32)
+        pb = np.array(pts_b, np.float32, copy=True)
+        st = np.zeros(len(pa), np.uint8)
+        self._ck(lib().mskf_op_klt(self.h, a.ctypes.data, b.ctypes.data, a.shape[0], a.shape[1], pa.ctypes.data,
+                                   pb.ctypes.data, st.ctypes.data, len(pa)))
+        return pb, st
