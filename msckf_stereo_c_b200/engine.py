@@ -98,8 +98,8 @@ class Engine:
             self._ck(lib().mskf_set_cuda_stream(self.h, C.c_void_p(cuda_stream)))
 
     def close(self):
-        if getattr(self, "h", None):
-            lib().mskf_destroy(self.h)
+        if getattr(self, "h", None) and _LIB is not None:  # _LIB is None again at interpreter shutdown
+            _LIB.mskf_destroy(self.h)
             self.h = None
 
     __del__ = close

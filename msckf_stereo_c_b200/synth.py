@@ -65,8 +65,8 @@ class Stream:
         self.na = cfg.noise_acc * np.sqrt(imu_rate) if imu_noise else 0.0
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().synth_destroy(self.h)
+        if getattr(self, "h", None) and _LIB is not None:
+            _LIB.synth_destroy(self.h)
             self.h = None
 
     def frame_time(self, k):

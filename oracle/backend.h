@@ -540,10 +540,8 @@ public:
         r = rq.block(3, 0, jacobian_row_size - 3, 1);
     }
 
-    // msckf_vio.cpp:778-907
-    void measurementUpdate(const Mat &H, const Mat &r) {
-        if (H.r == 0 || r.r == 0) return;
-        ++n_updates;
+    // msckf_vio.cpp:795-857,897-904: the linear algebra of measurementUpdate on (H, r, P)
+    static void update_math(const Mat &H, const Mat &r, const Mat &P, double obs_noise, Mat &delta_x, Mat &P_new) {
         Mat H_thin, r_thin;
         if (H.r > H.c) {
             // :795-810 SPQR (natural ordering): H_thin = (Q^T H)[0:n], r_thin = (Q^T r)[0:n]
@@ -552,7 +550,7 @@ public:
             householder_qr(QR, tau);
             Mat rq = r;
             apply_qt(QR, tau, rq);
-            int n = 21 + (int)cam_states.size() * 6;
+            int n = H.c;
             H_thin = Mat(n, H.c);
             for (int i = 0; i < n; ++i)
                 for (int j = i; j < H.c; ++j) H_thin(i, j) = QR(i, j);
@@ -561,13 +559,23 @@ public:
             H_thin = H;
             r_thin = r;
         }
-        const Mat &P = state_cov;
         Mat HP = H_thin * P;
         Mat S = HP * H_thin.t();
-        for (int i = 0; i < S.r; ++i) S(i, i) += observation_noise;
+        for (int i = 0; i < S.r; ++i) S(i, i) += obs_noise;
         Mat K_transpose = ldlt_solve(S, HP);  // :850
         Mat K = K_transpose.t();
-        Mat delta_x = K * r_thin;
+        delta_x = K * r_thin;
+        Mat I_KH = Mat::eye(K.r) - K * H_thin;
+        P_new = I_KH * P;
+        P_new = (P_new + P_new.t()) * 0.5;
+    }
+
+    // msckf_vio.cpp:778-907
+    void measurementUpdate(const Mat &H, const Mat &r) {
+        if (H.r == 0 || r.r == 0) return;
+        ++n_updates;
+        Mat delta_x, P_new;
+        update_math(H, r, state_cov, observation_noise, delta_x, P_new);
         last_delta_x = delta_x;
         auto seg3 = [&](int o) { return V3(delta_x(o, 0), delta_x(o + 1, 0), delta_x(o + 2, 0)); };
         const Quat dq_imu = small_angle_quat(seg3(0));
@@ -585,9 +593,7 @@ public:
             it->second.orientation = quat_mul(dq_cam, it->second.orientation);
             it->second.position = it->second.position + seg3(21 + i * 6 + 3);
         }
-        Mat I_KH = Mat::eye(K.r) - K * H_thin;
-        state_cov = I_KH * state_cov;
-        state_cov = (state_cov + state_cov.t()) * 0.5;
+        state_cov = P_new;
     }
 
     // msckf_vio.cpp:909-935

@@ -47,6 +47,15 @@ def lib():
         L.orc_klt.argtypes = [C.POINTER(abi.Config), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_undistort.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_distort.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_rodrigues.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_qr_thin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_ldlt_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_nullspace_update.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        L.orc_update_math.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
+                                      C.c_void_p]
+        L.orc_chi2.argtypes = [C.POINTER(abi.Config), C.c_int]
+        L.orc_chi2.restype = C.c_double
         _LIB = L
     return _LIB
 
@@ -65,8 +74,8 @@ class Oracle:
         self.h = lib().orc_create(C.byref(cfg))
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().orc_destroy(self.h)
+        if getattr(self, "h", None) and _LIB is not None:
+            _LIB.orc_destroy(self.h)
             self.h = None
 
     def imu(self, t, w, a):
@@ -176,3 +185,56 @@ def distort(pts, K, model, D):
     out = np.zeros_like(pts)
     lib().orc_distort(pts.ctypes.data, len(pts), K.ctypes.data, model, D.ctypes.data, out.ctypes.data)
     return out
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+def rodrigues(v):
+    v = _f64(v)
+    R = np.zeros((3, 3))
+    lib().orc_rodrigues(v.ctypes.data, R.ctypes.data)
+    return R
+
+
+def qr_thin(A, b):
+    A, b = _f64(A), _f64(b)
+    m, n = A.shape
+    R = np.zeros((n, n))
+    qtb = np.zeros(n)
+    lib().orc_qr_thin(A.ctypes.data, m, n, b.ctypes.data, R.ctypes.data, qtb.ctypes.data)
+    return R, qtb
+
+
+def ldlt_solve(S, B):
+    S, B = _f64(S), _f64(B)
+    B2 = B.reshape(len(S), -1)
+    X = np.zeros_like(B2)
+    lib().orc_ldlt_solve(S.ctypes.data, len(S), B2.ctypes.data, B2.shape[1], X.ctypes.data)
+    return X.reshape(B.shape)
+
+
+def nullspace_update(Hx, Hf, r, P, obs_noise, basis=None):
+    Hx, Hf, r, P = _f64(Hx), _f64(Hf), _f64(r), _f64(P)
+    rows, n = Hx.shape
+    dx = np.zeros(n)
+    Pn = np.zeros((n, n))
+    g = C.c_double()
+    b = _f64(basis) if basis is not None else None
+    lib().orc_nullspace_update(n, rows, Hx.ctypes.data, Hf.ctypes.data, r.ctypes.data, P.ctypes.data, obs_noise,
+                               b.ctypes.data if b is not None else None, dx.ctypes.data, Pn.ctypes.data, C.byref(g))
+    return dx, Pn, g.value
+
+
+def update_math(H, r, P, obs_noise):
+    H, r, P = _f64(H), _f64(r), _f64(P)
+    m, n = H.shape
+    dx = np.zeros(n)
+    Pn = np.zeros((n, n))
+    lib().orc_update_math(n, m, H.ctypes.data, r.ctypes.data, P.ctypes.data, obs_noise, dx.ctypes.data, Pn.ctypes.data)
+    return dx, Pn
+
+
+def chi2(cfg, dof):
+    return lib().orc_chi2(C.byref(cfg), dof)

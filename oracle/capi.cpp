@@ -218,4 +218,75 @@ void orc_last_update_debug(void *h, double *delta_x, int cap, int *n, double *ga
     *gamma = o->be.last_gamma;
 }
 
+// ---- linear-algebra hooks for the CPU tests (linalg.h / kin.h against numpy, and the
+// null-space basis invariance property of SURVEY 8c) ----------------------------------------
+void orc_rodrigues(const double v[3], double R[9]) {
+    M3 m = rodrigues(V3(v[0], v[1], v[2]));
+    for (int i = 0; i < 9; ++i) R[i] = m.m[i];
+}
+static Mat mat_from(const double *d, int r, int c) {
+    Mat m(r, c);
+    std::memcpy(m.d.data(), d, sizeof(double) * (size_t)r * c);
+    return m;
+}
+// thin QR: R (n x n, upper) and Q^T b (first n entries) of A (m x n), m >= n
+void orc_qr_thin(const double *A, int m, int n, const double *b, double *R, double *qtb) {
+    Mat QR = mat_from(A, m, n), rb = mat_from(b, m, 1);
+    std::vector<double> tau;
+    householder_qr(QR, tau);
+    apply_qt(QR, tau, rb);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) R[i * n + j] = j >= i ? QR(i, j) : 0.0;
+    for (int i = 0; i < n; ++i) qtb[i] = rb(i, 0);
+}
+void orc_ldlt_solve(const double *S, int n, const double *B, int nc, double *X) {
+    Mat x = ldlt_solve(mat_from(S, n, n), mat_from(B, n, nc));
+    std::memcpy(X, x.d.data(), sizeof(double) * (size_t)n * nc);
+}
+// featureJacobian's projection (msckf_vio.cpp:757-766) + gatingTest (:909-935) +
+// update_math on one feature block.  basis == nullptr: Householder basis (what the oracle
+// runs); otherwise `basis` is an explicit 4M x (4M-3) orthonormal null-space basis A, e.g.
+// the last columns of U from a full SVD as the reference computes it.
+void orc_nullspace_update(int n, int rows, const double *Hx, const double *Hf, const double *r, const double *P,
+                          double obs_noise, const double *basis, double *out_dx, double *out_P, double *out_gamma) {
+    Mat Hxj = mat_from(Hx, rows, n), Hfj = mat_from(Hf, rows, 3), rj = mat_from(r, rows, 1), Pm = mat_from(P, n, n);
+    Mat Hp, rp;
+    if (!basis) {
+        Mat QR = Hfj;
+        std::vector<double> tau;
+        householder_qr(QR, tau);
+        Mat Hq = Hxj, rq = rj;
+        apply_qt(QR, tau, Hq);
+        apply_qt(QR, tau, rq);
+        Hp = Hq.block(3, 0, rows - 3, n);
+        rp = rq.block(3, 0, rows - 3, 1);
+    } else {
+        Mat A = mat_from(basis, rows, rows - 3);
+        Hp = A.t() * Hxj;
+        rp = A.t() * rj;
+    }
+    Mat S = Hp * Pm * Hp.t();
+    for (int i = 0; i < S.r; ++i) S(i, i) += obs_noise;
+    Mat x = ldlt_solve(S, rp);
+    double g = 0;
+    for (int i = 0; i < rp.r; ++i) g += rp(i, 0) * x(i, 0);
+    *out_gamma = g;
+    Mat dx, Pn;
+    MsckfVio::update_math(Hp, rp, Pm, obs_noise, dx, Pn);
+    std::memcpy(out_dx, dx.d.data(), sizeof(double) * n);
+    std::memcpy(out_P, Pn.d.data(), sizeof(double) * (size_t)n * n);
+}
+// measurementUpdate's algebra alone (msckf_vio.cpp:795-857,897-904)
+void orc_update_math(int n, int m, const double *H, const double *r, const double *P, double obs_noise, double *out_dx,
+                     double *out_P) {
+    Mat dx, Pn;
+    MsckfVio::update_math(mat_from(H, m, n), mat_from(r, m, 1), mat_from(P, n, n), obs_noise, dx, Pn);
+    std::memcpy(out_dx, dx.d.data(), sizeof(double) * n);
+    std::memcpy(out_P, Pn.d.data(), sizeof(double) * (size_t)n * n);
+}
+double orc_chi2(const mskf_config *cfg, int dof) {
+    MsckfVio v(*cfg);
+    return v.chi2(dof);
+}
+
 }  // extern "C"
