@@ -215,6 +215,32 @@ int mskf_op_detect(mskf_handle *h, const uint8_t *img, int rows, int cols, const
 int mskf_op_klt(mskf_handle *h, const uint8_t *img_a, const uint8_t *img_b, int rows, int cols,
                 const float *pts_a, float *pts_b, uint8_t *status, int n);
 
+/* measurementUpdate (msckf_vio.cpp:778-907: QR compression, S, gain, delta_x, covariance update)
+ * as a stand-alone operator for the "identical inputs" parity test: H is m x n row-major with
+ * n = 21 + 6 n_cam (its 21 IMU columns are zero, msckf_vio.cpp:709-712), r has m entries, P is
+ * n x n; observation noise comes from the configuration.  Outputs delta_x (n) and the posterior P. */
+int mskf_op_ekf_update(mskf_handle *h, int n_cam, int m, const double *H, const double *r, const double *P,
+                       double *out_delta_x, double *out_P);
+
+/* ---- instrumentation (bench.py / tests; no reference counterpart) ------------------------ */
+/* Kernels launched by this handle so far. */
+long long mskf_launch_count(const mskf_handle *h);
+/* Number of measurements the last front-end step published for `stream` (the reference's
+ * curr_ids.size() in publish(), image_processor.cpp:1146-1164), without the stale tail. */
+int mskf_get_n_published(mskf_handle *h, int stream, int *n);
+/* Poses T_b_w (row-major 4x4, msckf_vio.cpp:1242-1246) of all streams in one device->host copy. */
+int mskf_get_poses(mskf_handle *h, double *out_T_b_w, int cap_streams);
+/* CUDA-event time per kernel class, recorded on the launching stream while enabled.
+ * mskf_profile_read returns 1 when `tag` is past the last class. */
+int mskf_profile_enable(mskf_handle *h, int on);
+int mskf_profile_read(mskf_handle *h, int tag, const char **name, double *ms, long long *count);
+/* The back end's feature map (MsckfVio::map_server) in ascending feature id. */
+int mskf_debug_get_map(mskf_handle *h, int stream, long long *ids, int *is_initialized, double *position,
+                       int *n_observations, int cap, int *n);
+/* mskf_op_detect that also returns the per-pixel FAST score map (0 = not a corner). */
+int mskf_debug_detect_scores(mskf_handle *h, const uint8_t *img, int rows, int cols, float *out_xy,
+                             double *out_response, int cap, int *n, uint8_t *score_map);
+
 #ifdef __cplusplus
 }
 #endif

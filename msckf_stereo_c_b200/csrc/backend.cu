@@ -1,11 +1,2421 @@
-// backend.cu — placeholder while the front end is brought up (replaced by the fp64 filter).
+// backend.cu — MsckfVio hot path on sm_100a, fp64, batched over independent streams.
+//
+// Every stream owns one filter (IMU state, <= NS camera states, covariance P, feature map).
+// The data-dependent control flow of the reference (which features are lost, how many
+// observations each has, gating results, the 1500-row cap, the prune decision) lives in
+// device memory: the host launches the same fixed kernel sequence every frame with
+// worst-case grids, and CTAs whose stream (or feature) has no work exit at once.
+//
+// Layout choices (DESIGN.md "back end"):
+//   * P is stored by physical camera SLOT: rows/cols [21+6*slot, +6).  Slots that hold no
+//     camera state are kept exactly zero, so every product can run over the full LD x LD
+//     matrix without masks, augmentation/pruning never shift memory (the reference
+//     conservative_resizes and block-moves P every frame: msckf_vio.cpp:564-566,1161-1181),
+//     and mskf_get_covariance gathers the logical (ascending state id) order on read-out.
+//   * Observations are [feature slot][camera slot][4]; a 32-bit mask per feature says which
+//     camera slots observe it.
+//   * The Kalman update uses the compact-column, square-root form of the reference's
+//     algebra: H only ever touches camera columns (msckf_vio.cpp:709-712), so with T the
+//     (QR-compressed) measurement matrix over the k active camera columns,
+//         S = T P_cc T^T + sigma^2 I = L L^T,  W = (P_:c T^T) L^-T,
+//         delta_x = W (L^-1 r),  P <- P - W W^T
+//     which equals K = P H^T S^-1, P <- (I - K H) P, (P + P^T)/2 of msckf_vio.cpp:833-904 in
+//     exact arithmetic and is symmetric by construction.  The posterior does not depend on
+//     the orthonormal basis chosen for the null-space projection or on the QR row signs
+//     (tests/test_oracle_backend.py::test_posterior_independent_of_nullspace_basis).
+//
+// Reference call sites replaced (msckf_core/src/msckf_vio.cpp, include/feature.hpp):
+//   be_gravity_kernel        initializeGravityAndBias :209-241
+//   be_propagate_kernel      batchImuProcessing :377-407, processModel :409-480, predictNewState :482-531
+//   be_augment_kernel        stateAugmentation :533-585
+//   be_add_obs_kernel        addFeatureObservations :587-608
+//   be_select_kernel         removeLostFeatures :943-975 (selection), pruneCamStateBuffer :1073-1124,
+//                            findRedundantCamStates :1026-1071
+//   be_triangulate_kernel    Feature::checkMotion / initializePosition feature.hpp:257-450
+//   be_layout_kernel         removeLostFeatures :965-990 bookkeeping
+//   be_feature_jac_kernel    measurementJacobian :610-677, featureJacobian :679-775, gatingTest :909-935
+//   be_stack_kernel          removeLostFeatures :992-1015 (stacking + row cap), pruneCamStateBuffer :1126-1150
+//   be_qr_kernel             measurementUpdate :795-810 (SPQR compression)
+//   be_gemm_kernel<...>, be_chol_kernel, be_apply_kernel   measurementUpdate :833-904
+//   be_prune_finish_kernel   pruneCamStateBuffer :1161-1181
+//   be_finish_kernel         publish :1238-1254, onlineReset :1186-1236
+#include <math.h>
+#include <stddef.h>
+#include <string.h>
+
+#include "chi2_table.h"
 #include "common.cuh"
-struct BeBuffers { int dummy; };
-int be_create(mskf_handle *h) { h->bb = new BeBuffers; return MSKF_OK; }
-void be_destroy(mskf_handle *h) { delete h->bb; h->bb = nullptr; }
-int be_step(mskf_handle *h, const std::vector<int> &, const mskf_feature *, int, int, double) { h->err = "back end not built"; return MSKF_ERR_STATE; }
-int be_init_gravity(mskf_handle *, int) { return MSKF_OK; }
-int be_get_state(mskf_handle *h, int, mskf_state *) { h->err = "back end not built"; return MSKF_ERR_STATE; }
-int be_get_cam_states(mskf_handle *h, int, mskf_cam_state *, int, int *) { h->err = "back end not built"; return MSKF_ERR_STATE; }
-int be_get_cov(mskf_handle *h, int, double *, int, int *) { h->err = "back end not built"; return MSKF_ERR_STATE; }
-int be_reset(mskf_handle *, int) { return MSKF_OK; }
+
+#define NSM 32          // camera-state slots (mask width)
+#define BE_IMU_CAP 256  // IMU samples per stream per propagate launch
+#define BE_THREADS 256
+
+namespace mskf {
+
+struct BeCam {
+    long long id;
+    double time;
+    double q[4], p[3], qn[4], pn[3];
+};
+
+struct BeState {
+    double time;
+    long long id, next_id;
+    double q[4], p[3], v[3], bg[3], ba[3];
+    double Ric[9], tci[3];  // R_imu_cam0, t_cam0_imu
+    double qn[4], pn[3], vn[3];
+    double g[3];
+    double tracking_rate;
+    double T_b_w[16];
+    long long n_updates, n_resets, n_overflow;
+    int n_cam, cur_slot;
+    unsigned cam_used;
+    int order[NSM];  // logical (ascending state id) -> slot
+    int n_feat;
+    int gravity_set;
+    // per-step scratch
+    int n_list;          // length of the current feature list
+    int m, k, mt;        // stacked rows, compact columns, rows after compression
+    int u_nslots;
+    int u_slots[NSM];
+    int colpos[NSM];
+    int prune_active;
+    int rm_slot[2];
+    unsigned rm_bits;
+    int do_update;
+    BeCam cam[NSM];
+};
+
+struct BeStep {
+    int active, first, n_imu, src;  // src 0: front-end message, 1: injected list
+    int n_inject, pad;
+    double t;
+};
+
+struct BeConst {
+    int S, NS, LD, KC;  // KC = 6 NS
+    int MF, HASH, ML;
+    int ecap;      // elements of per-feature Jacobian scratch per stream
+    int rcap;      // rows of per-feature residual scratch per stream
+    int hst_cap;   // elements of the stacked H per stream
+    int hst_rows;  // rows of the stacked residual per stream
+    int ent_cap;   // message entries per stream
+    int max_rows, max_cam, max_f;
+    int chi2_mode;
+    double gyro_noise, acc_noise, gyro_bias_noise, acc_bias_noise, obs_noise;
+    double R01[9], t01[3];  // T_cam0_cam1 (config T_cn_cnm1), msckf_vio.cpp:118-121
+    double Rib[9], tib[3];  // T_imu_body = inverse of the configured matrix, msckf_vio.cpp:124-126
+    double pos_std_thr, rot_thr, trans_thr, track_thr, feat_trans_thr;
+    double cov_gb, cov_v, cov_ab, cov_er, cov_et;
+};
+
+struct BeBuf {
+    BeState *st;       // [S]
+    BeStep *step;      // [S]
+    double *imu;       // [S][BE_IMU_CAP][7]
+    double *P;         // [S][LD*LD]
+    unsigned *f_id;    // [S][MF]
+    unsigned *f_mask;  // [S][MF]
+    uint8_t *f_live, *f_init;  // [S][MF]
+    double *f_pos;     // [S][MF][3]
+    double *f_obs;     // [S][MF][NS][4]
+    int *f_last;       // [S][MF]
+    int *freelist;     // [S][MF]
+    int *e_cell;       // [S][ent_cap+1]
+    mskf_feature *inject;  // [ent_cap]
+    // feature lists of the current phase
+    int *l_slot;       // [S][ML]
+    uint8_t *l_ok, *l_pass;  // [S][ML]
+    int *l_M, *l_eoff, *l_roff, *l_soff;  // [S][ML]
+    uint8_t *l_oslots; // [S][ML][NSM]
+    double *Hblk, *HPblk;  // [S][ecap]
+    double *rblk;      // [S][rcap]
+    double *Hst;       // [S][hst_cap]
+    double *rst;       // [S][hst_rows]
+    double *Tm;        // [S][KC*KC]
+    double *rt;        // [S][KC]
+    double *PHt;       // [S][LD*KC]
+    double *Sm;        // [S][KC*KC]
+    double *Linv;      // [S][KC*KC]
+    double *W;         // [S][LD*KC]
+    double *yv;        // [S][KC]
+    double *dxv;       // [S][LD] delta_x of the latest update
+    // front-end message (fb.stale / stale_hw / msg_total)
+    const mskf_feature *fe_msg;
+    const int *fe_hw;
+    const long long *fe_total;
+};
+
+__constant__ double c_chi2[2][99];
+
+// ======================================================================================
+// small fp64 helpers (the conventions of oracle/kin.h: JPL quaternion [x y z w])
+// ======================================================================================
+__device__ __forceinline__ void quat_to_rot(const double q[4], double R[9]) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double a = 2 * w * w - 1, b = 2 * w;
+    // (2w^2-1) I - 2w [q]x + 2 q q^T
+    R[0] = a + 2 * x * x;         R[1] = b * z + 2 * x * y;     R[2] = -b * y + 2 * x * z;
+    R[3] = -b * z + 2 * y * x;    R[4] = a + 2 * y * y;         R[5] = b * x + 2 * y * z;
+    R[6] = b * y + 2 * z * x;     R[7] = -b * x + 2 * z * y;    R[8] = a + 2 * z * z;
+}
+__device__ __forceinline__ void quat_normalize(double q[4]) {
+    double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+__device__ void rot_to_quat(const double R[9], double q[4]) {
+    double tr = R[0] + R[4] + R[8];
+    double score[4] = {R[0], R[4], R[8], tr};
+    int best = 0;
+    for (int i = 1; i < 4; ++i)
+        if (score[i] > score[best]) best = i;
+    if (best == 0) {
+        q[0] = sqrt(1 + 2 * R[0] - tr) / 2.0;
+        q[1] = (R[1] + R[3]) / (4 * q[0]);
+        q[2] = (R[2] + R[6]) / (4 * q[0]);
+        q[3] = (R[5] - R[7]) / (4 * q[0]);
+    } else if (best == 1) {
+        q[1] = sqrt(1 + 2 * R[4] - tr) / 2.0;
+        q[0] = (R[1] + R[3]) / (4 * q[1]);
+        q[2] = (R[5] + R[7]) / (4 * q[1]);
+        q[3] = (R[6] - R[2]) / (4 * q[1]);
+    } else if (best == 2) {
+        q[2] = sqrt(1 + 2 * R[8] - tr) / 2.0;
+        q[0] = (R[2] + R[6]) / (4 * q[2]);
+        q[1] = (R[5] + R[7]) / (4 * q[2]);
+        q[3] = (R[1] - R[3]) / (4 * q[2]);
+    } else {
+        q[3] = sqrt(1 + tr) / 2.0;
+        q[0] = (R[5] - R[7]) / (4 * q[3]);
+        q[1] = (R[6] - R[2]) / (4 * q[3]);
+        q[2] = (R[1] - R[3]) / (4 * q[3]);
+    }
+    if (q[3] < 0)
+        for (int i = 0; i < 4; ++i) q[i] = -q[i];
+    quat_normalize(q);
+}
+__device__ __forceinline__ void quat_mul(const double a[4], const double b[4], double r[4]) {
+    r[0] = a[3] * b[0] + a[2] * b[1] - a[1] * b[2] + a[0] * b[3];
+    r[1] = -a[2] * b[0] + a[3] * b[1] + a[0] * b[2] + a[1] * b[3];
+    r[2] = a[1] * b[0] - a[0] * b[1] + a[3] * b[2] + a[2] * b[3];
+    r[3] = -a[0] * b[0] - a[1] * b[1] - a[2] * b[2] + a[3] * b[3];
+    quat_normalize(r);
+}
+__device__ __forceinline__ void small_angle_quat(const double dth[3], double q[4]) {
+    double d0 = dth[0] / 2.0, d1 = dth[1] / 2.0, d2 = dth[2] / 2.0;
+    double n2 = d0 * d0 + d1 * d1 + d2 * d2;
+    if (n2 <= 1) {
+        q[0] = d0; q[1] = d1; q[2] = d2; q[3] = sqrt(1 - n2);
+    } else {
+        double s = sqrt(1 + n2);
+        q[0] = d0 / s; q[1] = d1 / s; q[2] = d2 / s; q[3] = 1.0 / s;
+    }
+}
+__device__ __forceinline__ void skew3(const double w[3], double K[9]) {
+    K[0] = 0; K[1] = -w[2]; K[2] = w[1];
+    K[3] = w[2]; K[4] = 0; K[5] = -w[0];
+    K[6] = -w[1]; K[7] = w[0]; K[8] = 0;
+}
+__device__ __forceinline__ void m3mul(const double *a, const double *b, double *c) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) c[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
+}
+__device__ __forceinline__ void m3mulT(const double *a, const double *b, double *c) {  // a * b^T
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) c[i * 3 + j] = a[i * 3] * b[j * 3] + a[i * 3 + 1] * b[j * 3 + 1] + a[i * 3 + 2] * b[j * 3 + 2];
+}
+__device__ __forceinline__ void m3Tmul(const double *a, const double *b, double *c) {  // a^T * b
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) c[i * 3 + j] = a[i] * b[j] + a[3 + i] * b[3 + j] + a[6 + i] * b[6 + j];
+}
+__device__ __forceinline__ void m3v(const double *a, const double *x, double *y) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) y[i] = a[i * 3] * x[0] + a[i * 3 + 1] * x[1] + a[i * 3 + 2] * x[2];
+}
+__device__ __forceinline__ void m3Tv(const double *a, const double *x, double *y) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) y[i] = a[i] * x[0] + a[3 + i] * x[1] + a[6 + i] * x[2];
+}
+// angle of Eigen::AngleAxisd(R) (msckf_vio.cpp:1054) via the Hamilton quaternion
+__device__ double rotation_angle(const double R[9]) {
+    double tr = R[0] + R[4] + R[8];
+    double x, y, z, w;
+    if (tr > 0) {
+        double s = sqrt(tr + 1.0) * 2;
+        w = 0.25 * s; x = (R[7] - R[5]) / s; y = (R[2] - R[6]) / s; z = (R[3] - R[1]) / s;
+    } else if (R[0] > R[4] && R[0] > R[8]) {
+        double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2;
+        w = (R[7] - R[5]) / s; x = 0.25 * s; y = (R[1] + R[3]) / s; z = (R[2] + R[6]) / s;
+    } else if (R[4] > R[8]) {
+        double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2;
+        w = (R[2] - R[6]) / s; x = (R[1] + R[3]) / s; y = 0.25 * s; z = (R[5] + R[7]) / s;
+    } else {
+        double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2;
+        w = (R[3] - R[1]) / s; x = (R[2] + R[6]) / s; y = (R[5] + R[7]) / s; z = 0.25 * s;
+    }
+    double n = sqrt(x * x + y * y + z * z);
+    return 2.0 * atan2(n, fabs(w));
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// exclusive block scan of one int per thread (BE_THREADS threads); returns the prefix, *total = sum
+__device__ int block_excl_scan(int v, int *total, int *s_tmp /* [BE_THREADS/32 + 1] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();
+    if (lane == 31) s_tmp[warp] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int w = 0; w < BE_THREADS / 32; ++w) {
+            int t = s_tmp[w];
+            s_tmp[w] = acc;
+            acc += t;
+        }
+        s_tmp[BE_THREADS / 32] = acc;
+    }
+    __syncthreads();
+    *total = s_tmp[BE_THREADS / 32];
+    return s_tmp[warp] + x - v;
+}
+
+__device__ __forceinline__ void reset_cov(const BeConst &bc, double *P) {  // msckf_vio.cpp:102-112
+    for (int i = threadIdx.x; i < bc.LD * bc.LD; i += blockDim.x) P[i] = 0.0;
+    __syncthreads();
+    if (threadIdx.x < 21) {
+        int i = threadIdx.x;
+        double v = 0.0;
+        if (i >= 3 && i < 6) v = bc.cov_gb;
+        else if (i >= 6 && i < 9) v = bc.cov_v;
+        else if (i >= 9 && i < 12) v = bc.cov_ab;
+        else if (i >= 15 && i < 18) v = bc.cov_er;
+        else if (i >= 18) v = bc.cov_et;
+        P[i * bc.LD + i] = v;
+    }
+}
+
+// ======================================================================================
+// initializeGravityAndBias (msckf_vio.cpp:209-241): sums in buffer order, one thread
+// ======================================================================================
+__global__ void be_gravity_kernel(BeConst bc, BeBuf bb, int s, int n) {
+    if (threadIdx.x != 0) return;
+    BeState &st = bb.st[s];
+    const double *imu = bb.imu + (size_t)s * BE_IMU_CAP * 7;
+    double sw[3] = {0, 0, 0}, sa[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            sw[k] = sw[k] + imu[i * 7 + 1 + k];
+            sa[k] = sa[k] + imu[i * 7 + 4 + k];
+        }
+    double gi[3];
+    for (int k = 0; k < 3; ++k) {
+        st.bg[k] = sw[k] / (double)n;
+        gi[k] = sa[k] / (double)n;
+    }
+    double gn = sqrt(gi[0] * gi[0] + gi[1] * gi[1] + gi[2] * gi[2]);
+    st.g[0] = 0.0; st.g[1] = 0.0; st.g[2] = -gn;
+    // from_two_vector(gravity_imu, -gravity) (Eigen FromTwoVectors semantics), transposed
+    double a[3] = {gi[0] / gn, gi[1] / gn, gi[2] / gn};
+    double b[3] = {0.0, 0.0, 1.0};
+    double c = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+    double R[9];
+    if (c < -1 + 1e-12) {
+        double ax[3] = {fabs(a[0]) < 0.9 ? 1.0 : 0.0, fabs(a[0]) < 0.9 ? 0.0 : 1.0, 0.0};
+        double kx[3] = {a[1] * ax[2] - a[2] * ax[1], a[2] * ax[0] - a[0] * ax[2], a[0] * ax[1] - a[1] * ax[0]};
+        double kn = sqrt(kx[0] * kx[0] + kx[1] * kx[1] + kx[2] * kx[2]);
+        for (int i = 0; i < 3; ++i) kx[i] /= kn;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) R[i * 3 + j] = kx[i] * kx[j] * 2.0 - (i == j ? 1.0 : 0.0);
+    } else {
+        double v[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+        double K[9], KK[9];
+        skew3(v, K);
+        m3mul(K, K, KK);
+        double f = 1.0 / (1.0 + c);
+        for (int i = 0; i < 9; ++i) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + K[i] + KK[i] * f;
+    }
+    double Rt[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Rt[i * 3 + j] = R[j * 3 + i];
+    rot_to_quat(Rt, st.q);
+    st.gravity_set = 1;
+}
+
+// ======================================================================================
+// batchImuProcessing / processModel / predictNewState.  One CTA per stream.  P11 and the
+// 21x21 work matrices live in shared memory; the per-sample transition matrices are
+// accumulated (Phi_tot = Phi_k ... Phi_1) and applied once to the IMU-camera blocks, which
+// the reference touches (and re-symmetrises) once per IMU sample.
+// ======================================================================================
+#define N21 21
+__device__ __forceinline__ void mm21(double *C, const double *A, const double *B) {  // C = A B
+    for (int e = threadIdx.x; e < N21 * N21; e += blockDim.x) {
+        int i = e / N21, j = e - i * N21;
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < N21; ++k) s += A[i * N21 + k] * B[k * N21 + j];
+        C[e] = s;
+    }
+}
+
+__device__ void predict_new_state(BeState &st, double dt, const double gyro[3], const double acc[3]) {
+    double gn = sqrt(gyro[0] * gyro[0] + gyro[1] * gyro[1] + gyro[2] * gyro[2]);
+    double Om[16];
+    for (int i = 0; i < 16; ++i) Om[i] = 0.0;
+    double sk[9];
+    skew3(gyro, sk);
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) Om[i * 4 + j] = -sk[i * 3 + j];
+        Om[i * 4 + 3] = gyro[i];
+        Om[12 + i] = -gyro[i];
+    }
+    double *q = st.q, *v = st.v, *p = st.p;
+    double dq[4], dq2[4];
+    double cI, cO, post, cI2, cO2, post2;
+    if (gn > 1e-5) {
+        cI = cos(gn * dt * 0.5); cO = 1 / gn * sin(gn * dt * 0.5); post = 1.0;
+        cI2 = cos(gn * dt * 0.25); cO2 = 1 / gn * sin(gn * dt * 0.25); post2 = 1.0;
+    } else {
+        cI = 1.0; cO = 0.5 * dt; post = cos(gn * dt * 0.5);
+        cI2 = 1.0; cO2 = 0.25 * dt; post2 = cos(gn * dt * 0.25);
+    }
+    for (int i = 0; i < 4; ++i) {
+        double s1 = 0, s2 = 0;
+        for (int j = 0; j < 4; ++j) {
+            s1 += ((i == j ? cI : 0.0) + cO * Om[i * 4 + j]) * post * q[j];
+            s2 += ((i == j ? cI2 : 0.0) + cO2 * Om[i * 4 + j]) * post2 * q[j];
+        }
+        dq[i] = s1;
+        dq2[i] = s2;
+    }
+    double Rq[9], Rd[9], Rd2[9];
+    quat_to_rot(q, Rq);
+    quat_to_rot(dq, Rd);
+    quat_to_rot(dq2, Rd2);
+    double k1v[3], k2v[3], k4v[3], t[3];
+    m3Tv(Rq, acc, t);
+    for (int i = 0; i < 3; ++i) k1v[i] = t[i] + st.g[i];
+    m3Tv(Rd2, acc, t);
+    for (int i = 0; i < 3; ++i) k2v[i] = t[i] + st.g[i];  // k3_v_dot == k2_v_dot (msckf_vio.cpp:516)
+    m3Tv(Rd, acc, t);
+    for (int i = 0; i < 3; ++i) k4v[i] = t[i] + st.g[i];
+    for (int i = 0; i < 3; ++i) {
+        double k1p = v[i];
+        double k1_v = v[i] + k1v[i] * dt / 2;
+        double k2p = k1_v;
+        double k2_v = v[i] + k2v[i] * dt / 2;
+        double k3p = k2_v;
+        double k3_v = v[i] + k2v[i] * dt;
+        double k4p = k3_v;
+        double vn = v[i] + dt / 6 * (k1v[i] + 2 * k2v[i] + 2 * k2v[i] + k4v[i]);
+        double pn = p[i] + dt / 6 * (k1p + 2 * k2p + 2 * k3p + k4p);
+        v[i] = vn;
+        p[i] = pn;
+    }
+    for (int i = 0; i < 4; ++i) q[i] = dq[i];
+    quat_normalize(q);
+}
+
+__global__ void __launch_bounds__(128) be_propagate_kernel(BeConst bc, BeBuf bb, int chunk) {
+    const int s = blockIdx.x;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    BeState &st = bb.st[s];
+    double *P = bb.P + (size_t)s * bc.LD * bc.LD;
+    const int LD = bc.LD;
+    __shared__ double F[N21 * N21], A[N21 * N21], B[N21 * N21], Phi[N21 * N21], PhiT[N21 * N21], P11[N21 * N21],
+        T[N21 * N21];
+    __shared__ double s_dt;
+    const int n0 = chunk * BE_IMU_CAP;
+    const int n_imu = min(sp.n_imu - n0, BE_IMU_CAP);
+    if (chunk == 0 && sp.first && threadIdx.x == 0) st.time = sp.t;  // msckf_vio.cpp:313-316
+    if (n_imu <= 0) return;
+    const double *imu = bb.imu + (size_t)s * BE_IMU_CAP * 7;
+    for (int e = threadIdx.x; e < N21 * N21; e += blockDim.x) {
+        int i = e / N21, j = e - i * N21;
+        P11[e] = P[i * LD + j];
+        PhiT[e] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int n = 0; n < n_imu; ++n) {
+        for (int e = threadIdx.x; e < N21 * N21; e += blockDim.x) F[e] = 0.0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double *m = imu + n * 7;
+            double gyro[3], acc[3];
+            for (int i = 0; i < 3; ++i) {
+                gyro[i] = m[1 + i] - st.bg[i];
+                acc[i] = m[4 + i] - st.ba[i];
+            }
+            double dt = m[0] - st.time;
+            s_dt = dt;
+            double R[9], sk[9], ska[9], RtSa[9];
+            quat_to_rot(st.q, R);
+            skew3(gyro, sk);
+            skew3(acc, ska);
+            m3Tmul(R, ska, RtSa);
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    F[i * N21 + j] = -sk[i * 3 + j];
+                    F[(6 + i) * N21 + j] = -RtSa[i * 3 + j];
+                    F[(6 + i) * N21 + 9 + j] = -R[j * 3 + i];
+                }
+            for (int i = 0; i < 3; ++i) {
+                F[i * N21 + 3 + i] = -1.0;
+                F[(12 + i) * N21 + 6 + i] = 1.0;
+            }
+        }
+        __syncthreads();
+        const double dt = s_dt;
+        for (int e = threadIdx.x; e < N21 * N21; e += blockDim.x) A[e] = F[e] * dt;
+        __syncthreads();
+        mm21(B, A, A);
+        __syncthreads();
+        mm21(T, B, A);
+        __syncthreads();
+        for (int e = threadIdx.x; e < N21 * N21; e += blockDim.x) {
+            int i = e / N21, j = e - i * N21;
+            Phi[e] = (i == j ? 1.0 : 0.0) + A[e] + 0.5 * B[e] + (1.0 / 6.0) * T[e];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double *m = imu + n * 7;
+            double gyro[3], acc[3];
+            for (int i = 0; i < 3; ++i) {
+                gyro[i] = m[1 + i] - st.bg[i];
+                acc[i] = m[4 + i] - st.ba[i];
+            }
+            predict_new_state(st, dt, gyro, acc);
+            // observability-constrained modification of Phi (msckf_vio.cpp:441-455)
+            double Rkk1[9], Rq[9], B00[9];
+            quat_to_rot(st.qn, Rkk1);
+            quat_to_rot(st.q, Rq);
+            m3mulT(Rq, Rkk1, B00);
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) Phi[i * N21 + j] = B00[i * 3 + j];
+            double u[3], sv[3];
+            m3v(Rkk1, st.g, u);
+            double uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+            for (int i = 0; i < 3; ++i) sv[i] = (1.0 / uu) * u[i];
+            for (int blk = 0; blk < 2; ++blk) {
+                const int r0 = blk == 0 ? 6 : 12;
+                double A1[9], d[3], w[3], K[9], au[3];
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) A1[i * 3 + j] = Phi[(r0 + i) * N21 + j];
+                if (blk == 0)
+                    for (int i = 0; i < 3; ++i) d[i] = st.vn[i] - st.v[i];
+                else
+                    for (int i = 0; i < 3; ++i) d[i] = dt * st.vn[i] + st.pn[i] - st.p[i];
+                skew3(d, K);
+                m3v(K, st.g, w);
+                m3v(A1, u, au);
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) Phi[(r0 + i) * N21 + j] = A1[i * 3 + j] - (au[i] - w[i]) * sv[j];
+            }
+            for (int i = 0; i < 4; ++i) st.qn[i] = st.q[i];
+            for (int i = 0; i < 3; ++i) {
+                st.pn[i] = st.p[i];
+                st.vn[i] = st.v[i];
+            }
+            st.time = m[0];
+        }
+        __syncthreads();
+        // P11 <- Phi P11 Phi^T + Phi G Qc G^T Phi^T dt, symmetrised (msckf_vio.cpp:457-469)
+        mm21(T, Phi, P11);
+        __syncthreads();
+        for (int e = threadIdx.x; e < N21 * N21; e += blockDim.x) {
+            int i = e / N21, j = e - i * N21;
+            double a = 0, q = 0;
+#pragma unroll
+            for (int k = 0; k < N21; ++k) a += T[i * N21 + k] * Phi[j * N21 + k];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                double d = k < 3 ? bc.gyro_noise : (k < 6 ? bc.gyro_bias_noise : (k < 9 ? bc.acc_noise : bc.acc_bias_noise));
+                q += Phi[i * N21 + k] * d * Phi[j * N21 + k];
+            }
+            A[e] = a + q * dt;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < N21 * N21; e += blockDim.x) {
+            int i = e / N21, j = e - i * N21;
+            P11[e] = (A[e] + A[j * N21 + i]) * 0.5;
+        }
+        mm21(T, Phi, PhiT);
+        __syncthreads();
+        for (int e = threadIdx.x; e < N21 * N21; e += blockDim.x) PhiT[e] = T[e];
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < N21 * N21; e += blockDim.x) {
+        int i = e / N21, j = e - i * N21;
+        P[i * LD + j] = P11[e];
+    }
+    // P12 <- Phi_tot P12, P21 <- its transpose (msckf_vio.cpp:461-466)
+    for (int c = N21 + threadIdx.x; c < LD; c += blockDim.x) {
+        double x[N21];
+#pragma unroll
+        for (int k = 0; k < N21; ++k) x[k] = P[k * LD + c];
+#pragma unroll 1
+        for (int i = 0; i < N21; ++i) {
+            double y = 0;
+#pragma unroll
+            for (int k = 0; k < N21; ++k) y += PhiT[i * N21 + k] * x[k];
+            P[i * LD + c] = y;
+            P[c * LD + i] = y;
+        }
+    }
+}
+
+// ======================================================================================
+// stateAugmentation.  One CTA per stream.
+// ======================================================================================
+__global__ void __launch_bounds__(BE_THREADS) be_augment_kernel(BeConst bc, BeBuf bb) {
+    const int s = blockIdx.x;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    BeState &st = bb.st[s];
+    double *P = bb.P + (size_t)s * bc.LD * bc.LD;
+    const int LD = bc.LD;
+    __shared__ double J[6 * N21];
+    __shared__ int s_slot;
+    for (int e = threadIdx.x; e < 6 * N21; e += blockDim.x) J[e] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st.id = st.next_id++;  // batchImuProcessing, msckf_vio.cpp:401
+        int slot = __ffs(~st.cam_used) - 1;
+        if (slot < 0 || slot >= bc.NS) slot = bc.NS - 1;  // cannot happen: pruning keeps n_cam < NS here
+        s_slot = slot;
+        st.cam_used |= 1u << slot;
+        st.order[st.n_cam++] = slot;
+        st.cur_slot = slot;
+        double Rwi[9], Rwc[9], tcw[3], v[3];
+        quat_to_rot(st.q, Rwi);
+        m3mul(st.Ric, Rwi, Rwc);
+        m3Tv(Rwi, st.tci, v);
+        for (int i = 0; i < 3; ++i) tcw[i] = st.p[i] + v[i];
+        BeCam &c = st.cam[slot];
+        c.id = st.id;
+        c.time = sp.t;
+        rot_to_quat(Rwc, c.q);
+        for (int i = 0; i < 3; ++i) c.p[i] = tcw[i];
+        for (int i = 0; i < 4; ++i) c.qn[i] = c.q[i];
+        for (int i = 0; i < 3; ++i) c.pn[i] = c.p[i];
+        double K[9];
+        skew3(v, K);
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) {
+                J[i * N21 + j] = st.Ric[i * 3 + j];
+                J[(3 + i) * N21 + j] = K[i * 3 + j];
+            }
+            J[i * N21 + 15 + i] = 1.0;
+            J[(3 + i) * N21 + 12 + i] = 1.0;
+            J[(3 + i) * N21 + 18 + i] = 1.0;
+        }
+    }
+    __syncthreads();
+    const int rb = N21 + 6 * s_slot;
+    for (int c = threadIdx.x; c < LD; c += blockDim.x) {
+        if (c >= rb && c < rb + 6) continue;
+        double x[N21];
+#pragma unroll
+        for (int k = 0; k < N21; ++k) x[k] = P[k * LD + c];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double y = 0;
+#pragma unroll
+            for (int k = 0; k < N21; ++k) y += J[i * N21 + k] * x[k];
+            P[(rb + i) * LD + c] = y;
+            P[c * LD + rb + i] = y;
+        }
+    }
+    __syncthreads();
+    __shared__ double C[36];
+    if (threadIdx.x < 36) {
+        int i = threadIdx.x / 6, j = threadIdx.x % 6;
+        double y = 0;
+        for (int k = 0; k < N21; ++k) y += P[(rb + i) * LD + k] * J[j * N21 + k];
+        C[threadIdx.x] = y;
+    }
+    __syncthreads();
+    if (threadIdx.x < 36) {
+        int i = threadIdx.x / 6, j = threadIdx.x % 6;
+        P[(rb + i) * LD + rb + j] = (C[i * 6 + j] + C[j * 6 + i]) * 0.5;
+    }
+}
+
+// ======================================================================================
+// addFeatureObservations.  One CTA per stream; open-addressing hash of the live feature ids
+// in shared memory; message entries are applied with last-write-wins semantics in message
+// order, exactly like the sequential map inserts of the reference (this matters for the
+// stale tail of SURVEY F4, where one id can occur twice in a message).
+// ======================================================================================
+__device__ __forceinline__ unsigned hash_u32(unsigned x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+__global__ void __launch_bounds__(BE_THREADS) be_add_obs_kernel(BeConst bc, BeBuf bb) {
+    const int s = blockIdx.x;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    BeState &st = bb.st[s];
+    extern __shared__ unsigned char be_smem[];
+    unsigned *h_key = (unsigned *)be_smem;           // [HASH] id + 1, 0 = empty
+    int *h_slot = (int *)(h_key + bc.HASH);          // [HASH]
+    int *h_owner = h_slot + bc.HASH;                 // [HASH]
+    __shared__ int s_tmp[BE_THREADS / 32 + 1];
+    __shared__ int s_nfree, s_over;
+    const size_t fo = (size_t)s * bc.MF;
+    unsigned *f_id = bb.f_id + fo, *f_mask = bb.f_mask + fo;
+    uint8_t *f_live = bb.f_live + fo, *f_init = bb.f_init + fo;
+    int *f_last = bb.f_last + fo, *freelist = bb.freelist + fo;
+    int *e_cell = bb.e_cell + (size_t)s * (bc.ent_cap + 1);
+    const unsigned hmask = (unsigned)bc.HASH - 1u;
+    const mskf_feature *ent;
+    int n_real;
+    long long n_zero;
+    if (sp.src == 0) {
+        ent = bb.fe_msg + (size_t)s * bc.max_f;
+        n_real = bb.fe_hw[s];
+        n_zero = bb.fe_total[s] - (long long)n_real;
+    } else {
+        ent = bb.inject;
+        n_real = sp.n_inject;
+        n_zero = 0;
+    }
+    const int n_ent = n_real + (n_zero > 0 ? 1 : 0);  // the value-initialised tail acts as one entry {id 0, zeros}
+    for (int c = threadIdx.x; c < bc.HASH; c += BE_THREADS) {
+        h_key[c] = 0u;
+        h_slot[c] = -1;
+        h_owner[c] = 0x7fffffff;
+    }
+    if (threadIdx.x == 0) { s_nfree = 0; s_over = 0; }
+    __syncthreads();
+    // live features -> hash; free slots -> ordered free list
+    int base = 0;
+    for (int start = 0; start < bc.MF; start += BE_THREADS) {
+        int slot = start + threadIdx.x;
+        int is_free = 0;
+        if (slot < bc.MF) {
+            if (f_live[slot]) {
+                unsigned key = f_id[slot] + 1u;
+                unsigned c = hash_u32(f_id[slot]) & hmask;
+                while (atomicCAS(&h_key[c], 0u, key) != 0u) c = (c + 1u) & hmask;
+                h_slot[c] = slot;
+                f_last[slot] = -1;
+            } else {
+                is_free = 1;
+            }
+        }
+        int tot;
+        int pos = block_excl_scan(is_free, &tot, s_tmp);
+        if (is_free) freelist[base + pos] = slot;
+        base += tot;
+    }
+    if (threadIdx.x == 0) s_nfree = base;
+    __syncthreads();
+    // find-or-insert every entry's id
+    for (int i = threadIdx.x; i < n_ent; i += BE_THREADS) {
+        unsigned id = i < n_real ? ent[i].id : 0u;
+        unsigned key = id + 1u;
+        unsigned c = hash_u32(id) & hmask;
+        while (true) {
+            unsigned old = atomicCAS(&h_key[c], 0u, key);
+            if (old == 0u || old == key) break;
+            c = (c + 1u) & hmask;
+        }
+        e_cell[i] = (int)c;
+        if (h_slot[c] < 0) atomicMin(&h_owner[c], i);
+    }
+    __syncthreads();
+    // new ids get slots in entry order (deterministic)
+    base = 0;
+    for (int start = 0; start < n_ent; start += BE_THREADS) {
+        int i = start + threadIdx.x;
+        int own = 0, c = 0;
+        if (i < n_ent) {
+            c = e_cell[i];
+            own = (h_slot[c] < 0 && h_owner[c] == i) ? 1 : 0;
+        }
+        int tot;
+        int pos = block_excl_scan(own, &tot, s_tmp);
+        if (own) {
+            int rank = base + pos;
+            if (rank < s_nfree) {
+                int slot = freelist[rank];
+                f_id[slot] = i < n_real ? ent[i].id : 0u;
+                f_mask[slot] = 0u;
+                f_init[slot] = 0;
+                f_live[slot] = 1;
+                f_last[slot] = -1;
+                h_owner[c] = -1 - slot;  // published after the barrier below
+            } else {
+                s_over = 1;
+            }
+        }
+        base += tot;
+    }
+    __syncthreads();
+    const int n_new = base;
+    for (int c = threadIdx.x; c < bc.HASH; c += BE_THREADS)
+        if (h_slot[c] < 0 && h_owner[c] < 0) h_slot[c] = -1 - h_owner[c];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_ent; i += BE_THREADS) {
+        int slot = h_slot[e_cell[i]];
+        if (slot >= 0) atomicMax(&f_last[slot], i);
+    }
+    __syncthreads();
+    const unsigned curbit = 1u << st.cur_slot;
+    for (int i = threadIdx.x; i < n_ent; i += BE_THREADS) {
+        int slot = h_slot[e_cell[i]];
+        if (slot < 0 || f_last[slot] != i) continue;
+        double *o = bb.f_obs + (((size_t)s * bc.MF + slot) * bc.NS + st.cur_slot) * 4;
+        if (i < n_real) {
+            o[0] = ent[i].u0; o[1] = ent[i].v0; o[2] = ent[i].u1; o[3] = ent[i].v1;
+        } else {
+            o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 0.0;
+        }
+        f_mask[slot] |= curbit;
+    }
+    if (threadIdx.x == 0) {
+        const int curr = st.n_feat;
+        const int added = s_over ? min(n_new, s_nfree) : n_new;
+        const long long tracked = (long long)n_real + n_zero - (long long)n_new;
+        st.n_feat = curr + added;
+        st.tracking_rate = (double)tracked / (double)curr;  // msckf_vio.cpp:604-606 (0/0 -> NaN as in the reference)
+        if (s_over) st.n_overflow++;
+    }
+}
+
+// ======================================================================================
+// Feature selection for the two update phases.  phase 0: removeLostFeatures, phase 1:
+// pruneCamStateBuffer.  The list is sorted by feature id (std::map order).
+// ======================================================================================
+__device__ void find_redundant(const BeConst &bc, BeState &st) {  // msckf_vio.cpp:1026-1071
+    int n = st.n_cam;
+    int key_i = n - 4, it = n - 3, first = 0;
+    const BeCam &key = st.cam[st.order[key_i]];
+    double Rk[9];
+    quat_to_rot(key.q, Rk);
+    long long rid[2];
+    int rslot[2];
+    for (int i = 0; i < 2; ++i) {
+        const BeCam &c = st.cam[st.order[it]];
+        double R[9], RR[9];
+        quat_to_rot(c.q, R);
+        double d[3] = {c.p[0] - key.p[0], c.p[1] - key.p[1], c.p[2] - key.p[2]};
+        double dist = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        m3mulT(R, Rk, RR);
+        double ang = rotation_angle(RR);
+        if (ang < bc.rot_thr && dist < bc.trans_thr && st.tracking_rate > bc.track_thr) {
+            rslot[i] = st.order[it];
+            rid[i] = c.id;
+            ++it;
+        } else {
+            rslot[i] = st.order[first];
+            rid[i] = st.cam[st.order[first]].id;
+            ++first;
+        }
+    }
+    if (rid[1] < rid[0]) {
+        int t = rslot[0];
+        rslot[0] = rslot[1];
+        rslot[1] = t;
+    }
+    st.rm_slot[0] = rslot[0];
+    st.rm_slot[1] = rslot[1];
+    st.rm_bits = (1u << rslot[0]) | (1u << rslot[1]);
+}
+
+__global__ void __launch_bounds__(BE_THREADS) be_select_kernel(BeConst bc, BeBuf bb, int phase, int sort_n) {
+    const int s = blockIdx.x;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    BeState &st = bb.st[s];
+    extern __shared__ unsigned char be_smem[];
+    unsigned long long *keys = (unsigned long long *)be_smem;  // [sort_n]
+    __shared__ int s_n, s_erased;
+    const size_t fo = (size_t)s * bc.MF;
+    unsigned *f_mask = bb.f_mask + fo;
+    if (threadIdx.x == 0) {
+        s_n = 0;
+        s_erased = 0;
+        st.do_update = 0;
+        st.m = 0;
+        if (phase == 1) {
+            st.prune_active = st.n_cam >= bc.max_cam ? 1 : 0;
+            if (st.prune_active) find_redundant(bc, st);
+        }
+    }
+    for (int i = threadIdx.x; i < sort_n; i += BE_THREADS) keys[i] = ~0ull;
+    __syncthreads();
+    if (phase == 1 && !st.prune_active) {
+        if (threadIdx.x == 0) st.n_list = 0;
+        return;
+    }
+    const unsigned curbit = 1u << st.cur_slot, rmbits = st.rm_bits;
+    for (int slot = threadIdx.x; slot < bc.MF; slot += BE_THREADS) {
+        if (!bb.f_live[fo + slot]) continue;
+        unsigned mask = f_mask[slot];
+        if (phase == 0) {
+            if (mask & curbit) continue;
+            if (__popc(mask) < 3) {  // msckf_vio.cpp:956-959
+                bb.f_live[fo + slot] = 0;
+                atomicAdd(&s_erased, 1);
+                continue;
+            }
+        } else {
+            unsigned inv = mask & rmbits;
+            int c = __popc(inv);
+            if (c == 0) continue;
+            if (c == 1) {  // msckf_vio.cpp:1096-1099
+                f_mask[slot] = mask & ~inv;
+                continue;
+            }
+        }
+        int pos = atomicAdd(&s_n, 1);
+        if (pos < sort_n) keys[pos] = ((unsigned long long)bb.f_id[fo + slot] << 32) | (unsigned)slot;
+    }
+    __syncthreads();
+    {
+        int need = 2;
+        while (need < s_n && need < sort_n) need <<= 1;
+        sort_n = need;  // keys beyond the candidates are ~0 and sort to the end
+    }
+    // bitonic sort ascending
+    for (int k = 2; k <= sort_n; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < sort_n; i += BE_THREADS) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = keys[i], b = keys[ixj];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    const int n = min(s_n, min(sort_n, bc.ML));
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += BE_THREADS) bb.l_slot[(size_t)s * bc.ML + i] = (int)(keys[i] & 0xffffffffu);
+    if (threadIdx.x == 0) {
+        st.n_list = n;
+        st.n_feat -= s_erased;
+    }
+}
+
+// ======================================================================================
+// Feature::checkMotion + initializePosition.  One warp per listed feature: lane l keeps the
+// poses (relative to the first observing camera) of stereo views l and l + 32 in registers;
+// cost / normal-equation sums are warp reductions; all lanes run the same LM control flow.
+// ======================================================================================
+struct Pose { double R[9], t[3]; };
+
+__device__ __forceinline__ void cam_pose_world(const BeCam &c, int cam1, const BeConst &bc, Pose &o) {
+    // cam0_pose = (R(q)^T, p); cam1_pose = cam0_pose * T_cam0_cam1.inv()  (feature.hpp:307-318)
+    double Rwc[9];
+    quat_to_rot(c.q, Rwc);
+    double R0[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R0[i * 3 + j] = Rwc[j * 3 + i];
+    if (!cam1) {
+        for (int i = 0; i < 9; ++i) o.R[i] = R0[i];
+        for (int i = 0; i < 3; ++i) o.t[i] = c.p[i];
+    } else {
+        double Ri[9], ti[3], tt[3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Ri[i * 3 + j] = bc.R01[j * 3 + i];
+        m3v(Ri, bc.t01, tt);
+        for (int i = 0; i < 3; ++i) ti[i] = -tt[i];
+        m3mul(R0, Ri, o.R);
+        m3v(R0, ti, tt);
+        for (int i = 0; i < 3; ++i) o.t[i] = tt[i] + c.p[i];
+    }
+}
+__device__ __forceinline__ void pose_rel(const Pose &pose, const Pose &Tc0w, Pose &o) {  // pose.inv() * T_c0_w
+    double Ri[9], ti[3], tt[3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Ri[i * 3 + j] = pose.R[j * 3 + i];
+    m3v(Ri, pose.t, tt);
+    for (int i = 0; i < 3; ++i) ti[i] = -tt[i];
+    m3mul(Ri, Tc0w.R, o.R);
+    m3v(Ri, Tc0w.t, tt);
+    for (int i = 0; i < 3; ++i) o.t[i] = tt[i] + ti[i];
+}
+__device__ __forceinline__ double lm_cost(const Pose &T, const double x[3], const double z[2]) {
+    double h0 = T.R[0] * x[0] + T.R[1] * x[1] + T.R[2] * 1.0 + x[2] * T.t[0];
+    double h1 = T.R[3] * x[0] + T.R[4] * x[1] + T.R[5] * 1.0 + x[2] * T.t[1];
+    double h2 = T.R[6] * x[0] + T.R[7] * x[1] + T.R[8] * 1.0 + x[2] * T.t[2];
+    double zx = h0 / h2 - z[0], zy = h1 / h2 - z[1];
+    return zx * zx + zy * zy;
+}
+__device__ __forceinline__ void lm_accumulate(const Pose &T, const double x[3], const double z[2], double huber,
+                                              double A[9], double b[3]) {
+    double h1 = T.R[0] * x[0] + T.R[1] * x[1] + T.R[2] * 1.0 + x[2] * T.t[0];
+    double h2 = T.R[3] * x[0] + T.R[4] * x[1] + T.R[5] * 1.0 + x[2] * T.t[1];
+    double h3 = T.R[6] * x[0] + T.R[7] * x[1] + T.R[8] * 1.0 + x[2] * T.t[2];
+    double W[9] = {T.R[0], T.R[1], T.t[0], T.R[3], T.R[4], T.t[1], T.R[6], T.R[7], T.t[2]};
+    double J[6], r[2];
+    for (int j = 0; j < 3; ++j) {
+        J[j] = 1 / h3 * W[j] - h1 / (h3 * h3) * W[6 + j];
+        J[3 + j] = 1 / h3 * W[3 + j] - h2 / (h3 * h3) * W[6 + j];
+    }
+    r[0] = h1 / h3 - z[0];
+    r[1] = h2 / h3 - z[1];
+    double e = sqrt(r[0] * r[0] + r[1] * r[1]);
+    double w = e <= huber ? 1.0 : sqrt(2.0 * huber / e);
+    double ws = (w == 1) ? 1.0 : w * w;
+    for (int a = 0; a < 3; ++a) {
+        for (int c = 0; c < 3; ++c) A[a * 3 + c] += ws * (J[a] * J[c] + J[3 + a] * J[3 + c]);
+        b[a] += ws * (J[a] * r[0] + J[3 + a] * r[1]);
+    }
+}
+__device__ __forceinline__ void ldlt3_solve(const double S[9], const double b[3], double x[3]) {
+    double L10, L20, L21, D0, D1, D2;
+    D0 = S[0];
+    L10 = S[3] / D0;
+    L20 = S[6] / D0;
+    D1 = S[4] - L10 * L10 * D0;
+    L21 = (S[7] - L20 * L10 * D0) / D1;
+    D2 = S[8] - L20 * L20 * D0 - L21 * L21 * D1;
+    double y0 = b[0], y1 = b[1] - L10 * y0, y2 = b[2] - L20 * y0 - L21 * y1;
+    y0 /= D0; y1 /= D1; y2 /= D2;
+    x[2] = y2;
+    x[1] = y1 - L21 * x[2];
+    x[0] = y0 - L10 * x[1] - L20 * x[2];
+}
+
+#define TRI_WARPS 4
+__device__ void triangulate_one(const BeConst &bc, const BeBuf &bb, const BeState &st, int s, int li, int lane, size_t fo);
+__global__ void __launch_bounds__(TRI_WARPS * 32) be_triangulate_kernel(BeConst bc, BeBuf bb, int phase) {
+    const int s = blockIdx.y;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    const BeState &st = bb.st[s];
+    const int lane = threadIdx.x & 31;
+    const size_t fo = (size_t)s * bc.MF;
+    const int n_list = st.n_list;
+    for (int li = blockIdx.x * TRI_WARPS + (threadIdx.x >> 5); li < n_list; li += gridDim.x * TRI_WARPS)
+        triangulate_one(bc, bb, st, s, li, lane, fo);
+}
+
+__device__ void triangulate_one(const BeConst &bc, const BeBuf &bb, const BeState &st, int s, int li, int lane, size_t fo) {
+    const int slot = bb.l_slot[(size_t)s * bc.ML + li];
+    uint8_t *ok = bb.l_ok + (size_t)s * bc.ML + li;
+    if (bb.f_init[fo + slot]) {
+        if (lane == 0) *ok = 1;
+        return;
+    }
+    const unsigned mask = bb.f_mask[fo + slot];
+    // observing camera slots in ascending state id order
+    int first_slot = -1, last_slot = -1, M = 0;
+    int my_slot[2] = {-1, -1};
+    for (int i = 0; i < st.n_cam; ++i) {
+        int cs = st.order[i];
+        if (!(mask & (1u << cs))) continue;
+        if (first_slot < 0) first_slot = cs;
+        last_slot = cs;
+        if (2 * M == lane || 2 * M + 1 == lane) my_slot[0] = cs;
+        if (2 * M == lane + 32 || 2 * M + 1 == lane + 32) my_slot[1] = cs;
+        ++M;
+    }
+    const double *obs = bb.f_obs + ((size_t)s * bc.MF + slot) * bc.NS * 4;
+    // ---- checkMotion (feature.hpp:257-287)
+    {
+        const BeCam &c0 = st.cam[first_slot], &c1 = st.cam[last_slot];
+        double R0w[9];
+        quat_to_rot(c0.q, R0w);
+        const double *o0 = obs + first_slot * 4;
+        double dir[3] = {o0[0], o0[1], 1.0};
+        double dn = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+        for (int i = 0; i < 3; ++i) dir[i] /= dn;
+        double dw[3];
+        m3Tv(R0w, dir, dw);
+        double tr[3] = {c1.p[0] - c0.p[0], c1.p[1] - c0.p[1], c1.p[2] - c0.p[2]};
+        double par = tr[0] * dw[0] + tr[1] * dw[1] + tr[2] * dw[2];
+        double orth[3] = {tr[0] - par * dw[0], tr[1] - par * dw[1], tr[2] - par * dw[2]};
+        double on = sqrt(orth[0] * orth[0] + orth[1] * orth[1] + orth[2] * orth[2]);
+        if (!(on > bc.feat_trans_thr)) {
+            if (lane == 0) *ok = 0;
+            return;
+        }
+    }
+    // ---- initializePosition (feature.hpp:289-450)
+    Pose Tc0w;
+    cam_pose_world(st.cam[first_slot], 0, bc, Tc0w);
+    const int np = 2 * M;
+    Pose my[2];
+    double mz[2][2];
+    bool have[2] = {lane < np, lane + 32 < np};
+    for (int h = 0; h < 2; ++h) {
+        if (!have[h]) continue;
+        int j = lane + 32 * h;
+        Pose w;
+        cam_pose_world(st.cam[my_slot[h]], j & 1, bc, w);
+        pose_rel(w, Tc0w, my[h]);
+        const double *o = obs + my_slot[h] * 4 + 2 * (j & 1);
+        mz[h][0] = o[0];
+        mz[h][1] = o[1];
+    }
+    double sol[3];
+    {
+        Pose wl, Tl;
+        cam_pose_world(st.cam[last_slot], 1, bc, wl);
+        pose_rel(wl, Tc0w, Tl);
+        const double *z1 = obs + first_slot * 4, *z2 = obs + last_slot * 4 + 2;
+        double m[3], zz[3] = {z1[0], z1[1], 1.0};
+        m3v(Tl.R, zz, m);
+        double A0 = m[0] - z2[0] * m[2], A1 = m[1] - z2[1] * m[2];
+        double b0 = z2[0] * Tl.t[2] - Tl.t[0], b1 = z2[1] * Tl.t[2] - Tl.t[1];
+        double depth = (1.0 / (A0 * A0 + A1 * A1)) * (A0 * b0 + A1 * b1);
+        double ip[3] = {z1[0] * depth, z1[1] * depth, depth};
+        sol[0] = ip[0] / ip[2];
+        sol[1] = ip[1] / ip[2];
+        sol[2] = 1.0 / ip[2];
+    }
+    const double huber = 0.01, est_prec = 5e-7;
+    double lambda = 1e-3;
+    int inner = 0, outer = 0;
+    bool reduced = false;
+    double delta_norm = 0;
+    double total_cost = 0;
+    {
+        double c = 0;
+        for (int h = 0; h < 2; ++h)
+            if (have[h]) c += lm_cost(my[h], sol, mz[h]);
+        total_cost = warp_sum_d(c);
+    }
+    do {
+        double A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+        for (int h = 0; h < 2; ++h)
+            if (have[h]) lm_accumulate(my[h], sol, mz[h], huber, A, b);
+        for (int i = 0; i < 9; ++i) A[i] = warp_sum_d(A[i]);
+        for (int i = 0; i < 3; ++i) b[i] = warp_sum_d(b[i]);
+        do {
+            double At[9];
+            for (int i = 0; i < 9; ++i) At[i] = A[i];
+            At[0] += lambda; At[4] += lambda; At[8] += lambda;
+            double delta[3], ns[3];
+            ldlt3_solve(At, b, delta);
+            for (int i = 0; i < 3; ++i) ns[i] = sol[i] - delta[i];
+            delta_norm = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
+            double c = 0;
+            for (int h = 0; h < 2; ++h)
+                if (have[h]) c += lm_cost(my[h], ns, mz[h]);
+            double new_cost = warp_sum_d(c);
+            if (new_cost < total_cost) {
+                reduced = true;
+                for (int i = 0; i < 3; ++i) sol[i] = ns[i];
+                total_cost = new_cost;
+                lambda = lambda / 10 > 1e-10 ? lambda / 10 : 1e-10;
+            } else {
+                reduced = false;
+                lambda = lambda * 10 < 1e12 ? lambda * 10 : 1e12;
+            }
+        } while (inner++ < 10 && !reduced);
+        inner = 0;
+    } while (outer++ < 10 && delta_norm > est_prec);
+    double fp[3] = {sol[0] / sol[2], sol[1] / sol[2], 1.0 / sol[2]};
+    bool valid = true;
+    for (int h = 0; h < 2; ++h)
+        if (have[h]) {
+            double z = my[h].R[6] * fp[0] + my[h].R[7] * fp[1] + my[h].R[8] * fp[2] + my[h].t[2];
+            if (z <= 0) valid = false;
+        }
+    valid = __all_sync(0xffffffffu, valid);
+    if (lane == 0) {
+        double pw[3];
+        m3v(Tc0w.R, fp, pw);
+        for (int i = 0; i < 3; ++i) bb.f_pos[(fo + slot) * 3 + i] = pw[i] + Tc0w.t[i];
+        if (valid) bb.f_init[fo + slot] = 1;
+        *ok = valid ? 1 : 0;
+    }
+}
+
+// ======================================================================================
+// List compaction + scratch layout for the per-feature Jacobian blocks.
+// ======================================================================================
+__global__ void __launch_bounds__(BE_THREADS) be_layout_kernel(BeConst bc, BeBuf bb, int phase) {
+    const int s = blockIdx.x;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    BeState &st = bb.st[s];
+    __shared__ int s_tmp[BE_THREADS / 32 + 1];
+    __shared__ int s_fit;
+    const int n = st.n_list;
+    if (n == 0) return;
+    if (threadIdx.x == 0) s_fit = 0;
+    __syncthreads();
+    const size_t fo = (size_t)s * bc.MF, lo = (size_t)s * bc.ML;
+    int base_n = 0, base_e = 0, base_r = 0, erased = 0, overflow = 0;
+    for (int start = 0; start < n; start += BE_THREADS) {
+        int i = start + threadIdx.x;
+        int keep = 0, slot = 0, M = 0;
+        if (i < n) {
+            slot = bb.l_slot[lo + i];
+            if (bb.l_ok[lo + i]) {
+                keep = 1;
+                M = phase == 0 ? __popc(bb.f_mask[fo + slot]) : 2;
+            } else if (phase == 0) {
+                bb.f_live[fo + slot] = 0;  // invalid_feature_ids, msckf_vio.cpp:961-972
+            } else {
+                bb.f_mask[fo + slot] &= ~st.rm_bits;  // msckf_vio.cpp:1102-1113
+            }
+        }
+        int tot, tot_e, tot_r, tot_x;
+        int pos = block_excl_scan(keep, &tot, s_tmp);
+        int pe = block_excl_scan(keep ? 4 * M * 6 * M : 0, &tot_e, s_tmp);
+        int pr = block_excl_scan(keep ? 4 * M : 0, &tot_r, s_tmp);
+        block_excl_scan((i < n && !keep) ? 1 : 0, &tot_x, s_tmp);
+        __syncthreads();  // every thread has read slot i before slot pos (<= i) is rewritten
+        if (keep) {
+            int eo = base_e + pe, ro = base_r + pr;
+            if (eo + 4 * M * 6 * M <= bc.ecap && ro + 4 * M <= bc.rcap) {
+                int d = base_n + pos;
+                bb.l_slot[lo + d] = slot;
+                bb.l_M[lo + d] = M;
+                bb.l_eoff[lo + d] = eo;
+                bb.l_roff[lo + d] = ro;
+                atomicAdd(&s_fit, 1);
+            } else {
+                overflow = 1;
+            }
+        }
+        __syncthreads();
+        base_n += tot;
+        base_e += tot_e;
+        base_r += tot_r;
+        erased += tot_x;
+    }
+    overflow = __syncthreads_or(overflow);
+    if (threadIdx.x == 0) {
+        // scratch offsets grow with the list index, so the blocks that fit are a prefix of the list;
+        // anything beyond (never seen with the default capacities) is dropped and counted
+        if (overflow) st.n_overflow++;
+        st.n_list = s_fit;
+        if (phase == 0) st.n_feat -= erased;
+    }
+}
+
+// ======================================================================================
+// CTA-level fp64 GEMM tile: C[i0.., j0..] (64 x 64) = sum_l A(i, l) B(l, j), operands fetched
+// through functors (gathers by camera slot, transposes), staged in shared memory, 4x4
+// register micro-tiles.  256 threads.
+// ======================================================================================
+#define GT 64
+#define GKK 16
+struct GemmSmem {
+    double a[GKK][GT + 1];
+    double b[GKK][GT + 1];
+};
+
+template <bool A_KFAST, bool B_KFAST, class FA, class FB, class FC>
+__device__ __forceinline__ void cta_gemm_tile(int M, int N, int K, int i0, int j0, FA fa, FB fb, FC fc, GemmSmem &sm) {
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int k0 = 0; k0 < K; k0 += GKK) {
+        __syncthreads();
+        for (int e = tid; e < GT * GKK; e += BE_THREADS) {
+            int i, l;
+            if (A_KFAST) { i = e / GKK; l = e - i * GKK; } else { l = e / GT; i = e - l * GT; }
+            int gi = i0 + i, gl = k0 + l;
+            sm.a[l][i] = (gi < M && gl < K) ? fa(gi, gl) : 0.0;
+        }
+        for (int e = tid; e < GT * GKK; e += BE_THREADS) {
+            int j, l;
+            if (B_KFAST) { j = e / GKK; l = e - j * GKK; } else { l = e / GT; j = e - l * GT; }
+            int gj = j0 + j, gl = k0 + l;
+            sm.b[l][j] = (gj < N && gl < K) ? fb(gl, gj) : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int l = 0; l < GKK; ++l) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) av[a] = sm.a[l][ty * 4 + a];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bv[b] = sm.b[l][tx * 4 + b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] += av[a] * bv[b];
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int gi = i0 + ty * 4 + a, gj = j0 + tx * 4 + b;
+            if (gi < M && gj < N) fc(gi, gj, acc[a][b]);
+        }
+}
+
+// In-place Cholesky of an n x n matrix in shared memory (row-major, leading dimension ld,
+// lower triangle), CTA-wide; then y <- L^-1 y.
+__device__ void cta_cholesky(double *S, int n, int ld) {
+    for (int k = 0; k < n; ++k) {
+        __syncthreads();
+        if (threadIdx.x == 0) S[k * ld + k] = sqrt(S[k * ld + k]);
+        __syncthreads();
+        const double d = S[k * ld + k];
+        for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) S[i * ld + k] /= d;
+        __syncthreads();
+        const int rem = n - k - 1;
+        for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
+            int a = e / rem, b = e - a * rem;
+            if (b > a) continue;
+            int i = k + 1 + a, j = k + 1 + b;
+            S[i * ld + j] -= S[i * ld + k] * S[j * ld + k];
+        }
+    }
+    __syncthreads();
+}
+
+// ======================================================================================
+// measurementJacobian + featureJacobian + gatingTest for one feature.  One CTA per listed
+// feature.  The stacked Jacobian of a feature is block diagonal over its observing cameras,
+// so it is kept compact: (4M) x (6M); the three Householder reflectors of H_f are applied
+// to it and to r, rows 3.. are the projected system.
+// ======================================================================================
+__global__ void __launch_bounds__(BE_THREADS) be_feature_jac_kernel(BeConst bc, BeBuf bb, int phase, int maxM) {
+    const int s = blockIdx.y;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    const BeState &st = bb.st[s];
+    const int n_list = st.n_list;
+    const size_t fo = (size_t)s * bc.MF, lo = (size_t)s * bc.ML;
+    for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
+    __syncthreads();
+    const int slot = bb.l_slot[lo + li], M = bb.l_M[lo + li];
+    const int R4 = 4 * M, C6 = 6 * M, rows = R4 - 3;
+    double *H = bb.Hblk + (size_t)s * bc.ecap + bb.l_eoff[lo + li];    // [R4][C6]
+    double *HP = bb.HPblk + (size_t)s * bc.ecap + bb.l_eoff[lo + li];  // [rows][C6]
+    double *rg = bb.rblk + (size_t)s * bc.rcap + bb.l_roff[lo + li];   // [R4]
+    const double *P = bb.P + (size_t)s * bc.LD * bc.LD;
+    const int LD = bc.LD;
+
+    extern __shared__ unsigned char be_smem[];
+    const int maxR4 = 4 * maxM, maxRows = 4 * maxM - 3, sld = maxRows + 1;
+    double *Hf = (double *)be_smem;          // [maxR4][3]
+    double *rv = Hf + maxR4 * 3;             // [maxR4]
+    double *Ssm = rv + maxR4;                // [maxRows][sld]
+    GemmSmem &gs = *(GemmSmem *)(Ssm + maxRows * sld);
+    __shared__ int oslot[NSM];
+    __shared__ double tau[3];
+    __shared__ double s_gamma;
+
+    if (threadIdx.x == 0) {
+        int m = 0;
+        if (phase == 0) {
+            const unsigned mask = bb.f_mask[fo + slot];
+            for (int i = 0; i < st.n_cam; ++i) {
+                int cs = st.order[i];
+                if (mask & (1u << cs)) oslot[m++] = cs;
+            }
+        } else {
+            oslot[0] = st.rm_slot[0];
+            oslot[1] = st.rm_slot[1];
+            m = 2;
+        }
+        for (int i = 0; i < M; ++i) bb.l_oslots[(lo + li) * NSM + i] = (uint8_t)oslot[i];
+    }
+    for (int e = threadIdx.x; e < R4 * C6; e += BE_THREADS) H[e] = 0.0;
+    __syncthreads();
+    if (threadIdx.x < M) {
+        // measurementJacobian, msckf_vio.cpp:610-677
+        const int t = threadIdx.x, cs = oslot[t];
+        const BeCam &c = st.cam[cs];
+        const double *z = bb.f_obs + (((size_t)s * bc.MF + slot) * bc.NS + cs) * 4;
+        const double *pw = bb.f_pos + (fo + slot) * 3;
+        double Rw0[9], Rw1[9], t1w[3], tmp[3];
+        quat_to_rot(c.q, Rw0);
+        m3mul(bc.R01, Rw0, Rw1);
+        m3Tv(Rw1, bc.t01, tmp);
+        for (int i = 0; i < 3; ++i) t1w[i] = c.p[i] - tmp[i];
+        double d0[3] = {pw[0] - c.p[0], pw[1] - c.p[1], pw[2] - c.p[2]};
+        double d1[3] = {pw[0] - t1w[0], pw[1] - t1w[1], pw[2] - t1w[2]};
+        double p0[3], p1[3];
+        m3v(Rw0, d0, p0);
+        m3v(Rw1, d1, p1);
+        double dz0[4][3] = {{1 / p0[2], 0, -p0[0] / (p0[2] * p0[2])}, {0, 1 / p0[2], -p0[1] / (p0[2] * p0[2])}, {0, 0, 0}, {0, 0, 0}};
+        double dz1[4][3] = {{0, 0, 0}, {0, 0, 0}, {1 / p1[2], 0, -p1[0] / (p1[2] * p1[2])}, {0, 1 / p1[2], -p1[1] / (p1[2] * p1[2])}};
+        double sk0[9], R01sk[9];
+        skew3(p0, sk0);
+        m3mul(bc.R01, sk0, R01sk);
+        double Hx[4][6];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double a = 0, b = 0;
+                for (int k = 0; k < 3; ++k) {
+                    a += dz0[i][k] * sk0[k * 3 + j] + dz1[i][k] * R01sk[k * 3 + j];
+                    b += dz0[i][k] * (-Rw0[k * 3 + j]) + dz1[i][k] * (-Rw1[k * 3 + j]);
+                }
+                Hx[i][j] = a;
+                Hx[i][3 + j] = b;
+            }
+        // observability projection: H_x <- A - A u (u^T u)^-1 u^T, H_f <- -H_x[:, 3:6]
+        double u[6], Rn[9], dn[3] = {pw[0] - c.pn[0], pw[1] - c.pn[1], pw[2] - c.pn[2]}, K[9];
+        quat_to_rot(c.qn, Rn);
+        m3v(Rn, st.g, u);
+        skew3(dn, K);
+        m3v(K, st.g, u + 3);
+        double utu = 0;
+        for (int i = 0; i < 6; ++i) utu += u[i] * u[i];
+        for (int i = 0; i < 4; ++i) {
+            double au = 0;
+            for (int k = 0; k < 6; ++k) au += Hx[i][k] * u[k];
+            au *= (1.0 / utu);
+            for (int k = 0; k < 6; ++k) H[(4 * t + i) * C6 + 6 * t + k] = Hx[i][k] - au * u[k];
+        }
+        for (int i = 0; i < 4; ++i)
+            for (int k = 0; k < 3; ++k) Hf[(4 * t + i) * 3 + k] = -H[(4 * t + i) * C6 + 6 * t + 3 + k];
+        rv[4 * t + 0] = z[0] - p0[0] / p0[2];
+        rv[4 * t + 1] = z[1] - p0[1] / p0[2];
+        rv[4 * t + 2] = z[2] - p1[0] / p1[2];
+        rv[4 * t + 3] = z[3] - p1[1] / p1[2];
+    }
+    __syncthreads();
+    // Householder QR of H_f (R4 x 3) by warp 0; reflector j is stored in column j, rows j..R4-1
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        for (int j = 0; j < 3; ++j) {
+            double xn = 0;
+            for (int i = j + 1 + lane; i < R4; i += 32) xn += Hf[i * 3 + j] * Hf[i * 3 + j];
+            xn = warp_sum_d(xn);
+            const double alpha = Hf[j * 3 + j];
+            double tj = 0.0;
+            if (xn != 0.0) {
+                double beta = -copysign(sqrt(alpha * alpha + xn), alpha);
+                tj = (beta - alpha) / beta;
+                double scale = 1.0 / (alpha - beta);
+                __syncwarp();
+                for (int i = j + 1 + lane; i < R4; i += 32) Hf[i * 3 + j] *= scale;
+                if (lane == 0) Hf[j * 3 + j] = beta;
+                __syncwarp();
+                for (int c = j + 1; c < 3; ++c) {
+                    double sacc = 0;
+                    for (int i = j + 1 + lane; i < R4; i += 32) sacc += Hf[i * 3 + j] * Hf[i * 3 + c];
+                    sacc = warp_sum_d(sacc) + Hf[j * 3 + c];
+                    sacc *= tj;
+                    __syncwarp();
+                    if (lane == 0) Hf[j * 3 + c] -= sacc;
+                    for (int i = j + 1 + lane; i < R4; i += 32) Hf[i * 3 + c] -= sacc * Hf[i * 3 + j];
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) tau[j] = tj;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // apply Q^T to [H | r]: one thread per column
+    for (int c = threadIdx.x; c <= C6; c += BE_THREADS) {
+        for (int j = 0; j < 3; ++j) {
+            const double tj = tau[j];
+            if (tj == 0.0) continue;
+            if (c < C6) {
+                double sacc = H[j * C6 + c];
+                for (int i = j + 1; i < R4; ++i) sacc += Hf[i * 3 + j] * H[i * C6 + c];
+                sacc *= tj;
+                H[j * C6 + c] -= sacc;
+                for (int i = j + 1; i < R4; ++i) H[i * C6 + c] -= sacc * Hf[i * 3 + j];
+            } else {
+                double sacc = rv[j];
+                for (int i = j + 1; i < R4; ++i) sacc += Hf[i * 3 + j] * rv[i];
+                sacc *= tj;
+                rv[j] -= sacc;
+                for (int i = j + 1; i < R4; ++i) rv[i] -= sacc * Hf[i * 3 + j];
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R4; i += BE_THREADS) rg[i] = rv[i];
+    const double *Hp = H + 3 * C6;  // projected Jacobian, rows x C6
+    // gatingTest: gamma = r^T (H P H^T + sigma^2 I)^-1 r
+    auto pidx = [&](int l) { return N21 + 6 * oslot[l / 6] + (l % 6); };
+    for (int ti = 0; ti < rows; ti += GT)
+        for (int tj = 0; tj < C6; tj += GT)
+            cta_gemm_tile<true, false>(
+                rows, C6, C6, ti, tj, [&](int i, int l) { return Hp[i * C6 + l]; },
+                [&](int l, int j) { return P[(size_t)pidx(l) * LD + pidx(j)]; },
+                [&](int i, int j, double v) { HP[i * C6 + j] = v; }, gs);
+    __syncthreads();
+    for (int ti = 0; ti < rows; ti += GT)
+        for (int tj = 0; tj < rows; tj += GT)
+            cta_gemm_tile<true, true>(
+                rows, rows, C6, ti, tj, [&](int i, int l) { return HP[i * C6 + l]; },
+                [&](int l, int j) { return Hp[j * C6 + l]; },
+                [&](int i, int j, double v) { Ssm[i * sld + j] = v + (i == j ? bc.obs_noise : 0.0); }, gs);
+    __syncthreads();
+    cta_cholesky(Ssm, rows, sld);
+    if (threadIdx.x < 32) {
+        // forward substitution y = L^-1 r (rows 3..), gamma = y^T y; warp-parallel dot products
+        const int lane = threadIdx.x;
+        double g = 0;
+        for (int i = 0; i < rows; ++i) {
+            double sacc = 0;
+            for (int k = lane; k < i; k += 32) sacc += Ssm[i * sld + k] * rv[3 + k];
+            sacc = warp_sum_d(sacc);
+            double y = (rv[3 + i] - sacc) / Ssm[i * sld + i];
+            __syncwarp();
+            if (lane == 0) rv[3 + i] = y;
+            __syncwarp();
+            g += y * y;
+        }
+        if (lane == 0) s_gamma = g;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int dof = phase == 0 ? M - 1 : M;  // msckf_vio.cpp:1001, :1145
+        const double thr = (dof >= 1 && dof <= 99) ? c_chi2[bc.chi2_mode][dof - 1] : 0.0;
+        bb.l_pass[lo + li] = s_gamma < thr ? 1 : 0;
+    }
+    }  // list loop
+}
+
+// ======================================================================================
+// Stack the gated blocks (row cap of removeLostFeatures), find the active camera columns.
+// ======================================================================================
+__global__ void __launch_bounds__(BE_THREADS) be_stack_kernel(BeConst bc, BeBuf bb, int phase) {
+    const int s = blockIdx.x;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    BeState &st = bb.st[s];
+    const int n = st.n_list;
+    const size_t fo = (size_t)s * bc.MF, lo = (size_t)s * bc.ML;
+    extern __shared__ unsigned char be_smem[];
+    int *s_soff = (int *)be_smem;                  // [ML]
+    unsigned *s_mask = (unsigned *)(s_soff + bc.ML);  // [ML]
+    uint8_t *s_M = (uint8_t *)(s_mask + bc.ML);    // [ML]
+    uint8_t *s_pass = s_M + bc.ML;                 // [ML]
+    __shared__ int s_m, s_k, s_nuse;
+    __shared__ int s_colpos[NSM];
+    for (int i = threadIdx.x; i < n; i += BE_THREADS) {
+        s_M[i] = (uint8_t)bb.l_M[lo + i];
+        s_pass[i] = bb.l_pass[lo + i];
+        s_mask[i] = phase == 0 ? bb.f_mask[fo + bb.l_slot[lo + i]] : st.rm_bits;
+        s_soff[i] = -1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int cntr = 0, nuse = n;
+        unsigned used = 0;
+        for (int i = 0; i < n; ++i) {
+            int rows = 4 * (int)s_M[i] - 3;
+            if (s_pass[i] && cntr + rows <= bc.hst_rows) {
+                s_soff[i] = cntr;
+                cntr += rows;
+                used |= s_mask[i];
+            }
+            if (phase == 0 && cntr > bc.max_rows) {  // msckf_vio.cpp:1009
+                nuse = i + 1;
+                break;
+            }
+        }
+        int k = 0;
+        for (int c = 0; c < bc.NS; ++c) {
+            s_colpos[c] = -1;
+            if (used & (1u << c)) {
+                st.u_slots[k] = c;
+                s_colpos[c] = k++;
+            }
+        }
+        st.u_nslots = k;
+        // the stacked matrix must fit: drop trailing blocks if a (pathological) case exceeds it
+        while ((long long)cntr * 6 * k > (long long)bc.hst_cap && nuse > 0) {
+            --nuse;
+            if (s_soff[nuse] >= 0) {
+                cntr = s_soff[nuse];
+                s_soff[nuse] = -1;
+                st.n_overflow++;
+            }
+        }
+        s_m = cntr;
+        s_k = 6 * k;
+        s_nuse = nuse;
+        st.m = cntr;
+        st.k = 6 * k;
+        st.do_update = cntr > 0 ? 1 : 0;
+    }
+    __syncthreads();
+    const int m = s_m, k = s_k, nuse = s_nuse;
+    double *Hst = bb.Hst + (size_t)s * bc.hst_cap, *rst = bb.rst + (size_t)s * bc.hst_rows;
+    for (int e = threadIdx.x; e < m * k; e += BE_THREADS) Hst[e] = 0.0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < nuse; i += BE_THREADS / 32) {
+        const int so = s_soff[i];
+        if (so < 0) continue;
+        const int M = s_M[i], C6 = 6 * M, rows = 4 * M - 3;
+        const double *Hp = bb.Hblk + (size_t)s * bc.ecap + bb.l_eoff[lo + i] + 3 * C6;
+        const double *rp = bb.rblk + (size_t)s * bc.rcap + bb.l_roff[lo + i] + 3;
+        const uint8_t *os = bb.l_oslots + (lo + i) * NSM;
+        for (int e = lane; e < rows * C6; e += 32) {
+            int r = e / C6, c = e - r * C6;
+            int col = 6 * s_colpos[os[c / 6]] + (c % 6);
+            Hst[(size_t)(so + r) * k + col] = Hp[e];
+        }
+        for (int r = lane; r < rows; r += 32) rst[so + r] = rp[r];
+    }
+    // the processed features leave the map (msckf_vio.cpp:1021-1023)
+    if (phase == 0) {
+        for (int i = threadIdx.x; i < n; i += BE_THREADS) bb.f_live[fo + bb.l_slot[lo + i]] = 0;
+        if (threadIdx.x == 0) st.n_feat -= n;
+    }
+}
+
+// ======================================================================================
+// QR compression of the stacked system (measurementUpdate :795-810): rows are folded 16 at a
+// time into an upper-triangular factor held in shared memory (packed, with Q^T r as an extra
+// column).  If m <= k the system is used as it is.
+// ======================================================================================
+#define QR_B 16
+__global__ void __launch_bounds__(BE_THREADS) be_qr_kernel(BeConst bc, BeBuf bb) {
+    const int s = blockIdx.x;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    BeState &st = bb.st[s];
+    if (!st.do_update) return;
+    const int m = st.m, k = st.k, KC = bc.KC;
+    const double *Hst = bb.Hst + (size_t)s * bc.hst_cap, *rst = bb.rst + (size_t)s * bc.hst_rows;
+    double *Tm = bb.Tm + (size_t)s * KC * KC, *rt = bb.rt + (size_t)s * KC;
+    if (m <= k) {
+        for (int e = threadIdx.x; e < m * k; e += BE_THREADS) Tm[e] = Hst[e];
+        for (int i = threadIdx.x; i < m; i += BE_THREADS) rt[i] = rst[i];
+        if (threadIdx.x == 0) st.mt = m;
+        return;
+    }
+    extern __shared__ unsigned char be_smem[];
+    const int kw = k + 1;
+    double *R = (double *)be_smem;                          // packed upper: row j holds columns j..k
+    double *B = R + (size_t)(KC + 1) * (KC + 2) / 2;        // [QR_B][kw]
+    __shared__ double vb[QR_B];
+    __shared__ double s_tau, s_beta;
+    auto roff = [&](int j) { return j * kw - (j * (j - 1)) / 2 - j; };  // R[j][c] at roff(j) + c
+    for (int e = threadIdx.x; e < (kw * (kw + 1)) / 2; e += BE_THREADS) R[e] = 0.0;
+    for (int r0 = 0; r0 < m; r0 += QR_B) {
+        const int nb = min(QR_B, m - r0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < QR_B * kw; e += BE_THREADS) {
+            int i = e / kw, c = e - i * kw;
+            double v = 0.0;
+            if (i < nb) v = c < k ? Hst[(size_t)(r0 + i) * k + c] : rst[r0 + i];
+            B[e] = v;
+        }
+        __syncthreads();
+        for (int j = 0; j < k; ++j) {
+            if (threadIdx.x < 32) {
+                const int lane = threadIdx.x;
+                double x = lane < QR_B ? B[lane * kw + j] : 0.0;
+                double xn = warp_sum_d(x * x);
+                const double alpha = R[roff(j) + j];
+                double tj = 0.0, beta = alpha, scale = 0.0;
+                if (xn != 0.0) {
+                    beta = -copysign(sqrt(alpha * alpha + xn), alpha);
+                    tj = (beta - alpha) / beta;
+                    scale = 1.0 / (alpha - beta);
+                }
+                if (lane < QR_B) vb[lane] = x * scale;
+                if (lane == 0) {
+                    s_tau = tj;
+                    s_beta = beta;
+                }
+            }
+            __syncthreads();
+            const double tj = s_tau;
+            if (tj != 0.0) {
+                for (int c = j + 1 + threadIdx.x; c < kw; c += BE_THREADS) {
+                    double s0 = R[roff(j) + c], s1 = 0.0;
+#pragma unroll
+                    for (int i = 0; i < QR_B; i += 2) {
+                        s0 += vb[i] * B[i * kw + c];
+                        s1 += vb[i + 1] * B[(i + 1) * kw + c];
+                    }
+                    double sacc = (s0 + s1) * tj;
+                    R[roff(j) + c] -= sacc;
+#pragma unroll
+                    for (int i = 0; i < QR_B; ++i) B[i * kw + c] -= sacc * vb[i];
+                }
+                if (threadIdx.x == 0) R[roff(j) + j] = s_beta;
+            }
+            __syncthreads();
+        }
+    }
+    for (int e = threadIdx.x; e < k * k; e += BE_THREADS) {
+        int i = e / k, c = e - i * k;
+        Tm[e] = c >= i ? R[roff(i) + c] : 0.0;
+    }
+    for (int i = threadIdx.x; i < k; i += BE_THREADS) rt[i] = R[roff(i) + k];
+    if (threadIdx.x == 0) st.mt = k;
+}
+
+// ======================================================================================
+// Grouped GEMMs of the update, one 64x64 tile per CTA, grid (tiles, S).
+//   OP 0: PHt (LD x mt) = P[:, cols] T^T          OP 1: S (mt x mt) = T PHt[cols, :] + sigma^2 I
+//   OP 2: W (LD x mt)  = PHt Linv^T               OP 3: P <- P - W W^T (lower tiles, mirrored)
+// ======================================================================================
+template <int OP>
+__global__ void __launch_bounds__(BE_THREADS) be_gemm_kernel(BeConst bc, BeBuf bb) {
+    const int s = blockIdx.y;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    const BeState &st = bb.st[s];
+    if (!st.do_update) return;
+    const int LD = bc.LD, KC = bc.KC, k = st.k, mt = st.mt;
+    __shared__ GemmSmem gs;
+    __shared__ int cols[6 * NSM];
+    for (int l = threadIdx.x; l < k; l += BE_THREADS) cols[l] = N21 + 6 * st.u_slots[l / 6] + (l % 6);
+    __syncthreads();
+    double *P = bb.P + (size_t)s * LD * LD;
+    const double *Tm = bb.Tm + (size_t)s * KC * KC;
+    double *PHt = bb.PHt + (size_t)s * LD * KC;
+    double *Sm = bb.Sm + (size_t)s * KC * KC;
+    const double *Linv = bb.Linv + (size_t)s * KC * KC;
+    double *W = bb.W + (size_t)s * LD * KC;
+    if (OP == 0) {
+        const int tn = (mt + GT - 1) / GT;
+        const int ti = blockIdx.x / tn, tj = blockIdx.x % tn;
+        if (ti * GT >= LD || tn == 0) return;
+        cta_gemm_tile<true, true>(
+            LD, mt, k, ti * GT, tj * GT, [&](int i, int l) { return P[(size_t)i * LD + cols[l]]; },
+            [&](int l, int j) { return Tm[j * k + l]; }, [&](int i, int j, double v) { PHt[(size_t)i * KC + j] = v; }, gs);
+    } else if (OP == 1) {
+        const int tn = (mt + GT - 1) / GT;
+        const int ti = blockIdx.x / tn, tj = blockIdx.x % tn;
+        if (ti >= tn) return;
+        cta_gemm_tile<true, false>(
+            mt, mt, k, ti * GT, tj * GT, [&](int i, int l) { return Tm[i * k + l]; },
+            [&](int l, int j) { return PHt[(size_t)cols[l] * KC + j]; },
+            [&](int i, int j, double v) { Sm[i * KC + j] = v + (i == j ? bc.obs_noise : 0.0); }, gs);
+    } else if (OP == 2) {
+        const int tn = (mt + GT - 1) / GT;
+        const int ti = blockIdx.x / tn, tj = blockIdx.x % tn;
+        if (ti * GT >= LD) return;
+        cta_gemm_tile<true, true>(
+            LD, mt, mt, ti * GT, tj * GT, [&](int i, int l) { return PHt[(size_t)i * KC + l]; },
+            [&](int l, int j) { return Linv[j * KC + l]; }, [&](int i, int j, double v) { W[(size_t)i * KC + j] = v; }, gs);
+    } else {
+        // lower-triangular tile pairs: blockIdx.x -> (ti >= tj)
+        int t = blockIdx.x, ti = 0;
+        while (t > ti) { t -= ti + 1; ++ti; }
+        const int tj = t;
+        if (ti * GT >= LD) return;
+        cta_gemm_tile<true, true>(
+            LD, LD, mt, ti * GT, tj * GT, [&](int i, int l) { return W[(size_t)i * KC + l]; },
+            [&](int l, int j) { return W[(size_t)j * KC + l]; },
+            [&](int i, int j, double v) {
+                if (ti != tj) {
+                    double x = P[(size_t)i * LD + j] - v;
+                    P[(size_t)i * LD + j] = x;
+                    P[(size_t)j * LD + i] = x;
+                } else if (j <= i) {
+                    // diagonal tile: (i, j) and (j, i) are computed from the same products in the
+                    // same order, so taking the lower one for both keeps P exactly symmetric
+                    double x = P[(size_t)i * LD + j] - v;
+                    P[(size_t)i * LD + j] = x;
+                    P[(size_t)j * LD + i] = x;
+                }
+            },
+            gs);
+    }
+}
+
+// S = L L^T (packed lower in shared memory), Linv = L^-1, y = Linv r.  One CTA per stream.
+__global__ void __launch_bounds__(BE_THREADS) be_chol_kernel(BeConst bc, BeBuf bb) {
+    const int s = blockIdx.x;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    const BeState &st = bb.st[s];
+    if (!st.do_update) return;
+    const int KC = bc.KC, n = st.mt;
+    extern __shared__ unsigned char be_smem[];
+    double *L = (double *)be_smem;  // packed lower, row i at i(i+1)/2
+    double *colv = L + (size_t)KC * (KC + 1) / 2;  // [KC]
+    const double *Sm = bb.Sm + (size_t)s * KC * KC;
+    double *Linv = bb.Linv + (size_t)s * KC * KC;
+    auto ix = [](int i, int j) { return i * (i + 1) / 2 + j; };
+    for (int e = threadIdx.x; e < n * n; e += BE_THREADS) {
+        int i = e / n, j = e - i * n;
+        if (j <= i) L[ix(i, j)] = Sm[i * KC + j];
+    }
+    for (int kk = 0; kk < n; ++kk) {
+        __syncthreads();
+        if (threadIdx.x == 0) L[ix(kk, kk)] = sqrt(L[ix(kk, kk)]);
+        __syncthreads();
+        const double d = L[ix(kk, kk)];
+        for (int i = kk + 1 + threadIdx.x; i < n; i += BE_THREADS) L[ix(i, kk)] /= d;
+        __syncthreads();
+        const int rem = n - kk - 1;
+        for (int e = threadIdx.x; e < rem * rem; e += BE_THREADS) {
+            int a = e / rem, b = e - a * rem;
+            if (b > a) continue;
+            int i = kk + 1 + a, j = kk + 1 + b;
+            L[ix(i, j)] -= L[ix(i, kk)] * L[ix(j, kk)];
+        }
+    }
+    __syncthreads();
+    // in-place inverse of the lower-triangular factor, last column first (dtrti2 order)
+    __shared__ double s_dj;
+    for (int j = n - 1; j >= 0; --j) {
+        for (int i = j + 1 + threadIdx.x; i < n; i += BE_THREADS) colv[i] = L[ix(i, j)];
+        if (threadIdx.x == 0) s_dj = 1.0 / L[ix(j, j)];
+        __syncthreads();
+        const double dj = s_dj;
+        for (int i = j + 1 + threadIdx.x; i < n; i += BE_THREADS) {
+            double sacc = 0;
+            for (int l = j + 1; l <= i; ++l) sacc += L[ix(i, l)] * colv[l];  // X[i][l] (already inverse) * L[l][j]
+            L[ix(i, j)] = -sacc * dj;
+        }
+        if (threadIdx.x == 0) L[ix(j, j)] = dj;
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < n * n; e += BE_THREADS) {
+        int i = e / n, j = e - i * n;
+        Linv[i * KC + j] = j <= i ? L[ix(i, j)] : 0.0;
+    }
+    const double *rt = bb.rt + (size_t)s * KC;
+    double *yv = bb.yv + (size_t)s * KC;
+    for (int i = threadIdx.x; i < n; i += BE_THREADS) {
+        double sacc = 0;
+        for (int l = 0; l <= i; ++l) sacc += L[ix(i, l)] * rt[l];
+        yv[i] = sacc;
+    }
+}
+
+// delta_x = W y and the state correction (measurementUpdate :860-894).  One CTA per stream.
+__global__ void __launch_bounds__(BE_THREADS) be_apply_kernel(BeConst bc, BeBuf bb) {
+    const int s = blockIdx.x;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    BeState &st = bb.st[s];
+    if (!st.do_update) return;
+    const int LD = bc.LD, KC = bc.KC, mt = st.mt;
+    __shared__ double dx[N21 + 6 * NSM];
+    const double *W = bb.W + (size_t)s * LD * KC, *yv = bb.yv + (size_t)s * KC;
+    for (int i = threadIdx.x; i < LD; i += BE_THREADS) {
+        double sacc = 0;
+        for (int l = 0; l < mt; ++l) sacc += W[(size_t)i * KC + l] * yv[l];
+        dx[i] = sacc;
+        bb.dxv[(size_t)s * LD + i] = sacc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double dq[4], qn[4];
+        small_angle_quat(dx, dq);
+        quat_mul(dq, st.q, qn);
+        for (int i = 0; i < 4; ++i) st.q[i] = qn[i];
+        for (int i = 0; i < 3; ++i) {
+            st.bg[i] += dx[3 + i];
+            st.v[i] += dx[6 + i];
+            st.ba[i] += dx[9 + i];
+            st.p[i] += dx[12 + i];
+        }
+        double de[4], Re[9], Rn[9];
+        small_angle_quat(dx + 15, de);
+        quat_to_rot(de, Re);
+        m3mul(Re, st.Ric, Rn);
+        for (int i = 0; i < 9; ++i) st.Ric[i] = Rn[i];
+        for (int i = 0; i < 3; ++i) st.tci[i] += dx[18 + i];
+        st.n_updates++;
+    }
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + bc.NS) {
+        const int cs = threadIdx.x - 32;
+        if (st.cam_used & (1u << cs)) {
+            BeCam &c = st.cam[cs];
+            double dq[4], qn[4];
+            small_angle_quat(dx + N21 + 6 * cs, dq);
+            quat_mul(dq, c.q, qn);
+            for (int i = 0; i < 4; ++i) c.q[i] = qn[i];
+            for (int i = 0; i < 3; ++i) c.p[i] += dx[N21 + 6 * cs + 3 + i];
+        }
+    }
+}
+
+// pruneCamStateBuffer :1161-1181: drop the two camera states.
+__global__ void __launch_bounds__(BE_THREADS) be_prune_finish_kernel(BeConst bc, BeBuf bb) {
+    const int s = blockIdx.x;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    BeState &st = bb.st[s];
+    if (!st.prune_active) return;
+    const int LD = bc.LD;
+    double *P = bb.P + (size_t)s * LD * LD;
+    const unsigned rm = st.rm_bits;
+    for (int q = 0; q < 2; ++q) {
+        const int rb = N21 + 6 * st.rm_slot[q];
+        for (int e = threadIdx.x; e < 6 * LD; e += BE_THREADS) {
+            int i = e / LD, c = e - i * LD;
+            P[(size_t)(rb + i) * LD + c] = 0.0;
+            P[(size_t)c * LD + rb + i] = 0.0;
+        }
+    }
+    const size_t fo = (size_t)s * bc.MF;
+    for (int slot = threadIdx.x; slot < bc.MF; slot += BE_THREADS)
+        if (bb.f_live[fo + slot]) bb.f_mask[fo + slot] &= ~rm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int w = 0;
+        for (int i = 0; i < st.n_cam; ++i) {
+            int cs = st.order[i];
+            if (rm & (1u << cs)) continue;
+            st.order[w++] = cs;
+        }
+        st.n_cam = w;
+        st.cam_used &= ~rm;
+        st.prune_active = 0;
+    }
+}
+
+// publish (pose) + onlineReset
+__global__ void __launch_bounds__(BE_THREADS) be_finish_kernel(BeConst bc, BeBuf bb) {
+    const int s = blockIdx.x;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    BeState &st = bb.st[s];
+    const int LD = bc.LD;
+    double *P = bb.P + (size_t)s * LD * LD;
+    __shared__ int s_reset;
+    if (threadIdx.x == 0) {
+        // T_b_w = T_imu_body * T_i_w * T_imu_body.inv(), msckf_vio.cpp:1242-1246
+        double Rwi[9], Riw[9];
+        quat_to_rot(st.q, Rwi);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Riw[i * 3 + j] = Rwi[j * 3 + i];
+        double Ra[9], ta[3], tmp[3];
+        m3mul(bc.Rib, Riw, Ra);
+        m3v(bc.Rib, st.p, tmp);
+        for (int i = 0; i < 3; ++i) ta[i] = tmp[i] + bc.tib[i];
+        double Rbi[9], tbi[3], Rr[9], tr[3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Rbi[i * 3 + j] = bc.Rib[j * 3 + i];
+        m3v(Rbi, bc.tib, tmp);
+        for (int i = 0; i < 3; ++i) tbi[i] = -tmp[i];
+        m3mul(Ra, Rbi, Rr);
+        m3v(Ra, tbi, tmp);
+        for (int i = 0; i < 3; ++i) tr[i] = tmp[i] + ta[i];
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) st.T_b_w[i * 4 + j] = Rr[i * 3 + j];
+            st.T_b_w[i * 4 + 3] = tr[i];
+            st.T_b_w[12 + i] = 0.0;
+        }
+        st.T_b_w[15] = 1.0;
+        int reset = 0;
+        if (bc.pos_std_thr > 0) {
+            double sx = sqrt(P[12 * LD + 12]), sy = sqrt(P[13 * LD + 13]), sz = sqrt(P[14 * LD + 14]);
+            if (!(sx < bc.pos_std_thr && sy < bc.pos_std_thr && sz < bc.pos_std_thr)) reset = 1;
+        }
+        s_reset = reset;
+        if (reset) {
+            st.n_resets++;
+            st.n_cam = 0;
+            st.cam_used = 0;
+            st.n_feat = 0;
+        }
+    }
+    __syncthreads();
+    if (!s_reset) return;
+    const size_t fo = (size_t)s * bc.MF;
+    for (int slot = threadIdx.x; slot < bc.MF; slot += BE_THREADS) bb.f_live[fo + slot] = 0;
+    reset_cov(bc, P);
+}
+
+// resetCallback (msckf_vio.cpp:243-304) / first-time initialisation of one stream
+__global__ void __launch_bounds__(BE_THREADS) be_reset_kernel(BeConst bc, BeBuf bb, int s, int full, mskf_config cfg) {
+    BeState &st = bb.st[s];
+    double *P = bb.P + (size_t)s * bc.LD * bc.LD;
+    const size_t fo = (size_t)s * bc.MF;
+    for (int slot = threadIdx.x; slot < bc.MF; slot += BE_THREADS) bb.f_live[fo + slot] = 0;
+    if (threadIdx.x == 0) {
+        st.time = 0.0;
+        st.q[0] = st.q[1] = st.q[2] = 0.0; st.q[3] = 1.0;
+        st.qn[0] = st.qn[1] = st.qn[2] = 0.0; st.qn[3] = 1.0;
+        for (int i = 0; i < 3; ++i) {
+            st.p[i] = 0; st.v[i] = 0; st.bg[i] = 0; st.ba[i] = 0; st.pn[i] = 0; st.vn[i] = 0;
+        }
+        st.n_cam = 0;
+        st.cam_used = 0;
+        st.n_feat = 0;
+        st.gravity_set = 0;
+        st.prune_active = 0;
+        st.do_update = 0;
+        st.n_list = 0;
+        if (full) {
+            // constructor state: loadParameters (msckf_vio.cpp:58-162) + initialize (:164-188)
+            st.id = 0;
+            st.next_id = 0;
+            st.tracking_rate = 0.0;
+            st.n_updates = 0; st.n_resets = 0; st.n_overflow = 0;
+            for (int i = 0; i < 3; ++i) st.v[i] = cfg.initial_velocity[i];
+            st.g[0] = 0; st.g[1] = 0; st.g[2] = -9.81;
+            // T_cam0_imu = inverse of the configured cam0/T_cam_imu; R_imu_cam0 = its rotation transposed
+            double Rc[9], tc[3];
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j < 3; ++j) Rc[i * 3 + j] = cfg.T_cam0_imu[i * 4 + j];
+                tc[i] = cfg.T_cam0_imu[i * 4 + 3];
+            }
+            // inv: R^T, -(R^T t); then R_imu_cam0 = (R^T)^T
+            double Rt[9], tt[3];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) Rt[i * 3 + j] = Rc[j * 3 + i];
+            m3v(Rt, tc, tt);
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) st.Ric[i * 3 + j] = Rt[j * 3 + i];
+            for (int i = 0; i < 3; ++i) st.tci[i] = -tt[i];
+            for (int i = 0; i < 16; ++i) st.T_b_w[i] = (i % 5 == 0) ? 1.0 : 0.0;
+        }
+    }
+    __syncthreads();
+    reset_cov(bc, P);
+}
+
+}  // namespace mskf
+
+using namespace mskf;
+
+struct BeBuffers {
+    BeConst bc;
+    BeBuf bb;
+    BeStep *h_step[4];
+    double *h_imu[4];
+    cudaEvent_t ev[4];
+    bool used[4];
+    int pos = 0;
+    size_t smem_add = 0, smem_sel = 0, smem_jac[2] = {0, 0}, smem_qr = 0, smem_chol = 0;
+    int sort_n = 0;
+};
+
+#define BE_RING 4
+
+int be_create(mskf_handle *h) {
+    const mskf_config &c = h->cfg;
+    if (c.max_cam_state_size < 5 || c.max_cam_state_size > NSM) {
+        h->err = "max_cam_state_size must be in [5, 32]";
+        return MSKF_ERR_ARG;
+    }
+    BeBuffers *B = new BeBuffers;
+    h->bb = B;
+    BeConst &bc = B->bc;
+    memset(&bc, 0, sizeof(bc));
+    bc.S = h->S;
+    bc.NS = c.max_cam_state_size;
+    bc.LD = 21 + 6 * bc.NS;
+    bc.KC = 6 * bc.NS;
+    bc.max_f = h->fc.max_f;
+    bc.MF = 2 * (h->fc.max_f + 1) + 64;
+    int hs = 1024;
+    while (hs < 2 * bc.MF) hs <<= 1;
+    bc.HASH = hs;
+    bc.ML = bc.MF;
+    bc.max_rows = c.max_jacobian_rows;
+    bc.max_cam = c.max_cam_state_size;
+    bc.ent_cap = h->fc.max_f > 16384 ? h->fc.max_f : 16384;
+    const int lost_rows = c.max_jacobian_rows + 4 * bc.NS;      // rows a lost-feature update can stack
+    const int prune_rows = 5 * bc.MF;                           // 5 rows per involved feature
+    bc.hst_rows = lost_rows > prune_rows ? lost_rows : prune_rows;
+    long long a = (long long)lost_rows * bc.KC, b = (long long)prune_rows * 12;
+    bc.hst_cap = (int)(a > b ? a : b);
+    bc.ecap = 4 * lost_rows * bc.KC;  // four times what one full update can use
+    if (bc.ecap < bc.MF * 96) bc.ecap = bc.MF * 96;
+    bc.rcap = bc.ecap / 6;
+    bc.chi2_mode = c.chi2_mode == MSKF_CHI2_Q95 ? 1 : 0;
+    bc.gyro_noise = c.noise_gyro * c.noise_gyro;
+    bc.acc_noise = c.noise_acc * c.noise_acc;
+    bc.gyro_bias_noise = c.noise_gyro_bias * c.noise_gyro_bias;
+    bc.acc_bias_noise = c.noise_acc_bias * c.noise_acc_bias;
+    bc.obs_noise = c.noise_feature * c.noise_feature;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            bc.R01[i * 3 + j] = c.T_cn_cnm1[i * 4 + j];
+            bc.Rib[i * 3 + j] = c.T_imu_body[j * 4 + i];  // inverse rotation
+        }
+        bc.t01[i] = c.T_cn_cnm1[i * 4 + 3];
+    }
+    for (int i = 0; i < 3; ++i) {
+        double sacc = 0;
+        for (int k = 0; k < 3; ++k) sacc += bc.Rib[i * 3 + k] * c.T_imu_body[k * 4 + 3];
+        bc.tib[i] = -sacc;
+    }
+    bc.pos_std_thr = c.position_std_threshold;
+    bc.rot_thr = c.rotation_threshold;
+    bc.trans_thr = c.translation_threshold;
+    bc.track_thr = c.tracking_rate_threshold;
+    bc.feat_trans_thr = c.feature_translation_threshold;
+    bc.cov_gb = c.cov_gyro_bias; bc.cov_v = c.cov_velocity; bc.cov_ab = c.cov_acc_bias;
+    bc.cov_er = c.cov_ext_rot; bc.cov_et = c.cov_ext_trans;
+
+    BeBuf &bb = B->bb;
+    memset(&bb, 0, sizeof(bb));
+    const size_t S = h->S;
+    int rc;
+#define A(p, n) if ((rc = dev_alloc(h, &(p), (size_t)(n))) != MSKF_OK) return rc
+    A(bb.st, S); A(bb.step, S); A(bb.imu, S * BE_IMU_CAP * 7);
+    A(bb.P, S * bc.LD * bc.LD);
+    A(bb.f_id, S * bc.MF); A(bb.f_mask, S * bc.MF); A(bb.f_live, S * bc.MF); A(bb.f_init, S * bc.MF);
+    A(bb.f_pos, S * bc.MF * 3); A(bb.f_obs, S * bc.MF * bc.NS * 4); A(bb.f_last, S * bc.MF); A(bb.freelist, S * bc.MF);
+    A(bb.e_cell, S * (bc.ent_cap + 1)); A(bb.inject, bc.ent_cap);
+    A(bb.l_slot, S * bc.ML); A(bb.l_ok, S * bc.ML); A(bb.l_pass, S * bc.ML); A(bb.l_M, S * bc.ML);
+    A(bb.l_eoff, S * bc.ML); A(bb.l_roff, S * bc.ML); A(bb.l_soff, S * bc.ML); A(bb.l_oslots, S * bc.ML * NSM);
+    A(bb.Hblk, S * bc.ecap); A(bb.HPblk, S * bc.ecap); A(bb.rblk, S * bc.rcap);
+    A(bb.Hst, S * bc.hst_cap); A(bb.rst, S * bc.hst_rows);
+    A(bb.Tm, S * bc.KC * bc.KC); A(bb.rt, S * bc.KC); A(bb.PHt, S * bc.LD * bc.KC); A(bb.Sm, S * bc.KC * bc.KC);
+    A(bb.Linv, S * bc.KC * bc.KC); A(bb.W, S * bc.LD * bc.KC); A(bb.yv, S * bc.KC); A(bb.dxv, S * bc.LD);
+#undef A
+    bb.fe_msg = h->fb.stale;
+    bb.fe_hw = h->fb.stale_hw;
+    bb.fe_total = h->fb.msg_total;
+    MSKF_CUDA_CHECK(h, cudaMemcpyToSymbol(c_chi2, kChi2Q05, sizeof(double) * 99, 0));
+    MSKF_CUDA_CHECK(h, cudaMemcpyToSymbol(c_chi2, kChi2Q95, sizeof(double) * 99, sizeof(double) * 99));
+    for (int i = 0; i < BE_RING; ++i) {
+        MSKF_CUDA_CHECK(h, cudaMallocHost((void **)&B->h_step[i], sizeof(BeStep) * S));
+        MSKF_CUDA_CHECK(h, cudaMallocHost((void **)&B->h_imu[i], sizeof(double) * S * BE_IMU_CAP * 7));
+        MSKF_CUDA_CHECK(h, cudaEventCreateWithFlags(&B->ev[i], cudaEventDisableTiming));
+        B->used[i] = false;
+    }
+    // dynamic shared memory sizes
+    B->smem_add = (size_t)bc.HASH * 12;
+    int sn = 256;
+    while (sn < bc.MF) sn <<= 1;
+    B->sort_n = sn;
+    B->smem_sel = (size_t)sn * 8;
+    for (int ph = 0; ph < 2; ++ph) {
+        int maxM = ph == 0 ? bc.NS : 2;
+        int maxR4 = 4 * maxM, maxRows = maxR4 - 3;
+        B->smem_jac[ph] = sizeof(double) * ((size_t)maxR4 * 4 + (size_t)maxRows * (maxRows + 1)) + sizeof(GemmSmem);
+    }
+    B->smem_qr = sizeof(double) * ((size_t)(bc.KC + 1) * (bc.KC + 2) / 2 + (size_t)QR_B * (bc.KC + 1));
+    B->smem_chol = sizeof(double) * ((size_t)bc.KC * (bc.KC + 1) / 2 + bc.KC);
+    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_add_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_add));
+    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_sel));
+    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_feature_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_jac[0]));
+    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_qr));
+    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_chol));
+    for (int s = 0; s < h->S; ++s) be_reset_kernel<<<1, BE_THREADS, 0, h->stream>>>(bc, bb, s, 1, h->cfg);
+    MSKF_CUDA_CHECK(h, cudaGetLastError());
+    return MSKF_OK;
+}
+
+void be_destroy(mskf_handle *h) {
+    BeBuffers *B = h->bb;
+    if (!B) return;
+    for (int i = 0; i < BE_RING; ++i) {
+        if (B->h_step[i]) cudaFreeHost(B->h_step[i]);
+        if (B->h_imu[i]) cudaFreeHost(B->h_imu[i]);
+        if (B->ev[i]) cudaEventDestroy(B->ev[i]);
+    }
+    delete B;
+    h->bb = nullptr;
+}
+
+int be_init_gravity(mskf_handle *h, int s) {
+    BeBuffers *B = h->bb;
+    HostStream &hs = h->hs[s];
+    const int n = (int)hs.be_imu.size();
+    if (n > BE_IMU_CAP) {
+        h->err = "gravity initialisation buffer larger than BE_IMU_CAP";
+        return MSKF_ERR_CAPACITY;
+    }
+    MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
+    std::vector<double> buf((size_t)n * 7);
+    for (int i = 0; i < n; ++i) {
+        buf[i * 7] = hs.be_imu[i].t;
+        for (int k = 0; k < 3; ++k) {
+            buf[i * 7 + 1 + k] = hs.be_imu[i].w[k];
+            buf[i * 7 + 4 + k] = hs.be_imu[i].a[k];
+        }
+    }
+    MSKF_CUDA_CHECK(h, cudaMemcpyAsync(B->bb.imu + (size_t)s * BE_IMU_CAP * 7, buf.data(), sizeof(double) * buf.size(),
+                                       cudaMemcpyHostToDevice, h->stream));
+    MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));  // buf is pageable and local
+    be_gravity_kernel<<<1, 32, 0, h->stream>>>(B->bc, B->bb, s, n);
+    h->launches++;
+    MSKF_CUDA_CHECK(h, cudaGetLastError());
+    return MSKF_OK;
+}
+
+// measurementUpdate on the stacked system of every stream with do_update set
+static void launch_update(mskf_handle *h) {
+    BeBuffers *B = h->bb;
+    const BeConst &bc = B->bc;
+    const BeBuf &bb = B->bb;
+    cudaStream_t q = h->stream;
+    const int S = h->S;
+    const int tiles_ld = (bc.LD + GT - 1) / GT, tiles_kc = (bc.KC + GT - 1) / GT;
+    MSKF_LAUNCH(h, PK_BE_QR, (be_qr_kernel<<<S, BE_THREADS, B->smem_qr, q>>>(bc, bb)));
+    MSKF_LAUNCH(h, PK_BE_GEMM_PHT, (be_gemm_kernel<0><<<dim3(tiles_ld * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
+    MSKF_LAUNCH(h, PK_BE_GEMM_S, (be_gemm_kernel<1><<<dim3(tiles_kc * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
+    MSKF_LAUNCH(h, PK_BE_CHOL, (be_chol_kernel<<<S, BE_THREADS, B->smem_chol, q>>>(bc, bb)));
+    MSKF_LAUNCH(h, PK_BE_GEMM_W, (be_gemm_kernel<2><<<dim3(tiles_ld * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
+    MSKF_LAUNCH(h, PK_BE_APPLY, (be_apply_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb)));
+    MSKF_LAUNCH(h, PK_BE_GEMM_PUPD, (be_gemm_kernel<3><<<dim3(tiles_ld * (tiles_ld + 1) / 2, S), BE_THREADS, 0, q>>>(bc, bb)));
+}
+
+int be_step(mskf_handle *h, const std::vector<int> &streams, const mskf_feature *inject, int n_inject, int inject_stream,
+            double inject_t) {
+    BeBuffers *B = h->bb;
+    const BeConst &bc = B->bc;
+    const BeBuf &bb = B->bb;
+    cudaStream_t q = h->stream;
+    const int S = h->S;
+    if (inject && n_inject > bc.ent_cap) {
+        h->err = "too many injected measurements";
+        return MSKF_ERR_CAPACITY;
+    }
+    const int slot = B->pos;
+    B->pos = (B->pos + 1) % BE_RING;
+    if (B->used[slot]) MSKF_CUDA_CHECK(h, cudaEventSynchronize(B->ev[slot]));
+    BeStep *hstep = B->h_step[slot];
+    double *himu = B->h_imu[slot];
+    memset(hstep, 0, sizeof(BeStep) * S);
+    int max_imu = 0;
+    for (int s : streams) {
+        HostStream &hs = h->hs[s];
+        BeStep &sp = hstep[s];
+        sp.active = 1;
+        sp.t = (inject_stream == s) ? inject_t : hs.msg_t;
+        sp.src = (inject_stream == s) ? 1 : 0;
+        sp.n_inject = (inject_stream == s) ? n_inject : 0;
+        sp.first = hs.be_first ? 1 : 0;
+        if (hs.be_first) {
+            hs.be_first = false;
+            hs.be_time = sp.t;
+        }
+        // batchImuProcessing bookkeeping, msckf_vio.cpp:380-406
+        size_t used = 0;
+        int n = 0;
+        for (const HostImu &m : hs.be_imu) {
+            if (m.t < hs.be_time) {
+                ++used;
+                continue;
+            }
+            if (m.t > sp.t) break;
+            if (n >= BE_IMU_CAP) break;  // the rest is taken by the next step (never with a 200 Hz IMU at 20 Hz frames)
+            double *d = himu + ((size_t)s * BE_IMU_CAP + n) * 7;
+            d[0] = m.t;
+            for (int k = 0; k < 3; ++k) {
+                d[1 + k] = m.w[k];
+                d[4 + k] = m.a[k];
+            }
+            hs.be_time = m.t;
+            ++n;
+            ++used;
+        }
+        hs.be_imu.erase(hs.be_imu.begin(), hs.be_imu.begin() + used);
+        sp.n_imu = n;
+        if (n > max_imu) max_imu = n;
+    }
+    MSKF_CUDA_CHECK(h, cudaMemcpyAsync(bb.step, hstep, sizeof(BeStep) * S, cudaMemcpyHostToDevice, q));
+    if (max_imu > 0) {
+        // one strided copy: the first max_imu samples of every stream
+        MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(bb.imu, sizeof(double) * BE_IMU_CAP * 7, himu, sizeof(double) * BE_IMU_CAP * 7,
+                                             sizeof(double) * 7 * max_imu, S, cudaMemcpyHostToDevice, q));
+    }
+    if (inject && n_inject > 0)
+        MSKF_CUDA_CHECK(h, cudaMemcpyAsync(bb.inject, inject, sizeof(mskf_feature) * n_inject, cudaMemcpyHostToDevice, q));
+    MSKF_CUDA_CHECK(h, cudaEventRecord(B->ev[slot], q));
+    B->used[slot] = true;
+    if (inject && n_inject > 0) MSKF_CUDA_CHECK(h, cudaStreamSynchronize(q));  // caller's buffer may be pageable
+
+    MSKF_LAUNCH(h, PK_BE_PROPAGATE, (be_propagate_kernel<<<S, 128, 0, q>>>(bc, bb, 0)));
+    MSKF_LAUNCH(h, PK_BE_AUGMENT, (be_augment_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb)));
+    MSKF_LAUNCH(h, PK_BE_ADD_OBS, (be_add_obs_kernel<<<S, BE_THREADS, B->smem_add, q>>>(bc, bb)));
+    for (int phase = 0; phase < 2; ++phase) {
+        const int maxM = phase == 0 ? bc.NS : 2;
+        MSKF_LAUNCH(h, PK_BE_SELECT, (be_select_kernel<<<S, BE_THREADS, B->smem_sel, q>>>(bc, bb, phase, B->sort_n)));
+        {
+            dim3 g(phase == 0 ? 8 : 16, S);
+            MSKF_LAUNCH(h, PK_BE_TRIANGULATE, (be_triangulate_kernel<<<g, TRI_WARPS * 32, 0, q>>>(bc, bb, phase)));
+        }
+        MSKF_LAUNCH(h, PK_BE_LAYOUT, (be_layout_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb, phase)));
+        {
+            dim3 g(phase == 0 ? 32 : 48, S);
+            MSKF_LAUNCH(h, PK_BE_FEATURE_JAC, (be_feature_jac_kernel<<<g, BE_THREADS, B->smem_jac[phase], q>>>(bc, bb, phase, maxM)));
+        }
+        MSKF_LAUNCH(h, PK_BE_STACK, (be_stack_kernel<<<S, BE_THREADS, (size_t)bc.ML * 10, q>>>(bc, bb, phase)));
+        launch_update(h);
+    }
+    MSKF_LAUNCH(h, PK_BE_PRUNE_FINISH, (be_prune_finish_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb)));
+    MSKF_LAUNCH(h, PK_BE_FINISH, (be_finish_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb)));
+    MSKF_CUDA_CHECK(h, cudaGetLastError());
+    return MSKF_OK;
+}
+
+static int fetch_state(mskf_handle *h, int s, BeState *st) {
+    MSKF_CUDA_CHECK(h, cudaMemcpy(st, h->bb->bb.st + s, sizeof(BeState), cudaMemcpyDeviceToHost));
+    return MSKF_OK;
+}
+
+int be_get_state(mskf_handle *h, int s, mskf_state *out) {
+    BeState st;
+    int rc = fetch_state(h, s, &st);
+    if (rc != MSKF_OK) return rc;
+    memset(out, 0, sizeof(*out));
+    out->time = st.time;
+    out->id = st.id;
+    for (int i = 0; i < 4; ++i) out->orientation[i] = st.q[i];
+    for (int i = 0; i < 3; ++i) {
+        out->position[i] = st.p[i]; out->velocity[i] = st.v[i]; out->gyro_bias[i] = st.bg[i];
+        out->acc_bias[i] = st.ba[i]; out->t_cam0_imu[i] = st.tci[i]; out->gravity[i] = st.g[i];
+    }
+    for (int i = 0; i < 9; ++i) out->R_imu_cam0[i] = st.Ric[i];
+    out->n_cam_states = st.n_cam;
+    out->cov_dim = 21 + 6 * st.n_cam;
+    out->is_gravity_set = st.gravity_set;
+    out->n_map_features = st.n_feat;
+    out->tracking_rate = st.tracking_rate;
+    for (int i = 0; i < 16; ++i) out->T_b_w[i] = st.T_b_w[i];
+    out->n_updates = st.n_updates;
+    out->n_resets = st.n_resets;
+    return MSKF_OK;
+}
+
+int be_get_cam_states(mskf_handle *h, int s, mskf_cam_state *out, int cap, int *n) {
+    BeState st;
+    int rc = fetch_state(h, s, &st);
+    if (rc != MSKF_OK) return rc;
+    *n = st.n_cam;
+    for (int i = 0; i < st.n_cam && i < cap && out; ++i) {
+        const BeCam &c = st.cam[st.order[i]];
+        out[i].id = c.id;
+        out[i].time = c.time;
+        for (int k = 0; k < 4; ++k) out[i].orientation[k] = c.q[k];
+        for (int k = 0; k < 3; ++k) out[i].position[k] = c.p[k];
+    }
+    return MSKF_OK;
+}
+
+int be_get_cov(mskf_handle *h, int s, double *out, int cap, int *dim) {
+    BeState st;
+    int rc = fetch_state(h, s, &st);
+    if (rc != MSKF_OK) return rc;
+    const int n = 21 + 6 * st.n_cam, LD = h->bb->bc.LD;
+    *dim = n;
+    if (!out) return MSKF_OK;
+    if (cap < n * n) return MSKF_ERR_CAPACITY;
+    std::vector<double> P((size_t)LD * LD);
+    MSKF_CUDA_CHECK(h, cudaMemcpy(P.data(), h->bb->bb.P + (size_t)s * LD * LD, sizeof(double) * P.size(), cudaMemcpyDeviceToHost));
+    std::vector<int> idx(n);
+    for (int i = 0; i < 21; ++i) idx[i] = i;
+    for (int c = 0; c < st.n_cam; ++c)
+        for (int k = 0; k < 6; ++k) idx[21 + 6 * c + k] = 21 + 6 * st.order[c] + k;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) out[(size_t)i * n + j] = P[(size_t)idx[i] * LD + idx[j]];
+    return MSKF_OK;
+}
+
+int be_reset(mskf_handle *h, int s) {
+    BeBuffers *B = h->bb;
+    be_reset_kernel<<<1, BE_THREADS, 0, h->stream>>>(B->bc, B->bb, s, 0, h->cfg);
+    h->launches++;
+    MSKF_CUDA_CHECK(h, cudaGetLastError());
+    return MSKF_OK;
+}
+
+// all streams' T_b_w with one strided device->host copy
+int be_get_poses(mskf_handle *h, double *out, int cap_streams) {
+    const int n = cap_streams < h->S ? cap_streams : h->S;
+    if (n <= 0) return MSKF_OK;
+    const char *src = (const char *)h->bb->bb.st + offsetof(BeState, T_b_w);
+    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(out, sizeof(double) * 16, src, sizeof(BeState), sizeof(double) * 16, n,
+                                         cudaMemcpyDeviceToHost, h->stream));
+    MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    return MSKF_OK;
+}
+
+#include <algorithm>
+int be_get_map(mskf_handle *h, int s, long long *ids, int *init, double *pos, int *nobs, int cap, int *n) {
+    const BeConst &bc = h->bb->bc;
+    const BeBuf &bb = h->bb->bb;
+    const size_t MF = bc.MF, fo = (size_t)s * MF;
+    std::vector<uint8_t> live(MF), fin(MF);
+    std::vector<unsigned> id(MF), mask(MF);
+    std::vector<double> p(MF * 3);
+    MSKF_CUDA_CHECK(h, cudaMemcpy(live.data(), bb.f_live + fo, MF, cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(h, cudaMemcpy(fin.data(), bb.f_init + fo, MF, cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(h, cudaMemcpy(id.data(), bb.f_id + fo, MF * 4, cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(h, cudaMemcpy(mask.data(), bb.f_mask + fo, MF * 4, cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(h, cudaMemcpy(p.data(), bb.f_pos + fo * 3, MF * 24, cudaMemcpyDeviceToHost));
+    std::vector<std::pair<unsigned, int>> order;
+    for (size_t i = 0; i < MF; ++i)
+        if (live[i]) order.push_back(std::make_pair(id[i], (int)i));
+    std::sort(order.begin(), order.end());
+    *n = (int)order.size();
+    for (int k = 0; k < *n && k < cap; ++k) {
+        int i = order[k].second;
+        ids[k] = order[k].first;
+        init[k] = fin[i];
+        for (int j = 0; j < 3; ++j) pos[k * 3 + j] = p[(size_t)i * 3 + j];
+        nobs[k] = __builtin_popcount(mask[i]);
+    }
+    return MSKF_OK;
+}
+
+// Stand-alone measurementUpdate (msckf_vio.cpp:778-907 algebra) on caller-supplied H (m x n), r, P (n x n),
+// n = 21 + 6 n_cam, run by the same kernels as the pipeline on stream 0 of a scratch handle.
+int be_op_update(mskf_handle *t, int n_cam, int m, const double *H, const double *r, const double *P, double *dx, double *Pn) {
+    BeBuffers *B = t->bb;
+    const BeConst &bc = B->bc;
+    const BeBuf &bb = B->bb;
+    const int n = 21 + 6 * n_cam, LD = bc.LD, k = 6 * n_cam;
+    if (n_cam < 1 || n_cam > bc.NS || m < 1 || m > bc.hst_rows || (long long)m * k > bc.hst_cap) {
+        t->err = "mskf_op_ekf_update: dimensions exceed the configured capacity";
+        return MSKF_ERR_CAPACITY;
+    }
+    MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->stream));
+    BeState st;
+    MSKF_CUDA_CHECK(t, cudaMemcpy(&st, bb.st, sizeof(BeState), cudaMemcpyDeviceToHost));
+    st.n_cam = n_cam;
+    st.cam_used = n_cam >= 32 ? 0xffffffffu : ((1u << n_cam) - 1u);
+    for (int i = 0; i < n_cam; ++i) {
+        st.order[i] = i;
+        st.u_slots[i] = i;
+        st.cam[i].q[0] = st.cam[i].q[1] = st.cam[i].q[2] = 0.0;
+        st.cam[i].q[3] = 1.0;
+    }
+    st.u_nslots = n_cam;
+    st.m = m;
+    st.k = k;
+    st.do_update = 1;
+    MSKF_CUDA_CHECK(t, cudaMemcpy(bb.st, &st, sizeof(BeState), cudaMemcpyHostToDevice));
+    BeStep sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.active = 1;
+    MSKF_CUDA_CHECK(t, cudaMemcpy(bb.step, &sp, sizeof(sp), cudaMemcpyHostToDevice));
+    std::vector<double> Pl((size_t)LD * LD, 0.0), Hc((size_t)m * k);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) Pl[(size_t)i * LD + j] = P[(size_t)i * n + j];
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < k; ++j) Hc[(size_t)i * k + j] = H[(size_t)i * n + 21 + j];
+    MSKF_CUDA_CHECK(t, cudaMemcpy(bb.P, Pl.data(), sizeof(double) * Pl.size(), cudaMemcpyHostToDevice));
+    MSKF_CUDA_CHECK(t, cudaMemcpy(bb.Hst, Hc.data(), sizeof(double) * Hc.size(), cudaMemcpyHostToDevice));
+    MSKF_CUDA_CHECK(t, cudaMemcpy(bb.rst, r, sizeof(double) * m, cudaMemcpyHostToDevice));
+    launch_update(t);
+    MSKF_CUDA_CHECK(t, cudaGetLastError());
+    MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->stream));
+    std::vector<double> dxl(LD);
+    MSKF_CUDA_CHECK(t, cudaMemcpy(Pl.data(), bb.P, sizeof(double) * Pl.size(), cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(t, cudaMemcpy(dxl.data(), bb.dxv, sizeof(double) * LD, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        dx[i] = dxl[i];
+        for (int j = 0; j < n; ++j) Pn[(size_t)i * n + j] = Pl[(size_t)i * LD + j];
+    }
+    return MSKF_OK;
+}

@@ -16,6 +16,8 @@
 
 #include "../../include/msckf_b200.h"
 
+#define MSKF_PROF_TAGS 32
+
 #define MSKF_CUDA_CHECK(h, expr)                                                            \
     do {                                                                                    \
         cudaError_t _e = (expr);                                                            \
@@ -143,7 +145,35 @@ struct mskf_handle {
     void *h_be_step = nullptr;         // backend step descriptors (pinned)
     std::vector<void *> allocs;
     long long launches = 0;            // kernels launched so far (bench: gpu_launches)
+    // per-kernel CUDA-event timing on the launching stream (bench.py's roofline leg)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
+    std::vector<int> prof_tag;
+    size_t prof_used = 0;
+    double prof_ms[MSKF_PROF_TAGS] = {0};
+    long long prof_n[MSKF_PROF_TAGS] = {0};
 };
+
+// kernel tags for the profiler
+enum {
+    PK_PYR_L1 = 0, PK_PYR_LN, PK_KLT_TEMPORAL, PK_KLT_STEREO, PK_KLT_NEW, PK_DETECT, PK_FE_BOOK,
+    PK_BE_PROPAGATE, PK_BE_AUGMENT, PK_BE_ADD_OBS, PK_BE_SELECT, PK_BE_TRIANGULATE, PK_BE_LAYOUT, PK_BE_FEATURE_JAC,
+    PK_BE_STACK, PK_BE_QR, PK_BE_GEMM_PHT, PK_BE_GEMM_S, PK_BE_CHOL, PK_BE_GEMM_W, PK_BE_APPLY, PK_BE_GEMM_PUPD,
+    PK_BE_PRUNE_FINISH, PK_BE_FINISH, PK_COUNT
+};
+const char *mskf_prof_name(int tag);
+void prof_begin(mskf_handle *h, int tag);
+void prof_end(mskf_handle *h);
+void prof_collect(mskf_handle *h);
+
+// launch + count + optional event bracket
+#define MSKF_LAUNCH(h, tag, ...)        \
+    do {                                \
+        prof_begin((h), (tag));         \
+        __VA_ARGS__;                    \
+        prof_end((h));                  \
+        (h)->launches++;                \
+    } while (0)
 
 // frontend.cu
 int fe_create(mskf_handle *h);
@@ -161,6 +191,9 @@ int be_get_state(mskf_handle *h, int s, mskf_state *out);
 int be_get_cam_states(mskf_handle *h, int s, mskf_cam_state *out, int cap, int *n);
 int be_get_cov(mskf_handle *h, int s, double *out, int cap, int *dim);
 int be_reset(mskf_handle *h, int s);
+int be_get_map(mskf_handle *h, int s, long long *ids, int *init, double *pos, int *nobs, int cap, int *n);
+int be_op_update(mskf_handle *t, int n_cam, int m, const double *H, const double *r, const double *P, double *dx, double *Pn);
+int be_get_poses(mskf_handle *h, double *out, int cap_streams);
 
 template <typename T>
 int dev_alloc(mskf_handle *h, T **p, size_t n) {

@@ -105,7 +105,65 @@ static void host_predict_homography(mskf_handle *h, HostStream &hs, double H0[9]
     m3_mul(KR, Ki, H0);
 }
 
+static const char *kProfNames[PK_COUNT] = {
+    "pyr_down_l1", "pyr_down_ln", "klt_temporal", "klt_stereo", "klt_new", "detect", "fe_bookkeeping",
+    "be_propagate", "be_augment", "be_add_obs", "be_select", "be_triangulate", "be_layout", "be_feature_jac",
+    "be_stack", "be_qr", "be_gemm_pht", "be_gemm_s", "be_chol", "be_gemm_w", "be_apply", "be_gemm_pupd",
+    "be_prune_finish", "be_finish"};
+const char *mskf_prof_name(int tag) { return tag >= 0 && tag < PK_COUNT ? kProfNames[tag] : "?"; }
+void prof_begin(mskf_handle *h, int tag) {
+    if (!h->prof_on) return;
+    if (h->prof_used + 2 > h->prof_ev.size()) {
+        for (int i = 0; i < 2; ++i) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            h->prof_ev.push_back(e);
+        }
+    }
+    h->prof_tag.push_back(tag);
+    cudaEventRecord(h->prof_ev[h->prof_used], h->stream);
+}
+void prof_end(mskf_handle *h) {
+    if (!h->prof_on) return;
+    cudaEventRecord(h->prof_ev[h->prof_used + 1], h->stream);
+    h->prof_used += 2;
+}
+void prof_collect(mskf_handle *h) {
+    for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess) {
+            int tag = h->prof_tag[i / 2];
+            h->prof_ms[tag] += ms;
+            h->prof_n[tag]++;
+        }
+    }
+    h->prof_used = 0;
+    h->prof_tag.clear();
+}
+
 extern "C" {
+
+// ---- bench instrumentation: CUDA-event time per kernel class on the launching stream
+int mskf_profile_enable(mskf_handle *h, int on) {
+    if (!h) return MSKF_ERR_ARG;
+    cudaStreamSynchronize(h->stream);
+    prof_collect(h);
+    h->prof_on = on != 0;
+    if (on) {
+        for (int i = 0; i < MSKF_PROF_TAGS; ++i) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+    }
+    return MSKF_OK;
+}
+int mskf_profile_read(mskf_handle *h, int tag, const char **name, double *ms, long long *count) {
+    if (!h || tag < 0) return MSKF_ERR_ARG;
+    if (tag >= PK_COUNT) return 1;
+    cudaStreamSynchronize(h->stream);
+    prof_collect(h);
+    if (name) *name = kProfNames[tag];
+    if (ms) *ms = h->prof_ms[tag];
+    if (count) *count = h->prof_n[tag];
+    return MSKF_OK;
+}
 
 int mskf_default_config(mskf_config *cfg, const char *preset) { return mskf_fill_preset(cfg, preset); }
 
@@ -153,6 +211,7 @@ void mskf_destroy(mskf_handle *h) {
         }
         delete ex;
     }
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     for (void *p : h->allocs) cudaFree(p);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -292,6 +351,7 @@ int mskf_sync(mskf_handle *h) {
     if (!h) return MSKF_ERR_ARG;
     MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
     MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    if (h->prof_on) prof_collect(h);
     return MSKF_OK;
 }
 
@@ -408,6 +468,17 @@ int mskf_get_covariance(mskf_handle *h, int s, double *out, int cap, int *dim) {
     if (rc != MSKF_OK) return rc;
     return be_get_cov(h, s, out, cap, dim);
 }
+int mskf_debug_get_map(mskf_handle *h, int s, long long *ids, int *init, double *pos, int *nobs, int cap, int *n) {
+    if (!h || s < 0 || s >= h->S || !n) return MSKF_ERR_ARG;
+    int rc = mskf_sync(h);
+    if (rc != MSKF_OK) return rc;
+    return be_get_map(h, s, ids, init, pos, nobs, cap, n);
+}
+int mskf_get_poses(mskf_handle *h, double *out, int cap_streams) {
+    if (!h || !out) return MSKF_ERR_ARG;
+    MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
+    return be_get_poses(h, out, cap_streams);
+}
 int mskf_reset(mskf_handle *h, int s) {
     if (!h || s < 0 || s >= h->S) return MSKF_ERR_ARG;
     int rc = mskf_sync(h);
@@ -502,6 +573,22 @@ int mskf_op_klt(mskf_handle *h, const uint8_t *img_a, const uint8_t *img_b, int 
     if (rc == MSKF_OK) rc = fe_op_klt(t, pts_a, pts_b, status, n);
     if (rc != MSKF_OK) h->err = t->err;
     mskf_destroy(t);
+    return rc;
+}
+
+// measurementUpdate as a stand-alone operator: H is m x n with n = 21 + 6 n_cam (IMU columns must be zero, as
+// featureJacobian leaves them: msckf_vio.cpp:709-712), observation noise from the configuration.
+int mskf_op_ekf_update(mskf_handle *h, int n_cam, int m, const double *H, const double *r, const double *P,
+                       double *out_delta_x, double *out_P) {
+    if (!h || !H || !r || !P || !out_delta_x || !out_P) return MSKF_ERR_ARG;
+    mskf_handle *t = nullptr;
+    mskf_config c = h->cfg;
+    if (n_cam > c.max_cam_state_size) c.max_cam_state_size = n_cam;
+    if (m > c.max_jacobian_rows) c.max_jacobian_rows = m;
+    int rc = mskf_create(&c, 1, h->device, &t);
+    if (rc == MSKF_OK) rc = be_op_update(t, n_cam, m, H, r, P, out_delta_x, out_P);
+    if (rc != MSKF_OK && t) h->err = t->err;
+    if (t) mskf_destroy(t);
     return rc;
 }
 

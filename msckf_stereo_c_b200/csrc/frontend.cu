@@ -428,6 +428,7 @@ __device__ __forceinline__ int grid_code(const FeConst &fc, float2 p) {
 }
 
 #define FE_THREADS 128
+#define FE_MAX_CELLS 128  // coarse grid cells incl. the overflow row (image_processor.cpp:663-665 can index past grid_row)
 
 // Order-preserving block compaction: returns the number kept; dst index of element i
 // (when flag) is written to pos[i].  Executed by all FE_THREADS threads.
@@ -536,7 +537,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_after_stereo(FeConst fc, FeBuff
     const FeStep st = fb.step[s];
     if (!st.active) return;
     __shared__ int s_warp[FE_THREADS / 32];
-    __shared__ int s_cnt[64], s_start[65];
+    __shared__ int s_cnt[FE_MAX_CELLS], s_start[FE_MAX_CELLS + 1];
     extern __shared__ int s_pos[];
     const size_t go = (size_t)s * fc.max_f, ko = (size_t)s * fc.cap_k;
     const int gc = fb.gslot[s] ^ 1;  // curr grid buffer
@@ -598,7 +599,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_sieve(FeConst fc, FeBuffers fb)
     const int s = blockIdx.x;
     const FeStep st = fb.step[s];
     if (!st.active) return;
-    __shared__ int s_n, s_cell_n[64], s_cell_off[65];
+    __shared__ int s_n, s_cell_n[FE_MAX_CELLS], s_cell_off[FE_MAX_CELLS + 1];
     extern __shared__ int s_sel[];  // [n_cells][grid_max] selected detect indices
     const size_t ko = (size_t)s * fc.cap_k, dofs = (size_t)s * fc.det_cells;
     // gather detections in fine-cell order (thread 0: <= det_cells entries)
@@ -692,7 +693,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_finish(FeConst fc, FeBuffers fb
     const FeStep st = fb.step[s];
     if (!st.active) return;
     __shared__ int s_warp[FE_THREADS / 32];
-    __shared__ int s_m, s_add[64], s_keep[64], s_idbase[65], s_outoff[65];
+    __shared__ int s_m, s_add[FE_MAX_CELLS], s_keep[FE_MAX_CELLS], s_idbase[FE_MAX_CELLS + 1], s_outoff[FE_MAX_CELLS + 1];
     extern __shared__ int s_dyn[];
     const size_t go = (size_t)s * fc.max_f, ko = (size_t)s * fc.cap_k, dofs = (size_t)s * fc.det_cells;
     const int gc = fb.gslot[s] ^ 1, gp = fb.gslot[s];
@@ -900,8 +901,8 @@ int fe_create(mskf_handle *h) {
     fc.n_cells = c.grid_row * c.grid_col;
     fc.n_cells_all = ((c.img_rows - 1) / fc.grid_h) * c.grid_col + (c.img_cols - 1) / fc.grid_w + 1;
     if (fc.n_cells_all < fc.n_cells) fc.n_cells_all = fc.n_cells;
-    if (fc.n_cells_all > 64 || fc.grid_min > fc.grid_max) {
-        h->err = "grid too large (max 64 cells incl. overflow) or grid_min > grid_max";
+    if (fc.n_cells_all > FE_MAX_CELLS || fc.grid_min > fc.grid_max) {
+        h->err = "grid too large (max 128 cells incl. overflow) or grid_min > grid_max";
         return MSKF_ERR_ARG;
     }
     fc.det_rows = c.det_rows; fc.det_cols = c.det_cols;
@@ -993,42 +994,38 @@ int fe_step(mskf_handle *h, bool any_first, int max_prev) {
     const FeBuffers &fb = h->fb;
     cudaStream_t q = h->stream;
     const int S = h->S;
-    // pyramids
-    for (int l = 1; l < fc.levels; ++l) {
-        dim3 g((fc.lvl_cols[l] + PD_TW - 1) / PD_TW, (fc.lvl_rows[l] + PD_TH - 1) / PD_TH, S * 2);
-        if (l == 1) pyr_down_kernel<true><<<g, 256, 0, q>>>(fc, fb, l);
-        else pyr_down_kernel<false><<<g, 256, 0, q>>>(fc, fb, l);
-        h->launches++;
-    }
     if (fc.levels == 1) {
         h->err = "pyramid_levels must be >= 2";
         return MSKF_ERR_ARG;
     }
+    // pyramids
+    for (int l = 1; l < fc.levels; ++l) {
+        dim3 g((fc.lvl_cols[l] + PD_TW - 1) / PD_TW, (fc.lvl_rows[l] + PD_TH - 1) / PD_TH, S * 2);
+        if (l == 1) MSKF_LAUNCH(h, PK_PYR_L1, (pyr_down_kernel<true><<<g, 256, 0, q>>>(fc, fb, l)));
+        else MSKF_LAUNCH(h, PK_PYR_LN, (pyr_down_kernel<false><<<g, 256, 0, q>>>(fc, fb, l)));
+    }
     const size_t klt_smem = (size_t)KLT_WARPS * ((fc.klt_win + 2) * (fc.klt_win + 2) + 2 * fc.klt_win * fc.klt_win) * sizeof(short);
     const size_t pos_smem = (size_t)fc.cap_k * sizeof(int);
-    fe_prep_track<<<S, FE_THREADS, 0, q>>>(fc, fb);
-    h->launches++;
+    MSKF_LAUNCH(h, PK_FE_BOOK, (fe_prep_track<<<S, FE_THREADS, 0, q>>>(fc, fb)));
     if (max_prev > 0) {
         dim3 g((max_prev + KLT_WARPS - 1) / KLT_WARPS, S);
-        klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 0);
-        fe_after_track<<<S, FE_THREADS, pos_smem, q>>>(fc, fb);
-        klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 1);
-        h->launches += 3;
+        MSKF_LAUNCH(h, PK_KLT_TEMPORAL, (klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 0)));
+        MSKF_LAUNCH(h, PK_FE_BOOK, (fe_after_track<<<S, FE_THREADS, pos_smem, q>>>(fc, fb)));
+        MSKF_LAUNCH(h, PK_KLT_STEREO, (klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 1)));
     }
-    fe_after_stereo<<<S, FE_THREADS, pos_smem, q>>>(fc, fb);
+    MSKF_LAUNCH(h, PK_FE_BOOK, (fe_after_stereo<<<S, FE_THREADS, pos_smem, q>>>(fc, fb)));
     {
         dim3 g((fc.cols + DT_W - 1) / DT_W, (fc.rows + DT_H - 1) / DT_H, S);
-        detect_kernel<<<g, 256, 0, q>>>(fc, fb);
+        MSKF_LAUNCH(h, PK_DETECT, (detect_kernel<<<g, 256, 0, q>>>(fc, fb)));
     }
-    fe_sieve<<<S, FE_THREADS, (size_t)fc.n_cells * fc.grid_max * sizeof(int), q>>>(fc, fb);
+    MSKF_LAUNCH(h, PK_FE_BOOK, (fe_sieve<<<S, FE_THREADS, (size_t)fc.n_cells * fc.grid_max * sizeof(int), q>>>(fc, fb)));
     {
         int cap = any_first ? fc.det_cells : fc.n_cells * fc.grid_max;
         dim3 g((cap + KLT_WARPS - 1) / KLT_WARPS, S);
-        klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 1);
+        MSKF_LAUNCH(h, PK_KLT_NEW, (klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 1)));
     }
     size_t fin_smem = ((size_t)fc.cap_k + (size_t)fc.n_cells * fc.grid_min + (size_t)fc.n_cells_all * fc.grid_max) * sizeof(int);
-    fe_finish<<<S, FE_THREADS, fin_smem, q>>>(fc, fb);
-    h->launches += 5;
+    MSKF_LAUNCH(h, PK_FE_BOOK, (fe_finish<<<S, FE_THREADS, fin_smem, q>>>(fc, fb)));
     MSKF_CUDA_CHECK(h, cudaGetLastError());
     return MSKF_OK;
 }

@@ -27,6 +27,8 @@ ABI_SYMBOLS = [
     "mskf_step", "mskf_sync", "mskf_backend_step_features", "mskf_get_features", "mskf_get_tracking_info",
     "mskf_get_grid", "mskf_get_pyramid", "mskf_get_state", "mskf_get_cam_states", "mskf_get_covariance",
     "mskf_reset", "mskf_op_pyramid", "mskf_op_detect", "mskf_op_klt",
+    "mskf_launch_count", "mskf_get_n_published", "mskf_get_poses", "mskf_profile_enable", "mskf_profile_read",
+    "mskf_debug_detect_scores", "mskf_debug_get_map", "mskf_op_ekf_update",
 ]
 
 
@@ -69,6 +71,11 @@ def lib():
         L.mskf_op_detect.argtypes = [P, P, I, I, P, I, P, P, I, C.POINTER(I)]
         L.mskf_op_klt.argtypes = [P, P, P, I, I, P, P, P, I]
         L.mskf_debug_detect_scores.argtypes = [P, P, I, I, P, P, I, C.POINTER(I), P]
+        L.mskf_get_poses.argtypes = [P, P, I]
+        L.mskf_op_ekf_update.argtypes = [P, I, I, P, P, P, P, P]
+        L.mskf_debug_get_map.argtypes = [P, I, P, P, P, P, I, C.POINTER(I)]
+        L.mskf_profile_enable.argtypes = [P, I]
+        L.mskf_profile_read.argtypes = [P, I, C.POINTER(C.c_char_p), C.POINTER(D), C.POINTER(C.c_longlong)]
         L.mskf_synth_render_device.argtypes = [P, P, P, P, P, P, I, I, I, P]
         _LIB = L
     return _LIB
@@ -157,6 +164,40 @@ class Engine:
     def backend(self):
         self.backend_callback()
 
+    # ---- instrumentation ----------------------------------------------------------------
+    def profile_enable(self, on=True):
+        self._ck(lib().mskf_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """{kernel class: (total ms, launches)} since profile_enable(True)."""
+        out, tag = {}, 0
+        while True:
+            name, ms, n = C.c_char_p(), C.c_double(), C.c_longlong()
+            rc = lib().mskf_profile_read(self.h, tag, C.byref(name), C.byref(ms), C.byref(n))
+            if rc == 1:
+                break
+            self._ck(rc)
+            out[name.value.decode()] = (ms.value, n.value)
+            tag += 1
+        return out
+
+    def feature_map(self, stream=0):
+        n = C.c_int()
+        cap = 8192
+        ids = np.zeros(cap, np.int64)
+        init = np.zeros(cap, np.int32)
+        pos = np.zeros((cap, 3))
+        nobs = np.zeros(cap, np.int32)
+        self._ck(lib().mskf_debug_get_map(self.h, stream, ids.ctypes.data, init.ctypes.data, pos.ctypes.data,
+                                          nobs.ctypes.data, cap, C.byref(n)))
+        k = n.value
+        return ids[:k], init[:k], pos[:k], nobs[:k]
+
+    def poses(self):
+        out = np.zeros((self.n_streams, 4, 4))
+        self._ck(lib().mskf_get_poses(self.h, out.ctypes.data, self.n_streams))
+        return out
+
     # ---- outputs -----------------------------------------------------------------------
     def launch_count(self):
         return int(lib().mskf_launch_count(self.h))
@@ -243,6 +284,17 @@ class Engine:
         self._ck(lib().mskf_op_detect(self.h, img.ctypes.data, img.shape[0], img.shape[1], occ.ctypes.data, len(occ),
                                       xy.ctypes.data, resp.ctypes.data, cap, C.byref(n)))
         return xy[:n.value], resp[:n.value]
+
+    def op_ekf_update(self, H, r, P):
+        H = np.ascontiguousarray(H, np.float64)
+        r = np.ascontiguousarray(r, np.float64)
+        P = np.ascontiguousarray(P, np.float64)
+        m, n = H.shape
+        dx = np.zeros(n)
+        Pn = np.zeros((n, n))
+        self._ck(lib().mskf_op_ekf_update(self.h, (n - 21) // 6, m, H.ctypes.data, r.ctypes.data, P.ctypes.data,
+                                          dx.ctypes.data, Pn.ctypes.data))
+        return dx, Pn
 
     def debug_detect_scores(self, img):
         img = np.ascontiguousarray(img, np.uint8)

@@ -574,6 +574,11 @@ public:
     void measurementUpdate(const Mat &H, const Mat &r) {
         if (H.r == 0 || r.r == 0) return;
         ++n_updates;
+        if (keep_last_update) {
+            last_H = H;
+            last_r = r;
+            last_P_prior = state_cov;
+        }
         Mat delta_x, P_new;
         update_math(H, r, state_cov, observation_noise, delta_x, P_new);
         last_delta_x = delta_x;
@@ -778,6 +783,8 @@ public:
     long long n_pub = 0, n_updates = 0, n_resets = 0;
     Mat last_delta_x;
     double last_gamma = 0;
+    bool keep_last_update = false;  // test hook: keep (H, r, P-) of the latest measurementUpdate
+    Mat last_H, last_r, last_P_prior;
 };
 
 }  // namespace orc

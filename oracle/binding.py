@@ -54,6 +54,9 @@ def lib():
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         L.orc_update_math.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
                                       C.c_void_p]
+        L.orc_keep_last_update.argtypes = [C.c_void_p, C.c_int]
+        L.orc_last_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.orc_get_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_chi2.argtypes = [C.POINTER(abi.Config), C.c_int]
         L.orc_chi2.restype = C.c_double
         _LIB = L
@@ -130,6 +133,29 @@ class Oracle:
         out = np.zeros(n, CAM_DT)
         lib().orc_get_cam_states(self.h, out.ctypes.data, n)
         return out
+
+    def feature_map(self):
+        """[(id, is_initialized, position, n_observations)] of map_server, ascending id."""
+        n = lib().orc_get_map(self.h, None, None, None, None, 0)
+        ids = np.zeros(n, np.int64)
+        init = np.zeros(n, np.int32)
+        pos = np.zeros((n, 3))
+        nobs = np.zeros(n, np.int32)
+        lib().orc_get_map(self.h, ids.ctypes.data, init.ctypes.data, pos.ctypes.data, nobs.ctypes.data, n)
+        return ids, init, pos, nobs
+
+    def keep_last_update(self, on=True):
+        lib().orc_keep_last_update(self.h, 1 if on else 0)
+
+    def last_update(self):
+        """(H, r, P-) of the latest measurementUpdate (needs keep_last_update())."""
+        n = C.c_int()
+        m = lib().orc_last_update(self.h, None, None, None, 0, C.byref(n))
+        H = np.zeros((m, n.value))
+        r = np.zeros(m)
+        P = np.zeros((n.value, n.value))
+        lib().orc_last_update(self.h, H.ctypes.data, r.ctypes.data, P.ctypes.data, max(H.size, P.size), C.byref(n))
+        return H, r, P
 
     def cov(self):
         n = lib().orc_get_cov(self.h, None, 0)

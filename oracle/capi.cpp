@@ -284,6 +284,32 @@ void orc_update_math(int n, int m, const double *H, const double *r, const doubl
     std::memcpy(out_dx, dx.d.data(), sizeof(double) * n);
     std::memcpy(out_P, Pn.d.data(), sizeof(double) * (size_t)n * n);
 }
+// test hook: (H, r, P-) of the latest measurementUpdate; returns rows, *n = cols
+void orc_keep_last_update(void *h, int on) { ((Oracle *)h)->be.keep_last_update = on != 0; }
+int orc_last_update(void *h, double *H, double *r, double *P, int cap, int *n) {
+    Oracle *o = (Oracle *)h;
+    const MsckfVio &b = o->be;
+    *n = b.last_H.c;
+    if (H && (int)b.last_H.d.size() <= cap) std::memcpy(H, b.last_H.d.data(), sizeof(double) * b.last_H.d.size());
+    if (r) std::memcpy(r, b.last_r.d.data(), sizeof(double) * b.last_r.d.size());
+    if (P && (int)b.last_P_prior.d.size() <= cap) std::memcpy(P, b.last_P_prior.d.data(), sizeof(double) * b.last_P_prior.d.size());
+    return b.last_H.r;
+}
+// test hook: the feature map (ascending id): id, is_initialized, position, observation count
+int orc_get_map(void *h, long long *ids, int *init, double *pos, int *nobs, int cap) {
+    Oracle *o = (Oracle *)h;
+    int n = 0;
+    for (const auto &kv : o->be.map_server) {
+        if (n < cap) {
+            ids[n] = kv.first;
+            init[n] = kv.second.is_initialized ? 1 : 0;
+            for (int i = 0; i < 3; ++i) pos[n * 3 + i] = kv.second.position[i];
+            nobs[n] = (int)kv.second.observations.size();
+        }
+        ++n;
+    }
+    return n;
+}
 double orc_chi2(const mskf_config *cfg, int dof) {
     MsckfVio v(*cfg);
     return v.chi2(dof);
