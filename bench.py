@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py — stereo frames/s of the per-frame hot path (front end + MSCKF update).
+
+Workload (BASELINE.json config 4, "batched fleet"): S = 256 independent synthetic stereo+IMU
+streams per GPU (752x480 @ 20 Hz, IMU @ 200 Hz, seed = global stream index), preset `bench`
+(4-level pyramid, 21x21 KLT, ~300 grid features, max_cam_state_size 30).  One step = one stereo
+frame of every stream through ImageProcessor::stereoCallback + MsckfVio::featureCallback
+(mskf_step).  Streams are sharded over ranks; there is no collective on the data path.
+
+  value  frames/s with the images already resident in HBM (device-rendered), CUDA-event timed
+  e2e    frames/s through the C ABI with HOST buffers: pinned images -> H2D, IMU rows, step,
+         poses read back every step
+  roofline     the dominant kernel class of the timed region: algorithmic work (counted by the
+               kernels themselves from the sizes they actually processed) / CUDA-event time
+  cpu_baseline the CPU oracle (a port: the reference cannot be compiled here) on one host core
+
+--impl reference times the same workload on the host cores through the oracle re-host of
+run_euroc_single_thread (one process per core, one stream each).
+"""
+import argparse
+import ctypes as C
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PRIME_FRAMES = 72   # untimed: static start, gravity init (200 IMU rows), window fill to 30 cam states
+METRIC = "stereo frames/s @752x480 (track+EKF)"
+UNIT = "frames/s"
+
+
+def shard(n_total, world, rank):
+    """Contiguous block of global stream indices owned by `rank` (stream-parallel, no overlap)."""
+    per = n_total // world
+    rem = n_total % world
+    lo = rank * per + min(rank, rem)
+    return list(range(lo, lo + per + (1 if rank < rem else 0)))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU, sampled while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU legs (oracle re-host of apps/run_euroc_single_thread.cpp:189-254; test infrastructure
+# used here only as the measured CPU baseline)
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, preset, prime, warm, steps, frames = args
+    from msckf_stereo_c_b200 import synth
+    from oracle import binding as ob
+
+    cfg = synth.default_config(preset)
+    s = synth.Stream(cfg, seed=seed, threads=1)
+    o = ob.Oracle(cfg)
+    if frames is None:  # render on the CPU (outside the timed region, like PNG decode in the reference runner)
+        frames = [s.render(k)[1:] for k in range(prime + warm + steps)]
+    j, t_timed = 0, 0.0
+    for k in range(prime + warm + steps):
+        t_img = s.frame_time(k)
+        rows = []
+        while True:
+            t, w, a = s.imu(j)
+            j += 1
+            rows.append((t, w, a))
+            if not (t <= t_img):
+                break
+        im0, im1 = frames[k]
+        t0 = time.perf_counter()
+        for t, w, a in rows:
+            o.imu(t, w, a)
+        o.stereo(t_img, im0, im1)
+        o.backend()
+        if k >= prime + warm:
+            t_timed += time.perf_counter() - t0
+    st = o.state()
+    return t_timed, st.n_cam_states, st.n_updates
+
+
+def cpu_leg(preset, n_procs, prime, warm, steps, seeds=None):
+    seeds = seeds or list(range(n_procs))
+    jobs = [(sd, preset, prime, warm, steps, None) for sd in seeds]
+    if n_procs == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(n_procs) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    t_max = max(r[0] for r in res)
+    return n_procs * steps / t_max, res
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    steps, warm = args.steps, args.warmup
+    # bounded sample: every core runs one stream for `steps` frames at filter steady state
+    prime = PRIME_FRAMES
+    t0 = time.time()
+    value, res = cpu_leg(args.preset, procs, prime, warm, steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * procs / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"fleet: {procs} independent 752x480 stereo+IMU streams (one per host core), preset {args.preset} "
+                               f"(L=4, KLT 21x21, ~300 features, N=30), {prime} untimed priming frames per stream",
+                   "streams": procs, "preset": args.preset},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": f"{procs} processes x 1 stream x {steps} frames after {prime}+{warm} untimed frames; oracle re-host of "
+                                   "run_euroc_single_thread (the reference needs vikit_cg/Eigen/SPQR/OpenCV, absent here); image "
+                                   "rendering excluded like PNG decode"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the engine; use --impl reference for the CPU leg)")
+    from msckf_stereo_c_b200 import engine, synth
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    cfg = synth.default_config(args.preset)
+    S = args.streams
+    seeds = [rank * S + i for i in range(S)]  # weak scaling: S streams per GPU, global index = seed
+    fleet = synth.Fleet(cfg, seeds)
+    K, W = args.steps, args.warmup
+    img = cfg.img_rows * cfg.img_cols
+    stream = torch.cuda.Stream(device=dev)
+    e = engine.Engine(cfg, S, device=local_rank, cuda_stream=stream.cuda_stream)
+
+    def feed_imu(k):
+        rows = fleet.imu_rows_for_frame(k)
+        e.push_imu_batch(rows)
+        return rows.nbytes
+
+    # ---- priming (untimed): frames rendered on the fly
+    scratch = torch.empty((S, 2, img), dtype=torch.uint8, device=dev)
+    tvec = np.zeros(S)
+    k = 0
+    with torch.cuda.stream(stream):
+        for _ in range(PRIME_FRAMES):
+            feed_imu(k)
+            fleet.render_device(k, scratch, stream.cuda_stream)
+            tvec[:] = fleet.frame_time(k)
+            e.push_stereo_batch(tvec, scratch.data_ptr(), scratch.data_ptr() + img, 2 * img, device=True)
+            e.step()
+            k += 1
+        e.sync()
+    # ---- pre-render the timed frames: device-resident set for `value`, pinned host set for `e2e`
+    n_dev = W + K
+    n_e2e = W + K
+    frames_dev = torch.empty((n_dev, S, 2, img), dtype=torch.uint8, device=dev)
+    frames_host = torch.empty((n_e2e, S, 2, img), dtype=torch.uint8).pin_memory()
+    with torch.cuda.stream(stream):
+        for i in range(n_dev):
+            fleet.render_device(k + i, frames_dev[i], stream.cuda_stream)
+        for i in range(n_e2e):
+            fleet.render_device(k + n_dev + i, scratch, stream.cuda_stream)
+            frames_host[i].copy_(scratch, non_blocking=True)
+    stream.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- leg 1: device-resident inputs ("value")
+    def step_dev(i, kk):
+        feed_imu(kk)
+        tvec[:] = fleet.frame_time(kk)
+        base = frames_dev[i].data_ptr()
+        e.push_stereo_batch(tvec, base, base + img, 2 * img, device=True)
+        e.step()
+
+    for i in range(W):
+        step_dev(i, k)
+        k += 1
+    e.sync()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = e.launch_count()
+    e.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record(stream)
+    for i in range(W, W + K):
+        step_dev(i, k)
+        k += 1
+    ev1.record(stream)
+    e.sync()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms_dev = ev0.elapsed_time(ev1)
+    prof = e.profile_read()
+    e.profile_enable(False)
+    launches = e.launch_count() - launches0
+    clk = clocks.stop()
+
+    # ---- leg 2: host buffers through the C ABI ("e2e")
+    poses = None
+    h2d = d2h = 0
+
+    def step_e2e(i, kk):
+        nonlocal poses, h2d, d2h
+        nb = feed_imu(kk)
+        tvec[:] = fleet.frame_time(kk)
+        base = frames_host[i].data_ptr()
+        e.push_stereo_batch(tvec, base, base + img, 2 * img, device=False)  # pinned host -> staging (H2D)
+        e.step()
+        poses = e.poses()  # device -> host read of every stream's T_b_w (synchronises)
+        h2d = 2 * img * S + nb
+        d2h = poses.nbytes
+
+    for i in range(W):
+        step_e2e(i, k)
+        k += 1
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_e0 = time.perf_counter()
+    ev2.record(stream)
+    for i in range(W, W + K):
+        step_e2e(i, k)
+        k += 1
+    ev3.record(stream)
+    e.sync()
+    barrier()
+    t_e2e_wall = time.perf_counter() - t_e0
+    ms_e2e = max(ev2.elapsed_time(ev3), 1e3 * t_e2e_wall)  # the host is inside the loop: take the slower clock
+
+    # sanity of the timed state: filters alive, windows full
+    st = e.state(0)
+    n_feat = len(e.grid(0))
+    assert np.isfinite(poses).all()
+
+    # ---- max over ranks
+    times = torch.tensor([ms_dev, ms_e2e, 1e3 * t_wall], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_dev_max, ms_e2e_max, wall_max = [float(x) for x in times.tolist()]
+    total_frames = world * S * K
+    value = total_frames / (ms_dev_max * 1e-3)
+    e2e_value = total_frames / (ms_e2e_max * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        # fp64 peak is not in MEASURED_PEAKS.json: measure a cuBLAS DGEMM here (burst, best of 5)
+        a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+        b = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+        best = 1e9
+        for _ in range(6):
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record()
+            torch.matmul(a, b)
+            x1.record()
+            torch.cuda.synchronize()
+            best = min(best, x0.elapsed_time(x1))
+        fp64_peak = 2 * 4096 ** 3 / (best * 1e-3) / 1e12
+        fe_classes = {"pyr_down_l1", "pyr_down_ln", "klt_temporal", "klt_stereo", "klt_new", "detect"}
+        per_kernel = []
+        tot_ms = sum(v[0] for v in prof.values())
+        for name, (ms, n, work) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+            if n == 0:
+                continue
+            ent = {"kernel": name, "launches": n, "ms_per_launch": ms / n, "share": ms / tot_ms}
+            if name in fe_classes:
+                ent.update(bound="hbm", achieved=work / (ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s")
+            elif work > 0:
+                ent.update(bound="fp64", achieved=work / (ms * 1e-3) / 1e12, peak=fp64_peak, unit="TFLOP/s")
+            if "achieved" in ent:
+                ent["frac"] = ent["achieved"] / ent["peak"]
+            per_kernel.append(ent)
+        top = next((x for x in per_kernel if "achieved" in x), None)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top["kernel"]) if top else None
+        except (OSError, ValueError):
+            pass
+        roofline = None
+        if top:
+            roofline = {"kernel": top["kernel"], "bound": "hbm" if top["bound"] == "hbm" else "tensor", "achieved": top["achieved"],
+                        "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": traffic,
+                        "peak_source": peak_src if top["bound"] == "hbm" else "cuBLAS DGEMM 4096^3 measured in this run (fp64 pipe incl. DMMA; "
+                        "MEASURED_PEAKS.json has no fp64 figure)", "share_of_step": top["share"]}
+        # CPU baseline: the oracle on one host core, a bounded sample of the same workload
+        cpu_steps = args.cpu_frames
+        t0 = time.time()
+        cpu_value, _ = cpu_leg(args.preset, 1, PRIME_FRAMES, 2, cpu_steps)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev_max / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"fleet (BASELINE.json config 4): {S} independent 752x480 stereo+IMU streams per GPU, preset {args.preset} "
+                                   f"(L=4, KLT 21x21, ~300 grid features, max_cam_state_size 30), full track+EKF per frame, "
+                                   f"{PRIME_FRAMES} untimed priming frames",
+                       "streams_per_gpu": S, "preset": args.preset, "features_stream0": n_feat, "cam_states_stream0": st.n_cam_states,
+                       "ekf_updates_stream0": int(st.n_updates), "l2": f"inputs larger than L2: {2 * img * S / 1e6:.0f} MB of new images per step",
+                       "front_end_dtype": "u8 / fixed point", "parallelism": f"stream-sharded x{world}, no collective on the data path"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e_max / K},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": roofline,
+            "kernels": per_kernel,
+            "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"1 stream x {cpu_steps} frames after {PRIME_FRAMES}+2 untimed frames, same preset; oracle re-host of "
+                                       "run_euroc_single_thread (reference not buildable here); rendering excluded",
+                             "wall_s": time.time() - t0},
+            "wall_ms_per_step": wall_max / K,
+        }
+        print(json.dumps(line), flush=True)
+    e.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=256, help="streams per GPU")
+    ap.add_argument("--preset", default="bench")
+    ap.add_argument("--cpu-frames", type=int, default=40, help="frames of the 1-core CPU baseline sample")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,6 +15,7 @@
 #ifndef MSCKF_B200_H
 #define MSCKF_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -166,6 +167,14 @@ int mskf_push_stereo(mskf_handle *h, int stream, double t, const uint8_t *cam0,
 int mskf_push_stereo_device(mskf_handle *h, int stream, double t, const uint8_t *d_cam0,
                             const uint8_t *d_cam1);
 
+/* Fleet variants of the three calls above (same semantics, fewer host calls): `samples` holds n rows
+ * {t, wx, wy, wz, ax, ay, az} for `stream`, or, with stream == -1, [n_streams][n][7]; the stereo batches
+ * take one image per stream at cam0 + s * stream_stride (bytes), time stamps t[n_streams]. */
+int mskf_push_imu_batch(mskf_handle *h, int stream, int n, const double *samples);
+int mskf_push_stereo_batch(mskf_handle *h, const double *t, const uint8_t *cam0, const uint8_t *cam1, size_t stream_stride);
+int mskf_push_stereo_device_batch(mskf_handle *h, const double *t, const uint8_t *d_cam0, const uint8_t *d_cam1,
+                                  size_t stream_stride);
+
 /* Replaces: System::stereo_callback (system.cpp:40-43) -> ImageProcessor::stereoCallback
  * (image_processor.cpp:139-203) for every stream with a staged pair. */
 int mskf_frontend_step(mskf_handle *h);
@@ -234,6 +243,9 @@ int mskf_get_poses(mskf_handle *h, double *out_T_b_w, int cap_streams);
  * mskf_profile_read returns 1 when `tag` is past the last class. */
 int mskf_profile_enable(mskf_handle *h, int on);
 int mskf_profile_read(mskf_handle *h, int tag, const char **name, double *ms, long long *count);
+/* Algorithmic work (bytes for the front-end classes, flops for the EKF classes) done by kernel class
+ * `tag` since mskf_profile_enable(h, 1): the numerator of bench.py's roofline figures. */
+int mskf_get_work(mskf_handle *h, int tag, double *total);
 /* The back end's feature map (MsckfVio::map_server) in ascending feature id. */
 int mskf_debug_get_map(mskf_handle *h, int stream, long long *ids, int *is_initialized, double *position,
                        int *n_observations, int cap, int *n);

@@ -140,6 +140,7 @@ struct BeBuf {
     double *W;         // [S][LD*KC]
     double *yv;        // [S][KC]
     double *dxv;       // [S][LD] delta_x of the latest update
+    double *work;      // [S][MSKF_PROF_TAGS] algorithmic flops done per kernel class (bench roofline)
     // front-end message (fb.stale / stale_hw / msg_total)
     const mskf_feature *fe_msg;
     const int *fe_hw;
@@ -1488,6 +1489,8 @@ __global__ void __launch_bounds__(BE_THREADS) be_feature_jac_kernel(BeConst bc, 
         const int dof = phase == 0 ? M - 1 : M;  // msckf_vio.cpp:1001, :1145
         const double thr = (dof >= 1 && dof <= 99) ? c_chi2[bc.chi2_mode][dof - 1] : 0.0;
         bb.l_pass[lo + li] = s_gamma < thr ? 1 : 0;
+        const double dr = rows, dc = C6;
+        atomicAdd(bb.work + (size_t)s * MSKF_PROF_TAGS + PK_BE_FEATURE_JAC, 2.0 * dr * dc * dc + 2.0 * dr * dr * dc + dr * dr * dr / 3.0);
     }
     }  // list loop
 }
@@ -1598,6 +1601,17 @@ __global__ void __launch_bounds__(BE_THREADS) be_qr_kernel(BeConst bc, BeBuf bb)
     const int m = st.m, k = st.k, KC = bc.KC;
     const double *Hst = bb.Hst + (size_t)s * bc.hst_cap, *rst = bb.rst + (size_t)s * bc.hst_rows;
     double *Tm = bb.Tm + (size_t)s * KC * KC, *rt = bb.rt + (size_t)s * KC;
+    if (threadIdx.x == 0) {
+        // algorithmic flops of this stream's update (dense-equivalent over the active columns)
+        const double dm = m, dk = k, dmt = m <= k ? m : k, dld = bc.LD;
+        double *w = bb.work + (size_t)s * MSKF_PROF_TAGS;
+        if (m > k) w[PK_BE_QR] += 2.0 * dm * dk * dk;
+        w[PK_BE_GEMM_PHT] += 2.0 * dld * dk * dmt;
+        w[PK_BE_GEMM_S] += 2.0 * dmt * dk * dmt;
+        w[PK_BE_CHOL] += 2.0 * dmt * dmt * dmt / 3.0;
+        w[PK_BE_GEMM_W] += dld * dmt * dmt;
+        w[PK_BE_GEMM_PUPD] += dld * dld * dmt;
+    }
     if (m <= k) {
         for (int e = threadIdx.x; e < m * k; e += BE_THREADS) Tm[e] = Hst[e];
         for (int i = threadIdx.x; i < m; i += BE_THREADS) rt[i] = rst[i];
@@ -2079,6 +2093,7 @@ int be_create(mskf_handle *h) {
     A(bb.Tm, S * bc.KC * bc.KC); A(bb.rt, S * bc.KC); A(bb.PHt, S * bc.LD * bc.KC); A(bb.Sm, S * bc.KC * bc.KC);
     A(bb.Linv, S * bc.KC * bc.KC); A(bb.W, S * bc.LD * bc.KC); A(bb.yv, S * bc.KC); A(bb.dxv, S * bc.LD);
 #undef A
+    bb.work = h->d_work;
     bb.fe_msg = h->fb.stale;
     bb.fe_hw = h->fb.stale_hw;
     bb.fe_total = h->fb.msg_total;

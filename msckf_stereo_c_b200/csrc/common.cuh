@@ -101,6 +101,7 @@ struct FeBuffers {
     long long *msg_total;   // [S] total length of the reference's growing vector
     mskf_tracking_info *info;  // [S]
     uint8_t *dbg_score;     // optional [rows*cols] FAST score map of stream 0 (tests only)
+    double *work;           // [S][MSKF_PROF_TAGS] algorithmic bytes / flops done, per kernel class (bench roofline)
 };
 
 }  // namespace mskf
@@ -150,6 +151,8 @@ struct mskf_handle {
     std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
     std::vector<int> prof_tag;
     size_t prof_used = 0;
+    double *d_work = nullptr;          // [S][MSKF_PROF_TAGS]
+    double work_host[MSKF_PROF_TAGS] = {0};  // work of kernels whose size the host knows
     double prof_ms[MSKF_PROF_TAGS] = {0};
     long long prof_n[MSKF_PROF_TAGS] = {0};
 };
@@ -177,7 +180,7 @@ void prof_collect(mskf_handle *h);
 
 // frontend.cu
 int fe_create(mskf_handle *h);
-int fe_step(mskf_handle *h, bool any_first, int max_prev);
+int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active);
 int fe_op_detect(mskf_handle *t, const float *occ, int n_occ, float *out_xy, double *out_resp, int cap, int *n,
                  uint8_t *score_map);
 int fe_op_klt(mskf_handle *t, const float *pts_a, float *pts_b, uint8_t *status, int n);

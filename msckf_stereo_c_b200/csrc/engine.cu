@@ -150,7 +150,8 @@ int mskf_profile_enable(mskf_handle *h, int on) {
     prof_collect(h);
     h->prof_on = on != 0;
     if (on) {
-        for (int i = 0; i < MSKF_PROF_TAGS; ++i) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+        for (int i = 0; i < MSKF_PROF_TAGS; ++i) { h->prof_ms[i] = 0; h->prof_n[i] = 0; h->work_host[i] = 0; }
+        cudaMemsetAsync(h->d_work, 0, sizeof(double) * (size_t)h->S * MSKF_PROF_TAGS, h->stream);
     }
     return MSKF_OK;
 }
@@ -181,7 +182,9 @@ int mskf_create(const mskf_config *cfg, int n_streams, int device, mskf_handle *
     MSKF_CUDA_CHECK(h, cudaSetDevice(device));
     MSKF_CUDA_CHECK(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
-    int rc = fe_create(h);
+    int rc = dev_alloc(h, &h->d_work, (size_t)n_streams * MSKF_PROF_TAGS);
+    if (rc != MSKF_OK) return rc;
+    rc = fe_create(h);
     if (rc != MSKF_OK) return rc;
     rc = be_create(h);
     if (rc != MSKF_OK) return rc;
@@ -246,6 +249,61 @@ int mskf_push_imu(mskf_handle *h, int s, double t, const double w[3], const doub
     return MSKF_OK;
 }
 
+int mskf_push_imu_batch(mskf_handle *h, int stream, int n, const double *samples) {
+    if (!h || !samples || n < 0 || stream < -1 || stream >= h->S) return MSKF_ERR_ARG;
+    const int s0 = stream < 0 ? 0 : stream, s1 = stream < 0 ? h->S : stream + 1;
+    for (int s = s0; s < s1; ++s) {
+        const double *p = samples + (stream < 0 ? (size_t)s * n * 7 : 0);
+        for (int i = 0; i < n; ++i) {
+            int rc = mskf_push_imu(h, s, p[i * 7], p + i * 7 + 1, p + i * 7 + 4);
+            if (rc != MSKF_OK) return rc;
+        }
+    }
+    return MSKF_OK;
+}
+
+int mskf_push_stereo_batch(mskf_handle *h, const double *t, const uint8_t *cam0, const uint8_t *cam1, size_t stream_stride) {
+    if (!h || !t || !cam0 || !cam1) return MSKF_ERR_ARG;
+    MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
+    const size_t img = (size_t)h->cfg.img_rows * h->cfg.img_cols;
+    if (stream_stride < img) return MSKF_ERR_ARG;
+    // one strided copy per camera: stream s lands at staging[s][cam]
+    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(h->fb.staging, 2 * img, cam0, stream_stride, img, h->S, cudaMemcpyHostToDevice, h->stream));
+    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(h->fb.staging + img, 2 * img, cam1, stream_stride, img, h->S, cudaMemcpyHostToDevice, h->stream));
+    for (int s = 0; s < h->S; ++s) {
+        HostStream &hs = h->hs[s];
+        hs.pending = true;
+        hs.pending_t = t[s];
+        hs.src0 = h->fb.staging + ((size_t)s * 2 + 0) * img;
+        hs.src1 = h->fb.staging + ((size_t)s * 2 + 1) * img;
+    }
+    return MSKF_OK;
+}
+
+int mskf_push_stereo_device_batch(mskf_handle *h, const double *t, const uint8_t *d_cam0, const uint8_t *d_cam1, size_t stream_stride) {
+    if (!h || !t || !d_cam0 || !d_cam1) return MSKF_ERR_ARG;
+    for (int s = 0; s < h->S; ++s) {
+        HostStream &hs = h->hs[s];
+        hs.pending = true;
+        hs.pending_t = t[s];
+        hs.src0 = d_cam0 + (size_t)s * stream_stride;
+        hs.src1 = d_cam1 + (size_t)s * stream_stride;
+    }
+    return MSKF_OK;
+}
+
+int mskf_get_work(mskf_handle *h, int tag, double *total) {
+    if (!h || !total || tag < 0 || tag >= MSKF_PROF_TAGS) return MSKF_ERR_ARG;
+    int rc = mskf_sync(h);
+    if (rc != MSKF_OK) return rc;
+    std::vector<double> w((size_t)h->S * MSKF_PROF_TAGS);
+    MSKF_CUDA_CHECK(h, cudaMemcpy(w.data(), h->d_work, sizeof(double) * w.size(), cudaMemcpyDeviceToHost));
+    double acc = h->work_host[tag];
+    for (int s = 0; s < h->S; ++s) acc += w[(size_t)s * MSKF_PROF_TAGS + tag];
+    *total = acc;
+    return MSKF_OK;
+}
+
 int mskf_push_stereo(mskf_handle *h, int s, double t, const uint8_t *cam0, const uint8_t *cam1, int rows, int cols,
                      int stride) {
     if (!h || s < 0 || s >= h->S || !cam0 || !cam1) return MSKF_ERR_ARG;
@@ -289,7 +347,7 @@ int mskf_frontend_step(mskf_handle *h) {
     FeStep *hstep = ex->h_step_ring[slot];
     const uint8_t **hsrc = ex->h_src_ring[slot];
     bool any = false, any_first = false;
-    int max_prev = 0;
+    int max_prev = 0, n_active = 0;
     for (int s = 0; s < S; ++s) {
         HostStream &hs = h->hs[s];
         FeStep &st = hstep[s];
@@ -298,6 +356,7 @@ int mskf_frontend_step(mskf_handle *h) {
         hsrc[S + s] = hs.src1;
         if (!hs.pending) continue;
         any = true;
+        ++n_active;
         st.active = 1;
         st.is_first = hs.fe_first ? 1 : 0;
         hs.fe_curr_t = hs.pending_t;
@@ -323,7 +382,7 @@ int mskf_frontend_step(mskf_handle *h) {
     MSKF_CUDA_CHECK(h, cudaMemcpyAsync(h->fb.src1, hsrc + S, sizeof(uint8_t *) * S, cudaMemcpyHostToDevice, h->stream));
     MSKF_CUDA_CHECK(h, cudaEventRecord(ex->ring_ev[slot], h->stream));
     ex->ring_used[slot] = true;
-    return fe_step(h, any_first, max_prev);
+    return fe_step(h, any_first, max_prev, n_active);
 }
 
 int mskf_backend_step(mskf_handle *h) {

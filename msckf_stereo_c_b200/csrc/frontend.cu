@@ -427,6 +427,12 @@ __device__ __forceinline__ int grid_code(const FeConst &fc, float2 p) {
     return row * fc.grid_col + col;
 }
 
+// compulsory window traffic of one feature through all levels: an (w+2)^2 template patch and a
+// (w+1)^2 search patch per level
+__host__ __device__ __forceinline__ double klt_bytes_per_feature(const FeConst &fc) {
+    return (double)fc.levels * (double)((fc.klt_win + 2) * (fc.klt_win + 2) + (fc.klt_win + 1) * (fc.klt_win + 1));
+}
+
 #define FE_THREADS 128
 #define FE_MAX_CELLS 128  // coarse grid cells incl. the overflow row (image_processor.cpp:663-665 can index past grid_row)
 
@@ -484,6 +490,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_prep_track(FeConst fc, FeBuffer
     if (threadIdx.x == 0) {
         fb.k_n[s] = n;
         fb.info[s].before_tracking = n;
+        fb.work[(size_t)s * MSKF_PROF_TAGS + PK_KLT_TEMPORAL] += (double)n * klt_bytes_per_feature(fc);
     }
 }
 
@@ -528,6 +535,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_after_track(FeConst fc, FeBuffe
     if (threadIdx.x == 0) {
         fb.k_n[s] = m;
         fb.info[s].after_tracking = m;
+        fb.work[(size_t)s * MSKF_PROF_TAGS + PK_KLT_STEREO] += (double)m * klt_bytes_per_feature(fc);
     }
 }
 
@@ -632,7 +640,10 @@ __global__ void __launch_bounds__(FE_THREADS) fe_sieve(FeConst fc, FeBuffers fb)
             fb.k_a[ko + i] = p;
             fb.k_b[ko + i] = distort_pt(fc, 1, undistort_pt(fc, 0, p, fc.R01));
         }
-        if (threadIdx.x == 0) fb.k_n[s] = n;
+        if (threadIdx.x == 0) {
+            fb.k_n[s] = n;
+            fb.work[(size_t)s * MSKF_PROF_TAGS + PK_KLT_NEW] += (double)n * klt_bytes_per_feature(fc);
+        }
         return;
     }
     // one thread per coarse cell: members in detect order, keep the grid_max best (stable)
@@ -675,6 +686,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_sieve(FeConst fc, FeBuffers fb)
         }
         s_cell_off[fc.n_cells] = acc;
         fb.k_n[s] = acc;
+        fb.work[(size_t)s * MSKF_PROF_TAGS + PK_KLT_NEW] += (double)acc * klt_bytes_per_feature(fc);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < fc.n_cells; c += FE_THREADS) {
@@ -986,10 +998,11 @@ int fe_create(mskf_handle *h) {
     A(fb.msg, S * fc.max_f); A(fb.msg_n, S); A(fb.stale, S * fc.max_f); A(fb.stale_hw, S); A(fb.msg_total, S);
     A(fb.info, S);
 #undef A
+    fb.work = h->d_work;
     return MSKF_OK;
 }
 
-int fe_step(mskf_handle *h, bool any_first, int max_prev) {
+int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active) {
     const FeConst &fc = h->fc;
     const FeBuffers &fb = h->fb;
     cudaStream_t q = h->stream;
@@ -1003,7 +1016,11 @@ int fe_step(mskf_handle *h, bool any_first, int max_prev) {
         dim3 g((fc.lvl_cols[l] + PD_TW - 1) / PD_TW, (fc.lvl_rows[l] + PD_TH - 1) / PD_TH, S * 2);
         if (l == 1) MSKF_LAUNCH(h, PK_PYR_L1, (pyr_down_kernel<true><<<g, 256, 0, q>>>(fc, fb, l)));
         else MSKF_LAUNCH(h, PK_PYR_LN, (pyr_down_kernel<false><<<g, 256, 0, q>>>(fc, fb, l)));
+        // algorithmic bytes: read level l-1, write level l (+ the level-0 landing copy at l == 1)
+        double in = (double)fc.lvl_rows[l - 1] * fc.lvl_cols[l - 1], out = (double)fc.lvl_rows[l] * fc.lvl_cols[l];
+        h->work_host[l == 1 ? PK_PYR_L1 : PK_PYR_LN] += 2.0 * n_active * (in + out + (l == 1 ? in : 0.0));
     }
+    h->work_host[PK_DETECT] += (double)n_active * fc.rows * fc.cols;
     const size_t klt_smem = (size_t)KLT_WARPS * ((fc.klt_win + 2) * (fc.klt_win + 2) + 2 * fc.klt_win * fc.klt_win) * sizeof(short);
     const size_t pos_smem = (size_t)fc.cap_k * sizeof(int);
     MSKF_LAUNCH(h, PK_FE_BOOK, (fe_prep_track<<<S, FE_THREADS, 0, q>>>(fc, fb)));

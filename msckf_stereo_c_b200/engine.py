@@ -28,7 +28,8 @@ ABI_SYMBOLS = [
     "mskf_get_grid", "mskf_get_pyramid", "mskf_get_state", "mskf_get_cam_states", "mskf_get_covariance",
     "mskf_reset", "mskf_op_pyramid", "mskf_op_detect", "mskf_op_klt",
     "mskf_launch_count", "mskf_get_n_published", "mskf_get_poses", "mskf_profile_enable", "mskf_profile_read",
-    "mskf_debug_detect_scores", "mskf_debug_get_map", "mskf_op_ekf_update",
+    "mskf_debug_detect_scores", "mskf_debug_get_map", "mskf_op_ekf_update", "mskf_push_imu_batch",
+    "mskf_push_stereo_batch", "mskf_push_stereo_device_batch", "mskf_get_work",
 ]
 
 
@@ -72,6 +73,10 @@ def lib():
         L.mskf_op_klt.argtypes = [P, P, P, I, I, P, P, P, I]
         L.mskf_debug_detect_scores.argtypes = [P, P, I, I, P, P, I, C.POINTER(I), P]
         L.mskf_get_poses.argtypes = [P, P, I]
+        L.mskf_push_imu_batch.argtypes = [P, I, I, P]
+        L.mskf_push_stereo_batch.argtypes = [P, P, P, P, C.c_size_t]
+        L.mskf_push_stereo_device_batch.argtypes = [P, P, P, P, C.c_size_t]
+        L.mskf_get_work.argtypes = [P, I, C.POINTER(D)]
         L.mskf_op_ekf_update.argtypes = [P, I, I, P, P, P, P, P]
         L.mskf_debug_get_map.argtypes = [P, I, P, P, P, P, I, C.POINTER(I)]
         L.mskf_profile_enable.argtypes = [P, I]
@@ -169,17 +174,30 @@ class Engine:
         self._ck(lib().mskf_profile_enable(self.h, 1 if on else 0))
 
     def profile_read(self):
-        """{kernel class: (total ms, launches)} since profile_enable(True)."""
+        """{kernel class: (total ms, launches, algorithmic work)} since profile_enable(True); work is
+        bytes for the front-end classes and flops for the EKF classes."""
         out, tag = {}, 0
         while True:
-            name, ms, n = C.c_char_p(), C.c_double(), C.c_longlong()
+            name, ms, n, w = C.c_char_p(), C.c_double(), C.c_longlong(), C.c_double()
             rc = lib().mskf_profile_read(self.h, tag, C.byref(name), C.byref(ms), C.byref(n))
             if rc == 1:
                 break
             self._ck(rc)
-            out[name.value.decode()] = (ms.value, n.value)
+            self._ck(lib().mskf_get_work(self.h, tag, C.byref(w)))
+            out[name.value.decode()] = (ms.value, n.value, w.value)
             tag += 1
         return out
+
+    # ---- fleet variants ----------------------------------------------------------------
+    def push_imu_batch(self, samples, stream=-1):
+        samples = np.ascontiguousarray(samples, np.float64)
+        n = samples.shape[-2]
+        self._ck(lib().mskf_push_imu_batch(self.h, stream, n, samples.ctypes.data))
+
+    def push_stereo_batch(self, t, p0, p1, stream_stride, device=False):
+        t = np.ascontiguousarray(t, np.float64)
+        f = lib().mskf_push_stereo_device_batch if device else lib().mskf_push_stereo_batch
+        self._ck(f(self.h, t.ctypes.data, C.c_void_p(p0), C.c_void_p(p1), stream_stride))
 
     def feature_map(self, stream=0):
         n = C.c_int()

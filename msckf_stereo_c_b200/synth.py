@@ -40,6 +40,9 @@ def lib():
         L.synth_cam.restype = C.c_void_p
         L.synth_cam.argtypes = [C.c_void_p, C.c_int]
         L.synth_default_config.argtypes = [C.POINTER(abi.Config), C.c_char_p]
+        L.synth_make_trajs.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        L.synth_imu_block.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        L.synth_traj_pose.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -118,3 +121,71 @@ def feed(stream, n_frames, sink):
         sink.stereo(t_img, im0, im1)
         sink.backend()
         yield k, t_img
+
+
+class Fleet:
+    """`n` synthetic streams sharing one calibration (BASELINE.json config 4: independent
+    stereo+IMU streams, seed = global stream index).  IMU rows come from the host generator; the
+    images can be rendered on the device (scene.h compiled by nvcc into the engine library) so a
+    256-stream batch does not wait for the CPU renderer.  Input generation only."""
+
+    def __init__(self, cfg, seeds, t0=1000.0, frame_rate=20.0, imu_rate=200.0, imu_noise=True):
+        self.cfg, self.n = cfg, len(seeds)
+        self.frame_dt, self.imu_dt, self.t0 = 1.0 / frame_rate, 1.0 / imu_rate, t0
+        self.ng = cfg.noise_gyro * np.sqrt(imu_rate) if imu_noise else 0.0
+        self.na = cfg.noise_acc * np.sqrt(imu_rate) if imu_noise else 0.0
+        L = lib()
+        self.tsz = L.synth_traj_size()
+        self.trajs = np.zeros(self.n * self.tsz, np.uint8)
+        sd = np.ascontiguousarray(seeds, np.uint32)
+        L.synth_make_trajs(sd.ctypes.data, self.n, t0, self.trajs.ctypes.data)
+        self.proto = Stream(cfg, seed=int(seeds[0]), t0=t0, frame_rate=frame_rate, imu_rate=imu_rate, imu_noise=imu_noise)
+        self._dev = None
+        self._j = 0
+
+    def frame_time(self, k):
+        return self.t0 + k * self.frame_dt + 0.25 * self.imu_dt
+
+    def imu_rows_for_frame(self, k):
+        """IMU rows the EuRoC feed order pushes before image k (rows up to and including the first
+        one with t > t_img): array [n][rows][7]."""
+        t_img = self.frame_time(k)
+        j1 = self._j
+        while True:  # same stamps for every stream
+            t = self.t0 + j1 * self.imu_dt
+            j1 += 1
+            if not (t <= t_img):
+                break
+        out = np.zeros((self.n, j1 - self._j, 7))
+        lib().synth_imu_block(self.trajs.ctypes.data, self.n, self._j, j1, self.imu_dt, self.ng, self.na, out.ctypes.data)
+        self._j = j1
+        return out
+
+    def pose(self, i, t):
+        R = np.zeros(9)
+        p = np.zeros(3)
+        lib().synth_traj_pose(self.trajs[i * self.tsz:].ctypes.data, t, R.ctypes.data, p.ctypes.data)
+        return R.reshape(3, 3), p
+
+    def render_device(self, k, out, cuda_stream=0):
+        """Render frame k of every stream into the CUDA uint8 tensor `out` [n][2][rows*cols]."""
+        import torch
+
+        from . import engine
+
+        if self._dev is None:
+            L = lib()
+            csz = L.synth_cam_size()
+            cams = np.concatenate([np.ctypeslib.as_array(C.cast(L.synth_cam(self.proto.h, c), C.POINTER(C.c_uint8)), shape=(csz,)).copy()
+                                   for c in (0, 1)])
+            dev = out.device
+            self._dev = dict(traj=torch.from_numpy(self.trajs.copy()).to(dev), cams=torch.from_numpy(cams).to(dev),
+                             r0=torch.from_numpy(self.proto.rays(0)).to(dev), r1=torch.from_numpy(self.proto.rays(1)).to(dev),
+                             t=torch.zeros(self.n, dtype=torch.float64, device=dev))
+        d = self._dev
+        d["t"].fill_(self.frame_time(k))
+        rc = engine.lib().mskf_synth_render_device(d["traj"].data_ptr(), d["cams"].data_ptr(), d["r0"].data_ptr(), d["r1"].data_ptr(),
+                                                   d["t"].data_ptr(), out.data_ptr(), self.n, self.cfg.img_rows, self.cfg.img_cols,
+                                                   C.c_void_p(cuda_stream))
+        if rc != 0:
+            raise RuntimeError("device render failed")

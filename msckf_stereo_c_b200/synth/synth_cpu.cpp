@@ -137,6 +137,27 @@ void synth_render(const synth_ctx *c, double t, int cam, uint8_t *out, int n_thr
     }
 }
 
+// ---- fleet helpers: many trajectories sharing one calibration (bench.py) ------------------
+int synth_traj_size() { return (int)sizeof(SynthTraj); }
+int synth_cam_size() { return (int)sizeof(SynthCam); }
+void synth_make_trajs(const uint32_t *seeds, int n, double t0, SynthTraj *out) {
+    for (int i = 0; i < n; ++i) synth_make_traj(&out[i], seeds[i], t0);
+}
+// IMU rows j0..j1-1 of every trajectory, rows {t, w, a} as synth_get_imu makes them; out [n][j1-j0][7]
+void synth_imu_block(const SynthTraj *trajs, int n, int j0, int j1, double imu_dt, double noise_gyro, double noise_acc,
+                     double *out) {
+    synth_ctx tmp;
+    for (int s = 0; s < n; ++s) {
+        tmp.traj = trajs[s];
+        for (int j = j0; j < j1; ++j) {
+            double *o = out + ((size_t)s * (j1 - j0) + (j - j0)) * 7;
+            o[0] = trajs[s].t0 + j * imu_dt;
+            synth_get_imu(&tmp, o[0], (uint32_t)j, noise_gyro, noise_acc, o + 1, o + 4);
+        }
+    }
+}
+void synth_traj_pose(const SynthTraj *traj, double t, double R[9], double p[3]) { synth_pose(traj, t, R, p); }
+
 const float *synth_rays(const synth_ctx *c, int cam) { return c->rays[cam].data(); }
 const SynthTraj *synth_traj(const synth_ctx *c) { return &c->traj; }
 const SynthCam *synth_cam(const synth_ctx *c, int cam) { return &c->cam[cam]; }
