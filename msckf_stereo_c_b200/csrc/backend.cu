@@ -132,6 +132,7 @@ struct BeBuf {
     double *rblk;      // [S][rcap]
     double *Hst;       // [S][hst_cap]
     double *rst;       // [S][hst_rows]
+    int *rst_j0;       // [S][hst_rows] first nonzero column of each stacked row
     double *Tm;        // [S][KC*KC]
     double *rt;        // [S][KC]
     double *PHt;       // [S][LD*KC]
@@ -1534,9 +1535,12 @@ __global__ void __launch_bounds__(BE_THREADS) be_stack_kernel(BeConst bc, BeBuf 
                 break;
             }
         }
+        // active camera columns in ascending state id: a feature lost now was seen by the most recent
+        // states, so its rows are zero left of a late column and the QR can start there
         int k = 0;
-        for (int c = 0; c < bc.NS; ++c) {
-            s_colpos[c] = -1;
+        for (int c = 0; c < bc.NS; ++c) s_colpos[c] = -1;
+        for (int i = 0; i < st.n_cam; ++i) {
+            const int c = st.order[i];
             if (used & (1u << c)) {
                 st.u_slots[k] = c;
                 s_colpos[c] = k++;
@@ -1577,7 +1581,12 @@ __global__ void __launch_bounds__(BE_THREADS) be_stack_kernel(BeConst bc, BeBuf 
             int col = 6 * s_colpos[os[c / 6]] + (c % 6);
             Hst[(size_t)(so + r) * k + col] = Hp[e];
         }
-        for (int r = lane; r < rows; r += 32) rst[so + r] = rp[r];
+        int j0 = 6 * s_colpos[os[0]];
+        for (int a = 1; a < M; ++a) j0 = min(j0, 6 * s_colpos[os[a]]);
+        for (int r = lane; r < rows; r += 32) {
+            rst[so + r] = rp[r];
+            bb.rst_j0[(size_t)s * bc.hst_rows + so + r] = j0;
+        }
     }
     // the processed features leave the map (msckf_vio.cpp:1021-1023)
     if (phase == 0) {
@@ -1591,7 +1600,7 @@ __global__ void __launch_bounds__(BE_THREADS) be_stack_kernel(BeConst bc, BeBuf 
 // time into an upper-triangular factor held in shared memory (packed, with Q^T r as an extra
 // column).  If m <= k the system is used as it is.
 // ======================================================================================
-#define QR_B 16
+#define QR_B 32
 __global__ void __launch_bounds__(BE_THREADS) be_qr_kernel(BeConst bc, BeBuf bb) {
     const int s = blockIdx.x;
     const BeStep sp = bb.step[s];
@@ -1600,6 +1609,7 @@ __global__ void __launch_bounds__(BE_THREADS) be_qr_kernel(BeConst bc, BeBuf bb)
     if (!st.do_update) return;
     const int m = st.m, k = st.k, KC = bc.KC;
     const double *Hst = bb.Hst + (size_t)s * bc.hst_cap, *rst = bb.rst + (size_t)s * bc.hst_rows;
+    const int *rj0 = bb.rst_j0 + (size_t)s * bc.hst_rows;
     double *Tm = bb.Tm + (size_t)s * KC * KC, *rt = bb.rt + (size_t)s * KC;
     if (threadIdx.x == 0) {
         // algorithmic flops of this stream's update (dense-equivalent over the active columns)
@@ -1618,14 +1628,19 @@ __global__ void __launch_bounds__(BE_THREADS) be_qr_kernel(BeConst bc, BeBuf bb)
         if (threadIdx.x == 0) st.mt = m;
         return;
     }
+    // Rows are folded QR_B at a time into the packed upper-triangular factor R (row j holds columns
+    // j..k, column k = Q^T r).  Column c of the row block is owned by the thread pair (2c, 2c+1): each
+    // half holds 16 of the 32 rows, partial dot products are combined with one shuffle.
     extern __shared__ unsigned char be_smem[];
     const int kw = k + 1;
-    double *R = (double *)be_smem;                          // packed upper: row j holds columns j..k
-    double *B = R + (size_t)(KC + 1) * (KC + 2) / 2;        // [QR_B][kw]
+    double *R = (double *)be_smem;
+    double *B = R + (size_t)(KC + 1) * (KC + 2) / 2;  // [QR_B][kw]
     __shared__ double vb[QR_B];
     __shared__ double s_tau, s_beta;
+    __shared__ int s_j0;
     auto roff = [&](int j) { return j * kw - (j * (j - 1)) / 2 - j; };  // R[j][c] at roff(j) + c
     for (int e = threadIdx.x; e < (kw * (kw + 1)) / 2; e += BE_THREADS) R[e] = 0.0;
+    const int half = threadIdx.x & 1, cpair = threadIdx.x >> 1;  // 128 column pairs per pass
     for (int r0 = 0; r0 < m; r0 += QR_B) {
         const int nb = min(QR_B, m - r0);
         __syncthreads();
@@ -1635,11 +1650,17 @@ __global__ void __launch_bounds__(BE_THREADS) be_qr_kernel(BeConst bc, BeBuf bb)
             if (i < nb) v = c < k ? Hst[(size_t)(r0 + i) * k + c] : rst[r0 + i];
             B[e] = v;
         }
+        if (threadIdx.x < 32) {
+            int j0 = threadIdx.x < nb ? rj0[r0 + threadIdx.x] : k;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) j0 = min(j0, __shfl_xor_sync(0xffffffffu, j0, o));
+            if (threadIdx.x == 0) s_j0 = j0;
+        }
         __syncthreads();
-        for (int j = 0; j < k; ++j) {
+        for (int j = s_j0; j < k; ++j) {
             if (threadIdx.x < 32) {
                 const int lane = threadIdx.x;
-                double x = lane < QR_B ? B[lane * kw + j] : 0.0;
+                double x = B[lane * kw + j];
                 double xn = warp_sum_d(x * x);
                 const double alpha = R[roff(j) + j];
                 double tj = 0.0, beta = alpha, scale = 0.0;
@@ -1648,7 +1669,7 @@ __global__ void __launch_bounds__(BE_THREADS) be_qr_kernel(BeConst bc, BeBuf bb)
                     tj = (beta - alpha) / beta;
                     scale = 1.0 / (alpha - beta);
                 }
-                if (lane < QR_B) vb[lane] = x * scale;
+                vb[lane] = x * scale;
                 if (lane == 0) {
                     s_tau = tj;
                     s_beta = beta;
@@ -1657,17 +1678,27 @@ __global__ void __launch_bounds__(BE_THREADS) be_qr_kernel(BeConst bc, BeBuf bb)
             __syncthreads();
             const double tj = s_tau;
             if (tj != 0.0) {
-                for (int c = j + 1 + threadIdx.x; c < kw; c += BE_THREADS) {
-                    double s0 = R[roff(j) + c], s1 = 0.0;
+                for (int c0 = j + 1; c0 < kw; c0 += BE_THREADS / 2) {  // warp-uniform trip count (shuffle inside)
+                    const int c = c0 + cpair;
+                    const bool act = c < kw;
+                    double s0 = 0.0, s1 = 0.0;
+                    double bv[QR_B / 2];
 #pragma unroll
-                    for (int i = 0; i < QR_B; i += 2) {
-                        s0 += vb[i] * B[i * kw + c];
-                        s1 += vb[i + 1] * B[(i + 1) * kw + c];
+                    for (int i = 0; i < QR_B / 2; ++i) bv[i] = act ? B[(2 * i + half) * kw + c] : 0.0;
+#pragma unroll
+                    for (int i = 0; i < QR_B / 2; i += 2) {
+                        s0 += vb[2 * i + half] * bv[i];
+                        s1 += vb[2 * (i + 1) + half] * bv[i + 1];
                     }
-                    double sacc = (s0 + s1) * tj;
-                    R[roff(j) + c] -= sacc;
+                    double sacc = s0 + s1;
+                    sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                    if (act) {
+                        const double rjc = R[roff(j) + c];
+                        sacc = (sacc + rjc) * tj;
+                        if (half == 0) R[roff(j) + c] = rjc - sacc;
 #pragma unroll
-                    for (int i = 0; i < QR_B; ++i) B[i * kw + c] -= sacc * vb[i];
+                        for (int i = 0; i < QR_B / 2; ++i) B[(2 * i + half) * kw + c] = bv[i] - sacc * vb[2 * i + half];
+                    }
                 }
                 if (threadIdx.x == 0) R[roff(j) + j] = s_beta;
             }
@@ -2089,7 +2120,7 @@ int be_create(mskf_handle *h) {
     A(bb.l_slot, S * bc.ML); A(bb.l_ok, S * bc.ML); A(bb.l_pass, S * bc.ML); A(bb.l_M, S * bc.ML);
     A(bb.l_eoff, S * bc.ML); A(bb.l_roff, S * bc.ML); A(bb.l_soff, S * bc.ML); A(bb.l_oslots, S * bc.ML * NSM);
     A(bb.Hblk, S * bc.ecap); A(bb.HPblk, S * bc.ecap); A(bb.rblk, S * bc.rcap);
-    A(bb.Hst, S * bc.hst_cap); A(bb.rst, S * bc.hst_rows);
+    A(bb.Hst, S * bc.hst_cap); A(bb.rst, S * bc.hst_rows); A(bb.rst_j0, S * bc.hst_rows);
     A(bb.Tm, S * bc.KC * bc.KC); A(bb.rt, S * bc.KC); A(bb.PHt, S * bc.LD * bc.KC); A(bb.Sm, S * bc.KC * bc.KC);
     A(bb.Linv, S * bc.KC * bc.KC); A(bb.W, S * bc.LD * bc.KC); A(bb.yv, S * bc.KC); A(bb.dxv, S * bc.LD);
 #undef A

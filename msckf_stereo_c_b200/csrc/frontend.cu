@@ -544,9 +544,9 @@ __global__ void __launch_bounds__(FE_THREADS) fe_after_stereo(FeConst fc, FeBuff
     const int s = blockIdx.x;
     const FeStep st = fb.step[s];
     if (!st.active) return;
-    __shared__ int s_warp[FE_THREADS / 32];
     __shared__ int s_cnt[FE_MAX_CELLS], s_start[FE_MAX_CELLS + 1];
-    extern __shared__ int s_pos[];
+    extern __shared__ int s_dyn[];
+    uint8_t *s_code = (uint8_t *)s_dyn;  // [max_f] grid cell of each survivor, 255 = dropped
     const size_t go = (size_t)s * fc.max_f, ko = (size_t)s * fc.cap_k;
     const int gc = fb.gslot[s] ^ 1;  // curr grid buffer
     // reset the detector tables of this stream
@@ -556,84 +556,117 @@ __global__ void __launch_bounds__(FE_THREADS) fe_after_stereo(FeConst fc, FeBuff
     }
     const int n = st.is_first ? 0 : fb.k_n[s];
     const bool tracked_any = !st.is_first && fb.info[s].before_tracking > 0;
-    uint8_t *flag = fb.k_status + ko;
+    const uint8_t *flag = fb.k_status + ko;
     for (int i = threadIdx.x; i < n; i += FE_THREADS) {
+        uint8_t code = 255;
         if (flag[i]) {
-            float2 c1 = fb.k_b[ko + i];
-            if (!in_image(fc, c1) || !epipolar_ok(fc, fb.k_a[ko + i], c1)) flag[i] = 0;
+            float2 c0 = fb.k_a[ko + i], c1 = fb.k_b[ko + i];
+            if (in_image(fc, c1) && epipolar_ok(fc, c0, c1)) code = (uint8_t)grid_code(fc, c0);
         }
+        s_code[i] = code;
     }
-    __syncthreads();
-    int m = block_compact_positions(flag, n, s_pos, s_warp);
-    // stable counting sort of the survivors by grid cell = publish order of the std::map
     for (int c = threadIdx.x; c < fc.n_cells_all; c += FE_THREADS) s_cnt[c] = 0;
     __syncthreads();
+    // stable counting sort by grid cell = publish order of the std::map; one warp per cell
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = warp; c < fc.n_cells_all; c += FE_THREADS / 32) {
+        int cnt = 0;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            int i = i0 + lane;
+            cnt += __popc(__ballot_sync(0xffffffffu, i < n && s_code[i] == c));
+        }
+        if (lane == 0) s_cnt[c] = cnt;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        for (int i = 0; i < n; ++i)
-            if (flag[i]) s_cnt[grid_code(fc, fb.k_a[ko + i])]++;
         int acc = 0;
         for (int c = 0; c < fc.n_cells_all; ++c) {
             s_start[c] = acc;
             acc += s_cnt[c];
-            s_cnt[c] = 0;
         }
         s_start[fc.n_cells_all] = acc;
-        for (int i = 0; i < n; ++i) {
-            if (!flag[i]) continue;
-            float2 c0 = fb.k_a[ko + i];
-            int code = grid_code(fc, c0);
-            int d = s_start[code] + s_cnt[code]++;
-            fb.g_id[gc][go + d] = fb.t_id[go + i];
-            fb.g_life[gc][go + d] = fb.t_life[go + i] + 1;
-            fb.g_resp[gc][go + d] = 0.0f;
-            fb.g_cam0[gc][go + d] = c0;
-            fb.g_cam1[gc][go + d] = fb.k_b[ko + i];
-            fb.g_cell[gc][go + d] = code;
-            // CornerDetector::set_grid_position on the truncated position (:634-647)
-            int x = (int)c0.x, y = (int)c0.y;
-            if (x >= 0 && y >= 0 && x < fc.cols && y < fc.rows)
-                fb.det_occ[(size_t)s * fc.det_cells + (y / fc.det_cell_h) * fc.det_cols + (x / fc.det_cell_w)] = 1;
-        }
-        fb.g_n[gc][s] = m;
+        fb.g_n[gc][s] = acc;
         if (tracked_any) {
-            fb.info[s].after_matching = m;
-            fb.info[s].after_ransac = m;
+            fb.info[s].after_matching = acc;
+            fb.info[s].after_ransac = acc;
+        }
+    }
+    __syncthreads();
+    for (int c = warp; c < fc.n_cells_all; c += FE_THREADS / 32) {
+        int off = s_start[c];
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            int i = i0 + lane;
+            bool mine = i < n && s_code[i] == c;
+            unsigned bal = __ballot_sync(0xffffffffu, mine);
+            if (mine) {
+                int d = off + __popc(bal & ((1u << lane) - 1));
+                float2 c0 = fb.k_a[ko + i];
+                fb.g_id[gc][go + d] = fb.t_id[go + i];
+                fb.g_life[gc][go + d] = fb.t_life[go + i] + 1;
+                fb.g_resp[gc][go + d] = 0.0f;
+                fb.g_cam0[gc][go + d] = c0;
+                fb.g_cam1[gc][go + d] = fb.k_b[ko + i];
+                fb.g_cell[gc][go + d] = c;
+                // CornerDetector::set_grid_position on the truncated position (:634-647)
+                int x = (int)c0.x, y = (int)c0.y;
+                if (x >= 0 && y >= 0 && x < fc.cols && y < fc.rows)
+                    fb.det_occ[(size_t)s * fc.det_cells + (y / fc.det_cell_h) * fc.det_cols + (x / fc.det_cell_w)] = 1;
+            }
+            off += __popc(bal);
         }
     }
 }
 
 // detector output -> candidate list for the stereo match of new features
-__global__ void __launch_bounds__(FE_THREADS) fe_sieve(FeConst fc, FeBuffers fb) {
+__global__ void __launch_bounds__(FE_THREADS) fe_sieve(FeConst fc, FeBuffers fb, int members_cap) {
     const int s = blockIdx.x;
     const FeStep st = fb.step[s];
     if (!st.active) return;
-    __shared__ int s_n, s_cell_n[FE_MAX_CELLS], s_cell_off[FE_MAX_CELLS + 1];
-    extern __shared__ int s_sel[];  // [n_cells][grid_max] selected detect indices
+    __shared__ int s_warp[FE_THREADS / 32];
+    __shared__ int s_cell_n[FE_MAX_CELLS], s_cell_off[FE_MAX_CELLS + 1];
+    __shared__ int s_base;
+    extern __shared__ int s_dyn[];
+    // dynamic: resp[det_cells] | xy[det_cells] (packed y << 16 | x) | sel[n_cells][grid_max] | mem[4][members_cap] | code[det_cells]
+    float *s_resp = (float *)s_dyn;
+    unsigned *s_xy = (unsigned *)(s_resp + fc.det_cells);
+    int *s_sel = (int *)(s_xy + fc.det_cells);
+    int *s_mem = s_sel + fc.n_cells * fc.grid_max;
+    uint8_t *s_code = (uint8_t *)(s_mem + (FE_THREADS / 32) * members_cap);
     const size_t ko = (size_t)s * fc.cap_k, dofs = (size_t)s * fc.det_cells;
-    // gather detections in fine-cell order (thread 0: <= det_cells entries)
-    // k_a temporarily holds the detect-order points in its upper half is not possible
-    // (cap_k = det_cells), so detections are decoded on the fly from det_best.
-    if (threadIdx.x == 0) {
-        int n = 0;
-        for (int k = 0; k < fc.det_cells; ++k) {
-            unsigned long long key = fb.det_best[dofs + k];
-            float resp = __uint_as_float((unsigned)(key >> 32));
-            if (key != 0ull && (double)resp > fc.detection_threshold) {
-                fb.nf_resp[dofs + n] = resp;
-                // compact the keys in place so that entry n describes detection n
-                fb.det_best[dofs + n] = key;
-                ++n;
-            }
-        }
-        s_n = n;
-        fb.nf_n[s] = n;
-    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // compact the per-fine-cell winners (cell-major = detect order) into shared memory
+    if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
-    const int n = s_n;
-    auto det_pt = [&](int i) {
-        unsigned ridx = 0xffffffffu - (unsigned)(fb.det_best[dofs + i] & 0xffffffffull);
-        return make_float2((float)(ridx % (unsigned)fc.cols), (float)(ridx / (unsigned)fc.cols));
-    };
+    for (int start = 0; start < fc.det_cells; start += FE_THREADS) {
+        int k = start + threadIdx.x;
+        unsigned long long key = k < fc.det_cells ? fb.det_best[dofs + k] : 0ull;
+        float resp = __uint_as_float((unsigned)(key >> 32));
+        int f = (key != 0ull && (double)resp > fc.detection_threshold) ? 1 : 0;
+        unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        if (f) {
+            int d = off + __popc(bal & ((1u << lane) - 1));
+            unsigned ridx = 0xffffffffu - (unsigned)(key & 0xffffffffull);
+            unsigned x = ridx % (unsigned)fc.cols, y = ridx / (unsigned)fc.cols;
+            s_resp[d] = resp;
+            s_xy[d] = (y << 16) | x;
+            s_code[d] = (uint8_t)grid_code(fc, make_float2((float)x, (float)y));
+            fb.nf_resp[dofs + d] = resp;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < FE_THREADS / 32; ++w) tot += s_warp[w];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+    const int n = s_base;
+    if (threadIdx.x == 0) fb.nf_n[s] = n;
+    auto det_pt = [&](int i) { return make_float2((float)(s_xy[i] & 0xffffu), (float)(s_xy[i] >> 16)); };
     if (st.is_first) {
         for (int i = threadIdx.x; i < n; i += FE_THREADS) {
             float2 p = det_pt(i);
@@ -646,36 +679,55 @@ __global__ void __launch_bounds__(FE_THREADS) fe_sieve(FeConst fc, FeBuffers fb)
         }
         return;
     }
-    // one thread per coarse cell: members in detect order, keep the grid_max best (stable)
-    for (int c = threadIdx.x; c < fc.n_cells; c += FE_THREADS) {
+    // one warp per coarse cell: members in detect order; more than grid_max -> the grid_max best
+    // responses (stable: ties keep detect order), image_processor.cpp:668-677
+    int *mem = s_mem + warp * members_cap;
+    for (int c = warp; c < fc.n_cells; c += FE_THREADS / 32) {
         int cnt = 0;
-        for (int i = 0; i < n; ++i)
-            if (grid_code(fc, det_pt(i)) == c) ++cnt;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            int i = i0 + lane;
+            bool mine = i < n && s_code[i] == c;
+            unsigned bal = __ballot_sync(0xffffffffu, mine);
+            if (mine) {
+                int d = cnt + __popc(bal & ((1u << lane) - 1));
+                if (d < members_cap) mem[d] = i;
+            }
+            cnt += __popc(bal);
+        }
+        cnt = min(cnt, members_cap);
+        __syncwarp();
         int *sel = s_sel + c * fc.grid_max;
         int kept = 0;
         if (cnt <= fc.grid_max) {
-            for (int i = 0; i < n; ++i)
-                if (grid_code(fc, det_pt(i)) == c) sel[kept++] = i;
+            for (int d = lane; d < cnt; d += 32) sel[d] = mem[d];
+            kept = cnt;
         } else {
-            // stable sort by response desc, truncated: repeated selection of the best not yet taken
             float last_r = 3.0e38f;
             int last_i = -1;
             for (int k = 0; k < fc.grid_max; ++k) {
-                int bi = -1;
+                // best not yet taken: max response, ties -> smallest index
                 float br = -1.0f;
-                for (int i = 0; i < n; ++i) {
-                    if (grid_code(fc, det_pt(i)) != c) continue;
-                    float r = fb.nf_resp[dofs + i];
+                int bi = 0x7fffffff;
+                for (int d = lane; d < cnt; d += 32) {
+                    int i = mem[d];
+                    float r = s_resp[i];
                     bool after_last = (r < last_r) || (r == last_r && i > last_i);
-                    if (!after_last) continue;
-                    if (bi < 0 || r > br) { bi = i; br = r; }
+                    if (after_last && (r > br || (r == br && i < bi))) { br = r; bi = i; }
                 }
-                sel[kept++] = bi;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    float r2 = __shfl_xor_sync(0xffffffffu, br, o);
+                    int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (r2 > br || (r2 == br && i2 < bi)) { br = r2; bi = i2; }
+                }
+                if (lane == 0) sel[k] = bi;
                 last_r = br;
                 last_i = bi;
             }
+            kept = fc.grid_max;
         }
-        s_cell_n[c] = kept;
+        if (lane == 0) s_cell_n[c] = kept;
+        __syncwarp();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -689,13 +741,13 @@ __global__ void __launch_bounds__(FE_THREADS) fe_sieve(FeConst fc, FeBuffers fb)
         fb.work[(size_t)s * MSKF_PROF_TAGS + PK_KLT_NEW] += (double)acc * klt_bytes_per_feature(fc);
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < fc.n_cells; c += FE_THREADS) {
-        for (int k = 0; k < s_cell_n[c]; ++k) {
-            float2 p = det_pt(s_sel[c * fc.grid_max + k]);
-            int d = s_cell_off[c] + k;
-            fb.k_a[ko + d] = p;
-            fb.k_b[ko + d] = distort_pt(fc, 1, undistort_pt(fc, 0, p, fc.R01));
-        }
+    for (int e = threadIdx.x; e < fc.n_cells * fc.grid_max; e += FE_THREADS) {
+        int c = e / fc.grid_max, k = e - c * fc.grid_max;
+        if (k >= s_cell_n[c]) continue;
+        float2 p = det_pt(s_sel[e]);
+        int d = s_cell_off[c] + k;
+        fb.k_a[ko + d] = p;
+        fb.k_b[ko + d] = distort_pt(fc, 1, undistort_pt(fc, 0, p, fc.R01));
     }
 }
 
@@ -706,6 +758,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_finish(FeConst fc, FeBuffers fb
     if (!st.active) return;
     __shared__ int s_warp[FE_THREADS / 32];
     __shared__ int s_m, s_add[FE_MAX_CELLS], s_keep[FE_MAX_CELLS], s_idbase[FE_MAX_CELLS + 1], s_outoff[FE_MAX_CELLS + 1];
+    __shared__ unsigned long long s_base_id;
     extern __shared__ int s_dyn[];
     const size_t go = (size_t)s * fc.max_f, ko = (size_t)s * fc.cap_k, dofs = (size_t)s * fc.det_cells;
     const int gc = fb.gslot[s] ^ 1, gp = fb.gslot[s];
@@ -713,6 +766,10 @@ __global__ void __launch_bounds__(FE_THREADS) fe_finish(FeConst fc, FeBuffers fb
     int *s_pos = s_dyn;                                  // [cap_k]
     int *s_addsel = s_dyn + fc.cap_k;                    // [n_cells][grid_min] inlier indices to add
     int *s_final = s_addsel + fc.n_cells * fc.grid_min;  // [n_cells_all][grid_max] encoded final members
+    float *s_iresp = (float *)(s_final + fc.n_cells_all * fc.grid_max);  // [cap_k] inlier responses
+    int *s_glife = (int *)(s_iresp + fc.cap_k);          // [max_f] lifetimes of the tracked grid entries
+    uint8_t *s_icode = (uint8_t *)(s_glife + fc.max_f);  // [cap_k] inlier cells
+    uint8_t *s_gcell = s_icode + fc.cap_k;               // [max_f] cells of the tracked grid entries
     uint8_t *flag = fb.k_status + ko;
     for (int i = threadIdx.x; i < n; i += FE_THREADS) {
         if (flag[i]) {
@@ -722,7 +779,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_finish(FeConst fc, FeBuffers fb
     }
     __syncthreads();
     int m = block_compact_positions(flag, n, s_pos, s_warp);
-    // compact inliers in place (dst <= src): cam0 -> k_a, cam1 -> k_b, response -> nf_resp'
+    // compact inliers in place (dst <= src): cam0 -> k_a, cam1 -> k_b
     // response_inliers[j] = new_features_responses[i] with i the POST-sieve index (:698)
     float *resp_in = fb.in_resp + ko;
     for (int start = 0; start < n; start += FE_THREADS) {
@@ -741,17 +798,22 @@ __global__ void __launch_bounds__(FE_THREADS) fe_finish(FeConst fc, FeBuffers fb
             fb.k_a[ko + d] = a;
             fb.k_b[ko + d] = b;
             resp_in[d] = r;
+            s_iresp[d] = r;
+            s_icode[d] = (uint8_t)grid_code(fc, a);
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) s_m = m;
-    __syncthreads();
     const int ncur = st.is_first ? 0 : fb.g_n[gc][s];
+    for (int i = threadIdx.x; i < ncur; i += FE_THREADS) {
+        s_gcell[i] = (uint8_t)fb.g_cell[gc][go + i];
+        s_glife[i] = fb.g_life[gc][go + i];
+    }
+    __syncthreads();
     // one thread per cell: choose the new features to add (best responses, stable)
     for (int c = threadIdx.x; c < fc.n_cells_all; c += FE_THREADS) {
         int cur = 0;
         for (int i = 0; i < ncur; ++i)
-            if (fb.g_cell[gc][go + i] == c) ++cur;
+            if (s_gcell[i] == c) ++cur;
         int add = 0;
         if (c < fc.n_cells && cur < fc.grid_min) {
             int vacancy = fc.grid_min - cur;
@@ -761,8 +823,8 @@ __global__ void __launch_bounds__(FE_THREADS) fe_finish(FeConst fc, FeBuffers fb
                 int bi = -1;
                 float br = -1.0f;
                 for (int i = 0; i < m; ++i) {
-                    if (grid_code(fc, fb.k_a[ko + i]) != c) continue;
-                    float r = resp_in[i];
+                    if (s_icode[i] != c) continue;
+                    float r = s_iresp[i];
                     bool after_last = (r < last_r) || (r == last_r && i > last_i);
                     if (!after_last) continue;
                     if (bi < 0 || r > br) { bi = i; br = r; }
@@ -781,15 +843,15 @@ __global__ void __launch_bounds__(FE_THREADS) fe_finish(FeConst fc, FeBuffers fb
         int *fin = s_final + c * fc.grid_max;
         if (total <= fc.grid_max) {
             for (int i = 0; i < ncur; ++i)
-                if (fb.g_cell[gc][go + i] == c) fin[keep++] = i;
+                if (s_gcell[i] == c) fin[keep++] = i;
             for (int k = 0; k < add; ++k) fin[keep++] = -1 - k;
         } else {
             int last_l = 0x7fffffff, last_o = -1;
             for (int k = 0; k < fc.grid_max; ++k) {
                 int bo = -1, bl = -1, benc = 0, o = 0;
                 for (int i = 0; i < ncur; ++i) {
-                    if (fb.g_cell[gc][go + i] != c) continue;
-                    int l = fb.g_life[gc][go + i];
+                    if (s_gcell[i] != c) continue;
+                    int l = s_glife[i];
                     bool after_last = (l < last_l) || (l == last_l && o > last_o);
                     if (after_last && (bo < 0 || l > bl)) { bo = o; bl = l; benc = i; }
                     ++o;
@@ -817,57 +879,53 @@ __global__ void __launch_bounds__(FE_THREADS) fe_finish(FeConst fc, FeBuffers fb
             acc_out += s_keep[c];
         }
         s_outoff[fc.n_cells_all] = acc_out;
+        s_base_id = base;
         fb.next_id[s] = base + (unsigned long long)acc_id;
-        s_idbase[fc.n_cells_all] = (int)0;
         fb.g_n[gp][s] = acc_out;  // the finished grid goes to the buffer that was "prev"
         fb.msg_n[s] = acc_out;
         s_m = acc_out;
     }
     __syncthreads();
-    const unsigned long long id0 = fb.next_id[s];  // already advanced; recompute base below
+    const unsigned long long base = s_base_id;
     // write the finished grid (publish order) into buffer gp and the measurement message
-    for (int c = threadIdx.x; c < fc.n_cells_all; c += FE_THREADS) {
-        unsigned long long total_added = 0;
-        for (int cc = 0; cc < fc.n_cells_all; ++cc) total_added += (unsigned long long)s_add[cc];
-        const unsigned long long base = id0 - total_added;
-        for (int k = 0; k < s_keep[c]; ++k) {
-            int enc = s_final[c * fc.grid_max + k];
-            int d = s_outoff[c] + k;
-            unsigned long long id;
-            float resp;
-            int life;
-            float2 c0, c1;
-            if (enc >= 0) {
-                id = fb.g_id[gc][go + enc];
-                resp = fb.g_resp[gc][go + enc];
-                life = fb.g_life[gc][go + enc];
-                c0 = fb.g_cam0[gc][go + enc];
-                c1 = fb.g_cam1[gc][go + enc];
-            } else {
-                int a = -1 - enc;
-                int src = s_addsel[c * fc.grid_min + a];
-                id = base + (unsigned long long)(s_idbase[c] + a);
-                resp = resp_in[src];
-                life = 1;
-                c0 = fb.k_a[ko + src];
-                c1 = fb.k_b[ko + src];
-            }
-            fb.g_id[gp][go + d] = id;
-            fb.g_resp[gp][go + d] = resp;
-            fb.g_life[gp][go + d] = life;
-            fb.g_cam0[gp][go + d] = c0;
-            fb.g_cam1[gp][go + d] = c1;
-            fb.g_cell[gp][go + d] = c;
-            float2 u0 = undistort_pt(fc, 0, c0, nullptr), u1 = undistort_pt(fc, 1, c1, nullptr);
-            mskf_feature f;
-            f.id = (uint32_t)id;
-            f.pad = 0;
-            f.u0 = (double)u0.x; f.v0 = (double)u0.y; f.u1 = (double)u1.x; f.v1 = (double)u1.y;
-            fb.msg[go + d] = f;
-            fb.stale[go + d] = f;
+    for (int e = threadIdx.x; e < fc.n_cells_all * fc.grid_max; e += FE_THREADS) {
+        const int c = e / fc.grid_max, k = e - c * fc.grid_max;
+        if (k >= s_keep[c]) continue;
+        int enc = s_final[e];
+        int d = s_outoff[c] + k;
+        unsigned long long id;
+        float resp;
+        int life;
+        float2 c0, c1;
+        if (enc >= 0) {
+            id = fb.g_id[gc][go + enc];
+            resp = fb.g_resp[gc][go + enc];
+            life = s_glife[enc];
+            c0 = fb.g_cam0[gc][go + enc];
+            c1 = fb.g_cam1[gc][go + enc];
+        } else {
+            int a = -1 - enc;
+            int src = s_addsel[c * fc.grid_min + a];
+            id = base + (unsigned long long)(s_idbase[c] + a);
+            resp = s_iresp[src];
+            life = 1;
+            c0 = fb.k_a[ko + src];
+            c1 = fb.k_b[ko + src];
         }
+        fb.g_id[gp][go + d] = id;
+        fb.g_resp[gp][go + d] = resp;
+        fb.g_life[gp][go + d] = life;
+        fb.g_cam0[gp][go + d] = c0;
+        fb.g_cam1[gp][go + d] = c1;
+        fb.g_cell[gp][go + d] = c;
+        float2 u0 = undistort_pt(fc, 0, c0, nullptr), u1 = undistort_pt(fc, 1, c1, nullptr);
+        mskf_feature f;
+        f.id = (uint32_t)id;
+        f.pad = 0;
+        f.u0 = (double)u0.x; f.v0 = (double)u0.y; f.u1 = (double)u1.x; f.v1 = (double)u1.y;
+        fb.msg[go + d] = f;
+        fb.stale[go + d] = f;
     }
-    __syncthreads();
     if (threadIdx.x == 0) {
         int nout = s_m;
         if (fc.compat_stale) {
@@ -885,6 +943,15 @@ __global__ void __launch_bounds__(FE_THREADS) fe_finish(FeConst fc, FeBuffers fb
 }  // namespace mskf
 
 using namespace mskf;
+
+static int fe_members_cap(const FeConst &fc) { return (fc.grid_w / fc.det_cell_w + 2) * (fc.grid_h / fc.det_cell_h + 2); }
+static size_t fe_sieve_smem(const FeConst &fc) {
+    return (size_t)fc.det_cells * 9 + 16 + sizeof(int) * ((size_t)fc.n_cells * fc.grid_max + (FE_THREADS / 32) * fe_members_cap(fc));
+}
+static size_t fe_finish_smem(const FeConst &fc) {
+    return ((size_t)fc.cap_k + (size_t)fc.n_cells * fc.grid_min + (size_t)fc.n_cells_all * fc.grid_max) * sizeof(int) +
+           (size_t)fc.cap_k * 5 + (size_t)fc.max_f * 5 + 16;
+}
 
 int fe_create(mskf_handle *h) {
     const mskf_config &c = h->cfg;
@@ -999,6 +1066,12 @@ int fe_create(mskf_handle *h) {
     A(fb.info, S);
 #undef A
     fb.work = h->d_work;
+    if (fe_sieve_smem(fc) > 200 * 1024 || fe_finish_smem(fc) > 200 * 1024) {
+        h->err = "detector grid / feature capacity too large for the bookkeeping kernels' shared memory";
+        return MSKF_ERR_ARG;
+    }
+    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(fe_sieve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_sieve_smem(fc)));
+    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(fe_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_finish_smem(fc)));
     return MSKF_OK;
 }
 
@@ -1030,18 +1103,18 @@ int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active) {
         MSKF_LAUNCH(h, PK_FE_BOOK, (fe_after_track<<<S, FE_THREADS, pos_smem, q>>>(fc, fb)));
         MSKF_LAUNCH(h, PK_KLT_STEREO, (klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 1)));
     }
-    MSKF_LAUNCH(h, PK_FE_BOOK, (fe_after_stereo<<<S, FE_THREADS, pos_smem, q>>>(fc, fb)));
+    MSKF_LAUNCH(h, PK_FE_BOOK, (fe_after_stereo<<<S, FE_THREADS, (size_t)fc.max_f + 16, q>>>(fc, fb)));
     {
         dim3 g((fc.cols + DT_W - 1) / DT_W, (fc.rows + DT_H - 1) / DT_H, S);
         MSKF_LAUNCH(h, PK_DETECT, (detect_kernel<<<g, 256, 0, q>>>(fc, fb)));
     }
-    MSKF_LAUNCH(h, PK_FE_BOOK, (fe_sieve<<<S, FE_THREADS, (size_t)fc.n_cells * fc.grid_max * sizeof(int), q>>>(fc, fb)));
+    MSKF_LAUNCH(h, PK_FE_BOOK, (fe_sieve<<<S, FE_THREADS, fe_sieve_smem(fc), q>>>(fc, fb, fe_members_cap(fc))));
     {
         int cap = any_first ? fc.det_cells : fc.n_cells * fc.grid_max;
         dim3 g((cap + KLT_WARPS - 1) / KLT_WARPS, S);
         MSKF_LAUNCH(h, PK_KLT_NEW, (klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 1)));
     }
-    size_t fin_smem = ((size_t)fc.cap_k + (size_t)fc.n_cells * fc.grid_min + (size_t)fc.n_cells_all * fc.grid_max) * sizeof(int);
+    const size_t fin_smem = fe_finish_smem(fc);
     MSKF_LAUNCH(h, PK_FE_BOOK, (fe_finish<<<S, FE_THREADS, fin_smem, q>>>(fc, fb)));
     MSKF_CUDA_CHECK(h, cudaGetLastError());
     return MSKF_OK;
