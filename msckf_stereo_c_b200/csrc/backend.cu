@@ -128,7 +128,7 @@ struct BeBuf {
     uint8_t *l_ok, *l_pass;  // [S][ML]
     int *l_M, *l_eoff, *l_roff, *l_soff;  // [S][ML]
     uint8_t *l_oslots; // [S][ML][NSM]
-    double *Hblk, *HPblk;  // [S][ecap]
+    double *Hblk;      // [S][ecap] projected per-feature Jacobians (features that pass the gate)
     double *rblk;      // [S][rcap]
     double *Hst;       // [S][hst_cap]
     double *rst;       // [S][hst_rows]
@@ -1292,11 +1292,40 @@ __device__ void cta_cholesky(double *S, int n, int ld) {
     __syncthreads();
 }
 
+// In-place Cholesky of the sub-matrix [lo, hi) x [lo, hi) of a packed lower triangle in shared
+// memory (entry (i, j), j <= i, at i (i + 1) / 2 + j).  256 threads as a 16 x 16 tile grid.
+__device__ void packed_cholesky(double *G, int lo, int hi) {
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    for (int kk = lo; kk < hi; ++kk) {
+        const int kb = kk * (kk + 1) / 2;
+        __syncthreads();
+        const double d = sqrt(G[kb + kk]);
+        __syncthreads();
+        if (threadIdx.x == 0) G[kb + kk] = d;
+        const double inv = 1.0 / d;
+        for (int i = kk + 1 + threadIdx.x; i < hi; i += BE_THREADS) G[i * (i + 1) / 2 + kk] *= inv;
+        __syncthreads();
+        for (int i = kk + 1 + ty; i < hi; i += 16) {
+            const int ib = i * (i + 1) / 2;
+            const double lik = G[ib + kk];
+            for (int j = kk + 1 + tx; j <= i; j += 16) G[ib + j] -= lik * G[j * (j + 1) / 2 + kk];
+        }
+    }
+    __syncthreads();
+}
+
 // ======================================================================================
 // measurementJacobian + featureJacobian + gatingTest for one feature.  One CTA per listed
-// feature.  The stacked Jacobian of a feature is block diagonal over its observing cameras,
-// so it is kept compact: (4M) x (6M); the three Householder reflectors of H_f are applied
-// to it and to r, rows 3.. are the projected system.
+// feature.  The stacked Jacobian H_xj of a feature is block diagonal over its observing
+// cameras (one 4x6 block per camera), which the kernel exploits instead of forming the dense
+// products of the reference:
+//   * Q = H0 H1 H2 = I - V T V^T are the three Householder reflectors of H_fj (4M x 3); the
+//     projected Jacobian is H' = (Q^T H_xj)[3:, :], column c needs V^T x_c with x_c 4-sparse;
+//   * gating needs S = H' P H'^T + sigma^2 I = (Q^T G Q)[3:, 3:] + sigma^2 I with
+//     G = H_xj P_sub H_xj^T assembled from M(M+1)/2 blocks Hx_a P_ab Hx_b^T (4x4 each), and
+//     Q^T G Q = G - V A^T - A V^T + V C V^T,  A = (G V) T,  C = T^T (V^T G V) T.
+// G / S live in shared memory as a packed lower triangle; H' is written to the scratch only
+// for features that pass the gate.
 // ======================================================================================
 __global__ void __launch_bounds__(BE_THREADS) be_feature_jac_kernel(BeConst bc, BeBuf bb, int phase, int maxM) {
     const int s = blockIdx.y;
@@ -1305,194 +1334,305 @@ __global__ void __launch_bounds__(BE_THREADS) be_feature_jac_kernel(BeConst bc, 
     const BeState &st = bb.st[s];
     const int n_list = st.n_list;
     const size_t fo = (size_t)s * bc.MF, lo = (size_t)s * bc.ML;
-    for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
-    __syncthreads();
-    const int slot = bb.l_slot[lo + li], M = bb.l_M[lo + li];
-    const int R4 = 4 * M, C6 = 6 * M, rows = R4 - 3;
-    double *H = bb.Hblk + (size_t)s * bc.ecap + bb.l_eoff[lo + li];    // [R4][C6]
-    double *HP = bb.HPblk + (size_t)s * bc.ecap + bb.l_eoff[lo + li];  // [rows][C6]
-    double *rg = bb.rblk + (size_t)s * bc.rcap + bb.l_roff[lo + li];   // [R4]
     const double *P = bb.P + (size_t)s * bc.LD * bc.LD;
     const int LD = bc.LD;
 
     extern __shared__ unsigned char be_smem[];
-    const int maxR4 = 4 * maxM, maxRows = 4 * maxM - 3, sld = maxRows + 1;
-    double *Hf = (double *)be_smem;          // [maxR4][3]
-    double *rv = Hf + maxR4 * 3;             // [maxR4]
-    double *Ssm = rv + maxR4;                // [maxRows][sld]
-    GemmSmem &gs = *(GemmSmem *)(Ssm + maxRows * sld);
+    const int maxR4 = 4 * maxM;
+    double *G = (double *)be_smem;                       // packed lower [maxR4 (maxR4 + 1) / 2]
+    double *Hx = G + (size_t)maxR4 * (maxR4 + 1) / 2;    // [maxM][4][6]
+    double *Hf = Hx + maxM * 24;                         // [maxR4][3]   V below the diagonal after the QR
+    double *rv = Hf + maxR4 * 3;                         // [maxR4]
+    double *Y = rv + maxR4;                              // [maxR4][3]
+    double *Am = Y + maxR4 * 3;                          // [maxR4][3]
+    double *U = Am + maxR4 * 3;                          // [6 maxM][3]
     __shared__ int oslot[NSM];
-    __shared__ double tau[3];
+    __shared__ double tau[3], Tm[9], Cm[9], Zm[9], ur[3];
     __shared__ double s_gamma;
+    __shared__ int s_pass;
+    auto gix = [](int i, int j) { return i * (i + 1) / 2 + j; };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (threadIdx.x == 0) {
-        int m = 0;
-        if (phase == 0) {
-            const unsigned mask = bb.f_mask[fo + slot];
-            for (int i = 0; i < st.n_cam; ++i) {
-                int cs = st.order[i];
-                if (mask & (1u << cs)) oslot[m++] = cs;
+    for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
+        __syncthreads();
+        const int slot = bb.l_slot[lo + li], M = bb.l_M[lo + li];
+        const int R4 = 4 * M, C6 = 6 * M, rows = R4 - 3;
+        double *H = bb.Hblk + (size_t)s * bc.ecap + bb.l_eoff[lo + li];   // [R4][C6], rows 3.. used
+        double *rg = bb.rblk + (size_t)s * bc.rcap + bb.l_roff[lo + li];  // [R4]
+        if (threadIdx.x == 0) {
+            if (phase == 0) {
+                const unsigned mask = bb.f_mask[fo + slot];
+                int m = 0;
+                for (int i = 0; i < st.n_cam; ++i) {
+                    int cs = st.order[i];
+                    if (mask & (1u << cs)) oslot[m++] = cs;
+                }
+            } else {
+                oslot[0] = st.rm_slot[0];
+                oslot[1] = st.rm_slot[1];
+            }
+            for (int i = 0; i < M; ++i) bb.l_oslots[(lo + li) * NSM + i] = (uint8_t)oslot[i];
+        }
+        __syncthreads();
+        if (threadIdx.x < M) {
+            // measurementJacobian, msckf_vio.cpp:610-677
+            const int t = threadIdx.x, cs = oslot[t];
+            const BeCam &c = st.cam[cs];
+            const double *z = bb.f_obs + (((size_t)s * bc.MF + slot) * bc.NS + cs) * 4;
+            const double *pw = bb.f_pos + (fo + slot) * 3;
+            double Rw0[9], Rw1[9], t1w[3], tmp[3];
+            quat_to_rot(c.q, Rw0);
+            m3mul(bc.R01, Rw0, Rw1);
+            m3Tv(Rw1, bc.t01, tmp);
+            for (int i = 0; i < 3; ++i) t1w[i] = c.p[i] - tmp[i];
+            double d0[3] = {pw[0] - c.p[0], pw[1] - c.p[1], pw[2] - c.p[2]};
+            double d1[3] = {pw[0] - t1w[0], pw[1] - t1w[1], pw[2] - t1w[2]};
+            double p0[3], p1[3];
+            m3v(Rw0, d0, p0);
+            m3v(Rw1, d1, p1);
+            double dz0[4][3] = {{1 / p0[2], 0, -p0[0] / (p0[2] * p0[2])}, {0, 1 / p0[2], -p0[1] / (p0[2] * p0[2])}, {0, 0, 0}, {0, 0, 0}};
+            double dz1[4][3] = {{0, 0, 0}, {0, 0, 0}, {1 / p1[2], 0, -p1[0] / (p1[2] * p1[2])}, {0, 1 / p1[2], -p1[1] / (p1[2] * p1[2])}};
+            double sk0[9], R01sk[9];
+            skew3(p0, sk0);
+            m3mul(bc.R01, sk0, R01sk);
+            double Hxl[4][6];
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    double a = 0, b = 0;
+                    for (int k = 0; k < 3; ++k) {
+                        a += dz0[i][k] * sk0[k * 3 + j] + dz1[i][k] * R01sk[k * 3 + j];
+                        b += dz0[i][k] * (-Rw0[k * 3 + j]) + dz1[i][k] * (-Rw1[k * 3 + j]);
+                    }
+                    Hxl[i][j] = a;
+                    Hxl[i][3 + j] = b;
+                }
+            // observability projection: H_x <- A - A u (u^T u)^-1 u^T, H_f <- -H_x[:, 3:6]
+            double u[6], Rn[9], dn[3] = {pw[0] - c.pn[0], pw[1] - c.pn[1], pw[2] - c.pn[2]}, K[9];
+            quat_to_rot(c.qn, Rn);
+            m3v(Rn, st.g, u);
+            skew3(dn, K);
+            m3v(K, st.g, u + 3);
+            double utu = 0;
+            for (int i = 0; i < 6; ++i) utu += u[i] * u[i];
+            for (int i = 0; i < 4; ++i) {
+                double au = 0;
+                for (int k = 0; k < 6; ++k) au += Hxl[i][k] * u[k];
+                au *= (1.0 / utu);
+                for (int k = 0; k < 6; ++k) Hx[(t * 4 + i) * 6 + k] = Hxl[i][k] - au * u[k];
+                for (int k = 0; k < 3; ++k) Hf[(4 * t + i) * 3 + k] = -(Hxl[i][3 + k] - au * u[3 + k]);
+            }
+            rv[4 * t + 0] = z[0] - p0[0] / p0[2];
+            rv[4 * t + 1] = z[1] - p0[1] / p0[2];
+            rv[4 * t + 2] = z[2] - p1[0] / p1[2];
+            rv[4 * t + 3] = z[3] - p1[1] / p1[2];
+        }
+        __syncthreads();
+        // ---- warp 0: Householder QR of H_f, T factor, Q^T r.  Other warps: G blocks.
+        if (warp == 0) {
+            for (int j = 0; j < 3; ++j) {
+                double xn = 0;
+                for (int i = j + 1 + lane; i < R4; i += 32) xn += Hf[i * 3 + j] * Hf[i * 3 + j];
+                xn = warp_sum_d(xn);
+                const double alpha = Hf[j * 3 + j];
+                double tj = 0.0;
+                if (xn != 0.0) {
+                    double beta = -copysign(sqrt(alpha * alpha + xn), alpha);
+                    tj = (beta - alpha) / beta;
+                    double scale = 1.0 / (alpha - beta);
+                    __syncwarp();
+                    for (int i = j + 1 + lane; i < R4; i += 32) Hf[i * 3 + j] *= scale;
+                    if (lane == 0) Hf[j * 3 + j] = beta;
+                    __syncwarp();
+                    for (int c = j + 1; c < 3; ++c) {
+                        double sacc = 0;
+                        for (int i = j + 1 + lane; i < R4; i += 32) sacc += Hf[i * 3 + j] * Hf[i * 3 + c];
+                        sacc = warp_sum_d(sacc) + Hf[j * 3 + c];
+                        sacc *= tj;
+                        __syncwarp();
+                        if (lane == 0) Hf[j * 3 + c] -= sacc;
+                        for (int i = j + 1 + lane; i < R4; i += 32) Hf[i * 3 + c] -= sacc * Hf[i * 3 + j];
+                        __syncwarp();
+                    }
+                } else {
+                    // zero reflector: make the stored column an explicit zero vector below the diagonal
+                    for (int i = j + 1 + lane; i < R4; i += 32) Hf[i * 3 + j] = 0.0;
+                }
+                if (lane == 0) tau[j] = tj;
+                __syncwarp();
+            }
+            // overwrite the R part with the implicit unit-lower structure of V: V(i, j) = 0 (i < j), 1 (i == j)
+            if (lane == 0) {
+                Hf[0 * 3 + 0] = 1.0; Hf[0 * 3 + 1] = 0.0; Hf[0 * 3 + 2] = 0.0;
+                Hf[1 * 3 + 1] = 1.0; Hf[1 * 3 + 2] = 0.0;
+                Hf[2 * 3 + 2] = 1.0;
+            }
+            __syncwarp();
+            double d01 = 0, d02 = 0, d12 = 0, w0 = 0, w1 = 0, w2 = 0;
+            for (int i = lane; i < R4; i += 32) {
+                const double a0 = Hf[i * 3], a1 = Hf[i * 3 + 1], a2 = Hf[i * 3 + 2], ri = rv[i];
+                d01 += a0 * a1; d02 += a0 * a2; d12 += a1 * a2;
+                w0 += a0 * ri; w1 += a1 * ri; w2 += a2 * ri;
+            }
+            d01 = warp_sum_d(d01); d02 = warp_sum_d(d02); d12 = warp_sum_d(d12);
+            w0 = warp_sum_d(w0); w1 = warp_sum_d(w1); w2 = warp_sum_d(w2);
+            if (lane == 0) {
+                const double t00 = tau[0], t11 = tau[1], t22 = tau[2];
+                const double t01 = -t11 * (t00 * d01);
+                const double t02 = -t22 * (t00 * d02 + t01 * d12);
+                const double t12 = -t22 * (t11 * d12);
+                Tm[0] = t00; Tm[1] = t01; Tm[2] = t02;
+                Tm[3] = 0.0; Tm[4] = t11; Tm[5] = t12;
+                Tm[6] = 0.0; Tm[7] = 0.0; Tm[8] = t22;
+                // Q^T r = r - V (T^T (V^T r))
+                ur[0] = t00 * w0;
+                ur[1] = t01 * w0 + t11 * w1;
+                ur[2] = t02 * w0 + t12 * w1 + t22 * w2;
             }
         } else {
-            oslot[0] = st.rm_slot[0];
-            oslot[1] = st.rm_slot[1];
-            m = 2;
-        }
-        for (int i = 0; i < M; ++i) bb.l_oslots[(lo + li) * NSM + i] = (uint8_t)oslot[i];
-    }
-    for (int e = threadIdx.x; e < R4 * C6; e += BE_THREADS) H[e] = 0.0;
-    __syncthreads();
-    if (threadIdx.x < M) {
-        // measurementJacobian, msckf_vio.cpp:610-677
-        const int t = threadIdx.x, cs = oslot[t];
-        const BeCam &c = st.cam[cs];
-        const double *z = bb.f_obs + (((size_t)s * bc.MF + slot) * bc.NS + cs) * 4;
-        const double *pw = bb.f_pos + (fo + slot) * 3;
-        double Rw0[9], Rw1[9], t1w[3], tmp[3];
-        quat_to_rot(c.q, Rw0);
-        m3mul(bc.R01, Rw0, Rw1);
-        m3Tv(Rw1, bc.t01, tmp);
-        for (int i = 0; i < 3; ++i) t1w[i] = c.p[i] - tmp[i];
-        double d0[3] = {pw[0] - c.p[0], pw[1] - c.p[1], pw[2] - c.p[2]};
-        double d1[3] = {pw[0] - t1w[0], pw[1] - t1w[1], pw[2] - t1w[2]};
-        double p0[3], p1[3];
-        m3v(Rw0, d0, p0);
-        m3v(Rw1, d1, p1);
-        double dz0[4][3] = {{1 / p0[2], 0, -p0[0] / (p0[2] * p0[2])}, {0, 1 / p0[2], -p0[1] / (p0[2] * p0[2])}, {0, 0, 0}, {0, 0, 0}};
-        double dz1[4][3] = {{0, 0, 0}, {0, 0, 0}, {1 / p1[2], 0, -p1[0] / (p1[2] * p1[2])}, {0, 1 / p1[2], -p1[1] / (p1[2] * p1[2])}};
-        double sk0[9], R01sk[9];
-        skew3(p0, sk0);
-        m3mul(bc.R01, sk0, R01sk);
-        double Hx[4][6];
-        for (int i = 0; i < 4; ++i)
-            for (int j = 0; j < 3; ++j) {
-                double a = 0, b = 0;
-                for (int k = 0; k < 3; ++k) {
-                    a += dz0[i][k] * sk0[k * 3 + j] + dz1[i][k] * R01sk[k * 3 + j];
-                    b += dz0[i][k] * (-Rw0[k * 3 + j]) + dz1[i][k] * (-Rw1[k * 3 + j]);
+            // G = H_xj P_sub H_xj^T, blocks (a >= b), one thread per block
+            const int nblk = M * (M + 1) / 2;
+            for (int e = threadIdx.x - 32; e < nblk; e += BE_THREADS - 32) {
+                int a = 0, t = e;
+                while (t > a) { t -= a + 1; ++a; }
+                const int b = t;
+                const double *Pa = P + (size_t)(N21 + 6 * oslot[a]) * LD + N21 + 6 * oslot[b];
+                const double *Ha = Hx + a * 24, *Hb = Hx + b * 24;
+                double HP[4][6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    double p[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) p[k] = Pa[(size_t)k * LD + j];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        double acc = 0;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) acc += Ha[i * 6 + k] * p[k];
+                        HP[i][j] = acc;
+                    }
                 }
-                Hx[i][j] = a;
-                Hx[i][3 + j] = b;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (a == b && j > i) continue;
+                        double acc = 0;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) acc += HP[i][k] * Hb[j * 6 + k];
+                        G[gix(4 * a + i, 4 * b + j)] = acc;
+                    }
             }
-        // observability projection: H_x <- A - A u (u^T u)^-1 u^T, H_f <- -H_x[:, 3:6]
-        double u[6], Rn[9], dn[3] = {pw[0] - c.pn[0], pw[1] - c.pn[1], pw[2] - c.pn[2]}, K[9];
-        quat_to_rot(c.qn, Rn);
-        m3v(Rn, st.g, u);
-        skew3(dn, K);
-        m3v(K, st.g, u + 3);
-        double utu = 0;
-        for (int i = 0; i < 6; ++i) utu += u[i] * u[i];
-        for (int i = 0; i < 4; ++i) {
-            double au = 0;
-            for (int k = 0; k < 6; ++k) au += Hx[i][k] * u[k];
-            au *= (1.0 / utu);
-            for (int k = 0; k < 6; ++k) H[(4 * t + i) * C6 + 6 * t + k] = Hx[i][k] - au * u[k];
         }
-        for (int i = 0; i < 4; ++i)
-            for (int k = 0; k < 3; ++k) Hf[(4 * t + i) * 3 + k] = -H[(4 * t + i) * C6 + 6 * t + 3 + k];
-        rv[4 * t + 0] = z[0] - p0[0] / p0[2];
-        rv[4 * t + 1] = z[1] - p0[1] / p0[2];
-        rv[4 * t + 2] = z[2] - p1[0] / p1[2];
-        rv[4 * t + 3] = z[3] - p1[1] / p1[2];
-    }
-    __syncthreads();
-    // Householder QR of H_f (R4 x 3) by warp 0; reflector j is stored in column j, rows j..R4-1
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        for (int j = 0; j < 3; ++j) {
-            double xn = 0;
-            for (int i = j + 1 + lane; i < R4; i += 32) xn += Hf[i * 3 + j] * Hf[i * 3 + j];
-            xn = warp_sum_d(xn);
-            const double alpha = Hf[j * 3 + j];
-            double tj = 0.0;
-            if (xn != 0.0) {
-                double beta = -copysign(sqrt(alpha * alpha + xn), alpha);
-                tj = (beta - alpha) / beta;
-                double scale = 1.0 / (alpha - beta);
-                __syncwarp();
-                for (int i = j + 1 + lane; i < R4; i += 32) Hf[i * 3 + j] *= scale;
-                if (lane == 0) Hf[j * 3 + j] = beta;
-                __syncwarp();
-                for (int c = j + 1; c < 3; ++c) {
-                    double sacc = 0;
-                    for (int i = j + 1 + lane; i < R4; i += 32) sacc += Hf[i * 3 + j] * Hf[i * 3 + c];
-                    sacc = warp_sum_d(sacc) + Hf[j * 3 + c];
-                    sacc *= tj;
-                    __syncwarp();
-                    if (lane == 0) Hf[j * 3 + c] -= sacc;
-                    for (int i = j + 1 + lane; i < R4; i += 32) Hf[i * 3 + c] -= sacc * Hf[i * 3 + j];
-                    __syncwarp();
+        __syncthreads();
+        // diagonal blocks: symmetrise exactly what the two triangles would have held (a == b blocks are
+        // computed once, lower part only) -- nothing to do; Y = G V
+        for (int e = threadIdx.x; e < R4 * 3; e += BE_THREADS) {
+            const int i = e / 3, a = e - i * 3;
+            double acc = 0;
+            for (int j = 0; j <= i; ++j) acc += G[gix(i, j)] * Hf[j * 3 + a];
+            for (int j = i + 1; j < R4; ++j) acc += G[gix(j, i)] * Hf[j * 3 + a];
+            Y[e] = acc;
+        }
+        // U[c] = T^T (V^T x_c) for the 6M sparse columns of H_xj
+        for (int c = threadIdx.x; c < C6; c += BE_THREADS) {
+            const int t = c / 6, cc = c - t * 6;
+            double w0 = 0, w1 = 0, w2 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double x = Hx[(t * 4 + i) * 6 + cc];
+                w0 += Hf[(4 * t + i) * 3] * x;
+                w1 += Hf[(4 * t + i) * 3 + 1] * x;
+                w2 += Hf[(4 * t + i) * 3 + 2] * x;
+            }
+            U[c * 3 + 0] = Tm[0] * w0;
+            U[c * 3 + 1] = Tm[1] * w0 + Tm[4] * w1;
+            U[c * 3 + 2] = Tm[2] * w0 + Tm[5] * w1 + Tm[8] * w2;
+        }
+        __syncthreads();
+        if (threadIdx.x < 9) {  // Z = V^T Y
+            const int a = threadIdx.x / 3, b = threadIdx.x % 3;
+            double acc = 0;
+            for (int i = 0; i < R4; ++i) acc += Hf[i * 3 + a] * Y[i * 3 + b];
+            Zm[threadIdx.x] = acc;
+        }
+        for (int e = threadIdx.x; e < R4 * 3; e += BE_THREADS) {  // A = Y T
+            const int i = e / 3, b = e - i * 3;
+            double acc = 0;
+            for (int a = 0; a <= b; ++a) acc += Y[i * 3 + a] * Tm[a * 3 + b];
+            Am[e] = acc;
+        }
+        for (int i = threadIdx.x; i < R4; i += BE_THREADS)  // r' = Q^T r
+            rv[i] = rv[i] - (Hf[i * 3] * ur[0] + Hf[i * 3 + 1] * ur[1] + Hf[i * 3 + 2] * ur[2]);
+        __syncthreads();
+        if (threadIdx.x < 9) {  // C = T^T Z T
+            const int a = threadIdx.x / 3, b = threadIdx.x % 3;
+            double acc = 0;
+            for (int p = 0; p < 3; ++p)
+                for (int q = 0; q < 3; ++q) acc += Tm[p * 3 + a] * Zm[p * 3 + q] * Tm[q * 3 + b];
+            Cm[threadIdx.x] = acc;
+        }
+        __syncthreads();
+        // S = (Q^T G Q)[3:, 3:] + sigma^2 I, in place on the packed lower triangle
+        {
+            const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+            for (int i = 3 + ty; i < R4; i += 16) {
+                const double vi0 = Hf[i * 3], vi1 = Hf[i * 3 + 1], vi2 = Hf[i * 3 + 2];
+                const double ai0 = Am[i * 3], ai1 = Am[i * 3 + 1], ai2 = Am[i * 3 + 2];
+                const double c0 = vi0 * Cm[0] + vi1 * Cm[3] + vi2 * Cm[6], c1 = vi0 * Cm[1] + vi1 * Cm[4] + vi2 * Cm[7],
+                             c2 = vi0 * Cm[2] + vi1 * Cm[5] + vi2 * Cm[8];
+                const int ib = i * (i + 1) / 2;
+                for (int j = 3 + tx; j <= i; j += 16) {
+                    const double vj0 = Hf[j * 3], vj1 = Hf[j * 3 + 1], vj2 = Hf[j * 3 + 2];
+                    double x = G[ib + j];
+                    x -= vi0 * Am[j * 3] + vi1 * Am[j * 3 + 1] + vi2 * Am[j * 3 + 2];
+                    x -= ai0 * vj0 + ai1 * vj1 + ai2 * vj2;
+                    x += c0 * vj0 + c1 * vj1 + c2 * vj2;
+                    if (i == j) x += bc.obs_noise;
+                    G[ib + j] = x;
                 }
             }
-            if (lane == 0) tau[j] = tj;
-            __syncwarp();
         }
-    }
-    __syncthreads();
-    // apply Q^T to [H | r]: one thread per column
-    for (int c = threadIdx.x; c <= C6; c += BE_THREADS) {
-        for (int j = 0; j < 3; ++j) {
-            const double tj = tau[j];
-            if (tj == 0.0) continue;
-            if (c < C6) {
-                double sacc = H[j * C6 + c];
-                for (int i = j + 1; i < R4; ++i) sacc += Hf[i * 3 + j] * H[i * C6 + c];
-                sacc *= tj;
-                H[j * C6 + c] -= sacc;
-                for (int i = j + 1; i < R4; ++i) H[i * C6 + c] -= sacc * Hf[i * 3 + j];
-            } else {
-                double sacc = rv[j];
-                for (int i = j + 1; i < R4; ++i) sacc += Hf[i * 3 + j] * rv[i];
-                sacc *= tj;
-                rv[j] -= sacc;
-                for (int i = j + 1; i < R4; ++i) rv[i] -= sacc * Hf[i * 3 + j];
+        // Cholesky of S (rows 3..R4-1 of the packed triangle)
+        packed_cholesky(G, 3, R4);
+        __syncthreads();
+        if (warp == 0) {
+            // y = L^-1 r', gamma = y^T y (gatingTest, msckf_vio.cpp:909-935)
+            double g = 0;
+            for (int i = 3; i < R4; ++i) {
+                double sacc = 0;
+                for (int k = 3 + lane; k < i; k += 32) sacc += G[gix(i, k)] * Y[k];  // Y reused as the solution vector
+                sacc = warp_sum_d(sacc);
+                const double y = (rv[i] - sacc) / G[gix(i, i)];
+                __syncwarp();
+                if (lane == 0) Y[i] = y;
+                __syncwarp();
+                g += y * y;
+            }
+            if (lane == 0) {
+                const int dof = phase == 0 ? M - 1 : M;  // msckf_vio.cpp:1001, :1145
+                const double thr = (dof >= 1 && dof <= 99) ? c_chi2[bc.chi2_mode][dof - 1] : 0.0;
+                s_gamma = g;
+                s_pass = g < thr ? 1 : 0;
+                bb.l_pass[lo + li] = (uint8_t)s_pass;
+                const double dm = M, dr = rows;
+                atomicAdd(bb.work + (size_t)s * MSKF_PROF_TAGS + PK_BE_FEATURE_JAC,
+                          dm * (dm + 1) * 0.5 * 480.0 + 6.0 * 16.0 * dm * dm + 18.0 * dr * dr + dr * dr * dr / 3.0 + 6.0 * dr * 6.0 * dm);
             }
         }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < R4; i += BE_THREADS) rg[i] = rv[i];
-    const double *Hp = H + 3 * C6;  // projected Jacobian, rows x C6
-    // gatingTest: gamma = r^T (H P H^T + sigma^2 I)^-1 r
-    auto pidx = [&](int l) { return N21 + 6 * oslot[l / 6] + (l % 6); };
-    for (int ti = 0; ti < rows; ti += GT)
-        for (int tj = 0; tj < C6; tj += GT)
-            cta_gemm_tile<true, false>(
-                rows, C6, C6, ti, tj, [&](int i, int l) { return Hp[i * C6 + l]; },
-                [&](int l, int j) { return P[(size_t)pidx(l) * LD + pidx(j)]; },
-                [&](int i, int j, double v) { HP[i * C6 + j] = v; }, gs);
-    __syncthreads();
-    for (int ti = 0; ti < rows; ti += GT)
-        for (int tj = 0; tj < rows; tj += GT)
-            cta_gemm_tile<true, true>(
-                rows, rows, C6, ti, tj, [&](int i, int l) { return HP[i * C6 + l]; },
-                [&](int l, int j) { return Hp[j * C6 + l]; },
-                [&](int i, int j, double v) { Ssm[i * sld + j] = v + (i == j ? bc.obs_noise : 0.0); }, gs);
-    __syncthreads();
-    cta_cholesky(Ssm, rows, sld);
-    if (threadIdx.x < 32) {
-        // forward substitution y = L^-1 r (rows 3..), gamma = y^T y; warp-parallel dot products
-        const int lane = threadIdx.x;
-        double g = 0;
-        for (int i = 0; i < rows; ++i) {
-            double sacc = 0;
-            for (int k = lane; k < i; k += 32) sacc += Ssm[i * sld + k] * rv[3 + k];
-            sacc = warp_sum_d(sacc);
-            double y = (rv[3 + i] - sacc) / Ssm[i * sld + i];
-            __syncwarp();
-            if (lane == 0) rv[3 + i] = y;
-            __syncwarp();
-            g += y * y;
+        __syncthreads();
+        if (s_pass) {
+            // H' = (Q^T H_xj)[3:, :] and r' to the scratch used by the stacking kernel
+            for (int c = threadIdx.x; c < C6; c += BE_THREADS) {
+                const int t = c / 6, cc = c - 6 * t;
+                const double u0 = U[c * 3], u1 = U[c * 3 + 1], u2 = U[c * 3 + 2];
+                for (int i = 3; i < R4; ++i) {
+                    double x = (i >= 4 * t && i < 4 * t + 4) ? Hx[i * 6 + cc] : 0.0;
+                    x -= Hf[i * 3] * u0 + Hf[i * 3 + 1] * u1 + Hf[i * 3 + 2] * u2;
+                    H[(size_t)i * C6 + c] = x;
+                }
+            }
+            for (int i = 3 + threadIdx.x; i < R4; i += BE_THREADS) rg[i] = rv[i];
         }
-        if (lane == 0) s_gamma = g;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int dof = phase == 0 ? M - 1 : M;  // msckf_vio.cpp:1001, :1145
-        const double thr = (dof >= 1 && dof <= 99) ? c_chi2[bc.chi2_mode][dof - 1] : 0.0;
-        bb.l_pass[lo + li] = s_gamma < thr ? 1 : 0;
-        const double dr = rows, dc = C6;
-        atomicAdd(bb.work + (size_t)s * MSKF_PROF_TAGS + PK_BE_FEATURE_JAC, 2.0 * dr * dc * dc + 2.0 * dr * dr * dc + dr * dr * dr / 3.0);
-    }
     }  // list loop
 }
 
@@ -1802,22 +1942,7 @@ __global__ void __launch_bounds__(BE_THREADS) be_chol_kernel(BeConst bc, BeBuf b
         int i = e / n, j = e - i * n;
         if (j <= i) L[ix(i, j)] = Sm[i * KC + j];
     }
-    for (int kk = 0; kk < n; ++kk) {
-        __syncthreads();
-        if (threadIdx.x == 0) L[ix(kk, kk)] = sqrt(L[ix(kk, kk)]);
-        __syncthreads();
-        const double d = L[ix(kk, kk)];
-        for (int i = kk + 1 + threadIdx.x; i < n; i += BE_THREADS) L[ix(i, kk)] /= d;
-        __syncthreads();
-        const int rem = n - kk - 1;
-        for (int e = threadIdx.x; e < rem * rem; e += BE_THREADS) {
-            int a = e / rem, b = e - a * rem;
-            if (b > a) continue;
-            int i = kk + 1 + a, j = kk + 1 + b;
-            L[ix(i, j)] -= L[ix(i, kk)] * L[ix(j, kk)];
-        }
-    }
-    __syncthreads();
+    packed_cholesky(L, 0, n);
     // in-place inverse of the lower-triangular factor, last column first (dtrti2 order)
     __shared__ double s_dj;
     for (int j = n - 1; j >= 0; --j) {
@@ -2119,7 +2244,7 @@ int be_create(mskf_handle *h) {
     A(bb.e_cell, S * (bc.ent_cap + 1)); A(bb.inject, bc.ent_cap);
     A(bb.l_slot, S * bc.ML); A(bb.l_ok, S * bc.ML); A(bb.l_pass, S * bc.ML); A(bb.l_M, S * bc.ML);
     A(bb.l_eoff, S * bc.ML); A(bb.l_roff, S * bc.ML); A(bb.l_soff, S * bc.ML); A(bb.l_oslots, S * bc.ML * NSM);
-    A(bb.Hblk, S * bc.ecap); A(bb.HPblk, S * bc.ecap); A(bb.rblk, S * bc.rcap);
+    A(bb.Hblk, S * bc.ecap); A(bb.rblk, S * bc.rcap);
     A(bb.Hst, S * bc.hst_cap); A(bb.rst, S * bc.hst_rows); A(bb.rst_j0, S * bc.hst_rows);
     A(bb.Tm, S * bc.KC * bc.KC); A(bb.rt, S * bc.KC); A(bb.PHt, S * bc.LD * bc.KC); A(bb.Sm, S * bc.KC * bc.KC);
     A(bb.Linv, S * bc.KC * bc.KC); A(bb.W, S * bc.LD * bc.KC); A(bb.yv, S * bc.KC); A(bb.dxv, S * bc.LD);
@@ -2144,8 +2269,8 @@ int be_create(mskf_handle *h) {
     B->smem_sel = (size_t)sn * 8;
     for (int ph = 0; ph < 2; ++ph) {
         int maxM = ph == 0 ? bc.NS : 2;
-        int maxR4 = 4 * maxM, maxRows = maxR4 - 3;
-        B->smem_jac[ph] = sizeof(double) * ((size_t)maxR4 * 4 + (size_t)maxRows * (maxRows + 1)) + sizeof(GemmSmem);
+        int maxR4 = 4 * maxM;
+        B->smem_jac[ph] = sizeof(double) * ((size_t)maxR4 * (maxR4 + 1) / 2 + (size_t)maxM * 24 + (size_t)maxR4 * 10 + (size_t)maxM * 18);
     }
     B->smem_qr = sizeof(double) * ((size_t)(bc.KC + 1) * (bc.KC + 2) / 2 + (size_t)QR_B * (bc.KC + 1));
     B->smem_chol = sizeof(double) * ((size_t)bc.KC * (bc.KC + 1) / 2 + bc.KC);

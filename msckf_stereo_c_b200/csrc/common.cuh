@@ -83,6 +83,7 @@ struct FeBuffers {
     // KLT work lists
     float2 *k_a, *k_b;      // [S][cap_k]
     uint8_t *k_status;      // [S][cap_k]
+    uint8_t *k_skip;        // [S][cap_k] new-feature candidates whose cell has no vacancy (not matched)
     int *k_n;               // [S]
     // tracked meta carried through the temporal track
     unsigned long long *t_id;  // [S][max_f]

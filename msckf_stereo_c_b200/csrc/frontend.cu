@@ -118,6 +118,13 @@ __device__ __forceinline__ long long warp_sum(long long v) {
 #define KLT_WARPS 4
 // mode 0: temporal (A = previous cam0 pyramid, B = current cam0 pyramid)
 // mode 1: stereo   (A = current cam0 pyramid,  B = current cam1 pyramid)
+// mode 2: stereo of new candidates: entries flagged in k_skip are not matched (their cell has no
+//         vacancy, so addNewFeatures (image_processor.cpp:735-750) never looks at them)
+//
+// Lane l owns image column x0 + l of the patch: per patch row it loads ONE byte (the row below),
+// keeps the row above in a register and takes the right-hand neighbours from lane l + 1 by
+// shuffle, so a bilinear sample costs one load and one shuffle instead of four clamped loads.
+// Needs win + 3 <= 32 lanes.
 __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffers fb, int mode) {
     const int s = blockIdx.y;
     const FeStep st = fb.step[s];
@@ -125,20 +132,24 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.x * KLT_WARPS + warp;
     if (f >= fb.k_n[s]) return;
+    if (mode == 2 && fb.k_skip[(size_t)s * fc.cap_k + f]) {
+        if (lane == 0) fb.k_status[(size_t)s * fc.cap_k + f] = 0;
+        return;
+    }
     const uint8_t *pa = (mode == 0 ? fb.pyr[st.slot ^ 1] : fb.pyr[st.slot]) + (size_t)s * fc.pyr_bytes;
     const uint8_t *pb = (mode == 0 ? fb.pyr[st.slot] : fb.pyr[2]) + (size_t)s * fc.pyr_bytes;
 
     const int win = fc.klt_win, half = win >> 1, tw = win + 2;
     extern __shared__ short klt_smem[];
-    short *T = klt_smem + (size_t)warp * (tw * tw + 2 * win * win);
-    short *Ix = T + tw * tw, *Iy = Ix + win * win;
+    short *T = klt_smem + (size_t)warp * ((tw * tw + 2 * win * win + 3) & ~3);
+    short2 *Gr = (short2 *)(T + tw * tw + ((tw * tw) & 1));  // (Ix, Iy) per window pixel, 4-byte aligned
 
     const float2 p0 = fb.k_a[(size_t)s * fc.cap_k + f];
     float2 q0 = fb.k_b[(size_t)s * fc.cap_k + f];
     int status = 1;
     const int L = fc.levels;
-    const float top = 1.0f / (float)(1 << (L - 1));
-    float qx = q0.x * top, qy = q0.y * top;
+    const float top_scale = 1.0f / (float)(1 << (L - 1));
+    float qx = q0.x * top_scale, qy = q0.y * top_scale;
     for (int l = L - 1; l >= 0; --l) {
         const int rows = fc.lvl_rows[l], cols = fc.lvl_cols[l];
         const uint8_t *A = pa + fc.lvl_off[l], *B = pb + fc.lvl_off[l];
@@ -146,21 +157,31 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
         const float px = p0.x * sc, py = p0.y * sc;
         const BilinW wa = bilin_weights(px, py);
         __syncwarp();
-        for (int idx = lane; idx < tw * tw; idx += 32) {
-            int j = idx / tw, i = idx - j * tw;
-            T[idx] = (short)sample_fx(A, rows, cols, wa, i - half - 1, j - half - 1);
+        {
+            // template patch T[j][i] = A sampled at (px + i - half - 1, py + j - half - 1), i, j in [0, tw)
+            const int xc = min(max(wa.ix - half - 1 + lane, 0), cols - 1);
+            const int y0 = wa.iy - half - 1;
+            int top = __ldg(A + (size_t)min(max(y0, 0), rows - 1) * cols + xc);
+            int rt = __shfl_down_sync(0xffffffffu, top, 1);
+            for (int j = 0; j < tw; ++j) {
+                const int bot = __ldg(A + (size_t)min(max(y0 + j + 1, 0), rows - 1) * cols + xc);
+                const int rb = __shfl_down_sync(0xffffffffu, bot, 1);
+                if (lane < tw) T[j * tw + lane] = (short)((wa.w00 * top + wa.w01 * rt + wa.w10 * bot + wa.w11 * rb + 256) >> 9);
+                top = bot;
+                rt = rb;
+            }
         }
         __syncwarp();
         long long A11 = 0, A12 = 0, A22 = 0;
-        for (int idx = lane; idx < win * win; idx += 32) {
-            int j = idx / win, i = idx - j * win;
-            int gx = (int)T[(j + 1) * tw + i + 2] - (int)T[(j + 1) * tw + i];
-            int gy = (int)T[(j + 2) * tw + i + 1] - (int)T[j * tw + i + 1];
-            Ix[idx] = (short)gx;
-            Iy[idx] = (short)gy;
-            A11 += (long long)(gx * gx);
-            A12 += (long long)(gx * gy);
-            A22 += (long long)(gy * gy);
+        if (lane < win) {
+            for (int j = 0; j < win; ++j) {
+                const int gx = (int)T[(j + 1) * tw + lane + 2] - (int)T[(j + 1) * tw + lane];
+                const int gy = (int)T[(j + 2) * tw + lane + 1] - (int)T[j * tw + lane + 1];
+                Gr[j * win + lane] = make_short2((short)gx, (short)gy);
+                A11 += (long long)(gx * gx);
+                A12 += (long long)(gx * gy);
+                A22 += (long long)(gy * gy);
+            }
         }
         A11 = warp_sum(A11); A12 = warp_sum(A12); A22 = warp_sum(A22);
         __syncwarp();
@@ -184,11 +205,26 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
                 }
                 const BilinW wb = bilin_weights(qx, qy);
                 long long b1 = 0, b2 = 0;
-                for (int idx = lane; idx < win * win; idx += 32) {
-                    int j = idx / win, i = idx - j * win;
-                    int diff = sample_fx(B, rows, cols, wb, i - half, j - half) - (int)T[(j + 1) * tw + i + 1];
-                    b1 += (long long)(diff * (int)Ix[idx]);
-                    b2 += (long long)(diff * (int)Iy[idx]);
+                {
+                    const int xc = min(max(wb.ix - half + lane, 0), cols - 1);
+                    const int y0 = wb.iy - half;
+                    int top = __ldg(B + (size_t)min(max(y0, 0), rows - 1) * cols + xc);
+                    int rt = __shfl_down_sync(0xffffffffu, top, 1);
+                    const short *Trow = T + tw + lane + 1;
+                    const short2 *Grow = Gr + lane;
+                    for (int j = 0; j < win; ++j) {
+                        const int bot = __ldg(B + (size_t)min(max(y0 + j + 1, 0), rows - 1) * cols + xc);
+                        const int rb = __shfl_down_sync(0xffffffffu, bot, 1);
+                        if (lane < win) {
+                            const int val = (wb.w00 * top + wb.w01 * rt + wb.w10 * bot + wb.w11 * rb + 256) >> 9;
+                            const int diff = val - (int)Trow[j * tw];
+                            const short2 g = Grow[j * win];
+                            b1 += (long long)(diff * (int)g.x);
+                            b2 += (long long)(diff * (int)g.y);
+                        }
+                        top = bot;
+                        rt = rb;
+                    }
                 }
                 b1 = warp_sum(b1); b2 = warp_sum(b2);
                 const double fb1 = (double)b1, fb2 = (double)b2;
@@ -268,30 +304,25 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
                 dark |= (unsigned)(d[k] > t) << k;
                 bright |= (unsigned)(d[k] < -t) << k;
             }
-            if (has_arc9(dark) || has_arc9(bright)) {
-                // S = max over the 16 arcs of min(d) and of min(-d): sliding minimum of width 9 by
-                // doubling (2, 4, 8, +1).  Only `min` chains are used on purpose: ptxas 12.9 for
-                // sm_100a miscompiles interleaved min/max chains when it fuses them into VIMNMX3
-                // (tools/scratch/t2.cu reproduces it), so the "brighter" side runs on n = -d.
-                int n[16], a2[16], b2[16], a4[16], b4[16];
+            const bool is_dark = has_arc9(dark);
+            if (is_dark || has_arc9(bright)) {
+                // S = max over the 16 arcs of 9 contiguous ring pixels of min(d) (darker ring) or min(-d)
+                // (brighter ring).  A ring cannot hold a darker and a brighter 9-arc at once, and the side
+                // without an arc scores <= t, so only the side that passed is evaluated.  Sliding minimum of
+                // width 9 by doubling (2, 4, 8, +1); only `min` chains on purpose: ptxas 12.9 for sm_100a
+                // miscompiles interleaved min/max chains fused into VIMNMX3 (tools/scratch/t2.cu).
+                int n[16], a2[16], a4[16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) n[k] = -d[k];
+                for (int k = 0; k < 16; ++k) n[k] = is_dark ? d[k] : -d[k];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    a2[k] = min(d[k], d[(k + 1) & 15]);
-                    b2[k] = min(n[k], n[(k + 1) & 15]);
-                }
+                for (int k = 0; k < 16; ++k) a2[k] = min(n[k], n[(k + 1) & 15]);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    a4[k] = min(a2[k], a2[(k + 2) & 15]);
-                    b4[k] = min(b2[k], b2[(k + 2) & 15]);
-                }
+                for (int k = 0; k < 16; ++k) a4[k] = min(a2[k], a2[(k + 2) & 15]);
                 int best = -255;
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
-                    int a9 = min(min(a4[k], a4[(k + 4) & 15]), d[(k + 8) & 15]);
-                    int b9 = min(min(b4[k], b4[(k + 4) & 15]), n[(k + 8) & 15]);
-                    best = max(best, max(a9, b9));
+                    int a9 = min(min(a4[k], a4[(k + 4) & 15]), n[(k + 8) & 15]);
+                    best = max(best, a9);
                 }
                 sc = (uint8_t)(best - 1);
             }
@@ -623,7 +654,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_sieve(FeConst fc, FeBuffers fb,
     const FeStep st = fb.step[s];
     if (!st.active) return;
     __shared__ int s_warp[FE_THREADS / 32];
-    __shared__ int s_cell_n[FE_MAX_CELLS], s_cell_off[FE_MAX_CELLS + 1];
+    __shared__ int s_cell_n[FE_MAX_CELLS], s_cell_off[FE_MAX_CELLS + 1], s_vac[FE_MAX_CELLS];
     __shared__ int s_base;
     extern __shared__ int s_dyn[];
     // dynamic: resp[det_cells] | xy[det_cells] (packed y << 16 | x) | sel[n_cells][grid_max] | mem[4][members_cap] | code[det_cells]
@@ -672,6 +703,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_sieve(FeConst fc, FeBuffers fb,
             float2 p = det_pt(i);
             fb.k_a[ko + i] = p;
             fb.k_b[ko + i] = distort_pt(fc, 1, undistort_pt(fc, 0, p, fc.R01));
+            fb.k_skip[ko + i] = 0;
         }
         if (threadIdx.x == 0) {
             fb.k_n[s] = n;
@@ -729,16 +761,32 @@ __global__ void __launch_bounds__(FE_THREADS) fe_sieve(FeConst fc, FeBuffers fb,
         if (lane == 0) s_cell_n[c] = kept;
         __syncwarp();
     }
+    // cells already holding grid_min tracked features take no new ones: their candidates keep their
+    // place in the list (the indices matter, image_processor.cpp:698) but are not stereo-matched
+    {
+        const int gc = fb.gslot[s] ^ 1;
+        const int ncur = fb.g_n[gc][s];
+        const size_t go = (size_t)s * fc.max_f;
+        for (int c = warp; c < fc.n_cells; c += FE_THREADS / 32) {
+            int cur = 0;
+            for (int i0 = 0; i0 < ncur; i0 += 32) {
+                int i = i0 + lane;
+                cur += __popc(__ballot_sync(0xffffffffu, i < ncur && fb.g_cell[gc][go + i] == c));
+            }
+            if (lane == 0) s_vac[c] = cur < fc.grid_min ? 1 : 0;
+        }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        int acc = 0;
+        int acc = 0, matched = 0;
         for (int c = 0; c < fc.n_cells; ++c) {
             s_cell_off[c] = acc;
             acc += s_cell_n[c];
+            if (s_vac[c]) matched += s_cell_n[c];
         }
         s_cell_off[fc.n_cells] = acc;
         fb.k_n[s] = acc;
-        fb.work[(size_t)s * MSKF_PROF_TAGS + PK_KLT_NEW] += (double)acc * klt_bytes_per_feature(fc);
+        fb.work[(size_t)s * MSKF_PROF_TAGS + PK_KLT_NEW] += (double)matched * klt_bytes_per_feature(fc);
     }
     __syncthreads();
     for (int e = threadIdx.x; e < fc.n_cells * fc.grid_max; e += FE_THREADS) {
@@ -748,6 +796,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_sieve(FeConst fc, FeBuffers fb,
         int d = s_cell_off[c] + k;
         fb.k_a[ko + d] = p;
         fb.k_b[ko + d] = distort_pt(fc, 1, undistort_pt(fc, 0, p, fc.R01));
+        fb.k_skip[ko + d] = s_vac[c] ? 0 : 1;
     }
 }
 
@@ -958,8 +1007,8 @@ int fe_create(mskf_handle *h) {
     FeConst &fc = h->fc;
     memset(&fc, 0, sizeof(fc));
     if (c.pyramid_levels < 1 || c.pyramid_levels > MSKF_MAX_LEVELS || (c.klt_win & 1) == 0 || c.klt_win < 3 ||
-        c.klt_win > 31) {
-        h->err = "bad pyramid_levels / klt_win";
+        c.klt_win > 29) {
+        h->err = "bad pyramid_levels / klt_win (odd, 3..29)";
         return MSKF_ERR_ARG;
     }
     fc.rows = c.img_rows; fc.cols = c.img_cols; fc.levels = c.pyramid_levels;
@@ -1058,7 +1107,7 @@ int fe_create(mskf_handle *h) {
         A(fb.g_n[g], S);
     }
     A(fb.gslot, S); A(fb.next_id, S);
-    A(fb.k_a, S * fc.cap_k); A(fb.k_b, S * fc.cap_k); A(fb.k_status, S * fc.cap_k); A(fb.k_n, S);
+    A(fb.k_a, S * fc.cap_k); A(fb.k_b, S * fc.cap_k); A(fb.k_status, S * fc.cap_k); A(fb.k_skip, S * fc.cap_k); A(fb.k_n, S);
     A(fb.t_id, S * fc.max_f); A(fb.t_life, S * fc.max_f);
     A(fb.det_best, S * fc.det_cells); A(fb.det_occ, S * fc.det_cells);
     A(fb.nf_resp, S * fc.det_cells); A(fb.nf_n, S); A(fb.in_resp, S * fc.cap_k);
@@ -1094,7 +1143,7 @@ int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active) {
         h->work_host[l == 1 ? PK_PYR_L1 : PK_PYR_LN] += 2.0 * n_active * (in + out + (l == 1 ? in : 0.0));
     }
     h->work_host[PK_DETECT] += (double)n_active * fc.rows * fc.cols;
-    const size_t klt_smem = (size_t)KLT_WARPS * ((fc.klt_win + 2) * (fc.klt_win + 2) + 2 * fc.klt_win * fc.klt_win) * sizeof(short);
+    const size_t klt_smem = (size_t)KLT_WARPS * ((((fc.klt_win + 2) * (fc.klt_win + 2) + 2 * fc.klt_win * fc.klt_win + 3) & ~3)) * sizeof(short) + 16;
     const size_t pos_smem = (size_t)fc.cap_k * sizeof(int);
     MSKF_LAUNCH(h, PK_FE_BOOK, (fe_prep_track<<<S, FE_THREADS, 0, q>>>(fc, fb)));
     if (max_prev > 0) {
@@ -1112,7 +1161,7 @@ int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active) {
     {
         int cap = any_first ? fc.det_cells : fc.n_cells * fc.grid_max;
         dim3 g((cap + KLT_WARPS - 1) / KLT_WARPS, S);
-        MSKF_LAUNCH(h, PK_KLT_NEW, (klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 1)));
+        MSKF_LAUNCH(h, PK_KLT_NEW, (klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 2)));
     }
     const size_t fin_smem = fe_finish_smem(fc);
     MSKF_LAUNCH(h, PK_FE_BOOK, (fe_finish<<<S, FE_THREADS, fin_smem, q>>>(fc, fb)));
@@ -1195,7 +1244,7 @@ int fe_op_klt(mskf_handle *t, const float *pts_a, float *pts_b, uint8_t *status,
     MSKF_CUDA_CHECK(t, cudaMemcpyAsync(t->fb.k_a, pts_a, sizeof(float2) * n, cudaMemcpyHostToDevice, t->stream));
     MSKF_CUDA_CHECK(t, cudaMemcpyAsync(t->fb.k_b, pts_b, sizeof(float2) * n, cudaMemcpyHostToDevice, t->stream));
     MSKF_CUDA_CHECK(t, cudaMemcpyAsync(t->fb.k_n, &n, sizeof(int), cudaMemcpyHostToDevice, t->stream));
-    const size_t klt_smem = (size_t)KLT_WARPS * ((fc.klt_win + 2) * (fc.klt_win + 2) + 2 * fc.klt_win * fc.klt_win) * sizeof(short);
+    const size_t klt_smem = (size_t)KLT_WARPS * ((((fc.klt_win + 2) * (fc.klt_win + 2) + 2 * fc.klt_win * fc.klt_win + 3) & ~3)) * sizeof(short) + 16;
     dim3 g((n + KLT_WARPS - 1) / KLT_WARPS, 1);
     klt_kernel<<<g, KLT_WARPS * 32, klt_smem, t->stream>>>(fc, t->fb, 1);
     MSKF_CUDA_CHECK(t, cudaGetLastError());
