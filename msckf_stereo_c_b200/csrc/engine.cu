@@ -282,6 +282,10 @@ int mskf_push_stereo_batch(mskf_handle *h, const double *t, const uint8_t *cam0,
 
 int mskf_push_stereo_device_batch(mskf_handle *h, const double *t, const uint8_t *d_cam0, const uint8_t *d_cam1, size_t stream_stride) {
     if (!h || !t || !d_cam0 || !d_cam1) return MSKF_ERR_ARG;
+    if ((((uintptr_t)d_cam0) | ((uintptr_t)d_cam1) | (uintptr_t)stream_stride) & 15) {
+        h->err = "device images (and the stream stride) must be 16-byte aligned";
+        return MSKF_ERR_ARG;
+    }
     for (int s = 0; s < h->S; ++s) {
         HostStream &hs = h->hs[s];
         hs.pending = true;
@@ -328,6 +332,10 @@ int mskf_push_stereo(mskf_handle *h, int s, double t, const uint8_t *cam0, const
 
 int mskf_push_stereo_device(mskf_handle *h, int s, double t, const uint8_t *d_cam0, const uint8_t *d_cam1) {
     if (!h || s < 0 || s >= h->S || !d_cam0 || !d_cam1) return MSKF_ERR_ARG;
+    if ((((uintptr_t)d_cam0) | ((uintptr_t)d_cam1)) & 15) {
+        h->err = "device images must be 16-byte aligned";
+        return MSKF_ERR_ARG;
+    }
     HostStream &hs = h->hs[s];
     hs.pending = true;
     hs.pending_t = t;

@@ -15,6 +15,8 @@
 //   fe_sieve             addNewFeatures :659-688 / initializeFirstFrame :261-268
 //   fe_finish            addNewFeatures :690-750, initializeFirstFrame :270-316,
 //                        pruneGridFeatures :758-768, publish :1137-1182, stereoCallback :192-200
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mskf {
@@ -78,6 +80,99 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(FeConst fc, FeBuffers fb,
             int v = hrow[2 * r][c] + 4 * hrow[2 * r + 1][c] + 6 * hrow[2 * r + 2][c] + 4 * hrow[2 * r + 3][c] +
                     hrow[2 * r + 4][c];
             dst[(size_t)oy * ocols + ox] = (uint8_t)((v + 128) >> 8);
+        }
+    }
+}
+
+// Bandwidth-oriented version used whenever the level width is a multiple of VEC bytes and the
+// row fits the strip buffer: one CTA makes a full-width strip of PS_ROWS output rows.
+//   stage   36 input rows -> shared memory with VEC-byte loads (16 B at level 0, 4 B below); the
+//           level-1 launch writes the same registers back as the level-0 landing copy
+//   filter  a thread owns two adjacent output columns and walks down the strip with a 5-row
+//           register window; the 5 taps run on two packed 16-bit lanes (255*16*16 < 2^16, so
+//           neither pass can carry between lanes): ~25 instructions per output pixel
+#define PS_ROWS 16
+#define PS_IN (2 * PS_ROWS + 4)
+#define PS_PAD 16  // pixel 0 of a staged row sits at byte 16 (16-byte aligned stores); halo at 14, 15
+
+__device__ __forceinline__ unsigned hfilt2(const uint8_t *row, int q) {
+    // two horizontal 5-tap sums centred on pixels 4q and 4q + 2, packed (lo, hi)
+    const unsigned *w = (const unsigned *)(row + PS_PAD - 4) + q;
+    const unsigned W0 = w[0], W1 = w[1], W2 = w[2];
+    const unsigned V = __funnelshift_r(W0, W1, 16);  // p-2 p-1 p0 p1
+    const unsigned X = __funnelshift_r(W1, W2, 16);  // p2 p3 p4 p5
+    const unsigned A = V & 0x00FF00FFu, B = (V >> 8) & 0x00FF00FFu;
+    const unsigned C = W1 & 0x00FF00FFu, D = (W1 >> 8) & 0x00FF00FFu;
+    const unsigned E = X & 0x00FF00FFu;
+    return A + E + 6u * C + 4u * (B + D);
+}
+
+template <bool COPY_SRC, int VEC>
+__global__ void __launch_bounds__(256) pyr_down_strip_kernel(FeConst fc, FeBuffers fb, int level, int row_stride) {
+    const int s = blockIdx.z >> 1, cam = blockIdx.z & 1;
+    const FeStep st = fb.step[s];
+    if (!st.active) return;
+    uint8_t *pyr = (cam == 0 ? fb.pyr[st.slot] : fb.pyr[2]) + (size_t)s * fc.pyr_bytes;
+    const int irows = fc.lvl_rows[level - 1], icols = fc.lvl_cols[level - 1];
+    const int orows = fc.lvl_rows[level], ocols = fc.lvl_cols[level];
+    const uint8_t *src = COPY_SRC ? (cam == 0 ? fb.src0[s] : fb.src1[s]) : pyr + fc.lvl_off[level - 1];
+    uint8_t *dst = pyr + fc.lvl_off[level];
+    extern __shared__ __align__(16) uint8_t ps_smem[];  // [PS_IN][row_stride]
+    const int oy0 = blockIdx.x * PS_ROWS;
+    const int iy0 = 2 * oy0 - 2;
+    typedef typename std::conditional<VEC == 16, uint4, unsigned>::type vec_t;
+    const int vpr = icols / VEC;  // vectors per row
+    for (int e = threadIdx.x; e < PS_IN * vpr; e += 256) {
+        const int r = e / vpr, v = e - r * vpr;
+        const int gy = reflect101(iy0 + r, irows);
+        const vec_t val = *(const vec_t *)(src + (size_t)gy * icols + (size_t)v * VEC);
+        *(vec_t *)(ps_smem + (size_t)r * row_stride + PS_PAD + v * VEC) = val;
+        if (COPY_SRC) {
+            const int yy = iy0 + r;  // interior rows of the strip = this CTA's share of the level-0 landing copy
+            if (r >= 2 && r < PS_IN - 2 && yy < irows) *(vec_t *)(pyr + (size_t)yy * icols + (size_t)v * VEC) = val;
+        }
+    }
+    __syncthreads();
+    // BORDER_REFLECT_101 columns: -2, -1 and icols, icols + 1 (+2 zero bytes read by the last pair)
+    for (int r = threadIdx.x; r < PS_IN; r += 256) {
+        uint8_t *row = ps_smem + (size_t)r * row_stride + PS_PAD;
+        row[-2] = row[reflect101(-2, icols)];
+        row[-1] = row[reflect101(-1, icols)];
+        row[icols] = row[reflect101(icols, icols)];
+        row[icols + 1] = row[reflect101(icols + 1, icols)];
+        row[icols + 2] = 0;
+        row[icols + 3] = 0;
+        row[icols + 4] = 0;
+        row[icols + 5] = 0;
+    }
+    __syncthreads();
+    const int ncp = (ocols + 1) >> 1;               // column pairs
+    const int cp = min(256, (ncp + 31) & ~31);      // threads per row group
+    const int groups = 256 / cp;                    // row groups working on disjoint output rows
+    const int g = threadIdx.x / cp, t = threadIdx.x - g * cp;
+    if (g >= groups) return;
+    const int rpg = (PS_ROWS + groups - 1) / groups;
+    const int r_begin = g * rpg, r_end = min(min(PS_ROWS, r_begin + rpg), orows - oy0);
+    if (r_begin >= r_end) return;
+    const bool odd_w = (ocols & 1) != 0;
+    for (int q = t; q < ncp; q += cp) {
+        const uint8_t *base = ps_smem + (size_t)(2 * r_begin) * row_stride;
+        unsigned h0 = hfilt2(base, q), h1 = hfilt2(base + row_stride, q), h2 = hfilt2(base + 2 * row_stride, q);
+        for (int r = r_begin; r < r_end; ++r) {
+            const uint8_t *rp = ps_smem + (size_t)(2 * r + 3) * row_stride;
+            const unsigned h3 = hfilt2(rp, q), h4 = hfilt2(rp + row_stride, q);
+            const unsigned v = h0 + h4 + 6u * h2 + 4u * (h1 + h3);
+            const unsigned o = ((v + 0x00800080u) >> 8) & 0x00FF00FFu;  // (sum + 128) >> 8 on both lanes
+            uint8_t *d = dst + (size_t)(oy0 + r) * ocols + 2 * q;
+            if (!odd_w) {
+                *(unsigned short *)d = (unsigned short)((o & 0xFFu) | ((o >> 8) & 0xFF00u));
+            } else {
+                d[0] = (uint8_t)(o & 0xFFu);
+                if (2 * q + 1 < ocols) d[1] = (uint8_t)(o >> 16);
+            }
+            h0 = h2;
+            h1 = h3;
+            h2 = h4;
         }
     }
 }
@@ -1124,6 +1219,34 @@ int fe_create(mskf_handle *h) {
     return MSKF_OK;
 }
 
+// pyramid level l for `images` (= 2 S) images: vectorised strip kernel when the geometry allows it
+static void launch_pyr_level(mskf_handle *h, int l, int images) {
+    const FeConst &fc = h->fc;
+    const FeBuffers &fb = h->fb;
+    cudaStream_t q = h->stream;
+    const int icols = fc.lvl_cols[l - 1];
+    const int row_stride = (PS_PAD + icols + 8 + 15) & ~15;
+    const size_t smem = (size_t)PS_IN * row_stride;
+    const int tag = l == 1 ? PK_PYR_L1 : PK_PYR_LN;
+    if (smem <= 200 * 1024 && (icols % 4) == 0 && icols >= 8) {
+        dim3 g((fc.lvl_rows[l] + PS_ROWS - 1) / PS_ROWS, 1, images);
+        if (l == 1 && (icols % 16) == 0) {
+            cudaFuncSetAttribute(pyr_down_strip_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            MSKF_LAUNCH(h, tag, (pyr_down_strip_kernel<true, 16><<<g, 256, smem, q>>>(fc, fb, l, row_stride)));
+        } else if (l == 1) {
+            cudaFuncSetAttribute(pyr_down_strip_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            MSKF_LAUNCH(h, tag, (pyr_down_strip_kernel<true, 4><<<g, 256, smem, q>>>(fc, fb, l, row_stride)));
+        } else {
+            cudaFuncSetAttribute(pyr_down_strip_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            MSKF_LAUNCH(h, tag, (pyr_down_strip_kernel<false, 4><<<g, 256, smem, q>>>(fc, fb, l, row_stride)));
+        }
+    } else {
+        dim3 g((fc.lvl_cols[l] + PD_TW - 1) / PD_TW, (fc.lvl_rows[l] + PD_TH - 1) / PD_TH, images);
+        if (l == 1) MSKF_LAUNCH(h, tag, (pyr_down_kernel<true><<<g, 256, 0, q>>>(fc, fb, l)));
+        else MSKF_LAUNCH(h, tag, (pyr_down_kernel<false><<<g, 256, 0, q>>>(fc, fb, l)));
+    }
+}
+
 int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active) {
     const FeConst &fc = h->fc;
     const FeBuffers &fb = h->fb;
@@ -1135,9 +1258,7 @@ int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active) {
     }
     // pyramids
     for (int l = 1; l < fc.levels; ++l) {
-        dim3 g((fc.lvl_cols[l] + PD_TW - 1) / PD_TW, (fc.lvl_rows[l] + PD_TH - 1) / PD_TH, S * 2);
-        if (l == 1) MSKF_LAUNCH(h, PK_PYR_L1, (pyr_down_kernel<true><<<g, 256, 0, q>>>(fc, fb, l)));
-        else MSKF_LAUNCH(h, PK_PYR_LN, (pyr_down_kernel<false><<<g, 256, 0, q>>>(fc, fb, l)));
+        launch_pyr_level(h, l, S * 2);
         // algorithmic bytes: read level l-1, write level l (+ the level-0 landing copy at l == 1)
         double in = (double)fc.lvl_rows[l - 1] * fc.lvl_cols[l - 1], out = (double)fc.lvl_rows[l] * fc.lvl_cols[l];
         h->work_host[l == 1 ? PK_PYR_L1 : PK_PYR_LN] += 2.0 * n_active * (in + out + (l == 1 ? in : 0.0));
@@ -1182,11 +1303,7 @@ static int op_prepare(mskf_handle *t) {
     MSKF_CUDA_CHECK(t, cudaMemcpyAsync(t->fb.src1, &hs.src1, sizeof(uint8_t *), cudaMemcpyHostToDevice, t->stream));
     MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->stream));
     const FeConst &fc = t->fc;
-    for (int l = 1; l < fc.levels; ++l) {
-        dim3 g((fc.lvl_cols[l] + PD_TW - 1) / PD_TW, (fc.lvl_rows[l] + PD_TH - 1) / PD_TH, 2);
-        if (l == 1) pyr_down_kernel<true><<<g, 256, 0, t->stream>>>(fc, t->fb, l);
-        else pyr_down_kernel<false><<<g, 256, 0, t->stream>>>(fc, t->fb, l);
-    }
+    for (int l = 1; l < fc.levels; ++l) launch_pyr_level(t, l, 2);
     MSKF_CUDA_CHECK(t, cudaGetLastError());
     hs.slot = 0;
     hs.pending = false;
