@@ -1106,6 +1106,11 @@ int fe_create(mskf_handle *h) {
         h->err = "bad pyramid_levels / klt_win (odd, 3..29)";
         return MSKF_ERR_ARG;
     }
+    if (c.use_ransac) {
+        // twoPointRansac is dead code in the reference (image_processor.cpp:482-493 commented out)
+        h->err = "use_ransac: twoPointRansac is not built (never called by the reference)";
+        return MSKF_ERR_ARG;
+    }
     fc.rows = c.img_rows; fc.cols = c.img_cols; fc.levels = c.pyramid_levels;
     unsigned off = 0;
     int r = c.img_rows, q = c.img_cols;
