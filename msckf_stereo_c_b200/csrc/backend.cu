@@ -133,6 +133,7 @@ struct BeBuf {
     double *Hst;       // [S][hst_cap]
     double *rst;       // [S][hst_rows]
     int *rst_j0;       // [S][hst_rows] first nonzero column of each stacked row
+    double *Rq;        // [S][(KC+1)^2] triangular factor of the QR compression (column c owned by thread c)
     double *Tm;        // [S][KC*KC]
     double *rt;        // [S][KC]
     double *PHt;       // [S][LD*KC]
@@ -1741,7 +1742,33 @@ __global__ void __launch_bounds__(BE_THREADS) be_stack_kernel(BeConst bc, BeBuf 
 // column).  If m <= k the system is used as it is.
 // ======================================================================================
 #define QR_B 32
-__global__ void __launch_bounds__(BE_THREADS) be_qr_kernel(BeConst bc, BeBuf bb) {
+#define QR_THREADS 192
+// fp64 1/sqrt(a) and 1/a from the fp32 special-function unit plus Newton steps: the reflector
+// scalars sit on the serial chain of the factorization, and DSQRT/DDIV sequences are ~2x longer
+__device__ __forceinline__ double fast_rsqrt(double a) {
+    if (!(a > 1e-30 && a < 1e30)) return 1.0 / sqrt(a);  // outside the fp32 seed's range
+    double y = (double)rsqrtf((float)a);
+    y = y * (1.5 - 0.5 * a * y * y);
+    y = y * (1.5 - 0.5 * a * y * y);
+    y = y * (1.5 - 0.5 * a * y * y);
+    return y;
+}
+__device__ __forceinline__ double fast_rcp(double a) {
+    if (!(fabs(a) > 1e-30 && fabs(a) < 1e30)) return 1.0 / a;
+    double y = (double)__frcp_rn((float)a);
+    y = y + y * (1.0 - a * y);
+    y = y + y * (1.0 - a * y);
+    y = y + y * (1.0 - a * y);
+    return y;
+}
+
+// Thread c owns column c of the system [H | r] (c = k is the residual column): the 32 rows of the
+// block being folded live in its registers, column c of the triangular factor R lives in global
+// memory (row-major, read two steps ahead), so no other thread ever touches its data and the only
+// communication per column step is the reflector (32 doubles + tau) through shared memory, with ONE
+// barrier per step (double-buffered).  ~60 KB of registers and 1 KB of shared memory per CTA keep
+// all streams of a 256-stream fleet resident at once.
+__global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb) {
     const int s = blockIdx.x;
     const BeStep sp = bb.step[s];
     if (!sp.active) return;
@@ -1763,93 +1790,95 @@ __global__ void __launch_bounds__(BE_THREADS) be_qr_kernel(BeConst bc, BeBuf bb)
         w[PK_BE_GEMM_PUPD] += dld * dld * dmt;
     }
     if (m <= k) {
-        for (int e = threadIdx.x; e < m * k; e += BE_THREADS) Tm[e] = Hst[e];
-        for (int i = threadIdx.x; i < m; i += BE_THREADS) rt[i] = rst[i];
+        for (int e = threadIdx.x; e < m * k; e += QR_THREADS) Tm[e] = Hst[e];
+        for (int i = threadIdx.x; i < m; i += QR_THREADS) rt[i] = rst[i];
         if (threadIdx.x == 0) st.mt = m;
         return;
     }
-    // Rows are folded QR_B at a time into the packed upper-triangular factor R (row j holds columns
-    // j..k, column k = Q^T r).  Column c of the row block is owned by the thread pair (2c, 2c+1): each
-    // half holds 16 of the 32 rows, partial dot products are combined with one shuffle.
-    extern __shared__ unsigned char be_smem[];
-    const int kw = k + 1;
-    double *R = (double *)be_smem;
-    double *B = R + (size_t)(KC + 1) * (KC + 2) / 2;  // [QR_B][kw]
-    __shared__ double vb[QR_B];
-    __shared__ double s_tau, s_beta;
+    const int kw = k + 1, ldr = KC + 1;
+    double *R = bb.Rq + (size_t)s * ldr * ldr;  // R[j][c] at j * ldr + c
+    __shared__ double vbuf[2][QR_B];
+    __shared__ double s_tau[2];
     __shared__ int s_j0;
-    auto roff = [&](int j) { return j * kw - (j * (j - 1)) / 2 - j; };  // R[j][c] at roff(j) + c
-    for (int e = threadIdx.x; e < (kw * (kw + 1)) / 2; e += BE_THREADS) R[e] = 0.0;
-    const int half = threadIdx.x & 1, cpair = threadIdx.x >> 1;  // 128 column pairs per pass
+    const int c = threadIdx.x;
+    const bool has_col = c < kw;
+    if (has_col)
+        for (int j = 0; j <= min(c, k - 1); ++j) R[j * ldr + c] = 0.0;
+    double x[QR_B];
     for (int r0 = 0; r0 < m; r0 += QR_B) {
         const int nb = min(QR_B, m - r0);
-        __syncthreads();
-        for (int e = threadIdx.x; e < QR_B * kw; e += BE_THREADS) {
-            int i = e / kw, c = e - i * kw;
-            double v = 0.0;
-            if (i < nb) v = c < k ? Hst[(size_t)(r0 + i) * k + c] : rst[r0 + i];
-            B[e] = v;
-        }
         if (threadIdx.x < 32) {
             int j0 = threadIdx.x < nb ? rj0[r0 + threadIdx.x] : k;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) j0 = min(j0, __shfl_xor_sync(0xffffffffu, j0, o));
             if (threadIdx.x == 0) s_j0 = j0;
         }
-        __syncthreads();
-        for (int j = s_j0; j < k; ++j) {
-            if (threadIdx.x < 32) {
-                const int lane = threadIdx.x;
-                double x = B[lane * kw + j];
-                double xn = warp_sum_d(x * x);
-                const double alpha = R[roff(j) + j];
-                double tj = 0.0, beta = alpha, scale = 0.0;
-                if (xn != 0.0) {
-                    beta = -copysign(sqrt(alpha * alpha + xn), alpha);
-                    tj = (beta - alpha) / beta;
-                    scale = 1.0 / (alpha - beta);
-                }
-                vb[lane] = x * scale;
-                if (lane == 0) {
-                    s_tau = tj;
-                    s_beta = beta;
-                }
-            }
-            __syncthreads();
-            const double tj = s_tau;
-            if (tj != 0.0) {
-                for (int c0 = j + 1; c0 < kw; c0 += BE_THREADS / 2) {  // warp-uniform trip count (shuffle inside)
-                    const int c = c0 + cpair;
-                    const bool act = c < kw;
-                    double s0 = 0.0, s1 = 0.0;
-                    double bv[QR_B / 2];
 #pragma unroll
-                    for (int i = 0; i < QR_B / 2; ++i) bv[i] = act ? B[(2 * i + half) * kw + c] : 0.0;
-#pragma unroll
-                    for (int i = 0; i < QR_B / 2; i += 2) {
-                        s0 += vb[2 * i + half] * bv[i];
-                        s1 += vb[2 * (i + 1) + half] * bv[i + 1];
-                    }
-                    double sacc = s0 + s1;
-                    sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-                    if (act) {
-                        const double rjc = R[roff(j) + c];
-                        sacc = (sacc + rjc) * tj;
-                        if (half == 0) R[roff(j) + c] = rjc - sacc;
-#pragma unroll
-                        for (int i = 0; i < QR_B / 2; ++i) B[(2 * i + half) * kw + c] = bv[i] - sacc * vb[2 * i + half];
-                    }
-                }
-                if (threadIdx.x == 0) R[roff(j) + j] = s_beta;
-            }
-            __syncthreads();
+        for (int i = 0; i < QR_B; ++i) {
+            double v = 0.0;
+            if (has_col && i < nb) v = c < k ? Hst[(size_t)(r0 + i) * k + c] : rst[r0 + i];
+            x[i] = v;
         }
+        __syncthreads();
+        const int jb = s_j0;
+        // R entries of my column for the next two steps
+        double rq0 = (has_col && jb <= c && jb < k) ? R[jb * ldr + c] : 0.0;
+        double rq1 = (has_col && jb + 1 <= c && jb + 1 < k) ? R[(jb + 1) * ldr + c] : 0.0;
+        for (int j = jb; j < k; ++j) {
+            const int p = j & 1;
+            double rq2 = 0.0;
+            if (has_col && j + 2 <= c && j + 2 < k) rq2 = R[(j + 2) * ldr + c];
+            if (c == j) {
+                double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+#pragma unroll
+                for (int i = 0; i < QR_B; i += 4) {
+                    n0 += x[i] * x[i];
+                    n1 += x[i + 1] * x[i + 1];
+                    n2 += x[i + 2] * x[i + 2];
+                    n3 += x[i + 3] * x[i + 3];
+                }
+                const double xn = (n0 + n1) + (n2 + n3);
+                const double alpha = rq0;
+                double tj = 0.0, scale = 0.0;
+                if (xn != 0.0) {
+                    const double nrm2 = alpha * alpha + xn;
+                    const double nrm = nrm2 * fast_rsqrt(nrm2);
+                    const double beta = -copysign(nrm, alpha);
+                    tj = (beta - alpha) * fast_rcp(beta);
+                    scale = fast_rcp(alpha - beta);
+                    R[j * ldr + j] = beta;
+                }
+#pragma unroll
+                for (int i = 0; i < QR_B; ++i) vbuf[p][i] = x[i] * scale;
+                s_tau[p] = tj;
+            }
+            __syncthreads();
+            const double tj = s_tau[p];
+            if (has_col && c > j && tj != 0.0) {
+                double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+                for (int i = 0; i < QR_B; i += 4) {
+                    s0 += vbuf[p][i] * x[i];
+                    s1 += vbuf[p][i + 1] * x[i + 1];
+                    s2 += vbuf[p][i + 2] * x[i + 2];
+                    s3 += vbuf[p][i + 3] * x[i + 3];
+                }
+                const double sacc = (rq0 + (s0 + s1) + (s2 + s3)) * tj;
+                R[j * ldr + c] = rq0 - sacc;
+#pragma unroll
+                for (int i = 0; i < QR_B; ++i) x[i] -= sacc * vbuf[p][i];
+            }
+            rq0 = rq1;
+            rq1 = rq2;
+        }
+        __syncthreads();
     }
-    for (int e = threadIdx.x; e < k * k; e += BE_THREADS) {
-        int i = e / k, c = e - i * k;
-        Tm[e] = c >= i ? R[roff(i) + c] : 0.0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < k * k; e += QR_THREADS) {
+        int i = e / k, cc = e - i * k;
+        Tm[e] = cc >= i ? R[i * ldr + cc] : 0.0;
     }
-    for (int i = threadIdx.x; i < k; i += BE_THREADS) rt[i] = R[roff(i) + k];
+    for (int i = threadIdx.x; i < k; i += QR_THREADS) rt[i] = R[i * ldr + k];
     if (threadIdx.x == 0) st.mt = k;
 }
 
@@ -2245,7 +2274,7 @@ int be_create(mskf_handle *h) {
     A(bb.l_slot, S * bc.ML); A(bb.l_ok, S * bc.ML); A(bb.l_pass, S * bc.ML); A(bb.l_M, S * bc.ML);
     A(bb.l_eoff, S * bc.ML); A(bb.l_roff, S * bc.ML); A(bb.l_soff, S * bc.ML); A(bb.l_oslots, S * bc.ML * NSM);
     A(bb.Hblk, S * bc.ecap); A(bb.rblk, S * bc.rcap);
-    A(bb.Hst, S * bc.hst_cap); A(bb.rst, S * bc.hst_rows); A(bb.rst_j0, S * bc.hst_rows);
+    A(bb.Hst, S * bc.hst_cap); A(bb.rst, S * bc.hst_rows); A(bb.rst_j0, S * bc.hst_rows); A(bb.Rq, S * (bc.KC + 1) * (bc.KC + 1));
     A(bb.Tm, S * bc.KC * bc.KC); A(bb.rt, S * bc.KC); A(bb.PHt, S * bc.LD * bc.KC); A(bb.Sm, S * bc.KC * bc.KC);
     A(bb.Linv, S * bc.KC * bc.KC); A(bb.W, S * bc.LD * bc.KC); A(bb.yv, S * bc.KC); A(bb.dxv, S * bc.LD);
 #undef A
@@ -2277,7 +2306,6 @@ int be_create(mskf_handle *h) {
     MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_add_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_add));
     MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_sel));
     MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_feature_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_jac[0]));
-    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_qr));
     MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_chol));
     for (int s = 0; s < h->S; ++s) be_reset_kernel<<<1, BE_THREADS, 0, h->stream>>>(bc, bb, s, 1, h->cfg);
     MSKF_CUDA_CHECK(h, cudaGetLastError());
@@ -2330,7 +2358,7 @@ static void launch_update(mskf_handle *h) {
     cudaStream_t q = h->stream;
     const int S = h->S;
     const int tiles_ld = (bc.LD + GT - 1) / GT, tiles_kc = (bc.KC + GT - 1) / GT;
-    MSKF_LAUNCH(h, PK_BE_QR, (be_qr_kernel<<<S, BE_THREADS, B->smem_qr, q>>>(bc, bb)));
+    MSKF_LAUNCH(h, PK_BE_QR, (be_qr_kernel<<<S, QR_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_GEMM_PHT, (be_gemm_kernel<0><<<dim3(tiles_ld * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_GEMM_S, (be_gemm_kernel<1><<<dim3(tiles_kc * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_CHOL, (be_chol_kernel<<<S, BE_THREADS, B->smem_chol, q>>>(bc, bb)));
