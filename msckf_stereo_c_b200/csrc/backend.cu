@@ -1616,7 +1616,7 @@ __global__ void __launch_bounds__(BE_THREADS) be_feature_jac_kernel(BeConst bc, 
                 s_pass = g < thr ? 1 : 0;
                 bb.l_pass[lo + li] = (uint8_t)s_pass;
                 const double dm = M, dr = rows;
-                atomicAdd(bb.work + (size_t)s * MSKF_PROF_TAGS + PK_BE_FEATURE_JAC,
+                atomicAdd(bb.work + (size_t)s * MSKF_PROF_TAGS + (phase == 0 ? PK_BE_FEATURE_JAC : PK_BE_FEATURE_JAC_PRUNE),
                           dm * (dm + 1) * 0.5 * 480.0 + 6.0 * 16.0 * dm * dm + 18.0 * dr * dr + dr * dr * dr / 3.0 + 6.0 * dr * 6.0 * dm);
             }
         }
@@ -1768,7 +1768,7 @@ __device__ __forceinline__ double fast_rcp(double a) {
 // communication per column step is the reflector (32 doubles + tau) through shared memory, with ONE
 // barrier per step (double-buffered).  ~60 KB of registers and 1 KB of shared memory per CTA keep
 // all streams of a 256-stream fleet resident at once.
-__global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb) {
+__global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb, int phase) {
     const int s = blockIdx.x;
     const BeStep sp = bb.step[s];
     if (!sp.active) return;
@@ -1782,7 +1782,7 @@ __global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb)
         // algorithmic flops of this stream's update (dense-equivalent over the active columns)
         const double dm = m, dk = k, dmt = m <= k ? m : k, dld = bc.LD;
         double *w = bb.work + (size_t)s * MSKF_PROF_TAGS;
-        if (m > k) w[PK_BE_QR] += 2.0 * dm * dk * dk;
+        if (m > k) w[phase == 0 ? PK_BE_QR : PK_BE_QR_PRUNE] += 2.0 * dm * dk * dk;
         w[PK_BE_GEMM_PHT] += 2.0 * dld * dk * dmt;
         w[PK_BE_GEMM_S] += 2.0 * dmt * dk * dmt;
         w[PK_BE_CHOL] += 2.0 * dmt * dmt * dmt / 3.0;
@@ -2351,14 +2351,14 @@ int be_init_gravity(mskf_handle *h, int s) {
 }
 
 // measurementUpdate on the stacked system of every stream with do_update set
-static void launch_update(mskf_handle *h) {
+static void launch_update(mskf_handle *h, int phase = 0) {
     BeBuffers *B = h->bb;
     const BeConst &bc = B->bc;
     const BeBuf &bb = B->bb;
     cudaStream_t q = h->stream;
     const int S = h->S;
     const int tiles_ld = (bc.LD + GT - 1) / GT, tiles_kc = (bc.KC + GT - 1) / GT;
-    MSKF_LAUNCH(h, PK_BE_QR, (be_qr_kernel<<<S, QR_THREADS, 0, q>>>(bc, bb)));
+    MSKF_LAUNCH(h, phase == 0 ? PK_BE_QR : PK_BE_QR_PRUNE, (be_qr_kernel<<<S, QR_THREADS, 0, q>>>(bc, bb, phase)));
     MSKF_LAUNCH(h, PK_BE_GEMM_PHT, (be_gemm_kernel<0><<<dim3(tiles_ld * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_GEMM_S, (be_gemm_kernel<1><<<dim3(tiles_kc * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_CHOL, (be_chol_kernel<<<S, BE_THREADS, B->smem_chol, q>>>(bc, bb)));
@@ -2446,10 +2446,10 @@ int be_step(mskf_handle *h, const std::vector<int> &streams, const mskf_feature 
         MSKF_LAUNCH(h, PK_BE_LAYOUT, (be_layout_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb, phase)));
         {
             dim3 g(phase == 0 ? 32 : 48, S);
-            MSKF_LAUNCH(h, PK_BE_FEATURE_JAC, (be_feature_jac_kernel<<<g, BE_THREADS, B->smem_jac[phase], q>>>(bc, bb, phase, maxM)));
+            MSKF_LAUNCH(h, phase == 0 ? PK_BE_FEATURE_JAC : PK_BE_FEATURE_JAC_PRUNE, (be_feature_jac_kernel<<<g, BE_THREADS, B->smem_jac[phase], q>>>(bc, bb, phase, maxM)));
         }
         MSKF_LAUNCH(h, PK_BE_STACK, (be_stack_kernel<<<S, BE_THREADS, (size_t)bc.ML * 10, q>>>(bc, bb, phase)));
-        launch_update(h);
+        launch_update(h, phase);
     }
     MSKF_LAUNCH(h, PK_BE_PRUNE_FINISH, (be_prune_finish_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_FINISH, (be_finish_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb)));

@@ -220,6 +220,7 @@ __device__ __forceinline__ long long warp_sum(long long v) {
 // keeps the row above in a register and takes the right-hand neighbours from lane l + 1 by
 // shuffle, so a bilinear sample costs one load and one shuffle instead of four clamped loads.
 // Needs win + 3 <= 32 lanes.
+template <int WIN>
 __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffers fb, int mode) {
     const int s = blockIdx.y;
     const FeStep st = fb.step[s];
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
     const uint8_t *pa = (mode == 0 ? fb.pyr[st.slot ^ 1] : fb.pyr[st.slot]) + (size_t)s * fc.pyr_bytes;
     const uint8_t *pb = (mode == 0 ? fb.pyr[st.slot] : fb.pyr[2]) + (size_t)s * fc.pyr_bytes;
 
-    const int win = fc.klt_win, half = win >> 1, tw = win + 2;
+    const int win = WIN ? WIN : fc.klt_win, half = win >> 1, tw = win + 2;
     extern __shared__ short klt_smem[];
     short *T = klt_smem + (size_t)warp * ((tw * tw + 2 * win * win + 3) & ~3);
     short2 *Gr = (short2 *)(T + tw * tw + ((tw * tw) & 1));  // (Ix, Iy) per window pixel, 4-byte aligned
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
             const int y0 = wa.iy - half - 1;
             int top = __ldg(A + (size_t)min(max(y0, 0), rows - 1) * cols + xc);
             int rt = __shfl_down_sync(0xffffffffu, top, 1);
+#pragma unroll
             for (int j = 0; j < tw; ++j) {
                 const int bot = __ldg(A + (size_t)min(max(y0 + j + 1, 0), rows - 1) * cols + xc);
                 const int rb = __shfl_down_sync(0xffffffffu, bot, 1);
@@ -269,6 +271,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
         __syncwarp();
         long long A11 = 0, A12 = 0, A22 = 0;
         if (lane < win) {
+#pragma unroll
             for (int j = 0; j < win; ++j) {
                 const int gx = (int)T[(j + 1) * tw + lane + 2] - (int)T[(j + 1) * tw + lane];
                 const int gy = (int)T[(j + 2) * tw + lane + 1] - (int)T[j * tw + lane + 1];
@@ -307,6 +310,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
                     int rt = __shfl_down_sync(0xffffffffu, top, 1);
                     const short *Trow = T + tw + lane + 1;
                     const short2 *Grow = Gr + lane;
+#pragma unroll
                     for (int j = 0; j < win; ++j) {
                         const int bot = __ldg(B + (size_t)min(max(y0 + j + 1, 0), rows - 1) * cols + xc);
                         const int rb = __shfl_down_sync(0xffffffffu, bot, 1);
@@ -425,6 +429,10 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
         score[r][c] = sc;
     }
     __syncthreads();
+    __shared__ int s_nmax;
+    __shared__ unsigned short s_max[DT_H * DT_W / 4];  // strict 3x3 maxima: at most one per 2x2 block
+    if (threadIdx.x == 0) s_nmax = 0;
+    __syncthreads();
     for (int idx = threadIdx.x; idx < DT_H * DT_W; idx += 256) {
         int r = idx / DT_W, c = idx - r * DT_W;
         int gy = y0 + r, gx = x0 + c;
@@ -437,29 +445,47 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
         if (!is_max) continue;
         int k = (gy / fc.det_cell_h) * fc.det_cols + (gx / fc.det_cell_w);
         if (fb.det_occ[(size_t)s * fc.det_cells + k]) continue;
-        float resp = 0.0f;
-        if (!(gx < 5 || gy < 5 || gx > cols - 6 || gy > rows - 6)) {
-            int dXX = 0, dYY = 0, dXY = 0;
-            const int tr = r + DT_HALO, tc = c + DT_HALO;
-            for (int yy = -4; yy < 4; ++yy)
-                for (int xx = -4; xx < 4; ++xx) {
-                    int dx = (int)tile[tr + yy][tc + xx + 1] - (int)tile[tr + yy][tc + xx - 1];
-                    int dy = (int)tile[tr + yy + 1][tc + xx] - (int)tile[tr + yy - 1][tc + xx];
-                    dXX += dx * dx;
-                    dYY += dy * dy;
-                    dXY += dx * dy;
-                }
+        if (gx < 5 || gy < 5 || gx > cols - 6 || gy > rows - 6) continue;  // response 0: never a candidate
+        s_max[atomicAdd(&s_nmax, 1)] = (unsigned short)idx;
+    }
+    __syncthreads();
+    // Shi-Tomasi response over the 8x8 box, one warp per maximum (integer sums: order-free)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int e = warp; e < s_nmax; e += 8) {
+        const int idx = s_max[e];
+        const int r = idx / DT_W, c = idx - r * DT_W;
+        const int gy = y0 + r, gx = x0 + c;
+        const int tr = r + DT_HALO, tc = c + DT_HALO;
+        int dXX = 0, dYY = 0, dXY = 0;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int p = lane + 32 * h2;
+            const int yy = (p >> 3) - 4, xx = (p & 7) - 4;
+            int dx = (int)tile[tr + yy][tc + xx + 1] - (int)tile[tr + yy][tc + xx - 1];
+            int dy = (int)tile[tr + yy + 1][tc + xx] - (int)tile[tr + yy - 1][tc + xx];
+            dXX += dx * dx;
+            dYY += dy * dy;
+            dXY += dx * dy;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dXX += __shfl_xor_sync(0xffffffffu, dXX, o);
+            dYY += __shfl_xor_sync(0xffffffffu, dYY, o);
+            dXY += __shfl_xor_sync(0xffffffffu, dXY, o);
+        }
+        if (lane == 0) {
             float fXX = (float)dXX / 128.0f, fYY = (float)dYY / 128.0f, fXY = (float)dXY / 128.0f;
             float trc = fXX + fYY;
             float d1 = fXX - fYY;
             float xy2 = fXY * fXY;
             float disc = d1 * d1 + 4.0f * xy2;
-            resp = 0.5f * (trc - sqrtf(disc));
-        }
-        if (resp > 0.0f) {
-            unsigned long long key = ((unsigned long long)__float_as_uint(resp) << 32) |
-                                     (unsigned long long)(0xffffffffu - (unsigned)(gy * cols + gx));
-            atomicMax(&fb.det_best[(size_t)s * fc.det_cells + k], key);
+            float resp = 0.5f * (trc - sqrtf(disc));
+            if (resp > 0.0f) {
+                int k = (gy / fc.det_cell_h) * fc.det_cols + (gx / fc.det_cell_w);
+                unsigned long long key = ((unsigned long long)__float_as_uint(resp) << 32) |
+                                         (unsigned long long)(0xffffffffu - (unsigned)(gy * cols + gx));
+                atomicMax(&fb.det_best[(size_t)s * fc.det_cells + k], key);
+            }
         }
     }
 }
@@ -1224,6 +1250,15 @@ int fe_create(mskf_handle *h) {
     return MSKF_OK;
 }
 
+static void launch_klt(mskf_handle *h, int tag, dim3 g, size_t smem, int mode) {
+    const FeConst &fc = h->fc;
+    const FeBuffers &fb = h->fb;
+    cudaStream_t q = h->stream;
+    if (fc.klt_win == 21) MSKF_LAUNCH(h, tag, (klt_kernel<21><<<g, KLT_WARPS * 32, smem, q>>>(fc, fb, mode)));
+    else if (fc.klt_win == 15) MSKF_LAUNCH(h, tag, (klt_kernel<15><<<g, KLT_WARPS * 32, smem, q>>>(fc, fb, mode)));
+    else MSKF_LAUNCH(h, tag, (klt_kernel<0><<<g, KLT_WARPS * 32, smem, q>>>(fc, fb, mode)));
+}
+
 // pyramid level l for `images` (= 2 S) images: vectorised strip kernel when the geometry allows it
 static void launch_pyr_level(mskf_handle *h, int l, int images) {
     const FeConst &fc = h->fc;
@@ -1274,9 +1309,9 @@ int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active) {
     MSKF_LAUNCH(h, PK_FE_BOOK, (fe_prep_track<<<S, FE_THREADS, 0, q>>>(fc, fb)));
     if (max_prev > 0) {
         dim3 g((max_prev + KLT_WARPS - 1) / KLT_WARPS, S);
-        MSKF_LAUNCH(h, PK_KLT_TEMPORAL, (klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 0)));
+        launch_klt(h, PK_KLT_TEMPORAL, g, klt_smem, 0);
         MSKF_LAUNCH(h, PK_FE_BOOK, (fe_after_track<<<S, FE_THREADS, pos_smem, q>>>(fc, fb)));
-        MSKF_LAUNCH(h, PK_KLT_STEREO, (klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 1)));
+        launch_klt(h, PK_KLT_STEREO, g, klt_smem, 1);
     }
     MSKF_LAUNCH(h, PK_FE_BOOK, (fe_after_stereo<<<S, FE_THREADS, (size_t)fc.max_f + 16, q>>>(fc, fb)));
     {
@@ -1287,7 +1322,7 @@ int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active) {
     {
         int cap = any_first ? fc.det_cells : fc.n_cells * fc.grid_max;
         dim3 g((cap + KLT_WARPS - 1) / KLT_WARPS, S);
-        MSKF_LAUNCH(h, PK_KLT_NEW, (klt_kernel<<<g, KLT_WARPS * 32, klt_smem, q>>>(fc, fb, 2)));
+        launch_klt(h, PK_KLT_NEW, g, klt_smem, 2);
     }
     const size_t fin_smem = fe_finish_smem(fc);
     MSKF_LAUNCH(h, PK_FE_BOOK, (fe_finish<<<S, FE_THREADS, fin_smem, q>>>(fc, fb)));
@@ -1368,7 +1403,7 @@ int fe_op_klt(mskf_handle *t, const float *pts_a, float *pts_b, uint8_t *status,
     MSKF_CUDA_CHECK(t, cudaMemcpyAsync(t->fb.k_n, &n, sizeof(int), cudaMemcpyHostToDevice, t->stream));
     const size_t klt_smem = (size_t)KLT_WARPS * ((((fc.klt_win + 2) * (fc.klt_win + 2) + 2 * fc.klt_win * fc.klt_win + 3) & ~3)) * sizeof(short) + 16;
     dim3 g((n + KLT_WARPS - 1) / KLT_WARPS, 1);
-    klt_kernel<<<g, KLT_WARPS * 32, klt_smem, t->stream>>>(fc, t->fb, 1);
+    launch_klt(t, PK_KLT_STEREO, g, klt_smem, 1);
     MSKF_CUDA_CHECK(t, cudaGetLastError());
     MSKF_CUDA_CHECK(t, cudaMemcpyAsync(pts_b, t->fb.k_b, sizeof(float2) * n, cudaMemcpyDeviceToHost, t->stream));
     MSKF_CUDA_CHECK(t, cudaMemcpyAsync(status, t->fb.k_status, n, cudaMemcpyDeviceToHost, t->stream));
