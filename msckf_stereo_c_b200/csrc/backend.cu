@@ -1638,6 +1638,219 @@ __global__ void __launch_bounds__(BE_THREADS) be_feature_jac_kernel(BeConst bc, 
 }
 
 // ======================================================================================
+// Prune-phase variant of the kernel above (pruneCamStateBuffer :1126-1150): every involved feature
+// has exactly the two camera states being removed (M = 2: an 8 x 12 Jacobian, 5 projected rows), and
+// there are hundreds of them per stream, so one WARP handles a feature: lanes 0 and 1 evaluate the
+// two measurementJacobians, lane c < 12 owns column c of H_xj (lane 12 the residual), applies the
+// three reflectors to it privately, and S = H' P_sub H'^T is formed with shuffles against the 12 x 12
+// covariance block staged once per CTA.
+// ======================================================================================
+#define JS_WARPS 8
+__global__ void __launch_bounds__(JS_WARPS * 32) be_feature_jac_prune_kernel(BeConst bc, BeBuf bb) {
+    const int s = blockIdx.y;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    const BeState &st = bb.st[s];
+    const int n_list = st.n_list;
+    if (n_list == 0) return;
+    const size_t fo = (size_t)s * bc.MF, lo = (size_t)s * bc.ML;
+    const double *P = bb.P + (size_t)s * bc.LD * bc.LD;
+    const int LD = bc.LD;
+    __shared__ double Ps[12][12];
+    __shared__ double sHx[JS_WARPS][2][4][6], sHf[JS_WARPS][8][3], sr[JS_WARPS][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int os[2] = {st.rm_slot[0], st.rm_slot[1]};
+    for (int e = threadIdx.x; e < 144; e += JS_WARPS * 32) {
+        const int i = e / 12, j = e - i * 12;
+        Ps[i][j] = P[(size_t)(N21 + 6 * os[i / 6] + i % 6) * LD + N21 + 6 * os[j / 6] + j % 6];
+    }
+    __syncthreads();
+    for (int li = blockIdx.x * JS_WARPS + warp; li < n_list; li += gridDim.x * JS_WARPS) {
+        const int slot = bb.l_slot[lo + li];
+        __syncwarp();
+        if (lane < 2) {
+            // measurementJacobian, msckf_vio.cpp:610-677
+            const int t = lane, cs = os[t];
+            const BeCam &c = st.cam[cs];
+            const double *z = bb.f_obs + (((size_t)s * bc.MF + slot) * bc.NS + cs) * 4;
+            const double *pw = bb.f_pos + (fo + slot) * 3;
+            double Rw0[9], Rw1[9], t1w[3], tmp[3];
+            quat_to_rot(c.q, Rw0);
+            m3mul(bc.R01, Rw0, Rw1);
+            m3Tv(Rw1, bc.t01, tmp);
+            for (int i = 0; i < 3; ++i) t1w[i] = c.p[i] - tmp[i];
+            double d0[3] = {pw[0] - c.p[0], pw[1] - c.p[1], pw[2] - c.p[2]};
+            double d1[3] = {pw[0] - t1w[0], pw[1] - t1w[1], pw[2] - t1w[2]};
+            double p0[3], p1[3];
+            m3v(Rw0, d0, p0);
+            m3v(Rw1, d1, p1);
+            double dz0[4][3] = {{1 / p0[2], 0, -p0[0] / (p0[2] * p0[2])}, {0, 1 / p0[2], -p0[1] / (p0[2] * p0[2])}, {0, 0, 0}, {0, 0, 0}};
+            double dz1[4][3] = {{0, 0, 0}, {0, 0, 0}, {1 / p1[2], 0, -p1[0] / (p1[2] * p1[2])}, {0, 1 / p1[2], -p1[1] / (p1[2] * p1[2])}};
+            double sk0[9], R01sk[9];
+            skew3(p0, sk0);
+            m3mul(bc.R01, sk0, R01sk);
+            double Hxl[4][6];
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    double a = 0, b = 0;
+                    for (int k = 0; k < 3; ++k) {
+                        a += dz0[i][k] * sk0[k * 3 + j] + dz1[i][k] * R01sk[k * 3 + j];
+                        b += dz0[i][k] * (-Rw0[k * 3 + j]) + dz1[i][k] * (-Rw1[k * 3 + j]);
+                    }
+                    Hxl[i][j] = a;
+                    Hxl[i][3 + j] = b;
+                }
+            double u[6], Rn[9], dn[3] = {pw[0] - c.pn[0], pw[1] - c.pn[1], pw[2] - c.pn[2]}, K[9];
+            quat_to_rot(c.qn, Rn);
+            m3v(Rn, st.g, u);
+            skew3(dn, K);
+            m3v(K, st.g, u + 3);
+            double utu = 0;
+            for (int i = 0; i < 6; ++i) utu += u[i] * u[i];
+            for (int i = 0; i < 4; ++i) {
+                double au = 0;
+                for (int k = 0; k < 6; ++k) au += Hxl[i][k] * u[k];
+                au *= (1.0 / utu);
+                for (int k = 0; k < 6; ++k) sHx[warp][t][i][k] = Hxl[i][k] - au * u[k];
+                for (int k = 0; k < 3; ++k) sHf[warp][4 * t + i][k] = -(Hxl[i][3 + k] - au * u[3 + k]);
+            }
+            sr[warp][4 * t + 0] = z[0] - p0[0] / p0[2];
+            sr[warp][4 * t + 1] = z[1] - p0[1] / p0[2];
+            sr[warp][4 * t + 2] = z[2] - p1[0] / p1[2];
+            sr[warp][4 * t + 3] = z[3] - p1[1] / p1[2];
+        }
+        __syncwarp();
+        // every lane: Householder QR of H_f (8 x 3), redundantly (it is tiny and needs no traffic)
+        double V[8][3], tau[3];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) V[i][k] = sHf[warp][i][k];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double xn = 0;
+#pragma unroll
+            for (int i = j + 1; i < 8; ++i) xn += V[i][j] * V[i][j];
+            const double alpha = V[j][j];
+            double tj = 0.0;
+            if (xn != 0.0) {
+                const double beta = -copysign(sqrt(alpha * alpha + xn), alpha);
+                tj = (beta - alpha) / beta;
+                const double scale = 1.0 / (alpha - beta);
+#pragma unroll
+                for (int i = j + 1; i < 8; ++i) V[i][j] *= scale;
+#pragma unroll
+                for (int cc = j + 1; cc < 3; ++cc) {
+                    double sacc = V[j][cc];
+#pragma unroll
+                    for (int i = j + 1; i < 8; ++i) sacc += V[i][j] * V[i][cc];
+                    sacc *= tj;
+                    V[j][cc] -= sacc;
+#pragma unroll
+                    for (int i = j + 1; i < 8; ++i) V[i][cc] -= sacc * V[i][j];
+                }
+            } else {
+#pragma unroll
+                for (int i = j + 1; i < 8; ++i) V[i][j] = 0.0;
+            }
+            tau[j] = tj;
+        }
+        // my column of [H_xj | r]: lane c < 12 -> camera block c / 6, column c % 6; lane 12 -> r
+        double col[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double v = 0.0;
+            if (lane < 12) {
+                if ((i >> 2) == lane / 6) v = sHx[warp][lane / 6][i & 3][lane % 6];
+            } else if (lane == 12) {
+                v = sr[warp][i];
+            }
+            col[i] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double sacc = col[j];
+#pragma unroll
+            for (int i = j + 1; i < 8; ++i) sacc += V[i][j] * col[i];
+            sacc *= tau[j];
+            col[j] -= sacc;
+#pragma unroll
+            for (int i = j + 1; i < 8; ++i) col[i] -= sacc * V[i][j];
+        }
+        // HP[:, d] for my column d (lanes < 12): sum_c H'[:, c] P[c][d]
+        double hp[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int cc = 0; cc < 12; ++cc) {
+            const double pcd = lane < 12 ? Ps[cc][lane] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) hp[i] += __shfl_sync(0xffffffffu, col[3 + i], cc) * pcd;
+        }
+        // S = HP H'^T (lower triangle), summed over the 12 column lanes
+        double S[15];
+        {
+            int q = 0;
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    double v = lane < 12 ? hp[i] * col[3 + j] : 0.0;
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    S[q++] = v + (i == j ? bc.obs_noise : 0.0);
+                }
+        }
+        double rp[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) rp[i] = __shfl_sync(0xffffffffu, col[3 + i], 12);
+        // Cholesky 5 x 5 + forward substitution (every lane of the first half-warp holds the same values)
+        double g = 0;
+        {
+            double L[15];
+            int q = 0;
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    double v = S[q];
+#pragma unroll
+                    for (int k = 0; k < j; ++k) v -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+                    L[q] = (i == j) ? sqrt(v) : v / L[j * (j + 1) / 2 + j];
+                    ++q;
+                }
+            double y[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                double v = rp[i];
+#pragma unroll
+                for (int k = 0; k < i; ++k) v -= L[i * (i + 1) / 2 + k] * y[k];
+                y[i] = v / L[i * (i + 1) / 2 + i];
+                g += y[i] * y[i];
+            }
+        }
+        const double thr = c_chi2[bc.chi2_mode][1];  // dof = involved.size() = 2, msckf_vio.cpp:1145
+        const int pass = g < thr ? 1 : 0;
+        double *H = bb.Hblk + (size_t)s * bc.ecap + bb.l_eoff[lo + li];   // [8][12], rows 3.. used
+        double *rg = bb.rblk + (size_t)s * bc.rcap + bb.l_roff[lo + li];  // [8]
+        if (pass) {
+            if (lane < 12) {
+#pragma unroll
+                for (int i = 3; i < 8; ++i) H[i * 12 + lane] = col[i];
+            } else if (lane == 12) {
+#pragma unroll
+                for (int i = 3; i < 8; ++i) rg[i] = col[i];
+            }
+        }
+        if (lane == 0) {
+            bb.l_pass[lo + li] = (uint8_t)pass;
+            bb.l_oslots[(lo + li) * NSM + 0] = (uint8_t)os[0];
+            bb.l_oslots[(lo + li) * NSM + 1] = (uint8_t)os[1];
+        }
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        bb.work[(size_t)s * MSKF_PROF_TAGS + PK_BE_FEATURE_JAC_PRUNE] += (double)n_list * (2.0 * 480.0 + 3.0 * 13.0 * 32.0 + 2.0 * 5.0 * 144.0 + 2.0 * 15.0 * 12.0 + 60.0);
+}
+
+// ======================================================================================
 // Stack the gated blocks (row cap of removeLostFeatures), find the active camera columns.
 // ======================================================================================
 __global__ void __launch_bounds__(BE_THREADS) be_stack_kernel(BeConst bc, BeBuf bb, int phase) {
@@ -2444,9 +2657,12 @@ int be_step(mskf_handle *h, const std::vector<int> &streams, const mskf_feature 
             MSKF_LAUNCH(h, PK_BE_TRIANGULATE, (be_triangulate_kernel<<<g, TRI_WARPS * 32, 0, q>>>(bc, bb, phase)));
         }
         MSKF_LAUNCH(h, PK_BE_LAYOUT, (be_layout_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb, phase)));
-        {
-            dim3 g(phase == 0 ? 32 : 48, S);
-            MSKF_LAUNCH(h, phase == 0 ? PK_BE_FEATURE_JAC : PK_BE_FEATURE_JAC_PRUNE, (be_feature_jac_kernel<<<g, BE_THREADS, B->smem_jac[phase], q>>>(bc, bb, phase, maxM)));
+        if (phase == 0) {
+            dim3 g(32, S);
+            MSKF_LAUNCH(h, PK_BE_FEATURE_JAC, (be_feature_jac_kernel<<<g, BE_THREADS, B->smem_jac[0], q>>>(bc, bb, 0, maxM)));
+        } else {
+            dim3 g(8, S);
+            MSKF_LAUNCH(h, PK_BE_FEATURE_JAC_PRUNE, (be_feature_jac_prune_kernel<<<g, JS_WARPS * 32, 0, q>>>(bc, bb)));
         }
         MSKF_LAUNCH(h, PK_BE_STACK, (be_stack_kernel<<<S, BE_THREADS, (size_t)bc.ML * 10, q>>>(bc, bb, phase)));
         launch_update(h, phase);
