@@ -8,8 +8,9 @@ frame of every stream through ImageProcessor::stereoCallback + MsckfVio::feature
 (mskf_step).  Streams are sharded over ranks; there is no collective on the data path.
 
   value  frames/s with the images already resident in HBM (device-rendered), CUDA-event timed
-  e2e    frames/s through the C ABI with HOST buffers: pinned images -> H2D, IMU rows, step,
-         poses read back every step
+  e2e    frames/s through the C ABI with HOST buffers: every step uploads one frame set from pinned
+         host memory (on the engine's copy stream, overlapping the previous frame's kernels), pushes
+         the IMU rows, runs the step and reads the poses back
   roofline     the dominant kernel class of the timed region: algorithmic work (counted by the
                kernels themselves from the sizes they actually processed) / CUDA-event time
   cpu_baseline the CPU oracle (a port: the reference cannot be compiled here) on one host core
@@ -207,7 +208,7 @@ def run_ours(args, rank, world, local_rank):
         e.sync()
     # ---- pre-render the timed frames: device-resident set for `value`, pinned host set for `e2e`
     n_dev = W + K
-    n_e2e = W + K
+    n_e2e = W + K + 1  # the upload of frame i+1 is issued while frame i computes
     frames_dev = torch.empty((n_dev, S, 2, img), dtype=torch.uint8, device=dev)
     frames_host = torch.empty((n_e2e, S, 2, img), dtype=torch.uint8).pin_memory()
     with torch.cuda.stream(stream):
@@ -261,17 +262,25 @@ def run_ours(args, rank, world, local_rank):
     poses = None
     h2d = d2h = 0
 
-    def step_e2e(i, kk):
-        nonlocal poses, h2d, d2h
-        nb = feed_imu(kk)
+    def push_host(i, kk):
+        nonlocal h2d
         tvec[:] = fleet.frame_time(kk)
         base = frames_host[i].data_ptr()
-        e.push_stereo_batch(tvec, base, base + img, 2 * img, device=False)  # pinned host -> staging (H2D)
+        e.push_stereo_batch(tvec, base, base + img, 2 * img, device=False)  # pinned host -> landing area, copy stream
+        h2d = 2 * img * S
+
+    def step_e2e(i, kk):
+        """One e2e step: IMU rows + step of frame i, upload of frame i+1 (overlaps the kernels of
+        frame i on the copy stream), poses of frame i read back to the host."""
+        nonlocal poses, h2d, d2h
+        nb = feed_imu(kk)
         e.step()
-        poses = e.poses()  # device -> host read of every stream's T_b_w (synchronises)
-        h2d = 2 * img * S + nb
+        push_host(i + 1, kk + 1)
+        poses = e.poses()  # device -> host read of every stream's T_b_w (synchronises the compute stream)
+        h2d += nb
         d2h = poses.nbytes
 
+    push_host(0, k)
     for i in range(W):
         step_e2e(i, k)
         k += 1

@@ -68,7 +68,7 @@ struct GridSoA {            // one grid of one stream, publish order (cell asc, 
 
 struct FeBuffers {
     uint8_t *pyr[3];        // [S][pyr_bytes] x3 : cam0 slot0, cam0 slot1, cam1
-    uint8_t *staging;       // [S][2][rows*cols]
+    uint8_t *staging;       // [2 slots][S][2][rows*cols]
     const uint8_t **src0, **src1;  // [S] device pointers to this step's level-0 sources
     FeStep *step;           // [S]
     // grids: prev and curr (index by ping-pong flag gslot[s])
@@ -135,6 +135,14 @@ struct mskf_handle {
     int S = 0, device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // host uploads run on their own stream into a double-buffered landing area, so the upload of
+    // frame k+1 overlaps the kernels of frame k (mskf_push_stereo* -> stage_*; engine.cu)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    bool consumed_valid[2] = {false, false};
+    int stage_cur = 0;          // slot the next pushes land in
+    bool stage_dirty = false;   // copies issued into stage_cur since the last step
+    bool stage_waited = false;  // the copy stream already waited for the slot to be consumed
     std::string err;
     mskf::FeConst fc;
     mskf::FeBuffers fb;
@@ -181,6 +189,8 @@ void prof_collect(mskf_handle *h);
 
 // frontend.cu
 int fe_create(mskf_handle *h);
+int stage_begin_consume(mskf_handle *h);  // compute stream waits for the uploads of this step
+int stage_end_consume(mskf_handle *h);    // level 0 has been landed: the slot may be overwritten
 int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active);
 int fe_op_detect(mskf_handle *t, const float *occ, int n_occ, float *out_xy, double *out_resp, int cap, int *n,
                  uint8_t *score_map);

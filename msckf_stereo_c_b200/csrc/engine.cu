@@ -141,6 +141,36 @@ void prof_collect(mskf_handle *h) {
     h->prof_tag.clear();
 }
 
+// ---- upload staging: copy stream + double-buffered landing area ----------------------------
+static uint8_t *stage_slot_base(mskf_handle *h) {
+    const size_t img = (size_t)h->cfg.img_rows * h->cfg.img_cols;
+    return h->fb.staging + (size_t)h->stage_cur * h->S * 2 * img;
+}
+static int stage_prepare_write(mskf_handle *h) {
+    if (!h->stage_waited) {
+        // the kernels that read this slot two steps ago must have finished with it
+        if (h->consumed_valid[h->stage_cur]) MSKF_CUDA_CHECK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[h->stage_cur], 0));
+        h->stage_waited = true;
+    }
+    h->stage_dirty = true;
+    return MSKF_OK;
+}
+int stage_begin_consume(mskf_handle *h) {
+    if (!h->stage_dirty) return MSKF_OK;
+    MSKF_CUDA_CHECK(h, cudaEventRecord(h->ev_copied[h->stage_cur], h->copy_stream));
+    MSKF_CUDA_CHECK(h, cudaStreamWaitEvent(h->stream, h->ev_copied[h->stage_cur], 0));
+    return MSKF_OK;
+}
+int stage_end_consume(mskf_handle *h) {
+    if (!h->stage_dirty) return MSKF_OK;
+    MSKF_CUDA_CHECK(h, cudaEventRecord(h->ev_consumed[h->stage_cur], h->stream));
+    h->consumed_valid[h->stage_cur] = true;
+    h->stage_cur ^= 1;
+    h->stage_dirty = false;
+    h->stage_waited = false;
+    return MSKF_OK;
+}
+
 extern "C" {
 
 // ---- bench instrumentation: CUDA-event time per kernel class on the launching stream
@@ -182,6 +212,11 @@ int mskf_create(const mskf_config *cfg, int n_streams, int device, mskf_handle *
     MSKF_CUDA_CHECK(h, cudaSetDevice(device));
     MSKF_CUDA_CHECK(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
+    MSKF_CUDA_CHECK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        MSKF_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+        MSKF_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));
+    }
     int rc = dev_alloc(h, &h->d_work, (size_t)n_streams * MSKF_PROF_TAGS);
     if (rc != MSKF_OK) return rc;
     rc = fe_create(h);
@@ -213,6 +248,14 @@ void mskf_destroy(mskf_handle *h) {
             cudaFreeHost((void *)ex->h_src_ring[i]);
         }
         delete ex;
+    }
+    if (h->copy_stream) {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamDestroy(h->copy_stream);
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+        if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
     }
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     for (void *p : h->allocs) cudaFree(p);
@@ -267,15 +310,18 @@ int mskf_push_stereo_batch(mskf_handle *h, const double *t, const uint8_t *cam0,
     MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
     const size_t img = (size_t)h->cfg.img_rows * h->cfg.img_cols;
     if (stream_stride < img) return MSKF_ERR_ARG;
-    // one strided copy per camera: stream s lands at staging[s][cam]
-    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(h->fb.staging, 2 * img, cam0, stream_stride, img, h->S, cudaMemcpyHostToDevice, h->stream));
-    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(h->fb.staging + img, 2 * img, cam1, stream_stride, img, h->S, cudaMemcpyHostToDevice, h->stream));
+    // one strided copy per camera on the copy stream: stream s lands at staging[slot][s][cam]
+    int rc = stage_prepare_write(h);
+    if (rc != MSKF_OK) return rc;
+    uint8_t *base = stage_slot_base(h);
+    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(base, 2 * img, cam0, stream_stride, img, h->S, cudaMemcpyHostToDevice, h->copy_stream));
+    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(base + img, 2 * img, cam1, stream_stride, img, h->S, cudaMemcpyHostToDevice, h->copy_stream));
     for (int s = 0; s < h->S; ++s) {
         HostStream &hs = h->hs[s];
         hs.pending = true;
         hs.pending_t = t[s];
-        hs.src0 = h->fb.staging + ((size_t)s * 2 + 0) * img;
-        hs.src1 = h->fb.staging + ((size_t)s * 2 + 1) * img;
+        hs.src0 = base + ((size_t)s * 2 + 0) * img;
+        hs.src1 = base + ((size_t)s * 2 + 1) * img;
     }
     return MSKF_OK;
 }
@@ -317,11 +363,13 @@ int mskf_push_stereo(mskf_handle *h, int s, double t, const uint8_t *cam0, const
     }
     MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
     const size_t img = (size_t)rows * cols;
-    uint8_t *d0 = h->fb.staging + ((size_t)s * 2 + 0) * img, *d1 = h->fb.staging + ((size_t)s * 2 + 1) * img;
+    int rc = stage_prepare_write(h);
+    if (rc != MSKF_OK) return rc;
+    uint8_t *d0 = stage_slot_base(h) + ((size_t)s * 2 + 0) * img, *d1 = stage_slot_base(h) + ((size_t)s * 2 + 1) * img;
     // pageable sources are staged by the runtime before the call returns; page-locked
     // sources are read asynchronously and must stay unchanged until the next mskf_sync()
-    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(d0, cols, cam0, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
-    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(d1, cols, cam1, stride, cols, rows, cudaMemcpyHostToDevice, h->stream));
+    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(d0, cols, cam0, stride, cols, rows, cudaMemcpyHostToDevice, h->copy_stream));
+    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(d1, cols, cam1, stride, cols, rows, cudaMemcpyHostToDevice, h->copy_stream));
     HostStream &hs = h->hs[s];
     hs.pending = true;
     hs.pending_t = t;
@@ -385,6 +433,10 @@ int mskf_frontend_step(mskf_handle *h) {
         hs.msg_t = st.t;
     }
     if (!any) return MSKF_OK;
+    {
+        int rc = stage_begin_consume(h);
+        if (rc != MSKF_OK) return rc;
+    }
     MSKF_CUDA_CHECK(h, cudaMemcpyAsync(h->fb.step, hstep, sizeof(FeStep) * S, cudaMemcpyHostToDevice, h->stream));
     MSKF_CUDA_CHECK(h, cudaMemcpyAsync(h->fb.src0, hsrc, sizeof(uint8_t *) * S, cudaMemcpyHostToDevice, h->stream));
     MSKF_CUDA_CHECK(h, cudaMemcpyAsync(h->fb.src1, hsrc + S, sizeof(uint8_t *) * S, cudaMemcpyHostToDevice, h->stream));
@@ -417,6 +469,7 @@ int mskf_step(mskf_handle *h) {
 int mskf_sync(mskf_handle *h) {
     if (!h) return MSKF_ERR_ARG;
     MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
+    MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->copy_stream));
     MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
     if (h->prof_on) prof_collect(h);
     return MSKF_OK;

@@ -1224,7 +1224,7 @@ int fe_create(mskf_handle *h) {
     int rc;
 #define A(p, n) if ((rc = dev_alloc(h, &(p), (n))) != MSKF_OK) return rc
     for (int i = 0; i < 3; ++i) A(fb.pyr[i], S * fc.pyr_bytes);
-    A(fb.staging, S * 2 * (size_t)fc.rows * fc.cols);
+    A(fb.staging, 2 * S * 2 * (size_t)fc.rows * fc.cols);
     A(fb.src0, S); A(fb.src1, S);
     A(fb.step, S);
     for (int g = 0; g < 2; ++g) {
@@ -1299,6 +1299,10 @@ int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active) {
     // pyramids
     for (int l = 1; l < fc.levels; ++l) {
         launch_pyr_level(h, l, S * 2);
+        if (l == 1) {
+            int rc = stage_end_consume(h);
+            if (rc != MSKF_OK) return rc;
+        }
         // algorithmic bytes: read level l-1, write level l (+ the level-0 landing copy at l == 1)
         double in = (double)fc.lvl_rows[l - 1] * fc.lvl_cols[l - 1], out = (double)fc.lvl_rows[l] * fc.lvl_cols[l];
         h->work_host[l == 1 ? PK_PYR_L1 : PK_PYR_LN] += 2.0 * n_active * (in + out + (l == 1 ? in : 0.0));
@@ -1338,12 +1342,22 @@ static int op_prepare(mskf_handle *t) {
     st.is_first = 1;
     st.slot = 0;
     HostStream &hs = t->hs[0];
+    {
+        int rc = stage_begin_consume(t);
+        if (rc != MSKF_OK) return rc;
+    }
     MSKF_CUDA_CHECK(t, cudaMemcpyAsync(t->fb.step, &st, sizeof(st), cudaMemcpyHostToDevice, t->stream));
     MSKF_CUDA_CHECK(t, cudaMemcpyAsync(t->fb.src0, &hs.src0, sizeof(uint8_t *), cudaMemcpyHostToDevice, t->stream));
     MSKF_CUDA_CHECK(t, cudaMemcpyAsync(t->fb.src1, &hs.src1, sizeof(uint8_t *), cudaMemcpyHostToDevice, t->stream));
     MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->stream));
     const FeConst &fc = t->fc;
-    for (int l = 1; l < fc.levels; ++l) launch_pyr_level(t, l, 2);
+    for (int l = 1; l < fc.levels; ++l) {
+        launch_pyr_level(t, l, 2);
+        if (l == 1) {
+            int rc = stage_end_consume(t);
+            if (rc != MSKF_OK) return rc;
+        }
+    }
     MSKF_CUDA_CHECK(t, cudaGetLastError());
     hs.slot = 0;
     hs.pending = false;
