@@ -1272,6 +1272,53 @@ __device__ __forceinline__ void cta_gemm_tile(int M, int N, int K, int i0, int j
         }
 }
 
+// Same tile, inner product on the fp64 tensor pipe: mma.sync m8n8k4 (DMMA).  Warp w owns rows
+// [8w, 8w+8) of the 64 x 64 tile and all eight 8-column sub-tiles (16 accumulator doubles per thread);
+// per k-step of 4 it loads one A fragment and eight B fragments from the staged tiles.
+__device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <bool A_KFAST, bool B_KFAST, class FA, class FB, class FC>
+__device__ __forceinline__ void cta_gemm_tile_dmma(int M, int N, int K, int i0, int j0, FA fa, FB fb, FC fc, GemmSmem &sm) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    double acc[8][2];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = 0.0;
+    for (int k0 = 0; k0 < K; k0 += GKK) {
+        __syncthreads();
+        for (int e = tid; e < GT * GKK; e += BE_THREADS) {
+            int i, l;
+            if (A_KFAST) { i = e / GKK; l = e - i * GKK; } else { l = e / GT; i = e - l * GT; }
+            int gi = i0 + i, gl = k0 + l;
+            sm.a[l][i] = (gi < M && gl < K) ? fa(gi, gl) : 0.0;
+        }
+        for (int e = tid; e < GT * GKK; e += BE_THREADS) {
+            int j, l;
+            if (B_KFAST) { j = e / GKK; l = e - j * GKK; } else { l = e / GT; j = e - l * GT; }
+            int gj = j0 + j, gl = k0 + l;
+            sm.b[l][j] = (gj < N && gl < K) ? fb(gl, gj) : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GKK; kk += 4) {
+            const double a = sm.a[kk + t4][warp * 8 + g];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) dmma_884(acc[n][0], acc[n][1], a, sm.b[kk + t4][n * 8 + g]);
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            int gi = i0 + warp * 8 + g, gj = j0 + n * 8 + 2 * t4 + h2;
+            if (gi < M && gj < N) fc(gi, gj, acc[n][h2]);
+        }
+}
+
 // In-place Cholesky of an n x n matrix in shared memory (row-major, leading dimension ld,
 // lower triangle), CTA-wide; then y <- L^-1 y.
 __device__ void cta_cholesky(double *S, int n, int ld) {
@@ -1960,16 +2007,14 @@ __global__ void __launch_bounds__(BE_THREADS) be_stack_kernel(BeConst bc, BeBuf 
 // scalars sit on the serial chain of the factorization, and DSQRT/DDIV sequences are ~2x longer
 __device__ __forceinline__ double fast_rsqrt(double a) {
     if (!(a > 1e-30 && a < 1e30)) return 1.0 / sqrt(a);  // outside the fp32 seed's range
-    double y = (double)rsqrtf((float)a);
-    y = y * (1.5 - 0.5 * a * y * y);
+    double y = (double)rsqrtf((float)a);  // relative error 2^-22 -> 2^-43 -> 2^-85 after two Newton steps
     y = y * (1.5 - 0.5 * a * y * y);
     y = y * (1.5 - 0.5 * a * y * y);
     return y;
 }
 __device__ __forceinline__ double fast_rcp(double a) {
     if (!(fabs(a) > 1e-30 && fabs(a) < 1e30)) return 1.0 / a;
-    double y = (double)__frcp_rn((float)a);
-    y = y + y * (1.0 - a * y);
+    double y = (double)__frcp_rn((float)a);  // 2^-24 -> 2^-48 -> 2^-96
     y = y + y * (1.0 - a * y);
     y = y + y * (1.0 - a * y);
     return y;
@@ -2011,7 +2056,7 @@ __global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb,
     const int kw = k + 1, ldr = KC + 1;
     double *R = bb.Rq + (size_t)s * ldr * ldr;  // R[j][c] at j * ldr + c
     __shared__ double vbuf[2][QR_B];
-    __shared__ double s_tau[2];
+    __shared__ double s_tau[2], s_w0[2];
     __shared__ int s_j0;
     const int c = threadIdx.x;
     const bool has_col = c < kw;
@@ -2037,37 +2082,39 @@ __global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb,
         // R entries of my column for the next two steps
         double rq0 = (has_col && jb <= c && jb < k) ? R[jb * ldr + c] : 0.0;
         double rq1 = (has_col && jb + 1 <= c && jb + 1 < k) ? R[(jb + 1) * ldr + c] : 0.0;
+        // Unnormalised reflectors: H_j = I - t w w^T with w = [alpha - beta; x] and t = 1 / (beta (beta - alpha)),
+        // so the owner can publish its column the moment it is up to date and only two scalars
+        // (w0, t) sit behind the rsqrt / rcp chain.  xn (the squared norm of my column) is carried
+        // along by the update that produces the column.
+        double xn = 0.0;
+        if (c == jb) {
+#pragma unroll
+            for (int i = 0; i < QR_B; ++i) xn += x[i] * x[i];
+        }
         for (int j = jb; j < k; ++j) {
             const int p = j & 1;
             double rq2 = 0.0;
             if (has_col && j + 2 <= c && j + 2 < k) rq2 = R[(j + 2) * ldr + c];
             if (c == j) {
-                double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
-                for (int i = 0; i < QR_B; i += 4) {
-                    n0 += x[i] * x[i];
-                    n1 += x[i + 1] * x[i + 1];
-                    n2 += x[i + 2] * x[i + 2];
-                    n3 += x[i + 3] * x[i + 3];
-                }
-                const double xn = (n0 + n1) + (n2 + n3);
+                for (int i = 0; i < QR_B; ++i) vbuf[p][i] = x[i];
                 const double alpha = rq0;
-                double tj = 0.0, scale = 0.0;
+                double t = 0.0, w0 = 0.0;
                 if (xn != 0.0) {
                     const double nrm2 = alpha * alpha + xn;
-                    const double nrm = nrm2 * fast_rsqrt(nrm2);
-                    const double beta = -copysign(nrm, alpha);
-                    tj = (beta - alpha) * fast_rcp(beta);
-                    scale = fast_rcp(alpha - beta);
+                    const double beta = -copysign(nrm2 * fast_rsqrt(nrm2), alpha);
+                    const double d = beta - alpha;
+                    t = fast_rcp(beta * d);
+                    w0 = -d;
                     R[j * ldr + j] = beta;
                 }
-#pragma unroll
-                for (int i = 0; i < QR_B; ++i) vbuf[p][i] = x[i] * scale;
-                s_tau[p] = tj;
+                s_w0[p] = w0;
+                s_tau[p] = t;
             }
             __syncthreads();
-            const double tj = s_tau[p];
-            if (has_col && c > j && tj != 0.0) {
+            const double t = s_tau[p];
+            if (has_col && c > j && t != 0.0) {
+                const double w0 = s_w0[p];
                 double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
                 for (int i = 0; i < QR_B; i += 4) {
@@ -2076,10 +2123,22 @@ __global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb,
                     s2 += vbuf[p][i + 2] * x[i + 2];
                     s3 += vbuf[p][i + 3] * x[i + 3];
                 }
-                const double sacc = (rq0 + (s0 + s1) + (s2 + s3)) * tj;
-                R[j * ldr + c] = rq0 - sacc;
+                const double sacc = (w0 * rq0 + (s0 + s1) + (s2 + s3)) * t;
+                R[j * ldr + c] = rq0 - sacc * w0;
 #pragma unroll
                 for (int i = 0; i < QR_B; ++i) x[i] -= sacc * vbuf[p][i];
+            }
+            if (c == j + 1) {
+                // I own the next reflector: squared norm of my (now final) column
+                double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+#pragma unroll
+                for (int i = 0; i < QR_B; i += 4) {
+                    n0 += x[i] * x[i];
+                    n1 += x[i + 1] * x[i + 1];
+                    n2 += x[i + 2] * x[i + 2];
+                    n3 += x[i + 3] * x[i + 3];
+                }
+                xn = (n0 + n1) + (n2 + n3);
             }
             rq0 = rq1;
             rq1 = rq2;
@@ -2122,14 +2181,14 @@ __global__ void __launch_bounds__(BE_THREADS) be_gemm_kernel(BeConst bc, BeBuf b
         const int tn = (mt + GT - 1) / GT;
         const int ti = blockIdx.x / tn, tj = blockIdx.x % tn;
         if (ti * GT >= LD || tn == 0) return;
-        cta_gemm_tile<true, true>(
+        cta_gemm_tile_dmma<true, true>(
             LD, mt, k, ti * GT, tj * GT, [&](int i, int l) { return P[(size_t)i * LD + cols[l]]; },
             [&](int l, int j) { return Tm[j * k + l]; }, [&](int i, int j, double v) { PHt[(size_t)i * KC + j] = v; }, gs);
     } else if (OP == 1) {
         const int tn = (mt + GT - 1) / GT;
         const int ti = blockIdx.x / tn, tj = blockIdx.x % tn;
         if (ti >= tn) return;
-        cta_gemm_tile<true, false>(
+        cta_gemm_tile_dmma<true, false>(
             mt, mt, k, ti * GT, tj * GT, [&](int i, int l) { return Tm[i * k + l]; },
             [&](int l, int j) { return PHt[(size_t)cols[l] * KC + j]; },
             [&](int i, int j, double v) { Sm[i * KC + j] = v + (i == j ? bc.obs_noise : 0.0); }, gs);
@@ -2137,7 +2196,7 @@ __global__ void __launch_bounds__(BE_THREADS) be_gemm_kernel(BeConst bc, BeBuf b
         const int tn = (mt + GT - 1) / GT;
         const int ti = blockIdx.x / tn, tj = blockIdx.x % tn;
         if (ti * GT >= LD) return;
-        cta_gemm_tile<true, true>(
+        cta_gemm_tile_dmma<true, true>(
             LD, mt, mt, ti * GT, tj * GT, [&](int i, int l) { return PHt[(size_t)i * KC + l]; },
             [&](int l, int j) { return Linv[j * KC + l]; }, [&](int i, int j, double v) { W[(size_t)i * KC + j] = v; }, gs);
     } else {
@@ -2146,7 +2205,7 @@ __global__ void __launch_bounds__(BE_THREADS) be_gemm_kernel(BeConst bc, BeBuf b
         while (t > ti) { t -= ti + 1; ++ti; }
         const int tj = t;
         if (ti * GT >= LD) return;
-        cta_gemm_tile<true, true>(
+        cta_gemm_tile_dmma<true, true>(
             LD, LD, mt, ti * GT, tj * GT, [&](int i, int l) { return W[(size_t)i * KC + l]; },
             [&](int l, int j) { return W[(size_t)j * KC + l]; },
             [&](int i, int j, double v) {
