@@ -239,6 +239,15 @@ long long mskf_launch_count(const mskf_handle *h);
 int mskf_get_n_published(mskf_handle *h, int stream, int *n);
 /* Poses T_b_w (row-major 4x4, msckf_vio.cpp:1242-1246) of all streams in one device->host copy. */
 int mskf_get_poses(mskf_handle *h, double *out_T_b_w, int cap_streams);
+/* Poses of the back-end step before the latest one (already on the host while the latest is in
+ * flight): lets a fleet driver read every step's result without draining the pipeline. */
+int mskf_get_poses_prev(mskf_handle *h, double *out_T_b_w, int cap_streams);
+/* The back end runs on its own CUDA stream and overlaps the next frame's front end.  mskf_join makes
+ * the handle's (front-end) stream wait for the back-end work launched so far, so that an event
+ * recorded on that stream afterwards brackets both; mskf_set_overlap(h, 0) serialises the two
+ * halves (used to time kernels in isolation). */
+int mskf_join(mskf_handle *h);
+int mskf_set_overlap(mskf_handle *h, int on);
 /* CUDA-event time per kernel class, recorded on the launching stream while enabled.
  * mskf_profile_read returns 1 when `tag` is past the last class. */
 int mskf_profile_enable(mskf_handle *h, int on);

@@ -2470,6 +2470,9 @@ struct BeBuffers {
     cudaEvent_t ev[4];
     bool used[4];
     int pos = 0;
+    double *h_poses[4];       // pinned [S][16], one slot per back-end step (ring)
+    cudaEvent_t ev_poses[4];
+    long long pose_seq = 0;   // back-end steps launched so far
     size_t smem_add = 0, smem_sel = 0, smem_jac[2] = {0, 0}, smem_qr = 0, smem_chol = 0;
     int sort_n = 0;
 };
@@ -2560,6 +2563,8 @@ int be_create(mskf_handle *h) {
         MSKF_CUDA_CHECK(h, cudaMallocHost((void **)&B->h_step[i], sizeof(BeStep) * S));
         MSKF_CUDA_CHECK(h, cudaMallocHost((void **)&B->h_imu[i], sizeof(double) * S * BE_IMU_CAP * 7));
         MSKF_CUDA_CHECK(h, cudaEventCreateWithFlags(&B->ev[i], cudaEventDisableTiming));
+        MSKF_CUDA_CHECK(h, cudaMallocHost((void **)&B->h_poses[i], sizeof(double) * 16 * S));
+        MSKF_CUDA_CHECK(h, cudaEventCreateWithFlags(&B->ev_poses[i], cudaEventDisableTiming));
         B->used[i] = false;
     }
     // dynamic shared memory sizes
@@ -2579,7 +2584,7 @@ int be_create(mskf_handle *h) {
     MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_sel));
     MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_feature_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_jac[0]));
     MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_chol));
-    for (int s = 0; s < h->S; ++s) be_reset_kernel<<<1, BE_THREADS, 0, h->stream>>>(bc, bb, s, 1, h->cfg);
+    for (int s = 0; s < h->S; ++s) be_reset_kernel<<<1, BE_THREADS, 0, h->be_stream>>>(bc, bb, s, 1, h->cfg);
     MSKF_CUDA_CHECK(h, cudaGetLastError());
     return MSKF_OK;
 }
@@ -2591,6 +2596,8 @@ void be_destroy(mskf_handle *h) {
         if (B->h_step[i]) cudaFreeHost(B->h_step[i]);
         if (B->h_imu[i]) cudaFreeHost(B->h_imu[i]);
         if (B->ev[i]) cudaEventDestroy(B->ev[i]);
+        if (B->h_poses[i]) cudaFreeHost(B->h_poses[i]);
+        if (B->ev_poses[i]) cudaEventDestroy(B->ev_poses[i]);
     }
     delete B;
     h->bb = nullptr;
@@ -2614,9 +2621,9 @@ int be_init_gravity(mskf_handle *h, int s) {
         }
     }
     MSKF_CUDA_CHECK(h, cudaMemcpyAsync(B->bb.imu + (size_t)s * BE_IMU_CAP * 7, buf.data(), sizeof(double) * buf.size(),
-                                       cudaMemcpyHostToDevice, h->stream));
-    MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));  // buf is pageable and local
-    be_gravity_kernel<<<1, 32, 0, h->stream>>>(B->bc, B->bb, s, n);
+                                       cudaMemcpyHostToDevice, h->be_stream));
+    MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->be_stream));  // buf is pageable and local
+    be_gravity_kernel<<<1, 32, 0, h->be_stream>>>(B->bc, B->bb, s, n);
     h->launches++;
     MSKF_CUDA_CHECK(h, cudaGetLastError());
     return MSKF_OK;
@@ -2627,7 +2634,7 @@ static void launch_update(mskf_handle *h, int phase = 0) {
     BeBuffers *B = h->bb;
     const BeConst &bc = B->bc;
     const BeBuf &bb = B->bb;
-    cudaStream_t q = h->stream;
+    cudaStream_t q = h->be_stream;
     const int S = h->S;
     const int tiles_ld = (bc.LD + GT - 1) / GT, tiles_kc = (bc.KC + GT - 1) / GT;
     MSKF_LAUNCH(h, phase == 0 ? PK_BE_QR : PK_BE_QR_PRUNE, (be_qr_kernel<<<S, QR_THREADS, 0, q>>>(bc, bb, phase)));
@@ -2644,8 +2651,17 @@ int be_step(mskf_handle *h, const std::vector<int> &streams, const mskf_feature 
     BeBuffers *B = h->bb;
     const BeConst &bc = B->bc;
     const BeBuf &bb = B->bb;
-    cudaStream_t q = h->stream;
+    // overlap on: own stream, ordered against the front end only through the message events;
+    // overlap off: everything in the front end's stream (serial, used for per-kernel profiling)
+    cudaStream_t q = h->be_stream;
+    h->cur = q;
     const int S = h->S;
+    if (!h->overlap) {
+        MSKF_CUDA_CHECK(h, cudaEventRecord(h->ev_join, h->stream));
+        MSKF_CUDA_CHECK(h, cudaStreamWaitEvent(q, h->ev_join, 0));
+    } else {
+        MSKF_CUDA_CHECK(h, cudaStreamWaitEvent(q, h->ev_msg_ready, 0));
+    }
     if (inject && n_inject > bc.ent_cap) {
         h->err = "too many injected measurements";
         return MSKF_ERR_CAPACITY;
@@ -2708,6 +2724,8 @@ int be_step(mskf_handle *h, const std::vector<int> &streams, const mskf_feature 
     MSKF_LAUNCH(h, PK_BE_PROPAGATE, (be_propagate_kernel<<<S, 128, 0, q>>>(bc, bb, 0)));
     MSKF_LAUNCH(h, PK_BE_AUGMENT, (be_augment_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_ADD_OBS, (be_add_obs_kernel<<<S, BE_THREADS, B->smem_add, q>>>(bc, bb)));
+    MSKF_CUDA_CHECK(h, cudaEventRecord(h->ev_msg_consumed, q));
+    h->msg_consumed_valid = true;
     for (int phase = 0; phase < 2; ++phase) {
         const int maxM = phase == 0 ? bc.NS : 2;
         MSKF_LAUNCH(h, PK_BE_SELECT, (be_select_kernel<<<S, BE_THREADS, B->smem_sel, q>>>(bc, bb, phase, B->sort_n)));
@@ -2729,6 +2747,20 @@ int be_step(mskf_handle *h, const std::vector<int> &streams, const mskf_feature 
     MSKF_LAUNCH(h, PK_BE_PRUNE_FINISH, (be_prune_finish_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_FINISH, (be_finish_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_CUDA_CHECK(h, cudaGetLastError());
+    // every step's poses go to pinned host memory right away (ring of BE_RING slots)
+    {
+        B->pose_seq++;
+        const int ps = (int)(B->pose_seq % BE_RING);
+        const char *src = (const char *)bb.st + offsetof(BeState, T_b_w);
+        MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(B->h_poses[ps], sizeof(double) * 16, src, sizeof(BeState), sizeof(double) * 16, S,
+                                             cudaMemcpyDeviceToHost, q));
+        MSKF_CUDA_CHECK(h, cudaEventRecord(B->ev_poses[ps], q));
+    }
+    if (!h->overlap) {
+        // serial mode: the next front-end step starts after this back-end step
+        MSKF_CUDA_CHECK(h, cudaEventRecord(h->ev_join, q));
+        MSKF_CUDA_CHECK(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    }
     return MSKF_OK;
 }
 
@@ -2797,20 +2829,26 @@ int be_get_cov(mskf_handle *h, int s, double *out, int cap, int *dim) {
 
 int be_reset(mskf_handle *h, int s) {
     BeBuffers *B = h->bb;
-    be_reset_kernel<<<1, BE_THREADS, 0, h->stream>>>(B->bc, B->bb, s, 0, h->cfg);
+    be_reset_kernel<<<1, BE_THREADS, 0, h->be_stream>>>(B->bc, B->bb, s, 0, h->cfg);
     h->launches++;
     MSKF_CUDA_CHECK(h, cudaGetLastError());
     return MSKF_OK;
 }
 
-// all streams' T_b_w with one strided device->host copy
-int be_get_poses(mskf_handle *h, double *out, int cap_streams) {
+// T_b_w of every stream after the latest (lag 0) or the one-before-latest (lag 1) back-end step: the
+// step already copied them to pinned host memory, so this only waits for that copy
+int be_get_poses(mskf_handle *h, double *out, int cap_streams, int lag) {
+    BeBuffers *B = h->bb;
     const int n = cap_streams < h->S ? cap_streams : h->S;
     if (n <= 0) return MSKF_OK;
-    const char *src = (const char *)h->bb->bb.st + offsetof(BeState, T_b_w);
-    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(out, sizeof(double) * 16, src, sizeof(BeState), sizeof(double) * 16, n,
-                                         cudaMemcpyDeviceToHost, h->stream));
-    MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    const long long seq = B->pose_seq - lag;
+    if (seq <= 0) {
+        for (int i = 0; i < n * 16; ++i) out[i] = (i % 5 == 0) ? 1.0 : 0.0;  // identity before the first step
+        return MSKF_OK;
+    }
+    const int ps = (int)(seq % BE_RING);
+    MSKF_CUDA_CHECK(h, cudaEventSynchronize(B->ev_poses[ps]));
+    memcpy(out, B->h_poses[ps], sizeof(double) * 16 * n);
     return MSKF_OK;
 }
 
@@ -2854,6 +2892,8 @@ int be_op_update(mskf_handle *t, int n_cam, int m, const double *H, const double
         return MSKF_ERR_CAPACITY;
     }
     MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->stream));
+    MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->be_stream));
+    t->cur = t->be_stream;
     BeState st;
     MSKF_CUDA_CHECK(t, cudaMemcpy(&st, bb.st, sizeof(BeState), cudaMemcpyDeviceToHost));
     st.n_cam = n_cam;
@@ -2883,7 +2923,7 @@ int be_op_update(mskf_handle *t, int n_cam, int m, const double *H, const double
     MSKF_CUDA_CHECK(t, cudaMemcpy(bb.rst, r, sizeof(double) * m, cudaMemcpyHostToDevice));
     launch_update(t);
     MSKF_CUDA_CHECK(t, cudaGetLastError());
-    MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->stream));
+    MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->be_stream));
     std::vector<double> dxl(LD);
     MSKF_CUDA_CHECK(t, cudaMemcpy(Pl.data(), bb.P, sizeof(double) * Pl.size(), cudaMemcpyDeviceToHost));
     MSKF_CUDA_CHECK(t, cudaMemcpy(dxl.data(), bb.dxv, sizeof(double) * LD, cudaMemcpyDeviceToHost));

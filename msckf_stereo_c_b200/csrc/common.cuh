@@ -137,6 +137,13 @@ struct mskf_handle {
     bool own_stream = false;
     // host uploads run on their own stream into a double-buffered landing area, so the upload of
     // frame k+1 overlaps the kernels of frame k (mskf_push_stereo* -> stage_*; engine.cu)
+    // The back end of frame k runs on its own stream so that the front end of frame k+1 overlaps it
+    // (the only shared data is the CameraMeasurement: ev_msg_ready / ev_msg_consumed).
+    cudaStream_t be_stream = nullptr;
+    cudaStream_t cur = nullptr;        // stream the MSKF_LAUNCH profiler brackets are recorded on
+    cudaEvent_t ev_msg_ready = nullptr, ev_msg_consumed = nullptr, ev_join = nullptr;
+    bool msg_consumed_valid = false;
+    bool overlap = true;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     bool consumed_valid[2] = {false, false};
@@ -207,7 +214,7 @@ int be_get_cov(mskf_handle *h, int s, double *out, int cap, int *dim);
 int be_reset(mskf_handle *h, int s);
 int be_get_map(mskf_handle *h, int s, long long *ids, int *init, double *pos, int *nobs, int cap, int *n);
 int be_op_update(mskf_handle *t, int n_cam, int m, const double *H, const double *r, const double *P, double *dx, double *Pn);
-int be_get_poses(mskf_handle *h, double *out, int cap_streams);
+int be_get_poses(mskf_handle *h, double *out, int cap_streams, int lag);
 
 template <typename T>
 int dev_alloc(mskf_handle *h, T **p, size_t n) {

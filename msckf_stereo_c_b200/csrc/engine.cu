@@ -121,11 +121,11 @@ void prof_begin(mskf_handle *h, int tag) {
         }
     }
     h->prof_tag.push_back(tag);
-    cudaEventRecord(h->prof_ev[h->prof_used], h->stream);
+    cudaEventRecord(h->prof_ev[h->prof_used], h->cur ? h->cur : h->stream);
 }
 void prof_end(mskf_handle *h) {
     if (!h->prof_on) return;
-    cudaEventRecord(h->prof_ev[h->prof_used + 1], h->stream);
+    cudaEventRecord(h->prof_ev[h->prof_used + 1], h->cur ? h->cur : h->stream);
     h->prof_used += 2;
 }
 void prof_collect(mskf_handle *h) {
@@ -177,6 +177,7 @@ extern "C" {
 int mskf_profile_enable(mskf_handle *h, int on) {
     if (!h) return MSKF_ERR_ARG;
     cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->be_stream);
     prof_collect(h);
     h->prof_on = on != 0;
     if (on) {
@@ -189,6 +190,7 @@ int mskf_profile_read(mskf_handle *h, int tag, const char **name, double *ms, lo
     if (!h || tag < 0) return MSKF_ERR_ARG;
     if (tag >= PK_COUNT) return 1;
     cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->be_stream);
     prof_collect(h);
     if (name) *name = kProfNames[tag];
     if (ms) *ms = h->prof_ms[tag];
@@ -213,6 +215,11 @@ int mskf_create(const mskf_config *cfg, int n_streams, int device, mskf_handle *
     MSKF_CUDA_CHECK(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
     MSKF_CUDA_CHECK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    MSKF_CUDA_CHECK(h, cudaStreamCreateWithFlags(&h->be_stream, cudaStreamNonBlocking));
+    MSKF_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->ev_msg_ready, cudaEventDisableTiming));
+    MSKF_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->ev_msg_consumed, cudaEventDisableTiming));
+    MSKF_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    h->cur = h->stream;
     for (int i = 0; i < 2; ++i) {
         MSKF_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
         MSKF_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));
@@ -232,6 +239,7 @@ int mskf_create(const mskf_config *cfg, int n_streams, int device, mskf_handle *
         MSKF_CUDA_CHECK(h, cudaMallocHost((void **)&ex->h_src_ring[i], sizeof(uint8_t *) * 2 * n_streams));
     }
     MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->be_stream));
     return MSKF_OK;
 }
 
@@ -239,6 +247,7 @@ void mskf_destroy(mskf_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->be_stream) cudaStreamSynchronize(h->be_stream);
     be_destroy(h);
     EngineExtra *ex = extra(h);
     if (ex) {
@@ -253,6 +262,10 @@ void mskf_destroy(mskf_handle *h) {
         cudaStreamSynchronize(h->copy_stream);
         cudaStreamDestroy(h->copy_stream);
     }
+    if (h->be_stream) cudaStreamDestroy(h->be_stream);
+    if (h->ev_msg_ready) cudaEventDestroy(h->ev_msg_ready);
+    if (h->ev_msg_consumed) cudaEventDestroy(h->ev_msg_consumed);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
         if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
@@ -270,6 +283,7 @@ int mskf_set_cuda_stream(mskf_handle *h, void *cuda_stream) {
     cudaStreamSynchronize(h->stream);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     h->stream = (cudaStream_t)cuda_stream;
+    h->cur = h->stream;
     h->own_stream = false;
     return MSKF_OK;
 }
@@ -471,6 +485,7 @@ int mskf_sync(mskf_handle *h) {
     MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
     MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->copy_stream));
     MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->be_stream));
     if (h->prof_on) prof_collect(h);
     return MSKF_OK;
 }
@@ -597,7 +612,25 @@ int mskf_debug_get_map(mskf_handle *h, int s, long long *ids, int *init, double 
 int mskf_get_poses(mskf_handle *h, double *out, int cap_streams) {
     if (!h || !out) return MSKF_ERR_ARG;
     MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
-    return be_get_poses(h, out, cap_streams);
+    return be_get_poses(h, out, cap_streams, 0);
+}
+int mskf_get_poses_prev(mskf_handle *h, double *out, int cap_streams) {
+    if (!h || !out) return MSKF_ERR_ARG;
+    MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
+    return be_get_poses(h, out, cap_streams, 1);
+}
+int mskf_join(mskf_handle *h) {
+    if (!h) return MSKF_ERR_ARG;
+    MSKF_CUDA_CHECK(h, cudaEventRecord(h->ev_join, h->be_stream));
+    MSKF_CUDA_CHECK(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    return MSKF_OK;
+}
+int mskf_set_overlap(mskf_handle *h, int on) {
+    if (!h) return MSKF_ERR_ARG;
+    int rc = mskf_sync(h);
+    if (rc != MSKF_OK) return rc;
+    h->overlap = on != 0;
+    return MSKF_OK;
 }
 int mskf_reset(mskf_handle *h, int s) {
     if (!h || s < 0 || s >= h->S) return MSKF_ERR_ARG;

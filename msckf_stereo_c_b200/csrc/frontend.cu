@@ -1288,6 +1288,7 @@ static void launch_pyr_level(mskf_handle *h, int l, int images) {
 }
 
 int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active) {
+    h->cur = h->stream;
     const FeConst &fc = h->fc;
     const FeBuffers &fb = h->fb;
     cudaStream_t q = h->stream;
@@ -1329,7 +1330,10 @@ int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active) {
         launch_klt(h, PK_KLT_NEW, g, klt_smem, 2);
     }
     const size_t fin_smem = fe_finish_smem(fc);
+    // fe_finish rewrites the CameraMeasurement: the back end of the previous frame must have read it
+    if (h->msg_consumed_valid) MSKF_CUDA_CHECK(h, cudaStreamWaitEvent(q, h->ev_msg_consumed, 0));
     MSKF_LAUNCH(h, PK_FE_BOOK, (fe_finish<<<S, FE_THREADS, fin_smem, q>>>(fc, fb)));
+    MSKF_CUDA_CHECK(h, cudaEventRecord(h->ev_msg_ready, q));
     MSKF_CUDA_CHECK(h, cudaGetLastError());
     return MSKF_OK;
 }

@@ -29,7 +29,8 @@ ABI_SYMBOLS = [
     "mskf_reset", "mskf_op_pyramid", "mskf_op_detect", "mskf_op_klt",
     "mskf_launch_count", "mskf_get_n_published", "mskf_get_poses", "mskf_profile_enable", "mskf_profile_read",
     "mskf_debug_detect_scores", "mskf_debug_get_map", "mskf_op_ekf_update", "mskf_push_imu_batch",
-    "mskf_push_stereo_batch", "mskf_push_stereo_device_batch", "mskf_get_work",
+    "mskf_push_stereo_batch", "mskf_push_stereo_device_batch", "mskf_get_work", "mskf_get_poses_prev", "mskf_join",
+    "mskf_set_overlap",
 ]
 
 
@@ -73,6 +74,9 @@ def lib():
         L.mskf_op_klt.argtypes = [P, P, P, I, I, P, P, P, I]
         L.mskf_debug_detect_scores.argtypes = [P, P, I, I, P, P, I, C.POINTER(I), P]
         L.mskf_get_poses.argtypes = [P, P, I]
+        L.mskf_get_poses_prev.argtypes = [P, P, I]
+        L.mskf_join.argtypes = [P]
+        L.mskf_set_overlap.argtypes = [P, I]
         L.mskf_push_imu_batch.argtypes = [P, I, I, P]
         L.mskf_push_stereo_batch.argtypes = [P, P, P, P, C.c_size_t]
         L.mskf_push_stereo_device_batch.argtypes = [P, P, P, P, C.c_size_t]
@@ -211,10 +215,19 @@ class Engine:
         k = n.value
         return ids[:k], init[:k], pos[:k], nobs[:k]
 
-    def poses(self):
+    def poses(self, prev=False):
+        """T_b_w of every stream after the latest back-end step (prev=True: the step before it, which
+        is on the host already while the latest one is still running)."""
         out = np.zeros((self.n_streams, 4, 4))
-        self._ck(lib().mskf_get_poses(self.h, out.ctypes.data, self.n_streams))
+        f = lib().mskf_get_poses_prev if prev else lib().mskf_get_poses
+        self._ck(f(self.h, out.ctypes.data, self.n_streams))
         return out
+
+    def join(self):
+        self._ck(lib().mskf_join(self.h))
+
+    def set_overlap(self, on=True):
+        self._ck(lib().mskf_set_overlap(self.h, 1 if on else 0))
 
     # ---- outputs -----------------------------------------------------------------------
     def launch_count(self):
