@@ -258,6 +258,9 @@ int mskf_get_work(mskf_handle *h, int tag, double *total);
 /* The back end's feature map (MsckfVio::map_server) in ascending feature id. */
 int mskf_debug_get_map(mskf_handle *h, int stream, long long *ids, int *is_initialized, double *position,
                        int *n_observations, int cap, int *n);
+/* Per stream {rows m, active columns k, listed features} of the lost-feature update and of the prune
+ * update of the last back-end step: out[n_streams][2][3]. */
+int mskf_debug_update_dims(mskf_handle *h, int *out);
 /* mskf_op_detect that also returns the per-pixel FAST score map (0 = not a corner). */
 int mskf_debug_detect_scores(mskf_handle *h, const uint8_t *img, int rows, int cols, float *out_xy,
                              double *out_response, int cap, int *n, uint8_t *score_map);

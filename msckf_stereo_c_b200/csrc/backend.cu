@@ -83,6 +83,7 @@ struct BeState {
     int rm_slot[2];
     unsigned rm_bits;
     int do_update;
+    int dbg_m[2], dbg_k[2], dbg_nlist[2];  // per phase: stacked rows, active columns, listed features (last step)
     BeCam cam[NSM];
 };
 
@@ -1963,6 +1964,9 @@ __global__ void __launch_bounds__(BE_THREADS) be_stack_kernel(BeConst bc, BeBuf 
         st.m = cntr;
         st.k = 6 * k;
         st.do_update = cntr > 0 ? 1 : 0;
+        st.dbg_m[phase] = cntr;
+        st.dbg_k[phase] = 6 * k;
+        st.dbg_nlist[phase] = n;
     }
     __syncthreads();
     const int m = s_m, k = s_k, nuse = s_nuse;
@@ -2023,20 +2027,117 @@ __device__ __forceinline__ double fast_rcp(double a) {
 // Thread c owns column c of the system [H | r] (c = k is the residual column): the 32 rows of the
 // block being folded live in its registers, column c of the triangular factor R lives in global
 // memory (row-major, read two steps ahead), so no other thread ever touches its data and the only
-// communication per column step is the reflector (32 doubles + tau) through shared memory, with ONE
-// barrier per step (double-buffered).  ~60 KB of registers and 1 KB of shared memory per CTA keep
-// all streams of a 256-stream fleet resident at once.
+// communication per column step is the reflector (32 doubles + two scalars) through shared memory,
+// with ONE barrier per step (double-buffered).
+//
+// A fleet's step time is set by its slowest stream.  On the synthetic fleet a lost-feature update
+// stacks 40-800 rows (tools/fleet_nan_check.py prints the distribution) and one CTA per stream is
+// the fastest arrangement; a stream that approaches the 1500-row cap (m > QR_SPLIT_MIN) splits its
+// rows over QR_G CTAs (TSQR): each folds its share into its own triangle, be_qr_combine_kernel folds
+// triangles 1.. into triangle 0 (9.1k column steps become 2.3k + 1.8k).
+#define QR_G 4
+#define QR_SPLIT_MIN 1024
+
+struct QrShared {
+    double vbuf[2][QR_B];
+    double tau[2], w0[2];
+    int j0;
+};
+
+// One sweep: fold the QR_B rows held in x[] (column c of each) into R, starting at column jb.
+// Unnormalised reflectors: H_j = I - t w w^T with w = [alpha - beta; x] and t = 1 / (beta (beta - alpha)),
+// so the owner publishes its column the moment it is up to date and only two scalars (w0, t) sit
+// behind the rsqrt / rcp chain.
+__device__ __forceinline__ void qr_sweep(double (&x)[QR_B], double *R, int ldr, int k, int kw, int c, int jb, QrShared &sh) {
+    const bool has_col = c < kw;
+    double rq0 = (has_col && jb <= c && jb < k) ? R[jb * ldr + c] : 0.0;
+    double rq1 = (has_col && jb + 1 <= c && jb + 1 < k) ? R[(jb + 1) * ldr + c] : 0.0;
+    double xn = 0.0;
+    if (c == jb) {
+#pragma unroll
+        for (int i = 0; i < QR_B; ++i) xn += x[i] * x[i];
+    }
+    for (int j = jb; j < k; ++j) {
+        const int p = j & 1;
+        double rq2 = 0.0;
+        if (has_col && j + 2 <= c && j + 2 < k) rq2 = R[(j + 2) * ldr + c];
+        if (c == j) {
+#pragma unroll
+            for (int i = 0; i < QR_B; ++i) sh.vbuf[p][i] = x[i];
+            const double alpha = rq0;
+            double t = 0.0, w0 = 0.0;
+            // Columns that an earlier reflector of the same block already annihilated carry rounding
+            // residue that shrinks by ~1e-16 per column; once xn leaves the normal range 1 / (beta d)
+            // would overflow.  Such a column is numerically zero: no reflector.
+            if (xn > 1e-200) {
+                const double nrm2 = alpha * alpha + xn;
+                const double beta = -copysign(nrm2 * fast_rsqrt(nrm2), alpha);
+                const double d = beta - alpha;
+                t = fast_rcp(beta * d);
+                w0 = -d;
+                R[j * ldr + j] = beta;
+            }
+            sh.w0[p] = w0;
+            sh.tau[p] = t;
+        }
+        __syncthreads();
+        const double t = sh.tau[p];
+        if (has_col && c > j && t != 0.0) {
+            const double w0 = sh.w0[p];
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+            for (int i = 0; i < QR_B; i += 4) {
+                s0 += sh.vbuf[p][i] * x[i];
+                s1 += sh.vbuf[p][i + 1] * x[i + 1];
+                s2 += sh.vbuf[p][i + 2] * x[i + 2];
+                s3 += sh.vbuf[p][i + 3] * x[i + 3];
+            }
+            const double sacc = (w0 * rq0 + (s0 + s1) + (s2 + s3)) * t;
+            R[j * ldr + c] = rq0 - sacc * w0;
+#pragma unroll
+            for (int i = 0; i < QR_B; ++i) x[i] -= sacc * sh.vbuf[p][i];
+        }
+        if (c == j + 1) {
+            // I own the next reflector: squared norm of my (now final) column
+            double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+#pragma unroll
+            for (int i = 0; i < QR_B; i += 4) {
+                n0 += x[i] * x[i];
+                n1 += x[i + 1] * x[i + 1];
+                n2 += x[i + 2] * x[i + 2];
+                n3 += x[i + 3] * x[i + 3];
+            }
+            xn = (n0 + n1) + (n2 + n3);
+        }
+        rq0 = rq1;
+        rq1 = rq2;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int qr_groups(int m, int k) { return (m > k && m > QR_SPLIT_MIN) ? QR_G : 1; }
+
+__device__ __forceinline__ void qr_extract(const double *R, int ldr, int k, double *Tm, double *rt) {
+    for (int e = threadIdx.x; e < k * k; e += QR_THREADS) {
+        int i = e / k, cc = e - i * k;
+        Tm[e] = cc >= i ? R[i * ldr + cc] : 0.0;
+    }
+    for (int i = threadIdx.x; i < k; i += QR_THREADS) rt[i] = R[i * ldr + k];
+}
+
 __global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb, int phase) {
-    const int s = blockIdx.x;
+    const int s = blockIdx.y, g = blockIdx.x;
     const BeStep sp = bb.step[s];
     if (!sp.active) return;
     BeState &st = bb.st[s];
     if (!st.do_update) return;
     const int m = st.m, k = st.k, KC = bc.KC;
+    const int ng = qr_groups(m, k);
+    if (g >= ng) return;
     const double *Hst = bb.Hst + (size_t)s * bc.hst_cap, *rst = bb.rst + (size_t)s * bc.hst_rows;
     const int *rj0 = bb.rst_j0 + (size_t)s * bc.hst_rows;
     double *Tm = bb.Tm + (size_t)s * KC * KC, *rt = bb.rt + (size_t)s * KC;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && g == 0) {
         // algorithmic flops of this stream's update (dense-equivalent over the active columns)
         const double dm = m, dk = k, dmt = m <= k ? m : k, dld = bc.LD;
         double *w = bb.work + (size_t)s * MSKF_PROF_TAGS;
@@ -2054,22 +2155,22 @@ __global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb,
         return;
     }
     const int kw = k + 1, ldr = KC + 1;
-    double *R = bb.Rq + (size_t)s * ldr * ldr;  // R[j][c] at j * ldr + c
-    __shared__ double vbuf[2][QR_B];
-    __shared__ double s_tau[2], s_w0[2];
-    __shared__ int s_j0;
+    double *R = bb.Rq + ((size_t)s * QR_G + g) * ldr * ldr;  // R[j][c] at j * ldr + c
+    __shared__ QrShared sh;
     const int c = threadIdx.x;
     const bool has_col = c < kw;
     if (has_col)
         for (int j = 0; j <= min(c, k - 1); ++j) R[j * ldr + c] = 0.0;
+    const int per = ((m + ng - 1) / ng + QR_B - 1) / QR_B * QR_B;
+    const int r_begin = g * per, r_end = min(m, r_begin + per);
     double x[QR_B];
-    for (int r0 = 0; r0 < m; r0 += QR_B) {
-        const int nb = min(QR_B, m - r0);
+    for (int r0 = r_begin; r0 < r_end; r0 += QR_B) {
+        const int nb = min(QR_B, r_end - r0);
         if (threadIdx.x < 32) {
             int j0 = threadIdx.x < nb ? rj0[r0 + threadIdx.x] : k;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) j0 = min(j0, __shfl_xor_sync(0xffffffffu, j0, o));
-            if (threadIdx.x == 0) s_j0 = j0;
+            if (threadIdx.x == 0) sh.j0 = j0;
         }
 #pragma unroll
         for (int i = 0; i < QR_B; ++i) {
@@ -2078,79 +2179,48 @@ __global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb,
             x[i] = v;
         }
         __syncthreads();
-        const int jb = s_j0;
-        // R entries of my column for the next two steps
-        double rq0 = (has_col && jb <= c && jb < k) ? R[jb * ldr + c] : 0.0;
-        double rq1 = (has_col && jb + 1 <= c && jb + 1 < k) ? R[(jb + 1) * ldr + c] : 0.0;
-        // Unnormalised reflectors: H_j = I - t w w^T with w = [alpha - beta; x] and t = 1 / (beta (beta - alpha)),
-        // so the owner can publish its column the moment it is up to date and only two scalars
-        // (w0, t) sit behind the rsqrt / rcp chain.  xn (the squared norm of my column) is carried
-        // along by the update that produces the column.
-        double xn = 0.0;
-        if (c == jb) {
-#pragma unroll
-            for (int i = 0; i < QR_B; ++i) xn += x[i] * x[i];
-        }
-        for (int j = jb; j < k; ++j) {
-            const int p = j & 1;
-            double rq2 = 0.0;
-            if (has_col && j + 2 <= c && j + 2 < k) rq2 = R[(j + 2) * ldr + c];
-            if (c == j) {
-#pragma unroll
-                for (int i = 0; i < QR_B; ++i) vbuf[p][i] = x[i];
-                const double alpha = rq0;
-                double t = 0.0, w0 = 0.0;
-                if (xn != 0.0) {
-                    const double nrm2 = alpha * alpha + xn;
-                    const double beta = -copysign(nrm2 * fast_rsqrt(nrm2), alpha);
-                    const double d = beta - alpha;
-                    t = fast_rcp(beta * d);
-                    w0 = -d;
-                    R[j * ldr + j] = beta;
-                }
-                s_w0[p] = w0;
-                s_tau[p] = t;
-            }
-            __syncthreads();
-            const double t = s_tau[p];
-            if (has_col && c > j && t != 0.0) {
-                const double w0 = s_w0[p];
-                double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll
-                for (int i = 0; i < QR_B; i += 4) {
-                    s0 += vbuf[p][i] * x[i];
-                    s1 += vbuf[p][i + 1] * x[i + 1];
-                    s2 += vbuf[p][i + 2] * x[i + 2];
-                    s3 += vbuf[p][i + 3] * x[i + 3];
-                }
-                const double sacc = (w0 * rq0 + (s0 + s1) + (s2 + s3)) * t;
-                R[j * ldr + c] = rq0 - sacc * w0;
-#pragma unroll
-                for (int i = 0; i < QR_B; ++i) x[i] -= sacc * vbuf[p][i];
-            }
-            if (c == j + 1) {
-                // I own the next reflector: squared norm of my (now final) column
-                double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-#pragma unroll
-                for (int i = 0; i < QR_B; i += 4) {
-                    n0 += x[i] * x[i];
-                    n1 += x[i + 1] * x[i + 1];
-                    n2 += x[i + 2] * x[i + 2];
-                    n3 += x[i + 3] * x[i + 3];
-                }
-                xn = (n0 + n1) + (n2 + n3);
-            }
-            rq0 = rq1;
-            rq1 = rq2;
-        }
-        __syncthreads();
+        qr_sweep(x, R, ldr, k, kw, c, sh.j0, sh);
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < k * k; e += QR_THREADS) {
-        int i = e / k, cc = e - i * k;
-        Tm[e] = cc >= i ? R[i * ldr + cc] : 0.0;
+    if (ng == 1) {
+        qr_extract(R, ldr, k, Tm, rt);
+        if (threadIdx.x == 0) st.mt = k;
     }
-    for (int i = threadIdx.x; i < k; i += QR_THREADS) rt[i] = R[i * ldr + k];
+}
+
+// TSQR combine: fold the triangles of groups 1.. into the triangle of group 0 (row i of a
+// triangle is zero left of column i, so the sweep of a 32-row block starts at its first row index).
+__global__ void __launch_bounds__(QR_THREADS) be_qr_combine_kernel(BeConst bc, BeBuf bb) {
+    const int s = blockIdx.x;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    BeState &st = bb.st[s];
+    if (!st.do_update) return;
+    const int m = st.m, k = st.k, KC = bc.KC;
+    const int ng = qr_groups(m, k);
+    if (ng == 1) return;
+    const int kw = k + 1, ldr = KC + 1;
+    double *R0 = bb.Rq + (size_t)s * QR_G * ldr * ldr;
+    __shared__ QrShared sh;
+    const int c = threadIdx.x;
+    const bool has_col = c < kw;
+    double x[QR_B];
+    for (int g = 1; g < ng; ++g) {
+        const double *Rg = R0 + (size_t)g * ldr * ldr;
+        for (int r0 = 0; r0 < k; r0 += QR_B) {
+            const int nb = min(QR_B, k - r0);
+#pragma unroll
+            for (int i = 0; i < QR_B; ++i) {
+                double v = 0.0;
+                if (has_col && i < nb && c >= r0 + i) v = Rg[(r0 + i) * ldr + c];
+                x[i] = v;
+            }
+            __syncthreads();
+            qr_sweep(x, R0, ldr, k, kw, c, r0, sh);
+        }
+    }
+    __syncthreads();
+    qr_extract(R0, ldr, k, bb.Tm + (size_t)s * KC * KC, bb.rt + (size_t)s * KC);
     if (threadIdx.x == 0) st.mt = k;
 }
 
@@ -2549,7 +2619,7 @@ int be_create(mskf_handle *h) {
     A(bb.l_slot, S * bc.ML); A(bb.l_ok, S * bc.ML); A(bb.l_pass, S * bc.ML); A(bb.l_M, S * bc.ML);
     A(bb.l_eoff, S * bc.ML); A(bb.l_roff, S * bc.ML); A(bb.l_soff, S * bc.ML); A(bb.l_oslots, S * bc.ML * NSM);
     A(bb.Hblk, S * bc.ecap); A(bb.rblk, S * bc.rcap);
-    A(bb.Hst, S * bc.hst_cap); A(bb.rst, S * bc.hst_rows); A(bb.rst_j0, S * bc.hst_rows); A(bb.Rq, S * (bc.KC + 1) * (bc.KC + 1));
+    A(bb.Hst, S * bc.hst_cap); A(bb.rst, S * bc.hst_rows); A(bb.rst_j0, S * bc.hst_rows); A(bb.Rq, S * QR_G * (bc.KC + 1) * (bc.KC + 1));
     A(bb.Tm, S * bc.KC * bc.KC); A(bb.rt, S * bc.KC); A(bb.PHt, S * bc.LD * bc.KC); A(bb.Sm, S * bc.KC * bc.KC);
     A(bb.Linv, S * bc.KC * bc.KC); A(bb.W, S * bc.LD * bc.KC); A(bb.yv, S * bc.KC); A(bb.dxv, S * bc.LD);
 #undef A
@@ -2637,7 +2707,8 @@ static void launch_update(mskf_handle *h, int phase = 0) {
     cudaStream_t q = h->be_stream;
     const int S = h->S;
     const int tiles_ld = (bc.LD + GT - 1) / GT, tiles_kc = (bc.KC + GT - 1) / GT;
-    MSKF_LAUNCH(h, phase == 0 ? PK_BE_QR : PK_BE_QR_PRUNE, (be_qr_kernel<<<S, QR_THREADS, 0, q>>>(bc, bb, phase)));
+    MSKF_LAUNCH(h, phase == 0 ? PK_BE_QR : PK_BE_QR_PRUNE, (be_qr_kernel<<<dim3(QR_G, S), QR_THREADS, 0, q>>>(bc, bb, phase)));
+    MSKF_LAUNCH(h, phase == 0 ? PK_BE_QR : PK_BE_QR_PRUNE, (be_qr_combine_kernel<<<S, QR_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_GEMM_PHT, (be_gemm_kernel<0><<<dim3(tiles_ld * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_GEMM_S, (be_gemm_kernel<1><<<dim3(tiles_kc * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_CHOL, (be_chol_kernel<<<S, BE_THREADS, B->smem_chol, q>>>(bc, bb)));
@@ -2931,5 +3002,18 @@ int be_op_update(mskf_handle *t, int n_cam, int m, const double *H, const double
         dx[i] = dxl[i];
         for (int j = 0; j < n; ++j) Pn[(size_t)i * n + j] = Pl[(size_t)i * LD + j];
     }
+    return MSKF_OK;
+}
+
+// bring-up / analysis: per stream {m, k, listed features} of the lost-feature and the prune update of the last step
+int be_debug_update_dims(mskf_handle *h, int *out6) {
+    std::vector<BeState> st(h->S);
+    MSKF_CUDA_CHECK(h, cudaMemcpy(st.data(), h->bb->bb.st, sizeof(BeState) * h->S, cudaMemcpyDeviceToHost));
+    for (int s = 0; s < h->S; ++s)
+        for (int ph = 0; ph < 2; ++ph) {
+            out6[s * 6 + ph * 3 + 0] = st[s].dbg_m[ph];
+            out6[s * 6 + ph * 3 + 1] = st[s].dbg_k[ph];
+            out6[s * 6 + ph * 3 + 2] = st[s].dbg_nlist[ph];
+        }
     return MSKF_OK;
 }

@@ -214,6 +214,7 @@ int be_get_cov(mskf_handle *h, int s, double *out, int cap, int *dim);
 int be_reset(mskf_handle *h, int s);
 int be_get_map(mskf_handle *h, int s, long long *ids, int *init, double *pos, int *nobs, int cap, int *n);
 int be_op_update(mskf_handle *t, int n_cam, int m, const double *H, const double *r, const double *P, double *dx, double *Pn);
+int be_debug_update_dims(mskf_handle *h, int *out6);
 int be_get_poses(mskf_handle *h, double *out, int cap_streams, int lag);
 
 template <typename T>

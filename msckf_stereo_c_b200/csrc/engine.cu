@@ -215,7 +215,13 @@ int mskf_create(const mskf_config *cfg, int n_streams, int device, mskf_handle *
     MSKF_CUDA_CHECK(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
     MSKF_CUDA_CHECK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    MSKF_CUDA_CHECK(h, cudaStreamCreateWithFlags(&h->be_stream, cudaStreamNonBlocking));
+    {
+        // the back end is a chain of short, latency-bound kernels: high priority lets its CTAs jump the
+        // queue of the front end's large grids, which then fill whatever the chain leaves idle
+        int lo = 0, hi = 0;
+        MSKF_CUDA_CHECK(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        MSKF_CUDA_CHECK(h, cudaStreamCreateWithPriority(&h->be_stream, cudaStreamNonBlocking, hi));
+    }
     MSKF_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->ev_msg_ready, cudaEventDisableTiming));
     MSKF_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->ev_msg_consumed, cudaEventDisableTiming));
     MSKF_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
@@ -608,6 +614,12 @@ int mskf_debug_get_map(mskf_handle *h, int s, long long *ids, int *init, double 
     int rc = mskf_sync(h);
     if (rc != MSKF_OK) return rc;
     return be_get_map(h, s, ids, init, pos, nobs, cap, n);
+}
+int mskf_debug_update_dims(mskf_handle *h, int *out6) {
+    if (!h || !out6) return MSKF_ERR_ARG;
+    int rc = mskf_sync(h);
+    if (rc != MSKF_OK) return rc;
+    return be_debug_update_dims(h, out6);
 }
 int mskf_get_poses(mskf_handle *h, double *out, int cap_streams) {
     if (!h || !out) return MSKF_ERR_ARG;

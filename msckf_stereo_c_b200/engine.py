@@ -12,7 +12,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmsckf_b200.so")
+LIB_PATH = os.environ.get("MSKF_B200_LIB", os.path.join(_HERE, "libmsckf_b200.so"))  # override: A/B kernel experiments
 _LIB = None
 
 GRID_DT = np.dtype([("id", "<u8"), ("response", "<f4"), ("lifetime", "<i4"), ("cam0", "<f4", 2), ("cam1", "<f4", 2),
@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "mskf_launch_count", "mskf_get_n_published", "mskf_get_poses", "mskf_profile_enable", "mskf_profile_read",
     "mskf_debug_detect_scores", "mskf_debug_get_map", "mskf_op_ekf_update", "mskf_push_imu_batch",
     "mskf_push_stereo_batch", "mskf_push_stereo_device_batch", "mskf_get_work", "mskf_get_poses_prev", "mskf_join",
-    "mskf_set_overlap",
+    "mskf_set_overlap", "mskf_debug_update_dims",
 ]
 
 
@@ -76,6 +76,7 @@ def lib():
         L.mskf_get_poses.argtypes = [P, P, I]
         L.mskf_get_poses_prev.argtypes = [P, P, I]
         L.mskf_join.argtypes = [P]
+        L.mskf_debug_update_dims.argtypes = [P, P]
         L.mskf_set_overlap.argtypes = [P, I]
         L.mskf_push_imu_batch.argtypes = [P, I, I, P]
         L.mskf_push_stereo_batch.argtypes = [P, P, P, P, C.c_size_t]
@@ -221,6 +222,11 @@ class Engine:
         out = np.zeros((self.n_streams, 4, 4))
         f = lib().mskf_get_poses_prev if prev else lib().mskf_get_poses
         self._ck(f(self.h, out.ctypes.data, self.n_streams))
+        return out
+
+    def update_dims(self):
+        out = np.zeros((self.n_streams, 2, 3), np.int32)
+        self._ck(lib().mskf_debug_update_dims(self.h, out.ctypes.data))
         return out
 
     def join(self):

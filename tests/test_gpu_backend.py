@@ -313,3 +313,24 @@ def test_reset_callback(eng, ob, synth):
         seen = seen or o.state().n_updates > 0
     assert o.state().n_updates > 0
     e.close()
+
+
+def test_op_ekf_update_rank_deficient_tail_group(eng, ob, synth):
+    """m = 385 rows splits into four row groups for the QR compression and the last group holds a single
+    row: after its one reflector every further column of that group is rounding residue shrinking towards
+    the denormal range (regression test: the reflector scalars must not overflow there)."""
+    rng = np.random.default_rng(7)
+    n_cam, m = 20, 385
+    n = 21 + 6 * n_cam
+    P = _spd(rng, n)
+    H = np.zeros((m, n))
+    H[:, 21:] = rng.standard_normal((m, 6 * n_cam))
+    r = rng.standard_normal(m) * 1e-2
+    cfg = copy_cfg(synth.default_config("bench"))
+    e = eng.Engine(cfg, 1)
+    dx_g, P_g = e.op_ekf_update(H, r, P)
+    dx_o, P_o = ob.update_math(H, r, P, cfg.noise_feature ** 2)
+    assert np.isfinite(P_g).all() and np.isfinite(dx_g).all()
+    assert np.abs(P_g - P_o).max() <= UPDATE_TOL * np.abs(P_o).max()
+    assert np.abs(dx_g - dx_o).max() <= UPDATE_TOL * max(np.abs(dx_o).max(), 1e-12)
+    e.close()

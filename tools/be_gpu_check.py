@@ -9,7 +9,7 @@ nf = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 stale = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 cfg = synth.default_config(preset)
 cfg.compat_stale_features = stale
-s = synth.Stream(cfg, seed=0)
+s = synth.Stream(cfg, seed=int(sys.argv[4]) if len(sys.argv) > 4 else 0)
 e = engine.Engine(cfg, 1)
 o = ob.Oracle(cfg)
 class Both:
