@@ -1969,34 +1969,49 @@ __global__ void __launch_bounds__(BE_THREADS) be_stack_kernel(BeConst bc, BeBuf 
         st.dbg_nlist[phase] = n;
     }
     __syncthreads();
-    const int m = s_m, k = s_k, nuse = s_nuse;
-    double *Hst = bb.Hst + (size_t)s * bc.hst_cap, *rst = bb.rst + (size_t)s * bc.hst_rows;
-    for (int e = threadIdx.x; e < m * k; e += BE_THREADS) Hst[e] = 0.0;
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = warp; i < nuse; i += BE_THREADS / 32) {
-        const int so = s_soff[i];
-        if (so < 0) continue;
-        const int M = s_M[i], C6 = 6 * M, rows = 4 * M - 3;
-        const double *Hp = bb.Hblk + (size_t)s * bc.ecap + bb.l_eoff[lo + i] + 3 * C6;
-        const double *rp = bb.rblk + (size_t)s * bc.rcap + bb.l_roff[lo + i] + 3;
-        const uint8_t *os = bb.l_oslots + (lo + i) * NSM;
-        for (int e = lane; e < rows * C6; e += 32) {
-            int r = e / C6, c = e - r * C6;
-            int col = 6 * s_colpos[os[c / 6]] + (c % 6);
-            Hst[(size_t)(so + r) * k + col] = Hp[e];
-        }
-        int j0 = 6 * s_colpos[os[0]];
-        for (int a = 1; a < M; ++a) j0 = min(j0, 6 * s_colpos[os[a]]);
-        for (int r = lane; r < rows; r += 32) {
-            rst[so + r] = rp[r];
-            bb.rst_j0[(size_t)s * bc.hst_rows + so + r] = j0;
-        }
-    }
+    // row offsets for the scatter kernel (-1: not stacked)
+    const int nuse = s_nuse;
+    for (int i = threadIdx.x; i < n; i += BE_THREADS) bb.l_soff[lo + i] = i < nuse ? s_soff[i] : -1;
+    for (int c = threadIdx.x; c < bc.NS; c += BE_THREADS) st.colpos[c] = s_colpos[c];
     // the processed features leave the map (msckf_vio.cpp:1021-1023)
     if (phase == 0) {
         for (int i = threadIdx.x; i < n; i += BE_THREADS) bb.f_live[fo + bb.l_slot[lo + i]] = 0;
         if (threadIdx.x == 0) st.n_feat -= n;
+    }
+}
+
+// Copies the gated per-feature blocks into the stacked system (rows from be_stack_kernel, columns
+// compacted to the active camera slots).  grid (G, S): CTA g takes features g, g + G, ...; every
+// feature owns its rows of H, so the CTA also zero-fills them.
+__global__ void __launch_bounds__(BE_THREADS) be_scatter_kernel(BeConst bc, BeBuf bb) {
+    const int s = blockIdx.y;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    const BeState &st = bb.st[s];
+    if (!st.do_update) return;
+    const int n = st.n_list, k = st.k;
+    const size_t lo = (size_t)s * bc.ML;
+    double *Hst = bb.Hst + (size_t)s * bc.hst_cap, *rst = bb.rst + (size_t)s * bc.hst_rows;
+    __shared__ int s_col[6 * NSM];
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int so = bb.l_soff[lo + i];
+        if (so < 0) continue;
+        const int M = bb.l_M[lo + i], C6 = 6 * M, rows = 4 * M - 3;
+        const double *Hp = bb.Hblk + (size_t)s * bc.ecap + bb.l_eoff[lo + i] + 3 * C6;
+        const double *rp = bb.rblk + (size_t)s * bc.rcap + bb.l_roff[lo + i] + 3;
+        const uint8_t *os = bb.l_oslots + (lo + i) * NSM;
+        __syncthreads();
+        for (int c = threadIdx.x; c < C6; c += BE_THREADS) s_col[c] = 6 * st.colpos[os[c / 6]] + (c % 6);
+        for (int e = threadIdx.x; e < rows * k; e += BE_THREADS) Hst[(size_t)so * k + e] = 0.0;
+        __syncthreads();
+        int j0 = k;
+        for (int a = 0; a < M; ++a) j0 = min(j0, 6 * st.colpos[os[a]]);
+        for (int r = threadIdx.x / 32; r < rows; r += BE_THREADS / 32)
+            for (int c = threadIdx.x & 31; c < C6; c += 32) Hst[(size_t)(so + r) * k + s_col[c]] = Hp[r * C6 + c];
+        for (int r = threadIdx.x; r < rows; r += BE_THREADS) {
+            rst[so + r] = rp[r];
+            bb.rst_j0[(size_t)s * bc.hst_rows + so + r] = j0;
+        }
     }
 }
 
@@ -2813,6 +2828,7 @@ int be_step(mskf_handle *h, const std::vector<int> &streams, const mskf_feature 
             MSKF_LAUNCH(h, PK_BE_FEATURE_JAC_PRUNE, (be_feature_jac_prune_kernel<<<g, JS_WARPS * 32, 0, q>>>(bc, bb)));
         }
         MSKF_LAUNCH(h, PK_BE_STACK, (be_stack_kernel<<<S, BE_THREADS, (size_t)bc.ML * 10, q>>>(bc, bb, phase)));
+        MSKF_LAUNCH(h, PK_BE_STACK, (be_scatter_kernel<<<dim3(16, S), BE_THREADS, 0, q>>>(bc, bb)));
         launch_update(h, phase);
     }
     MSKF_LAUNCH(h, PK_BE_PRUNE_FINISH, (be_prune_finish_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb)));

@@ -178,3 +178,8 @@ def test_bad_arguments(eng, synth):
     e.close()
     with pytest.raises(eng.EngineError):
         eng.Engine(copy_cfg(cfg, klt_win=16), 1)
+
+
+def test_frontend_pipeline_stress_preset(eng, ob, synth):
+    """BASELINE.json config 5 geometry: 1280x1024, 6 pyramid levels, 8x10 grid (~1000 features)."""
+    _run_pipeline(eng, ob, synth, synth.default_config("stress"), 3, 6)
