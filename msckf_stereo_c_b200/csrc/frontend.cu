@@ -257,15 +257,27 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
             // template patch T[j][i] = A sampled at (px + i - half - 1, py + j - half - 1), i, j in [0, tw)
             const int xc = min(max(wa.ix - half - 1 + lane, 0), cols - 1);
             const int y0 = wa.iy - half - 1;
-            int top = __ldg(A + (size_t)min(max(y0, 0), rows - 1) * cols + xc);
-            int rt = __shfl_down_sync(0xffffffffu, top, 1);
+            if (WIN) {
+                int px[(WIN ? WIN : 1) + 3], nx[(WIN ? WIN : 1) + 3];
 #pragma unroll
-            for (int j = 0; j < tw; ++j) {
-                const int bot = __ldg(A + (size_t)min(max(y0 + j + 1, 0), rows - 1) * cols + xc);
-                const int rb = __shfl_down_sync(0xffffffffu, bot, 1);
-                if (lane < tw) T[j * tw + lane] = (short)((wa.w00 * top + wa.w01 * rt + wa.w10 * bot + wa.w11 * rb + 256) >> 9);
-                top = bot;
-                rt = rb;
+                for (int j = 0; j <= WIN + 2; ++j) px[j] = __ldg(A + (size_t)min(max(y0 + j, 0), rows - 1) * cols + xc);
+#pragma unroll
+                for (int j = 0; j <= WIN + 2; ++j) nx[j] = __shfl_down_sync(0xffffffffu, px[j], 1);
+                if (lane < tw) {
+#pragma unroll
+                    for (int j = 0; j < WIN + 2; ++j)
+                        T[j * tw + lane] = (short)((wa.w00 * px[j] + wa.w01 * nx[j] + wa.w10 * px[j + 1] + wa.w11 * nx[j + 1] + 256) >> 9);
+                }
+            } else {
+                int top = __ldg(A + (size_t)min(max(y0, 0), rows - 1) * cols + xc);
+                int rt = __shfl_down_sync(0xffffffffu, top, 1);
+                for (int j = 0; j < tw; ++j) {
+                    const int bot = __ldg(A + (size_t)min(max(y0 + j + 1, 0), rows - 1) * cols + xc);
+                    const int rb = __shfl_down_sync(0xffffffffu, bot, 1);
+                    if (lane < tw) T[j * tw + lane] = (short)((wa.w00 * top + wa.w01 * rt + wa.w10 * bot + wa.w11 * rb + 256) >> 9);
+                    top = bot;
+                    rt = rb;
+                }
             }
         }
         __syncwarp();
@@ -306,23 +318,42 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
                 {
                     const int xc = min(max(wb.ix - half + lane, 0), cols - 1);
                     const int y0 = wb.iy - half;
-                    int top = __ldg(B + (size_t)min(max(y0, 0), rows - 1) * cols + xc);
-                    int rt = __shfl_down_sync(0xffffffffu, top, 1);
                     const short *Trow = T + tw + lane + 1;
                     const short2 *Grow = Gr + lane;
+                    if (WIN) {
+                        // all rows of my column first (independent loads in flight together), then the
+                        // neighbours by shuffle, then the arithmetic
+                        int px[(WIN ? WIN : 1) + 1], nx[(WIN ? WIN : 1) + 1];
 #pragma unroll
-                    for (int j = 0; j < win; ++j) {
-                        const int bot = __ldg(B + (size_t)min(max(y0 + j + 1, 0), rows - 1) * cols + xc);
-                        const int rb = __shfl_down_sync(0xffffffffu, bot, 1);
+                        for (int j = 0; j <= WIN; ++j) px[j] = __ldg(B + (size_t)min(max(y0 + j, 0), rows - 1) * cols + xc);
+#pragma unroll
+                        for (int j = 0; j <= WIN; ++j) nx[j] = __shfl_down_sync(0xffffffffu, px[j], 1);
                         if (lane < win) {
-                            const int val = (wb.w00 * top + wb.w01 * rt + wb.w10 * bot + wb.w11 * rb + 256) >> 9;
-                            const int diff = val - (int)Trow[j * tw];
-                            const short2 g = Grow[j * win];
-                            b1 += (long long)(diff * (int)g.x);
-                            b2 += (long long)(diff * (int)g.y);
+#pragma unroll
+                            for (int j = 0; j < WIN; ++j) {
+                                const int val = (wb.w00 * px[j] + wb.w01 * nx[j] + wb.w10 * px[j + 1] + wb.w11 * nx[j + 1] + 256) >> 9;
+                                const int diff = val - (int)Trow[j * tw];
+                                const short2 g = Grow[j * win];
+                                b1 += (long long)(diff * (int)g.x);
+                                b2 += (long long)(diff * (int)g.y);
+                            }
                         }
-                        top = bot;
-                        rt = rb;
+                    } else {
+                        int top = __ldg(B + (size_t)min(max(y0, 0), rows - 1) * cols + xc);
+                        int rt = __shfl_down_sync(0xffffffffu, top, 1);
+                        for (int j = 0; j < win; ++j) {
+                            const int bot = __ldg(B + (size_t)min(max(y0 + j + 1, 0), rows - 1) * cols + xc);
+                            const int rb = __shfl_down_sync(0xffffffffu, bot, 1);
+                            if (lane < win) {
+                                const int val = (wb.w00 * top + wb.w01 * rt + wb.w10 * bot + wb.w11 * rb + 256) >> 9;
+                                const int diff = val - (int)Trow[j * tw];
+                                const short2 g = Grow[j * win];
+                                b1 += (long long)(diff * (int)g.x);
+                                b2 += (long long)(diff * (int)g.y);
+                            }
+                            top = bot;
+                            rt = rb;
+                        }
                     }
                 }
                 b1 = warp_sum(b1); b2 = warp_sum(b2);
