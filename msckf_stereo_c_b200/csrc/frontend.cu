@@ -419,31 +419,40 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
     }
     __syncthreads();
     const int t = fc.fast_threshold;
+    // Ring offsets as immediates: one LDS per ring pixel.  Bresenham circle of radius 3, k = 0 at (0, +3).
+#define DT_STRIDE (DT_W + 2 * DT_HALO + 2)
+#define RING_PX(pc, dx, dy) ((int)(pc)[(dy) * DT_STRIDE + (dx)])
+#define RING_LIST(X) X(0, 0, 3) X(1, 1, 3) X(2, 2, 2) X(3, 3, 1) X(4, 3, 0) X(5, 3, -1) X(6, 2, -2) X(7, 1, -3) \
+    X(8, 0, -3) X(9, -1, -3) X(10, -2, -2) X(11, -3, -1) X(12, -3, 0) X(13, -3, 1) X(14, -2, 2) X(15, -1, 3)
     for (int idx = threadIdx.x; idx < (DT_H + 2) * (DT_W + 2); idx += 256) {
         int r = idx / (DT_W + 2), c = idx - r * (DT_W + 2);
         int gy = y0 - 1 + r, gx = x0 - 1 + c;
         uint8_t sc = 0;
         if (gy >= 3 && gy < rows - 3 && gx >= 3 && gx < cols - 3) {
-            const int tr = r + DT_HALO - 1, tc = c + DT_HALO - 1;
-            const int v = tile[tr][tc];
-            int d[16];
+            const uint8_t *pc = &tile[r + DT_HALO - 1][c + DT_HALO - 1];
+            const int v = pc[0];
+            const int lo = v - t, hi = v + t;  // darker ring pixel: p < lo (d = v - p > t); brighter: p > hi
+            int p[16];
             unsigned dark = 0, bright = 0;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                d[k] = v - (int)tile[tr + c_fdy[k]][tc + c_fdx[k]];
-                dark |= (unsigned)(d[k] > t) << k;
-                bright |= (unsigned)(d[k] < -t) << k;
-            }
+            // sign bit of (p - lo) / (hi - p) shifted into the masks (bit order reversed: irrelevant on a ring)
+#define RING_TEST(k, dx, dy)                                               \
+    p[k] = RING_PX(pc, dx, dy);                                            \
+    dark = __funnelshift_l((unsigned)(p[k] - lo), dark, 1);                \
+    bright = __funnelshift_l((unsigned)(hi - p[k]), bright, 1);
+            RING_LIST(RING_TEST)
+#undef RING_TEST
             const bool is_dark = has_arc9(dark);
             if (is_dark || has_arc9(bright)) {
                 // S = max over the 16 arcs of 9 contiguous ring pixels of min(d) (darker ring) or min(-d)
-                // (brighter ring).  A ring cannot hold a darker and a brighter 9-arc at once, and the side
-                // without an arc scores <= t, so only the side that passed is evaluated.  Sliding minimum of
-                // width 9 by doubling (2, 4, 8, +1); only `min` chains on purpose: ptxas 12.9 for sm_100a
-                // miscompiles interleaved min/max chains fused into VIMNMX3 (tools/scratch/t2.cu).
+                // (brighter ring), d = centre - ring.  A ring cannot hold a darker and a brighter 9-arc at
+                // once, and the side without an arc scores <= t, so only the side that passed is evaluated.
+                // Sliding minimum of width 9 by doubling (2, 4, 8, +1); only `min` chains on purpose: ptxas
+                // 12.9 for sm_100a miscompiles interleaved min/max chains fused into VIMNMX3
+                // (tools/scratch/t2.cu).
+                const int sg = is_dark ? 1 : -1;
                 int n[16], a2[16], a4[16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) n[k] = is_dark ? d[k] : -d[k];
+                for (int k = 0; k < 16; ++k) n[k] = (v - p[k]) * sg;
 #pragma unroll
                 for (int k = 0; k < 16; ++k) a2[k] = min(n[k], n[(k + 1) & 15]);
 #pragma unroll
@@ -459,6 +468,8 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
         }
         score[r][c] = sc;
     }
+#undef RING_LIST
+#undef RING_PX
     __syncthreads();
     __shared__ int s_nmax;
     __shared__ unsigned short s_max[DT_H * DT_W / 4];  // strict 3x3 maxima: at most one per 2x2 block
