@@ -210,7 +210,8 @@ def run_ours(args, rank, world, local_rank):
         e.sync()
     # ---- pre-render the timed frames: device-resident set for `value`, pinned host set for `e2e`
     KP = min(K, 10)  # steps of the serial per-kernel profiling pass
-    n_dev = W + K + KP
+    KH = 3           # steps of the host-enqueue measurement
+    n_dev = W + K + KP + KH
     n_e2e = W + K + 1  # the upload of frame i+1 is issued while frame i computes
     frames_dev = torch.empty((n_dev, S, 2, img), dtype=torch.uint8, device=dev)
     frames_host = torch.empty((n_e2e, S, 2, img), dtype=torch.uint8).pin_memory()
@@ -258,6 +259,15 @@ def run_ours(args, rank, world, local_rank):
     ms_dev = ev0.elapsed_time(ev1)
     launches = e.launch_count() - launches0
     clk = clocks.stop()
+
+    # ---- how long the host needs to enqueue one step (no waiting: 3 steps fit the engine's descriptor ring)
+    e.sync()
+    t_h0 = time.perf_counter()
+    for i in range(W + K + KP, W + K + KP + KH):
+        step_dev(i, k)
+        k += 1
+    host_ms = 1e3 * (time.perf_counter() - t_h0) / KH
+    e.sync()
 
     # ---- per-kernel pass: the two halves serialised, CUDA events around every kernel class
     e.set_overlap(False)
@@ -362,7 +372,8 @@ def run_ours(args, rank, world, local_rank):
         top = next((x for x in per_kernel if "achieved" in x), None)
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top["kernel"]) if top else None
+            per_stream = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top["kernel"]) if top else None
+            traffic = per_stream * S if per_stream else None  # ncu dram bytes per stream per launch (S = 64 capture) x S
         except (OSError, ValueError):
             pass
         roofline = None
@@ -396,6 +407,7 @@ def run_ours(args, rank, world, local_rank):
                                        "run_euroc_single_thread (reference not buildable here); rendering excluded",
                              "wall_s": time.time() - t0},
             "wall_ms_per_step": wall_max / K,
+            "host_enqueue_ms_per_step": host_ms,
         }
         print(json.dumps(line), flush=True)
     e.close()
