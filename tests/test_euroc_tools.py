@@ -62,7 +62,7 @@ def test_run_euroc_on_synthetic_mav0(tmp_path, synth):
     est = euroc.read_tum(out)
     # the same feed through ctypes, reading the files back exactly like the runner
     e = engine.Engine(cfg, 1)
-    cam = [[l.strip().split(",") for l in open(os.path.join(d, f"cam{c}", "data.csv")).read().split("\r\n")[1:] if l] for c in (0, 1)]
+    cam = [[l.strip().split(",") for l in open(os.path.join(d, f"cam{c}", "data.csv"), newline="").read().split("\r\n")[1:] if l] for c in (0, 1)]
     imu = [l.split(",") for l in open(os.path.join(d, "imu0", "data.csv")).read().splitlines()[1:]]
     stamp = lambda sns: (int(sns[:-9]) * 1e9 + int(sns[-9:])) * 1e-9
     j, poses = 0, []
