@@ -15,6 +15,8 @@
 //   fe_sieve             addNewFeatures :659-688 / initializeFirstFrame :261-268
 //   fe_finish            addNewFeatures :690-750, initializeFirstFrame :270-316,
 //                        pruneGridFeatures :758-768, publish :1137-1182, stereoCallback :192-200
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -175,6 +177,115 @@ __global__ void __launch_bounds__(256) pyr_down_strip_kernel(FeConst fc, FeBuffe
             h2 = h4;
         }
     }
+}
+
+// Level 0 -> 1 with the strip staged by the TMA engine: when a strip's 36 input rows are one
+// contiguous span of the image (every strip except the top and bottom ones, whose reflected rows are
+// fetched row by row) ONE cp.async.bulk moves 27 KB global -> shared and signals an mbarrier, and the
+// level-0 landing copy is ONE cp.async.bulk shared -> global of the 32 interior rows: no thread touches
+// the staging.  Rows are packed (stride = icols, no halo columns); the two edge column pairs patch
+// their BORDER_REFLECT_101 bytes in registers.  Needs icols % 16 == 0.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ unsigned hfilt2_packed(const uint8_t *row, int q, bool first, bool last) {
+    const unsigned *w = (const unsigned *)(row - 4) + q;
+    unsigned W0 = w[0], W2 = w[2];
+    const unsigned W1 = w[1];
+    if (first) W0 = __byte_perm(W1, 0u, 0x1200);  // p[-2] = p[2], p[-1] = p[1]
+    if (last) W2 = (W1 >> 16) & 0xFFu;             // p[icols] = p[icols - 2]
+    const unsigned V = __funnelshift_r(W0, W1, 16);
+    const unsigned X = __funnelshift_r(W1, W2, 16);
+    const unsigned A = V & 0x00FF00FFu, B = (V >> 8) & 0x00FF00FFu;
+    const unsigned C = W1 & 0x00FF00FFu, D = (W1 >> 8) & 0x00FF00FFu;
+    const unsigned E = X & 0x00FF00FFu;
+    return A + E + 6u * C + 4u * (B + D);
+}
+
+template <bool COPY_SRC>
+__global__ void __launch_bounds__(256) pyr_down_bulk_kernel(FeConst fc, FeBuffers fb, int level) {
+    const int s = blockIdx.z >> 1, cam = blockIdx.z & 1;
+    const FeStep st = fb.step[s];
+    if (!st.active) return;
+    uint8_t *pyr = (cam == 0 ? fb.pyr[st.slot] : fb.pyr[2]) + (size_t)s * fc.pyr_bytes;
+    const int irows = fc.lvl_rows[level - 1], icols = fc.lvl_cols[level - 1];
+    const int orows = fc.lvl_rows[level], ocols = fc.lvl_cols[level];
+    const uint8_t *src = COPY_SRC ? (cam == 0 ? fb.src0[s] : fb.src1[s]) : pyr + fc.lvl_off[level - 1];
+    uint8_t *dst = pyr + fc.lvl_off[level];
+    extern __shared__ __align__(128) uint8_t ps_smem[];  // 16 B pad | PS_IN rows of icols bytes | 16 B pad
+    __shared__ __align__(8) unsigned long long bar;
+    uint8_t *tile = ps_smem + 16;
+    const int oy0 = blockIdx.x * PS_ROWS;
+    const int iy0 = 2 * oy0 - 2;
+    const unsigned bar_a = smem_u32(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = (unsigned)(PS_IN * icols);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(total) : "memory");
+        if (iy0 >= 0 && iy0 + PS_IN <= irows) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(tile)),
+                         "l"(src + (size_t)iy0 * icols), "r"(total), "r"(bar_a)
+                         : "memory");
+        } else {
+            for (int r = 0; r < PS_IN; ++r) {
+                const int gy = reflect101(iy0 + r, irows);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(tile + (size_t)r * icols)),
+                             "l"(src + (size_t)gy * icols), "r"((unsigned)icols), "r"(bar_a)
+                             : "memory");
+            }
+        }
+    }
+    {
+        // every thread waits for the bytes to land (phase 0 of the barrier)
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(done)
+                : "r"(bar_a), "r"(0)
+                : "memory");
+        }
+    }
+    if (COPY_SRC && threadIdx.x == 0) {
+        // level-0 landing copy: the interior rows of the strip are image rows [2 oy0, 2 oy0 + 2 PS_ROWS)
+        const int y_begin = 2 * oy0, n_rows = min(2 * PS_ROWS, irows - y_begin);
+        if (n_rows > 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(pyr + (size_t)y_begin * icols),
+                         "r"(smem_u32(tile + 2 * icols)), "r"((unsigned)(n_rows * icols))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    const int ncp = ocols >> 1;  // icols % 16 == 0 => ocols even
+    const int cp = min(256, (ncp + 31) & ~31);
+    const int groups = 256 / cp;
+    const int g = threadIdx.x / cp, t = threadIdx.x - g * cp;
+    const int rpg = (PS_ROWS + groups - 1) / groups;
+    const int r_begin = g * rpg, r_end = min(min(PS_ROWS, r_begin + rpg), orows - oy0);
+    if (g < groups && r_begin < r_end) {
+        for (int q = t; q < ncp; q += cp) {
+            const bool first = q == 0, last = q == ncp - 1;
+            const uint8_t *base = tile + (size_t)(2 * r_begin) * icols;
+            unsigned h0 = hfilt2_packed(base, q, first, last), h1 = hfilt2_packed(base + icols, q, first, last),
+                     h2 = hfilt2_packed(base + 2 * icols, q, first, last);
+            for (int r = r_begin; r < r_end; ++r) {
+                const uint8_t *rp = tile + (size_t)(2 * r + 3) * icols;
+                const unsigned h3 = hfilt2_packed(rp, q, first, last), h4 = hfilt2_packed(rp + icols, q, first, last);
+                const unsigned v = h0 + h4 + 6u * h2 + 4u * (h1 + h3);
+                const unsigned o = ((v + 0x00800080u) >> 8) & 0x00FF00FFu;
+                *(unsigned short *)(dst + (size_t)(oy0 + r) * ocols + 2 * q) = (unsigned short)((o & 0xFFu) | ((o >> 8) & 0xFF00u));
+                h0 = h2;
+                h1 = h3;
+                h2 = h4;
+            }
+        }
+    }
+    // the bulk store reads shared memory asynchronously: it must have finished before the CTA retires
+    if (COPY_SRC && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ======================================================================================
@@ -1312,7 +1423,11 @@ static void launch_pyr_level(mskf_handle *h, int l, int images) {
     const int tag = l == 1 ? PK_PYR_L1 : PK_PYR_LN;
     if (smem <= 200 * 1024 && (icols % 4) == 0 && icols >= 8) {
         dim3 g((fc.lvl_rows[l] + PS_ROWS - 1) / PS_ROWS, 1, images);
-        if (l == 1 && (icols % 16) == 0) {
+        if (l == 1 && (icols % 16) == 0 && !getenv("MSKF_PYR_NO_TMA")) {
+            const size_t bsmem = (size_t)PS_IN * icols + 32;
+            cudaFuncSetAttribute(pyr_down_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+            MSKF_LAUNCH(h, tag, (pyr_down_bulk_kernel<true><<<g, 256, bsmem, q>>>(fc, fb, l)));
+        } else if (l == 1 && (icols % 16) == 0) {
             cudaFuncSetAttribute(pyr_down_strip_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             MSKF_LAUNCH(h, tag, (pyr_down_strip_kernel<true, 16><<<g, 256, smem, q>>>(fc, fb, l, row_stride)));
         } else if (l == 1) {
