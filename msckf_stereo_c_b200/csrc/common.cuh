@@ -49,6 +49,8 @@ struct FeConst {
     double E[9];        // essential matrix (image_processor.cpp:591)
     double stereo_gate; // stereo_threshold * norm_pixel_unit (image_processor.cpp:606,615)
     int compat_stale;
+    int use_ransac;
+    double ransac_threshold;
 };
 
 // per-stream, per-step descriptor written by the host before each front-end step
@@ -56,6 +58,7 @@ struct FeStep {
     int active, is_first, slot, pad;
     double t;
     double H0[9];  // K R_p_c K^-1 for cam0 (image_processor.cpp:340)
+    double R0[9], R1[9];  // cam0_R_p_c, cam1_R_p_c (integrateImuData, image_processor.cpp:882-883): twoPointRansac
 };
 
 struct GridSoA {            // one grid of one stream, publish order (cell asc, insertion order)
@@ -88,6 +91,8 @@ struct FeBuffers {
     // tracked meta carried through the temporal track
     unsigned long long *t_id;  // [S][max_f]
     int *t_life;               // [S][max_f]
+    float2 *t_p0, *t_p1;       // [S][max_f] previous cam0 / cam1 points of the tracked features (twoPointRansac)
+    unsigned *track_calls;     // [S] trackFeatures calls that reached the RANSAC stage (seeds its sampler)
     // detector
     unsigned long long *det_best;  // [S][det_cells] packed (score bits << 32 | ~raster)
     uint8_t *det_occ;              // [S][det_cells]

@@ -69,7 +69,7 @@ static void rodrigues_t(const double v[3], double Rt[9]) {
 
 // ImageProcessor::integrateImuData (image_processor.cpp:850-889) + the homography of
 // predictFeatureTracking (:335-340) for cam0.
-static void host_predict_homography(mskf_handle *h, HostStream &hs, double H0[9]) {
+static void host_predict_homography(mskf_handle *h, HostStream &hs, double H0[9], double R0[9], double R1[9]) {
     const mskf_config &c = h->cfg;
     const double prev_t = c.fix_prev_image_alias ? hs.fe_prev_t : hs.fe_curr_t;  // defect F6
     size_t begin = 0;
@@ -97,6 +97,20 @@ static void host_predict_homography(mskf_handle *h, HostStream &hs, double H0[9]
     double v[3] = {cam0_w[0] * dtime, cam0_w[1] * dtime, cam0_w[2] * dtime};
     double Rpc[9];
     rodrigues_t(v, Rpc);
+    {
+        // cam1: R_cam1_imu^T = rot(T_cn_cnm1 * T_cam0_imu) (image_processor.cpp:66-72, :878-883)
+        double R1m[9], cam1_w[3], v1[3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double sacc = 0;
+                for (int k = 0; k < 3; ++k) sacc += c.T_cn_cnm1[i * 4 + k] * c.T_cam0_imu[k * 4 + j];
+                R1m[i * 3 + j] = sacc;
+            }
+        for (int i = 0; i < 3; ++i) cam1_w[i] = R1m[i * 3 + 0] * mean[0] + R1m[i * 3 + 1] * mean[1] + R1m[i * 3 + 2] * mean[2];
+        for (int i = 0; i < 3; ++i) v1[i] = cam1_w[i] * dtime;
+        rodrigues_t(v1, R1);
+        for (int i = 0; i < 9; ++i) R0[i] = Rpc[i];
+    }
     hs.fe_imu.erase(hs.fe_imu.begin(), hs.fe_imu.begin() + end);
     double K[9] = {c.cam0_intrinsics[0], 0, c.cam0_intrinsics[2], 0, c.cam0_intrinsics[1], c.cam0_intrinsics[3], 0, 0, 1.0};
     double KR[9], Ki[9];
@@ -442,7 +456,7 @@ int mskf_frontend_step(mskf_handle *h) {
             hs.slot = 0;
         } else {
             hs.slot ^= 1;  // std::swap(prev_cam0_pyramid_, curr_cam0_pyramid_), image_processor.cpp:194
-            host_predict_homography(h, hs, st.H0);
+            host_predict_homography(h, hs, st.H0, st.R0, st.R1);
             max_prev = h->fc.max_f;
         }
         st.slot = hs.slot;

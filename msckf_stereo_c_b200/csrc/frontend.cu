@@ -791,6 +791,8 @@ __global__ void __launch_bounds__(FE_THREADS) fe_prep_track(FeConst fc, FeBuffer
         fb.k_b[ko + i] = make_float2((float)(p20 / p22), (float)(p21 / p22));
         fb.t_id[go + i] = fb.g_id[gp][go + i];
         fb.t_life[go + i] = fb.g_life[gp][go + i];
+        fb.t_p0[go + i] = p;
+        fb.t_p1[go + i] = fb.g_cam1[gp][go + i];
     }
     if (threadIdx.x == 0) {
         fb.k_n[s] = n;
@@ -818,13 +820,15 @@ __global__ void __launch_bounds__(FE_THREADS) fe_after_track(FeConst fc, FeBuffe
     for (int start = 0; start < n; start += FE_THREADS) {
         int i = start + threadIdx.x;
         bool keep = i < n && flag[i];
-        float2 c0 = make_float2(0, 0);
+        float2 c0 = make_float2(0, 0), q0 = c0, q1 = c0;
         unsigned long long id = 0;
         int life = 0;
         if (keep) {
             c0 = fb.k_b[ko + i];
             id = fb.t_id[go + i];
             life = fb.t_life[go + i];
+            q0 = fb.t_p0[go + i];
+            q1 = fb.t_p1[go + i];
         }
         __syncthreads();
         if (keep) {
@@ -832,6 +836,8 @@ __global__ void __launch_bounds__(FE_THREADS) fe_after_track(FeConst fc, FeBuffe
             fb.k_a[ko + d] = c0;  // current cam0 point becomes the stereo template point
             fb.t_id[go + d] = id;
             fb.t_life[go + d] = life;
+            fb.t_p0[go + d] = q0;
+            fb.t_p1[go + d] = q1;
             float2 u = undistort_pt(fc, 0, c0, fc.R01);
             fb.k_b[ko + d] = distort_pt(fc, 1, u);
         }
@@ -842,6 +848,166 @@ __global__ void __launch_bounds__(FE_THREADS) fe_after_track(FeConst fc, FeBuffe
         fb.info[s].after_tracking = m;
         fb.work[(size_t)s * MSKF_PROF_TAGS + PK_KLT_STEREO] += (double)m * klt_bytes_per_feature(fc);
     }
+}
+
+// ======================================================================================
+// twoPointRansac (image_processor.cpp:911-1135) for one camera, executed by the whole CTA of a
+// stream.  Dead code in the reference (both calls are commented out, :482-493): runs only with
+// use_ransac.  The sequential float / double sums of the reference are kept sequential (one thread)
+// so that the result is bit-identical to the oracle; the seven hypotheses run on seven threads.
+// cg::uniform_integer is unseeded in the reference: SPEC = counter-based hash shared with the oracle.
+// ======================================================================================
+__device__ __forceinline__ unsigned ransac_hash(unsigned a, unsigned b) {
+    unsigned h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du;
+    h ^= h >> 12; h *= 0x297A2D39u;
+    h ^= h >> 15;
+    return h;
+}
+__device__ __forceinline__ int ransac_uniform(unsigned call, int cam, int iter, int draw, int lo, int hi) {
+    return lo + (int)(ransac_hash(call * 2u + (unsigned)cam, (unsigned)(iter * 2 + draw)) % (unsigned)(hi - lo + 1));
+}
+#define RANSAC_ITERS 7  // ceil(log(1 - 0.99) / log(1 - 0.7 * 0.7)), image_processor.cpp:927
+
+struct RansacSmem {       // carved from dynamic shared memory, n = matched features
+    float2 *p1, *p2;      // [n]
+    double *coeff;        // [n][3]
+    double *dist;         // [n]
+    float *sq;            // [2n]
+    int *raw;             // [n]
+    unsigned *sets;       // [RANSAC_ITERS][words]
+    uint8_t *marker;      // [n]
+};
+
+__device__ void ransac_one_cam(const FeConst &fc, int cam, const double *R, int n, const int *mlist, const float2 *prev, const float2 *curr,
+                               unsigned call, RansacSmem sm, uint8_t *out_marker) {
+    __shared__ float s_sf;
+    __shared__ double s_npu, s_mean;
+    __shared__ int s_cnt, s_mode, s_nraw, s_count[RANSAC_ITERS], s_best;
+    const int words = (n + 31) / 32;
+    for (int j = threadIdx.x; j < n; j += FE_THREADS) {
+        const int i = mlist[j];
+        float2 u1 = undistort_pt(fc, cam, prev[i], nullptr), u2 = undistort_pt(fc, cam, curr[i], nullptr);
+        const double x = (double)u1.x, y = (double)u1.y;
+        u1.x = (float)(R[0] * x + R[1] * y + R[2] * 1.0);
+        u1.y = (float)(R[3] * x + R[4] * y + R[5] * 1.0);
+        sm.p1[j] = u1;
+        sm.p2[j] = u2;
+        sm.sq[2 * j] = sqrtf(u1.x * u1.x + u1.y * u1.y);
+        sm.sq[2 * j + 1] = sqrtf(u2.x * u2.x + u2.y * u2.y);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // rescalePoints, image_processor.cpp:891-909 (sequential float sum)
+        float sf = 0.0f;
+        for (int j = 0; j < n; ++j) {
+            sf += sm.sq[2 * j];
+            sf += sm.sq[2 * j + 1];
+        }
+        sf = (float)(2 * n) / sf * sqrtf(2.0f);
+        s_sf = sf;
+        s_npu = 2.0 / (fc.K[cam][0] + fc.K[cam][1]) * (double)sf;
+    }
+    __syncthreads();
+    const float sf = s_sf;
+    const double npu = s_npu;
+    for (int j = threadIdx.x; j < n; j += FE_THREADS) {
+        float2 a = sm.p1[j], b = sm.p2[j];
+        a.x *= sf; a.y *= sf; b.x *= sf; b.y *= sf;
+        const float dx = a.x - b.x, dy = a.y - b.y;
+        const double d = (double)sqrtf(dx * dx + dy * dy);
+        sm.dist[j] = d;
+        sm.marker[j] = d > 50.0 * npu ? 0 : 1;
+        sm.coeff[3 * j + 0] = (double)dy;
+        sm.coeff[3 * j + 1] = (double)(-dx);
+        sm.coeff[3 * j + 2] = (double)(a.x * b.y - a.y * b.x);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mean = 0.0;
+        int cnt = 0, nraw = 0;
+        for (int j = 0; j < n; ++j)
+            if (sm.marker[j]) {
+                mean += sm.dist[j];
+                ++cnt;
+                sm.raw[nraw++] = j;
+            }
+        mean /= cnt;
+        s_mean = mean;
+        s_cnt = cnt;
+        s_nraw = nraw;
+        s_mode = cnt < 3 ? 0 : (mean < npu ? 1 : 2);
+    }
+    __syncthreads();
+    if (s_mode == 0) {
+        for (int j = threadIdx.x; j < n; j += FE_THREADS) out_marker[j] = 0;
+        __syncthreads();
+        return;
+    }
+    if (s_mode == 1) {  // degenerate motion: threshold the point distance
+        for (int j = threadIdx.x; j < n; j += FE_THREADS) out_marker[j] = (sm.marker[j] && !(sm.dist[j] > fc.ransac_threshold * npu)) ? 1 : 0;
+        __syncthreads();
+        return;
+    }
+    for (int e = threadIdx.x; e < RANSAC_ITERS * words; e += FE_THREADS) sm.sets[e] = 0u;
+    __syncthreads();
+    if (threadIdx.x < RANSAC_ITERS) {
+        const int it = threadIdx.x, nraw = s_nraw;
+        const int i1 = ransac_uniform(call, cam, it, 0, 0, nraw - 1);
+        const int idf = ransac_uniform(call, cam, it, 1, 1, nraw - 1);
+        const int i2 = i1 + idf < nraw ? i1 + idf : i1 + idf - nraw;
+        const int pa = sm.raw[i1], pb = sm.raw[i2];
+        double c[3][2];
+        for (int k = 0; k < 3; ++k) {
+            c[k][0] = sm.coeff[3 * pa + k];
+            c[k][1] = sm.coeff[3 * pb + k];
+        }
+        double l1[3];
+        for (int k = 0; k < 3; ++k) l1[k] = fabs(c[k][0]) + fabs(c[k][1]);
+        int base = 0;
+        for (int k = 1; k < 3; ++k)
+            if (l1[k] < l1[base]) base = k;
+        const int ia = base == 0 ? 1 : 0, ib = base == 2 ? 1 : 2;
+        double mdl[3];
+        {
+            const double a00 = c[ia][0], a01 = c[ib][0], a10 = c[ia][1], a11 = c[ib][1];
+            const double det = a00 * a11 - a01 * a10, id = 1.0 / det;
+            const double i00 = a11 * id, i01 = -a01 * id, i10 = -a10 * id, i11 = a00 * id;
+            const double b0 = -c[base][0], b1 = -c[base][1];
+            mdl[base] = 1.0;
+            mdl[ia] = i00 * b0 + i01 * b1;
+            mdl[ib] = i10 * b0 + i11 * b1;
+        }
+        int count = 0;
+        unsigned *set = sm.sets + it * words;
+        for (int j = 0; j < n; ++j) {
+            if (!sm.marker[j]) continue;
+            double e = sm.coeff[3 * j] * mdl[0];
+            e += sm.coeff[3 * j + 1] * mdl[1];
+            e += sm.coeff[3 * j + 2] * mdl[2];
+            if (fabs(e) < fc.ransac_threshold * npu) {
+                set[j >> 5] |= 1u << (j & 31);
+                ++count;
+            }
+        }
+        // hypotheses with too few inliers are skipped (:1064); the refit (:1067-1112) only feeds
+        // best_error, which never influences the result
+        s_count[it] = ((double)count < 0.2 * (double)n) ? -1 : count;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = -1, best_count = 0;
+        for (int it = 0; it < RANSAC_ITERS; ++it)
+            if (s_count[it] > best_count) {
+                best_count = s_count[it];
+                best = it;
+            }
+        s_best = best;
+    }
+    __syncthreads();
+    const int best = s_best;
+    for (int j = threadIdx.x; j < n; j += FE_THREADS)
+        out_marker[j] = (best >= 0 && ((sm.sets[best * words + (j >> 5)] >> (j & 31)) & 1u)) ? 1 : 0;
+    __syncthreads();
 }
 
 // after the stereo match of tracked features: gates, compaction, re-bucket into the grid
@@ -872,6 +1038,41 @@ __global__ void __launch_bounds__(FE_THREADS) fe_after_stereo(FeConst fc, FeBuff
     }
     for (int c = threadIdx.x; c < fc.n_cells_all; c += FE_THREADS) s_cnt[c] = 0;
     __syncthreads();
+    if (fc.use_ransac && tracked_any) {
+        // matched list in index order, then twoPointRansac on the temporal pairs of cam0 and cam1
+        // (the commented-out calls at image_processor.cpp:482-493)
+        __shared__ int s_nm;
+        uint8_t *base = (uint8_t *)s_dyn + ((fc.max_f + 15) & ~15);
+        int *mlist = (int *)base;                                   // [max_f]
+        RansacSmem sm;
+        sm.p1 = (float2 *)(mlist + fc.max_f);
+        sm.p2 = sm.p1 + fc.max_f;
+        sm.coeff = (double *)(sm.p2 + fc.max_f);
+        sm.dist = sm.coeff + 3 * fc.max_f;
+        sm.sq = (float *)(sm.dist + fc.max_f);
+        sm.raw = (int *)(sm.sq + 2 * fc.max_f);
+        sm.sets = (unsigned *)(sm.raw + fc.max_f);
+        sm.marker = (uint8_t *)(sm.sets + RANSAC_ITERS * ((fc.max_f + 31) / 32));
+        uint8_t *mk0 = sm.marker + fc.max_f, *mk1 = mk0 + fc.max_f;
+        if (threadIdx.x == 0) {
+            int m = 0;
+            for (int i = 0; i < n; ++i)
+                if (s_code[i] != 255) mlist[m++] = i;
+            s_nm = m;
+            fb.info[s].after_matching = m;
+        }
+        __syncthreads();
+        const int nm = s_nm;
+        const unsigned call = fb.track_calls[s];
+        if (nm > 0) {
+            ransac_one_cam(fc, 0, st.R0, nm, mlist, fb.t_p0 + go, fb.k_a + ko, call, sm, mk0);
+            ransac_one_cam(fc, 1, st.R1, nm, mlist, fb.t_p1 + go, fb.k_b + ko, call, sm, mk1);
+            for (int j = threadIdx.x; j < nm; j += FE_THREADS)
+                if (mk0[j] == 0 || mk1[j] == 0) s_code[mlist[j]] = 255;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) fb.track_calls[s] = call + 1;
+    }
     // stable counting sort by grid cell = publish order of the std::map; one warp per cell
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int c = warp; c < fc.n_cells_all; c += FE_THREADS / 32) {
@@ -892,7 +1093,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_after_stereo(FeConst fc, FeBuff
         s_start[fc.n_cells_all] = acc;
         fb.g_n[gc][s] = acc;
         if (tracked_any) {
-            fb.info[s].after_matching = acc;
+            if (!fc.use_ransac) fb.info[s].after_matching = acc;
             fb.info[s].after_ransac = acc;
         }
     }
@@ -1271,6 +1472,12 @@ static int fe_members_cap(const FeConst &fc) { return (fc.grid_w / fc.det_cell_w
 static size_t fe_sieve_smem(const FeConst &fc) {
     return (size_t)fc.det_cells * 9 + 16 + sizeof(int) * ((size_t)fc.n_cells * fc.grid_max + (FE_THREADS / 32) * fe_members_cap(fc));
 }
+static size_t fe_after_stereo_smem(const FeConst &fc) {
+    size_t b = ((size_t)fc.max_f + 15) & ~(size_t)15;
+    if (fc.use_ransac)
+        b += (size_t)fc.max_f * (4 + 8 + 8 + 24 + 8 + 8 + 4 + 3) + 4 * RANSAC_ITERS * (((size_t)fc.max_f + 31) / 32) + 64;
+    return b + 16;
+}
 static size_t fe_finish_smem(const FeConst &fc) {
     return ((size_t)fc.cap_k + (size_t)fc.n_cells * fc.grid_min + (size_t)fc.n_cells_all * fc.grid_max) * sizeof(int) +
            (size_t)fc.cap_k * 5 + (size_t)fc.max_f * 5 + 16;
@@ -1283,11 +1490,6 @@ int fe_create(mskf_handle *h) {
     if (c.pyramid_levels < 1 || c.pyramid_levels > MSKF_MAX_LEVELS || (c.klt_win & 1) == 0 || c.klt_win < 3 ||
         c.klt_win > 29) {
         h->err = "bad pyramid_levels / klt_win (odd, 3..29)";
-        return MSKF_ERR_ARG;
-    }
-    if (c.use_ransac) {
-        // twoPointRansac is dead code in the reference (image_processor.cpp:482-493 commented out)
-        h->err = "use_ransac: twoPointRansac is not built (never called by the reference)";
         return MSKF_ERR_ARG;
     }
     fc.rows = c.img_rows; fc.cols = c.img_cols; fc.levels = c.pyramid_levels;
@@ -1325,6 +1527,8 @@ int fe_create(mskf_handle *h) {
         fc.K[1][i] = c.cam1_intrinsics[i]; fc.D[1][i] = c.cam1_distortion[i];
     }
     fc.compat_stale = c.compat_stale_features;
+    fc.use_ransac = c.use_ransac;  // the reference never calls twoPointRansac (image_processor.cpp:482-493): default 0
+    fc.ransac_threshold = c.ransac_threshold;
     // extrinsics as ImageProcessor::loadParameters derives them (image_processor.cpp:63-72)
     auto R = [](const double *T, int i, int j) { return T[i * 4 + j]; };
     double R_c0_imu[9], t_c0_imu[3], T1[16], R_c1_imu[9], t_c1_imu[3];
@@ -1387,7 +1591,7 @@ int fe_create(mskf_handle *h) {
     }
     A(fb.gslot, S); A(fb.next_id, S);
     A(fb.k_a, S * fc.cap_k); A(fb.k_b, S * fc.cap_k); A(fb.k_status, S * fc.cap_k); A(fb.k_skip, S * fc.cap_k); A(fb.k_n, S);
-    A(fb.t_id, S * fc.max_f); A(fb.t_life, S * fc.max_f);
+    A(fb.t_id, S * fc.max_f); A(fb.t_life, S * fc.max_f); A(fb.t_p0, S * fc.max_f); A(fb.t_p1, S * fc.max_f); A(fb.track_calls, S);
     A(fb.det_best, S * fc.det_cells); A(fb.det_occ, S * fc.det_cells);
     A(fb.nf_resp, S * fc.det_cells); A(fb.nf_n, S); A(fb.in_resp, S * fc.cap_k);
     A(fb.msg, S * fc.max_f); A(fb.msg_n, S); A(fb.stale, S * fc.max_f); A(fb.stale_hw, S); A(fb.msg_total, S);
@@ -1398,6 +1602,11 @@ int fe_create(mskf_handle *h) {
         h->err = "detector grid / feature capacity too large for the bookkeeping kernels' shared memory";
         return MSKF_ERR_ARG;
     }
+    if (fe_after_stereo_smem(fc) > 200 * 1024) {
+        h->err = "feature capacity too large for twoPointRansac's shared memory";
+        return MSKF_ERR_ARG;
+    }
+    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(fe_after_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_after_stereo_smem(fc)));
     MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(fe_sieve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_sieve_smem(fc)));
     MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(fe_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_finish_smem(fc)));
     return MSKF_OK;
@@ -1475,7 +1684,7 @@ int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active) {
         MSKF_LAUNCH(h, PK_FE_BOOK, (fe_after_track<<<S, FE_THREADS, pos_smem, q>>>(fc, fb)));
         launch_klt(h, PK_KLT_STEREO, g, klt_smem, 1);
     }
-    MSKF_LAUNCH(h, PK_FE_BOOK, (fe_after_stereo<<<S, FE_THREADS, (size_t)fc.max_f + 16, q>>>(fc, fb)));
+    MSKF_LAUNCH(h, PK_FE_BOOK, (fe_after_stereo<<<S, FE_THREADS, fe_after_stereo_smem(fc), q>>>(fc, fb)));
     {
         dim3 g((fc.cols + DT_W - 1) / DT_W, (fc.rows + DT_H - 1) / DT_H, S);
         MSKF_LAUNCH(h, PK_DETECT, (detect_kernel<<<g, 256, 0, q>>>(fc, fb)));

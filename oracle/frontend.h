@@ -10,6 +10,7 @@
 //   F6 cam0_prev_img_ptr aliases cam0_curr_img_ptr (image_processor.cpp:192) -> dt = 0 in :881
 //   std::sort is unstable -> SPEC fixes stable order (ties keep insertion order)
 #pragma once
+#include <array>
 #include <map>
 #include <memory>
 #include <string>
@@ -248,9 +249,19 @@ public:
         removeUnmarkedElements(curr_cam1_points, match_inliers, curr_matched_cam1_points);
         after_matching = (int)curr_matched_cam0_points.size();
 
-        // :482-493 the two twoPointRansac calls are commented out in the reference
+        // :482-493 the two twoPointRansac calls are commented out in the reference; with
+        // use_ransac they run as the commented code reads
+        std::vector<int> cam0_ransac_inliers, cam1_ransac_inliers;
+        if (cfg.use_ransac) {
+            twoPointRansac(prev_matched_cam0_points, curr_matched_cam0_points, cam0_R_p_c, cfg.cam0_intrinsics, cfg.cam0_model,
+                           cfg.cam0_distortion, cfg.ransac_threshold, 0.99, cam0_ransac_inliers, 0);
+            twoPointRansac(prev_matched_cam1_points, curr_matched_cam1_points, cam1_R_p_c, cfg.cam1_intrinsics, cfg.cam1_model,
+                           cfg.cam1_distortion, cfg.ransac_threshold, 0.99, cam1_ransac_inliers, 1);
+        }
+        ++track_calls;
         after_ransac = 0;
         for (size_t i = 0; i < curr_matched_cam0_points.size(); ++i) {
+            if (cfg.use_ransac && (cam0_ransac_inliers[i] == 0 || cam1_ransac_inliers[i] == 0)) continue;
             int row = (int)(curr_matched_cam0_points[i].y / grid_height);
             int col = (int)(curr_matched_cam0_points[i].x / grid_width);
             int code = row * cfg.grid_col + col;
@@ -372,6 +383,149 @@ public:
         }
     }
 
+    // cg::uniform_integer(lo, hi) lives in vikit_cg and is unseeded (image_processor.cpp:1026-1027).
+    // SPEC: a counter-based hash of (trackFeatures call, camera, iteration, draw) so that the CPU
+    // oracle and the CUDA engine draw the same pairs; only statistical parity with the reference.
+    static uint32_t ransac_hash(uint32_t a, uint32_t b) {
+        uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u;
+        h ^= h >> 15; h *= 0x2C1B3C6Du;
+        h ^= h >> 12; h *= 0x297A2D39u;
+        h ^= h >> 15;
+        return h;
+    }
+    static int uniform_integer(uint32_t call, int cam, int iter, int draw, int lo, int hi) {
+        uint32_t h = ransac_hash(call * 2u + (uint32_t)cam, (uint32_t)(iter * 2 + draw));
+        return lo + (int)(h % (uint32_t)(hi - lo + 1));
+    }
+
+    // image_processor.cpp:891-909
+    static void rescalePoints(std::vector<Pt> &pts1, std::vector<Pt> &pts2, float &scaling_factor) {
+        scaling_factor = 0.0f;
+        for (size_t i = 0; i < pts1.size(); ++i) {
+            scaling_factor += std::sqrt(pts1[i].x * pts1[i].x + pts1[i].y * pts1[i].y);
+            scaling_factor += std::sqrt(pts2[i].x * pts2[i].x + pts2[i].y * pts2[i].y);
+        }
+        scaling_factor = (float)(pts1.size() + pts2.size()) / scaling_factor * std::sqrt(2.0f);
+        for (size_t i = 0; i < pts1.size(); ++i) {
+            pts1[i].x *= scaling_factor; pts1[i].y *= scaling_factor;
+            pts2[i].x *= scaling_factor; pts2[i].y *= scaling_factor;
+        }
+    }
+
+    // image_processor.cpp:911-1135
+    void twoPointRansac(const std::vector<Pt> &pts1, const std::vector<Pt> &pts2, const M3 &R_p_c, const double intr[4], int model,
+                        const double dist[4], double inlier_error, double success_probability, std::vector<int> &inlier_markers,
+                        int cam) {
+        double norm_pixel_unit = 2.0 / (intr[0] + intr[1]);
+        int iter_num = (int)std::ceil(std::log(1 - success_probability) / std::log(1 - 0.7 * 0.7));
+        inlier_markers.assign(pts1.size(), 1);
+        std::vector<Pt> p1(pts1.size()), p2(pts2.size());
+        undistortPoints(pts1, intr, model, dist, p1);
+        undistortPoints(pts2, intr, model, dist, p2);
+        for (auto &pt : p1) {
+            V3 pt_hc = R_p_c * V3((double)pt.x, (double)pt.y, 1.0);
+            pt.x = (float)pt_hc[0];
+            pt.y = (float)pt_hc[1];
+        }
+        float scaling_factor = 0.0f;
+        rescalePoints(p1, p2, scaling_factor);
+        norm_pixel_unit *= (double)scaling_factor;
+        const size_t n = p1.size();
+        std::vector<Pt> diff(n);
+        for (size_t i = 0; i < n; ++i) diff[i] = Pt(p1[i].x - p2[i].x, p1[i].y - p2[i].y);
+        double mean_pt_distance = 0.0;
+        int raw_inlier_cntr = 0;
+        for (size_t i = 0; i < n; ++i) {
+            double distance = (double)std::sqrt(diff[i].x * diff[i].x + diff[i].y * diff[i].y);
+            if (distance > 50.0 * norm_pixel_unit) {
+                inlier_markers[i] = 0;
+            } else {
+                mean_pt_distance += distance;
+                ++raw_inlier_cntr;
+            }
+        }
+        mean_pt_distance /= raw_inlier_cntr;
+        if (raw_inlier_cntr < 3) {
+            for (auto &m : inlier_markers) m = 0;
+            return;
+        }
+        if (mean_pt_distance < norm_pixel_unit) {  // degenerate (no translation)
+            for (size_t i = 0; i < n; ++i) {
+                if (inlier_markers[i] == 0) continue;
+                if ((double)std::sqrt(diff[i].x * diff[i].x + diff[i].y * diff[i].y) > inlier_error * norm_pixel_unit) inlier_markers[i] = 0;
+            }
+            return;
+        }
+        std::vector<std::array<double, 3>> coeff_t(n);
+        for (size_t i = 0; i < n; ++i) {
+            coeff_t[i][0] = (double)diff[i].y;
+            coeff_t[i][1] = (double)(-diff[i].x);
+            coeff_t[i][2] = (double)(p1[i].x * p2[i].y - p1[i].y * p2[i].x);
+        }
+        std::vector<int> raw_inlier_idx;
+        for (size_t i = 0; i < n; ++i)
+            if (inlier_markers[i] != 0) raw_inlier_idx.push_back((int)i);
+        std::vector<int> best_inlier_set;
+        const int nraw = (int)raw_inlier_idx.size();
+        for (int iter_idx = 0; iter_idx < iter_num; ++iter_idx) {
+            int select_idx1 = uniform_integer(track_calls, cam, iter_idx, 0, 0, nraw - 1);
+            int select_idx_diff = uniform_integer(track_calls, cam, iter_idx, 1, 1, nraw - 1);
+            int select_idx2 = select_idx1 + select_idx_diff < nraw ? select_idx1 + select_idx_diff : select_idx1 + select_idx_diff - nraw;
+            int pair_idx1 = raw_inlier_idx[select_idx1], pair_idx2 = raw_inlier_idx[select_idx2];
+            double c[3][2];
+            for (int k = 0; k < 3; ++k) {
+                c[k][0] = coeff_t[pair_idx1][k];
+                c[k][1] = coeff_t[pair_idx2][k];
+            }
+            double l1[3];
+            for (int k = 0; k < 3; ++k) l1[k] = std::fabs(c[k][0]) + std::fabs(c[k][1]);
+            int base = 0;
+            for (int k = 1; k < 3; ++k)
+                if (l1[k] < l1[base]) base = k;
+            const int ia = base == 0 ? 1 : 0, ib = base == 2 ? 1 : 2;  // the two non-base coefficient columns
+            // A = [c[ia] c[ib]] (2x2, columns), solution = A^-1 (-c[base])
+            double mdl[3];
+            {
+                double a00 = c[ia][0], a01 = c[ib][0], a10 = c[ia][1], a11 = c[ib][1];
+                double det = a00 * a11 - a01 * a10, id = 1.0 / det;
+                double i00 = a11 * id, i01 = -a01 * id, i10 = -a10 * id, i11 = a00 * id;
+                double b0 = -c[base][0], b1 = -c[base][1];
+                mdl[base] = 1.0;
+                mdl[ia] = i00 * b0 + i01 * b1;
+                mdl[ib] = i10 * b0 + i11 * b1;
+            }
+            std::vector<int> inlier_set;
+            for (size_t i = 0; i < n; ++i) {
+                if (inlier_markers[i] == 0) continue;
+                double e = coeff_t[i][0] * mdl[0];
+                e += coeff_t[i][1] * mdl[1];
+                e += coeff_t[i][2] * mdl[2];
+                if (std::fabs(e) < inlier_error * norm_pixel_unit) inlier_set.push_back((int)i);
+            }
+            if ((double)inlier_set.size() < 0.2 * (double)n) continue;
+            // refit: solution = ((A^T A)^-1 A^T) (-b) with A = [coeff ia, coeff ib] over the inlier set
+            double ata00 = 0, ata01 = 0, ata11 = 0;
+            for (int idx : inlier_set) {
+                ata00 += coeff_t[idx][ia] * coeff_t[idx][ia];
+                ata01 += coeff_t[idx][ia] * coeff_t[idx][ib];
+                ata11 += coeff_t[idx][ib] * coeff_t[idx][ib];
+            }
+            double det = ata00 * ata11 - ata01 * ata01, id = 1.0 / det;
+            double m00 = ata11 * id, m01 = -ata01 * id, m11 = ata00 * id;
+            double s0 = 0, s1 = 0;
+            for (int idx : inlier_set) {
+                double nb = -coeff_t[idx][base];
+                s0 += (m00 * coeff_t[idx][ia] + m01 * coeff_t[idx][ib]) * nb;
+                s1 += (m01 * coeff_t[idx][ia] + m11 * coeff_t[idx][ib]) * nb;
+            }
+            (void)s0;
+            (void)s1;  // model_better only feeds this_error / best_error, which never influence the result (:1117-1121)
+            if (inlier_set.size() > best_inlier_set.size()) best_inlier_set = inlier_set;
+        }
+        inlier_markers.assign(pts1.size(), 0);
+        for (int idx : best_inlier_set) inlier_markers[idx] = 1;
+    }
+
     // image_processor.cpp:758-768
     void pruneGridFeatures() {
         for (auto &item : *curr_features) {
@@ -460,6 +614,7 @@ public:
     int grid_height = 1, grid_width = 1;
     int n_published = 0;
     std::vector<Pt> last_detected;
+    uint32_t track_calls = 0;  // trackFeatures calls so far (seeds the RANSAC sampler)
 };
 
 }  // namespace orc

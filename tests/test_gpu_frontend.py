@@ -183,3 +183,23 @@ def test_bad_arguments(eng, synth):
 def test_frontend_pipeline_stress_preset(eng, ob, synth):
     """BASELINE.json config 5 geometry: 1280x1024, 6 pyramid levels, 8x10 grid (~1000 features)."""
     _run_pipeline(eng, ob, synth, synth.default_config("stress"), 3, 6)
+
+
+@pytest.mark.parametrize("fix_alias", [0, 1])
+def test_frontend_pipeline_with_two_point_ransac(eng, ob, synth, fix_alias):
+    """twoPointRansac (image_processor.cpp:911-1135) is dead code in the reference (:482-493); with
+    use_ransac the engine and the oracle run it as the commented-out calls read, with a shared
+    counter-based sampler in place of the unseeded cg::uniform_integer: identical grids and counters,
+    through the static start (degenerate-motion branch) and the moving part (RANSAC branch)."""
+    cfg = copy_cfg(synth.default_config("ref"), use_ransac=1, fix_prev_image_alias=fix_alias)
+    _run_pipeline(eng, ob, synth, cfg, 0, 64)
+    # the check must have had something to reject: the oracle drops features at the RANSAC stage
+    s = synth.Stream(cfg, seed=0)
+    o = ob.Oracle(cfg)
+    dropped = 0
+    for k in range(64):
+        t, a, b = s.render(k)
+        o.stereo(t, a, b)
+        ti = o.tracking_info()
+        dropped += ti.after_matching - ti.after_ransac
+    assert dropped > 0
