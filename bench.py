@@ -58,6 +58,8 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        if os.environ.get("MSKF_BENCH_NO_CLOCKS"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -167,6 +169,28 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------
+class Group:
+    """One engine handle with its share of the GPU's streams (a fleet is driven as a few handles per GPU
+    so that their kernel chains interleave), its input generator and its torch stream."""
+
+    def __init__(self, torch, engine, synth, cfg, seeds, dev, local_rank):
+        self.S = len(seeds)
+        self.fleet = synth.Fleet(cfg, seeds)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.e = engine.Engine(cfg, self.S, device=local_rank, cuda_stream=self.stream.cuda_stream)
+        self.tvec = np.zeros(self.S)
+        self.img = cfg.img_rows * cfg.img_cols
+
+    def feed_imu(self, k):
+        rows = self.fleet.imu_rows_for_frame(k)
+        self.e.push_imu_batch(rows)
+        return rows.nbytes
+
+    def push(self, k, base_ptr, device):
+        self.tvec[:] = self.fleet.frame_time(k)
+        self.e.push_stereo_batch(self.tvec, base_ptr, base_ptr + self.img, 2 * self.img, device=device)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
 
@@ -182,46 +206,18 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     cfg = synth.default_config(args.preset)
-    S = args.streams
-    seeds = [rank * S + i for i in range(S)]  # weak scaling: S streams per GPU, global index = seed
-    fleet = synth.Fleet(cfg, seeds)
+    S, H = args.streams, args.handles
+    if S % H:
+        raise SystemExit("--streams must be a multiple of --handles")
+    Sh = S // H
     K, W = args.steps, args.warmup
     img = cfg.img_rows * cfg.img_cols
-    stream = torch.cuda.Stream(device=dev)
-    e = engine.Engine(cfg, S, device=local_rank, cuda_stream=stream.cuda_stream)
+    seeds = [rank * S + i for i in range(S)]  # weak scaling: S streams per GPU, global index = seed
+    groups = [Group(torch, engine, synth, cfg, seeds[h * Sh:(h + 1) * Sh], dev, local_rank) for h in range(H)]
 
-    def feed_imu(k):
-        rows = fleet.imu_rows_for_frame(k)
-        e.push_imu_batch(rows)
-        return rows.nbytes
-
-    # ---- priming (untimed): frames rendered on the fly
-    scratch = torch.empty((S, 2, img), dtype=torch.uint8, device=dev)
-    tvec = np.zeros(S)
-    k = 0
-    with torch.cuda.stream(stream):
-        for _ in range(PRIME_FRAMES):
-            feed_imu(k)
-            fleet.render_device(k, scratch, stream.cuda_stream)
-            tvec[:] = fleet.frame_time(k)
-            e.push_stereo_batch(tvec, scratch.data_ptr(), scratch.data_ptr() + img, 2 * img, device=True)
-            e.step()
-            k += 1
-        e.sync()
-    # ---- pre-render the timed frames: device-resident set for `value`, pinned host set for `e2e`
-    KP = min(K, 10)  # steps of the serial per-kernel profiling pass
-    KH = 3           # steps of the host-enqueue measurement
-    n_dev = W + K + KP + KH
-    n_e2e = W + K + 1  # the upload of frame i+1 is issued while frame i computes
-    frames_dev = torch.empty((n_dev, S, 2, img), dtype=torch.uint8, device=dev)
-    frames_host = torch.empty((n_e2e, S, 2, img), dtype=torch.uint8).pin_memory()
-    with torch.cuda.stream(stream):
-        for i in range(n_dev):
-            fleet.render_device(k + i, frames_dev[i], stream.cuda_stream)
-        for i in range(n_e2e):
-            fleet.render_device(k + n_dev + i, scratch, stream.cuda_stream)
-            frames_host[i].copy_(scratch, non_blocking=True)
-    stream.synchronize()
+    def sync_all():
+        for g in groups:
+            g.e.sync()
 
     def barrier():
         torch.cuda.synchronize()
@@ -229,79 +225,106 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def slab(buf, h):  # stream block of handle h inside a [S][2][img] frame set
+        return buf.data_ptr() + h * Sh * 2 * img
+
+    def close_region(ev):
+        """Record `ev` on handle 0's stream after every handle's front-end AND back-end work."""
+        for h, g in enumerate(groups):
+            g.e.join()
+            if h:
+                done = torch.cuda.Event()
+                done.record(g.stream)
+                groups[0].stream.wait_event(done)
+        ev.record(groups[0].stream)
+
+    # ---- priming (untimed): frames rendered on the fly
+    scratch = torch.empty((S, 2, img), dtype=torch.uint8, device=dev)
+    k = 0
+    for _ in range(PRIME_FRAMES):
+        for h, g in enumerate(groups):
+            g.feed_imu(k)
+            g.fleet.render_device(k, scratch[h * Sh:(h + 1) * Sh], g.stream.cuda_stream)
+            g.push(k, slab(scratch, h), True)
+            g.e.step()
+        k += 1
+    sync_all()
+    # ---- pre-render the timed frames: device-resident set for `value`, pinned host set for `e2e`
+    KH = 3  # steps of the host-enqueue measurement
+    n_dev = W + K + KH
+    n_e2e = W + K + 1  # the upload of frame i+1 is issued while frame i computes
+    frames_dev = torch.empty((n_dev, S, 2, img), dtype=torch.uint8, device=dev)
+    frames_host = torch.empty((n_e2e, S, 2, img), dtype=torch.uint8).pin_memory()
+    for h, g in enumerate(groups):
+        with torch.cuda.stream(g.stream):
+            for i in range(n_dev):
+                g.fleet.render_device(k + i, frames_dev[i, h * Sh:(h + 1) * Sh], g.stream.cuda_stream)
+            for i in range(n_e2e):
+                g.fleet.render_device(k + n_dev + i, scratch[h * Sh:(h + 1) * Sh], g.stream.cuda_stream)
+                frames_host[i, h * Sh:(h + 1) * Sh].copy_(scratch[h * Sh:(h + 1) * Sh], non_blocking=True)
+    torch.cuda.synchronize()
+
     # ---- leg 1: device-resident inputs ("value")
     def step_dev(i, kk):
-        feed_imu(kk)
-        tvec[:] = fleet.frame_time(kk)
-        base = frames_dev[i].data_ptr()
-        e.push_stereo_batch(tvec, base, base + img, 2 * img, device=True)
-        e.step()
+        for h, g in enumerate(groups):
+            g.feed_imu(kk)
+            g.push(kk, slab(frames_dev[i], h), True)
+            g.e.step()
 
     for i in range(W):
         step_dev(i, k)
         k += 1
-    e.sync()
+    sync_all()
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    launches0 = e.launch_count()
+    launches0 = sum(g.e.launch_count() for g in groups)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
-    ev0.record(stream)
+    ev0.record(groups[0].stream)
     for i in range(W, W + K):
         step_dev(i, k)
         k += 1
-    e.join()  # the back end runs on its own stream: the closing event must see it too
-    ev1.record(stream)
-    e.sync()
+    close_region(ev1)
+    sync_all()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     ms_dev = ev0.elapsed_time(ev1)
-    launches = e.launch_count() - launches0
+    launches = sum(g.e.launch_count() for g in groups) - launches0
     clk = clocks.stop()
 
-    # ---- how long the host needs to enqueue one step (no waiting: 3 steps fit the engine's descriptor ring)
-    e.sync()
+    # ---- how long the host needs to enqueue one step (no waiting: 3 steps fit the engines' descriptor rings)
     t_h0 = time.perf_counter()
-    for i in range(W + K + KP, W + K + KP + KH):
+    for i in range(W + K, W + K + KH):
         step_dev(i, k)
         k += 1
     host_ms = 1e3 * (time.perf_counter() - t_h0) / KH
-    e.sync()
-
-    # ---- per-kernel pass: the two halves serialised, CUDA events around every kernel class
-    e.set_overlap(False)
-    e.profile_enable(True)
-    for i in range(W + K, W + K + KP):
-        step_dev(i, k)
-        k += 1
-    e.sync()
-    prof = e.profile_read()
-    e.profile_enable(False)
-    e.set_overlap(True)
+    sync_all()
 
     # ---- leg 2: host buffers through the C ABI ("e2e")
-    poses = None
+    poses = [None] * H
     h2d = d2h = 0
 
     def push_host(i, kk):
-        nonlocal h2d
-        tvec[:] = fleet.frame_time(kk)
-        base = frames_host[i].data_ptr()
-        e.push_stereo_batch(tvec, base, base + img, 2 * img, device=False)  # pinned host -> landing area, copy stream
-        h2d = 2 * img * S
+        for h, g in enumerate(groups):
+            g.push(kk, slab(frames_host[i], h), False)  # pinned host -> landing area, on the engine's copy stream
 
     def step_e2e(i, kk):
-        """One e2e step: IMU rows + step of frame i, upload of frame i+1 (overlaps the kernels of
-        frame i on the copy stream), poses of frame i read back to the host."""
-        nonlocal poses, h2d, d2h
-        nb = feed_imu(kk)
-        e.step()  # ends with the device -> pinned host copy of every stream's T_b_w
+        """One e2e step: IMU rows + step of frame i, upload of frame i+1 (overlaps the kernels of frame i
+        on the copy streams), poses of the previous step read back (already on the host: the pipeline
+        stays full; every step's poses are copied to pinned memory by the step itself)."""
+        nonlocal h2d, d2h
+        nb = 0
+        for g in groups:
+            nb += g.feed_imu(kk)
+            g.e.step()
         push_host(i + 1, kk + 1)
-        poses = e.poses(prev=True)  # result of the previous step: already on the host, the pipeline stays full
-        h2d += nb
-        d2h = poses.nbytes
+        for h, g in enumerate(groups):
+            poses[h] = g.e.poses(prev=True)
+        h2d = 2 * img * S + nb
+        d2h = sum(p.nbytes for p in poses)
 
+    k += n_dev - (W + K + KH)  # frames_host starts after the device-resident set
     push_host(0, k)
     for i in range(W):
         step_e2e(i, k)
@@ -309,22 +332,25 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_e0 = time.perf_counter()
-    ev2.record(stream)
+    ev2.record(groups[0].stream)
     for i in range(W, W + K):
         step_e2e(i, k)
         k += 1
-    poses = e.poses()  # the last step's result (blocks until it is on the host)
-    e.join()
-    ev3.record(stream)
-    e.sync()
+    for h, g in enumerate(groups):
+        poses[h] = g.e.poses()  # the last step's result (blocks until it is on the host)
+    close_region(ev3)
+    sync_all()
     barrier()
     t_e2e_wall = time.perf_counter() - t_e0
     ms_e2e = max(ev2.elapsed_time(ev3), 1e3 * t_e2e_wall)  # the host is inside the loop: take the slower clock
 
     # sanity of the timed state: filters alive, windows full
-    st = e.state(0)
-    n_feat = len(e.grid(0))
-    assert np.isfinite(poses).all()
+    st = groups[0].e.state(0)
+    n_feat = len(groups[0].e.grid(0))
+    assert all(np.isfinite(p).all() for p in poses)
+    for g in groups:
+        g.e.close()
+    del frames_host
 
     # ---- max over ranks
     times = torch.tensor([ms_dev, ms_e2e, 1e3 * t_wall], dtype=torch.float64, device=dev)
@@ -336,6 +362,23 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = total_frames / (ms_e2e_max * 1e-3)
 
     if rank == 0:
+        # ---- per-kernel pass: ONE handle with all S streams, front end and back end serialised, CUDA events
+        # around every kernel class (the timed legs interleave H handles and overlap the two halves)
+        KP = min(K, 10)
+        gp = Group(torch, engine, synth, cfg, seeds, dev, local_rank)
+        for kk in range(PRIME_FRAMES + KP):
+            if kk == PRIME_FRAMES:
+                gp.e.sync()
+                gp.e.set_overlap(False)
+                gp.e.profile_enable(True)
+            gp.feed_imu(kk)
+            gp.fleet.render_device(kk, scratch, gp.stream.cuda_stream)
+            gp.push(kk, scratch.data_ptr(), True)
+            gp.e.step()
+        gp.e.sync()
+        prof = gp.e.profile_read()
+        gp.e.close()
+
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -389,16 +432,17 @@ def run_ours(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"fleet (BASELINE.json config 4): {S} independent 752x480 stereo+IMU streams per GPU, preset {args.preset} "
-                                   f"(L=4, KLT 21x21, ~300 grid features, max_cam_state_size 30), full track+EKF per frame, "
-                                   f"{PRIME_FRAMES} untimed priming frames",
-                       "streams_per_gpu": S, "preset": args.preset, "features_stream0": n_feat, "cam_states_stream0": st.n_cam_states,
-                       "ekf_updates_stream0": int(st.n_updates), "l2": f"inputs larger than L2: {2 * img * S / 1e6:.0f} MB of new images per step",
+            "config": {"workload": f"fleet (BASELINE.json config 4): {S} independent 752x480 stereo+IMU streams per GPU driven as {H} engine "
+                                   f"handles x {Sh} streams, preset {args.preset} (L=4, KLT 21x21, ~300 grid features, max_cam_state_size 30), "
+                                   f"full track+EKF per frame, {PRIME_FRAMES} untimed priming frames",
+                       "streams_per_gpu": S, "handles_per_gpu": H, "preset": args.preset, "features_stream0": n_feat,
+                       "cam_states_stream0": st.n_cam_states, "ekf_updates_stream0": int(st.n_updates),
+                       "l2": f"inputs larger than L2: {2 * img * S / 1e6:.0f} MB of new images per step",
                        "front_end_dtype": "u8 / fixed point", "parallelism": f"stream-sharded x{world}, no collective on the data path"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e_max / K},
             "gpu_launches": int(launches),
-            "kernel_pass": {"steps": KP, "mode": "front end and back end serialised (mskf_set_overlap 0)"},
+            "kernel_pass": {"steps": KP, "mode": f"one handle x {S} streams, front end and back end serialised (mskf_set_overlap 0)"},
             "clocks": clk,
             "roofline": roofline,
             "kernels": per_kernel,
@@ -410,7 +454,6 @@ def run_ours(args, rank, world, local_rank):
             "host_enqueue_ms_per_step": host_ms,
         }
         print(json.dumps(line), flush=True)
-    e.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -423,6 +466,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=256, help="streams per GPU")
+    ap.add_argument("--handles", type=int, default=4, help="engine handles per GPU (the streams are split evenly)")
     ap.add_argument("--preset", default="bench")
     ap.add_argument("--cpu-frames", type=int, default=40, help="frames of the 1-core CPU baseline sample")
     args = ap.parse_args()

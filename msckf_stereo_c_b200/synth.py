@@ -183,7 +183,10 @@ class Fleet:
                              r0=torch.from_numpy(self.proto.rays(0)).to(dev), r1=torch.from_numpy(self.proto.rays(1)).to(dev),
                              t=torch.zeros(self.n, dtype=torch.float64, device=dev))
         d = self._dev
-        d["t"].fill_(self.frame_time(k))
+        # the time stamps must be written on the stream the render kernel runs on
+        ctx = torch.cuda.stream(torch.cuda.ExternalStream(cuda_stream)) if cuda_stream else torch.cuda.stream(torch.cuda.current_stream())
+        with ctx:
+            d["t"].fill_(self.frame_time(k))
         rc = engine.lib().mskf_synth_render_device(d["traj"].data_ptr(), d["cams"].data_ptr(), d["r0"].data_ptr(), d["r1"].data_ptr(),
                                                    d["t"].data_ptr(), out.data_ptr(), self.n, self.cfg.img_rows, self.cfg.img_cols,
                                                    C.c_void_p(cuda_stream))
