@@ -2045,13 +2045,14 @@ __device__ __forceinline__ double fast_rcp(double a) {
 // communication per column step is the reflector (32 doubles + two scalars) through shared memory,
 // with ONE barrier per step (double-buffered).
 //
-// A fleet's step time is set by its slowest stream.  On the synthetic fleet a lost-feature update
-// stacks 40-800 rows (tools/fleet_nan_check.py prints the distribution) and one CTA per stream is
-// the fastest arrangement; a stream that approaches the 1500-row cap (m > QR_SPLIT_MIN) splits its
-// rows over QR_G CTAs (TSQR): each folds its share into its own triangle, be_qr_combine_kernel folds
-// triangles 1.. into triangle 0 (9.1k column steps become 2.3k + 1.8k).
+// A fleet's step time is set by its slowest stream, and the row count m has a heavy tail (on the
+// synthetic fleet a lost-feature update stacks 40-800 rows, tools/fleet_nan_check.py prints the
+// distribution; the reference's cap is 1500).  Streams with m > QR_SPLIT_MIN split their rows over
+// QR_G = 4 CTAs (TSQR): each folds its share into its own triangle, then a two-level tree of
+// be_qr_combine_kernel launches folds the triangles pairwise (m = 733, k = 174: 4.3k serial column
+// steps become 1.0k + 2 x 0.56k).
 #define QR_G 4
-#define QR_SPLIT_MIN 1024
+#define QR_SPLIT_MIN 320
 
 struct QrShared {
     double vbuf[2][QR_B];
@@ -2203,40 +2204,41 @@ __global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb,
     }
 }
 
-// TSQR combine: fold the triangles of groups 1.. into the triangle of group 0 (row i of a
-// triangle is zero left of column i, so the sweep of a 32-row block starts at its first row index).
-__global__ void __launch_bounds__(QR_THREADS) be_qr_combine_kernel(BeConst bc, BeBuf bb) {
-    const int s = blockIdx.x;
+// TSQR combine, a binary tree over the QR_G = 4 triangles: level 1 (grid (2, S)) folds triangle 1 into 0
+// and 3 into 2 in parallel, level 2 (grid (1, S)) folds 2 into 0 and extracts T.  Row i of a triangle is
+// zero left of column i, so the sweep of a 32-row block starts at its first row index.
+__global__ void __launch_bounds__(QR_THREADS) be_qr_combine_kernel(BeConst bc, BeBuf bb, int level) {
+    const int s = blockIdx.y;
     const BeStep sp = bb.step[s];
     if (!sp.active) return;
     BeState &st = bb.st[s];
     if (!st.do_update) return;
     const int m = st.m, k = st.k, KC = bc.KC;
-    const int ng = qr_groups(m, k);
-    if (ng == 1) return;
+    if (qr_groups(m, k) == 1) return;
     const int kw = k + 1, ldr = KC + 1;
-    double *R0 = bb.Rq + (size_t)s * QR_G * ldr * ldr;
+    const int dst_g = level == 1 ? 2 * blockIdx.x : 0, src_g = level == 1 ? 2 * blockIdx.x + 1 : 2;
+    double *Rd = bb.Rq + ((size_t)s * QR_G + dst_g) * ldr * ldr;
+    const double *Rs = bb.Rq + ((size_t)s * QR_G + src_g) * ldr * ldr;
     __shared__ QrShared sh;
     const int c = threadIdx.x;
     const bool has_col = c < kw;
     double x[QR_B];
-    for (int g = 1; g < ng; ++g) {
-        const double *Rg = R0 + (size_t)g * ldr * ldr;
-        for (int r0 = 0; r0 < k; r0 += QR_B) {
-            const int nb = min(QR_B, k - r0);
+    for (int r0 = 0; r0 < k; r0 += QR_B) {
+        const int nb = min(QR_B, k - r0);
 #pragma unroll
-            for (int i = 0; i < QR_B; ++i) {
-                double v = 0.0;
-                if (has_col && i < nb && c >= r0 + i) v = Rg[(r0 + i) * ldr + c];
-                x[i] = v;
-            }
-            __syncthreads();
-            qr_sweep(x, R0, ldr, k, kw, c, r0, sh);
+        for (int i = 0; i < QR_B; ++i) {
+            double v = 0.0;
+            if (has_col && i < nb && c >= r0 + i) v = Rs[(r0 + i) * ldr + c];
+            x[i] = v;
         }
+        __syncthreads();
+        qr_sweep(x, Rd, ldr, k, kw, c, r0, sh);
     }
-    __syncthreads();
-    qr_extract(R0, ldr, k, bb.Tm + (size_t)s * KC * KC, bb.rt + (size_t)s * KC);
-    if (threadIdx.x == 0) st.mt = k;
+    if (level == 2) {
+        __syncthreads();
+        qr_extract(Rd, ldr, k, bb.Tm + (size_t)s * KC * KC, bb.rt + (size_t)s * KC);
+        if (threadIdx.x == 0) st.mt = k;
+    }
 }
 
 // ======================================================================================
@@ -2723,7 +2725,8 @@ static void launch_update(mskf_handle *h, int phase = 0) {
     const int S = h->S;
     const int tiles_ld = (bc.LD + GT - 1) / GT, tiles_kc = (bc.KC + GT - 1) / GT;
     MSKF_LAUNCH(h, phase == 0 ? PK_BE_QR : PK_BE_QR_PRUNE, (be_qr_kernel<<<dim3(QR_G, S), QR_THREADS, 0, q>>>(bc, bb, phase)));
-    MSKF_LAUNCH(h, phase == 0 ? PK_BE_QR : PK_BE_QR_PRUNE, (be_qr_combine_kernel<<<S, QR_THREADS, 0, q>>>(bc, bb)));
+    MSKF_LAUNCH(h, phase == 0 ? PK_BE_QR : PK_BE_QR_PRUNE, (be_qr_combine_kernel<<<dim3(2, S), QR_THREADS, 0, q>>>(bc, bb, 1)));
+    MSKF_LAUNCH(h, phase == 0 ? PK_BE_QR : PK_BE_QR_PRUNE, (be_qr_combine_kernel<<<dim3(1, S), QR_THREADS, 0, q>>>(bc, bb, 2)));
     MSKF_LAUNCH(h, PK_BE_GEMM_PHT, (be_gemm_kernel<0><<<dim3(tiles_ld * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_GEMM_S, (be_gemm_kernel<1><<<dim3(tiles_kc * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_CHOL, (be_chol_kernel<<<S, BE_THREADS, B->smem_chol, q>>>(bc, bb)));
