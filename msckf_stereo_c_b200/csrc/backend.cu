@@ -134,7 +134,8 @@ struct BeBuf {
     double *Hst;       // [S][hst_cap]
     double *rst;       // [S][hst_rows]
     int *rst_j0;       // [S][hst_rows] first nonzero column of each stacked row
-    double *Rq;        // [S][(KC+1)^2] triangular factor of the QR compression (column c owned by thread c)
+    double *Rq;        // [S][QR_G][(KC+1)^2] triangular factors of the QR compression (row-major, column c owned by its lanes)
+    unsigned char *Rfill;  // [S][QR_G][KC+1] pivot rows of each triangle that hold a reflector result
     double *Tm;        // [S][KC*KC]
     double *rt;        // [S][KC]
     double *PHt;       // [S][LD*KC]
@@ -2016,117 +2017,207 @@ __global__ void __launch_bounds__(BE_THREADS) be_scatter_kernel(BeConst bc, BeBu
 }
 
 // ======================================================================================
-// QR compression of the stacked system (measurementUpdate :795-810): rows are folded 16 at a
-// time into an upper-triangular factor held in shared memory (packed, with Q^T r as an extra
-// column).  If m <= k the system is used as it is.
-// ======================================================================================
-#define QR_B 32
-#define QR_THREADS 192
-// fp64 1/sqrt(a) and 1/a from the fp32 special-function unit plus Newton steps: the reflector
-// scalars sit on the serial chain of the factorization, and DSQRT/DDIV sequences are ~2x longer
-__device__ __forceinline__ double fast_rsqrt(double a) {
-    if (!(a > 1e-30 && a < 1e30)) return 1.0 / sqrt(a);  // outside the fp32 seed's range
-    double y = (double)rsqrtf((float)a);  // relative error 2^-22 -> 2^-43 -> 2^-85 after two Newton steps
-    y = y * (1.5 - 0.5 * a * y * y);
-    y = y * (1.5 - 0.5 * a * y * y);
-    return y;
-}
-__device__ __forceinline__ double fast_rcp(double a) {
-    if (!(fabs(a) > 1e-30 && fabs(a) < 1e30)) return 1.0 / a;
-    double y = (double)__frcp_rn((float)a);  // 2^-24 -> 2^-48 -> 2^-96
-    y = y + y * (1.0 - a * y);
-    y = y + y * (1.0 - a * y);
-    return y;
-}
-
-// Thread c owns column c of the system [H | r] (c = k is the residual column): the 32 rows of the
-// block being folded live in its registers, column c of the triangular factor R lives in global
-// memory (row-major, read two steps ahead), so no other thread ever touches its data and the only
-// communication per column step is the reflector (32 doubles + two scalars) through shared memory,
-// with ONE barrier per step (double-buffered).
+// QR compression of the stacked system (measurementUpdate :795-810): Householder reflectors fold
+// the rows, 64 at a time, into an upper-triangular factor R (with Q^T r as an extra column).  If
+// m <= k the system is used as it is.
+//
+// The factorization is a serial chain of column steps, so everything here is about the latency of
+// one step (tools/micro/fp64_pipe.cu: DFMA 8.4 cycles dependent, 64 lanes/clk/SM; STS+BAR+LDS 72):
+//  * a 64-row block is held in registers as 8 x 4 tiles: QR_T = 8 adjacent lanes share four columns,
+//    8 rows each, so a step loads 8 reflector values per lane for 64 FMAs (shared-memory bandwidth, not
+//    the fp64 pipe, limited a one-column-per-lane layout), the dot products and the next column's norm
+//    are 8-long plus three shuffles, and a sweep folds 64 rows for the price of one chain;
+//  * unnormalised reflectors H_j = I - t w w^T, w = [alpha - beta; x], t = 1 / (beta (beta - alpha)):
+//    the owner publishes its column the moment it is up to date and only two scalars sit behind
+//    the rsqrt / rcp chain (MUFU.RSQ64H / RCP64H seeds + two Newton steps each, no branches);
+//  * column c of R lives in global memory (L2), read one step ahead; ONE barrier per step;
+//  * a sweep stops as soon as its rows are used up: a reflector whose pivot row of R was empty
+//    moves one direction of the block's (<= 64-dimensional) row space into R and leaves the block
+//    orthogonal to it, so after nb such reflectors the block is zero and the remaining columns have
+//    nothing to do.  Folding the b-th block of a fresh triangle costs min(k, 64 (b + 1)) steps, not k.
 //
 // A fleet's step time is set by its slowest stream, and the row count m has a heavy tail (on the
 // synthetic fleet a lost-feature update stacks 40-800 rows, tools/fleet_nan_check.py prints the
 // distribution; the reference's cap is 1500).  Streams with m > QR_SPLIT_MIN split their rows over
 // QR_G = 4 CTAs (TSQR): each folds its share into its own triangle, then a two-level tree of
-// be_qr_combine_kernel launches folds the triangles pairwise (m = 733, k = 174: 4.3k serial column
-// steps become 1.0k + 2 x 0.56k).
+// be_qr_combine_kernel launches folds the triangles pairwise.
+// ======================================================================================
+#define QR_T 8     // lanes per column pair
+#define QR_RPT 8   // rows per lane
+#define QR_CPT 4   // columns per lane
+#define QR_B (QR_T * QR_RPT)
+#define QR_THREADS 384  // 48 column quads = 192 column slots >= 6 * 31 + 1
+#define QR_COLS (QR_THREADS / QR_T * QR_CPT)
 #define QR_G 4
-#define QR_SPLIT_MIN 320
+#define QR_SPLIT_MIN 448
+#define QR_VS (QR_RPT + 2)  // chunk stride of the reflector buffer: the 8 lanes read 16-byte pieces in distinct banks
+// A column whose squared norm fell below this fraction of the block's largest column is rounding residue
+// of earlier annihilations: it gets no reflector (and does not count as a consumed row, see below).
+#define QR_RESIDUE 1e-22
 
 struct QrShared {
-    double vbuf[2][QR_B];
+    double vbuf[2][QR_T * QR_VS];
     double tau[2], w0[2];
-    int j0;
+    double red[32];
+    double scale, floor2;
+    double diag[QR_COLS];
+    int stop[2];
+    int j0, nbe, nf;
+    unsigned char filled[QR_COLS];
 };
 
-// One sweep: fold the QR_B rows held in x[] (column c of each) into R, starting at column jb.
-// Unnormalised reflectors: H_j = I - t w w^T with w = [alpha - beta; x] and t = 1 / (beta (beta - alpha)),
-// so the owner publishes its column the moment it is up to date and only two scalars (w0, t) sit
-// behind the rsqrt / rcp chain.
-__device__ __forceinline__ void qr_sweep(double (&x)[QR_B], double *R, int ldr, int k, int kw, int c, int jb, QrShared &sh) {
-    const bool has_col = c < kw;
-    double rq0 = (has_col && jb <= c && jb < k) ? R[jb * ldr + c] : 0.0;
-    double rq1 = (has_col && jb + 1 <= c && jb + 1 < k) ? R[(jb + 1) * ldr + c] : 0.0;
-    double xn = 0.0;
-    if (c == jb) {
+// Reflector scalars for pivot alpha and squared column norm xn (> 0): beta = -sign(alpha) sqrt(alpha^2 + xn),
+// w0 = alpha - beta, t = 1 / (beta (beta - alpha)) = 1 / (a + |alpha| sqrt(a)).  The hardware seeds look at
+// the upper word only (relative error ~2^-22); two Newton steps take them to fp64 round-off.
+__device__ __forceinline__ void qr_reflector(double alpha, double xn, double &t, double &w0, double &beta) {
+    const double a = fma(alpha, alpha, xn);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    y = fma(y, fma(-h, y * y, 0.5), y);
+    y = fma(y, fma(-h, y * y, 0.5), y);
+    double sq = a * y;
+    sq = fma(fma(-sq, sq, a), 0.5 * y, sq);
+    const double den = fma(fabs(alpha), sq, a);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    r = fma(r, fma(-den, r, 1.0), r);
+    r = fma(r, fma(-den, r, 1.0), r);
+    t = r;
+    beta = -copysign(sq, alpha);
+    w0 = alpha - beta;
+}
+
+// sum over the 8 lanes that share a column pair
+__device__ __forceinline__ double qr_oct_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+
+__device__ __forceinline__ double qr_norm2(const double (&x)[QR_RPT]) {
+    double n0 = 0, n1 = 0;
 #pragma unroll
-        for (int i = 0; i < QR_B; ++i) xn += x[i] * x[i];
+    for (int i = 0; i < QR_RPT; i += 2) {
+        n0 = fma(x[i], x[i], n0);
+        n1 = fma(x[i + 1], x[i + 1], n1);
     }
-    for (int j = jb; j < k; ++j) {
-        const int p = j & 1;
-        double rq2 = 0.0;
-        if (has_col && j + 2 <= c && j + 2 < k) rq2 = R[(j + 2) * ldr + c];
-        if (c == j) {
+    return qr_oct_sum(n0 + n1);
+}
+
+// largest squared column norm of the block held in x (all threads get it)
+__device__ __forceinline__ double qr_block_scale(const double (&x)[QR_CPT][QR_RPT], QrShared &sh) {
+    double v = fmax(fmax(qr_norm2(x[0]), qr_norm2(x[1])), fmax(qr_norm2(x[2]), qr_norm2(x[3])));
 #pragma unroll
-            for (int i = 0; i < QR_B; ++i) sh.vbuf[p][i] = x[i];
-            const double alpha = rq0;
-            double t = 0.0, w0 = 0.0;
-            // Columns that an earlier reflector of the same block already annihilated carry rounding
-            // residue that shrinks by ~1e-16 per column; once xn leaves the normal range 1 / (beta d)
-            // would overflow.  Such a column is numerically zero: no reflector.
-            if (xn > 1e-200) {
-                const double nrm2 = alpha * alpha + xn;
-                const double beta = -copysign(nrm2 * fast_rsqrt(nrm2), alpha);
-                const double d = beta - alpha;
-                t = fast_rcp(beta * d);
-                w0 = -d;
-                R[j * ldr + j] = beta;
+    for (int o = 16; o >= QR_T; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double w = threadIdx.x < QR_THREADS / 32 ? sh.red[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w = fmax(w, __shfl_xor_sync(0xffffffffu, w, o));
+        if (threadIdx.x == 0) sh.scale = w;
+    }
+    __syncthreads();
+    return sh.scale;
+}
+
+// squared norm of column `which` (0..3) of the lane's four: a switch, so that x[][] stays in registers
+__device__ __forceinline__ double qr_norm2_of(const double (&x)[QR_CPT][QR_RPT], int which) {
+    switch (which) {
+    case 0: return qr_norm2(x[0]);
+    case 1: return qr_norm2(x[1]);
+    case 2: return qr_norm2(x[2]);
+    default: return qr_norm2(x[3]);
+    }
+}
+
+// One sweep: fold the QR_B rows held in x[][] (lane (cq, q) has rows 8q.. of columns 4cq .. 4cq+3) into R,
+// starting at column jb.  sh.nbe = number of non-zero rows in the block: the sweep ends after that many
+// reflectors on empty pivot rows; sh.filled[] marks the pivot rows of R that hold a reflector result and
+// sh.diag[] mirrors the diagonal of R (the pivot the next reflector needs at once).
+__device__ __forceinline__ void qr_sweep(double (&x)[QR_CPT][QR_RPT], double *R, int ldr, int k, int kw, int cq, int q, int jb, QrShared &sh) {
+    const double sc = qr_block_scale(x, sh);
+    if (threadIdx.x == 0) {
+        sh.floor2 = fmax(1e-200, QR_RESIDUE * sc);
+        sh.nf = 0;
+    }
+    const int wc0 = (int)(threadIdx.x >> 5) * (32 / QR_T * QR_CPT), wc1 = wc0 + 32 / QR_T * QR_CPT - 1;  // this warp's columns
+    const int c0 = QR_CPT * cq;
+    double xn = 0.0;
+    if (jb >= wc0 && jb <= wc1) xn = qr_norm2_of(x, jb & 3);
+    __syncthreads();
+    double *Rc = R + (size_t)jb * ldr + c0;  // row j of R at this lane's columns
+    const double4 *vs0 = reinterpret_cast<const double4 *>(&sh.vbuf[0][q * QR_VS]), *vs1 = reinterpret_cast<const double4 *>(&sh.vbuf[1][q * QR_VS]);
+    for (int j = jb; j < k; ++j, Rc += ldr) {
+        const int b = j & 1;
+        // row j of R for this lane's columns: needed after the barrier and the dot products, which hide the L2 latency
+        double rq[QR_CPT];
+#pragma unroll
+        for (int i = 0; i < QR_CPT; ++i) rq[i] = (c0 + i > j && c0 + i < kw) ? Rc[i] : 0.0;
+        if (cq == (j >> 2)) {
+            double4 *dst = const_cast<double4 *>(b ? vs1 : vs0);
+            switch (j & 3) {
+            case 0: dst[0] = make_double4(x[0][0], x[0][1], x[0][2], x[0][3]); dst[1] = make_double4(x[0][4], x[0][5], x[0][6], x[0][7]); break;
+            case 1: dst[0] = make_double4(x[1][0], x[1][1], x[1][2], x[1][3]); dst[1] = make_double4(x[1][4], x[1][5], x[1][6], x[1][7]); break;
+            case 2: dst[0] = make_double4(x[2][0], x[2][1], x[2][2], x[2][3]); dst[1] = make_double4(x[2][4], x[2][5], x[2][6], x[2][7]); break;
+            default: dst[0] = make_double4(x[3][0], x[3][1], x[3][2], x[3][3]); dst[1] = make_double4(x[3][4], x[3][5], x[3][6], x[3][7]); break;
             }
-            sh.w0[p] = w0;
-            sh.tau[p] = t;
+            const bool gen = xn > sh.floor2;
+            double t = 0.0, w0 = 0.0, beta = 0.0;
+            if (gen) qr_reflector(sh.diag[j], xn, t, w0, beta);
+            __syncwarp(0xffu << (threadIdx.x & 24));  // every lane has read the pivot before lane 0 replaces it
+            if (q == 0) {
+                sh.tau[b] = t;
+                sh.w0[b] = w0;
+                int nf = sh.nf;
+                if (gen) {
+                    if (!sh.filled[j]) sh.nf = ++nf;
+                    sh.filled[j] = 1;
+                    sh.diag[j] = beta;
+                    Rc[j - c0] = beta;
+                }
+                sh.stop[b] = nf >= sh.nbe;
+            }
         }
         __syncthreads();
-        const double t = sh.tau[p];
-        if (has_col && c > j && t != 0.0) {
-            const double w0 = sh.w0[p];
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        const double t = sh.tau[b];
+        const bool stop = sh.stop[b] != 0;
+        if (wc1 > j && t != 0.0) {
+            const double w0 = sh.w0[b];
+            const double4 *vs = b ? vs1 : vs0;
+            const double4 u0 = vs[0], u1 = vs[1];
+            const double v[QR_RPT] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+            double d[QR_CPT];
 #pragma unroll
-            for (int i = 0; i < QR_B; i += 4) {
-                s0 += sh.vbuf[p][i] * x[i];
-                s1 += sh.vbuf[p][i + 1] * x[i + 1];
-                s2 += sh.vbuf[p][i + 2] * x[i + 2];
-                s3 += sh.vbuf[p][i + 3] * x[i + 3];
+            for (int i = 0; i < QR_CPT; ++i) {
+                double e0 = v[0] * x[i][0], e1 = v[1] * x[i][1];
+#pragma unroll
+                for (int r = 2; r < QR_RPT; r += 2) {
+                    e0 = fma(v[r], x[i][r], e0);
+                    e1 = fma(v[r + 1], x[i][r + 1], e1);
+                }
+                d[i] = e0 + e1;
             }
-            const double sacc = (w0 * rq0 + (s0 + s1) + (s2 + s3)) * t;
-            R[j * ldr + c] = rq0 - sacc * w0;
 #pragma unroll
-            for (int i = 0; i < QR_B; ++i) x[i] -= sacc * sh.vbuf[p][i];
-        }
-        if (c == j + 1) {
-            // I own the next reflector: squared norm of my (now final) column
-            double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+            for (int o = 1; o < QR_T; o <<= 1) {
 #pragma unroll
-            for (int i = 0; i < QR_B; i += 4) {
-                n0 += x[i] * x[i];
-                n1 += x[i + 1] * x[i + 1];
-                n2 += x[i + 2] * x[i + 2];
-                n3 += x[i + 3] * x[i + 3];
+                for (int i = 0; i < QR_CPT; ++i) d[i] += __shfl_xor_sync(0xffffffffu, d[i], o);
             }
-            xn = (n0 + n1) + (n2 + n3);
+#pragma unroll
+            for (int i = 0; i < QR_CPT; ++i) {
+                if (c0 + i > j && c0 + i < kw) {
+                    const double sacc = fma(w0, rq[i], d[i]) * t;
+                    if (q == 0) Rc[i] = fma(-sacc, w0, rq[i]);
+#pragma unroll
+                    for (int r = 0; r < QR_RPT; ++r) x[i][r] = fma(-sacc, v[r], x[i][r]);
+                }
+            }
         }
-        rq0 = rq1;
-        rq1 = rq2;
+        // the warp that owns the next reflector: squared norm of its (now final) column
+        if (j + 1 >= wc0 && j + 1 <= wc1) xn = qr_norm2_of(x, (j + 1) & 3);
+        if (stop) break;
     }
     __syncthreads();
 }
@@ -2173,40 +2264,60 @@ __global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb,
     const int kw = k + 1, ldr = KC + 1;
     double *R = bb.Rq + ((size_t)s * QR_G + g) * ldr * ldr;  // R[j][c] at j * ldr + c
     __shared__ QrShared sh;
-    const int c = threadIdx.x;
-    const bool has_col = c < kw;
-    if (has_col)
-        for (int j = 0; j <= min(c, k - 1); ++j) R[j * ldr + c] = 0.0;
+    const int cp = threadIdx.x / QR_T, q = threadIdx.x % QR_T;
+    for (int cc = 0; cc < QR_CPT; ++cc) {
+        const int c = QR_CPT * cp + cc;
+        if (c < kw)
+            for (int j = q; j <= min(c, k - 1); j += QR_T) R[j * ldr + c] = 0.0;
+    }
+    for (int j = threadIdx.x; j < QR_COLS; j += QR_THREADS) {
+        sh.filled[j] = 0;
+        sh.diag[j] = 0.0;
+    }
     const int per = ((m + ng - 1) / ng + QR_B - 1) / QR_B * QR_B;
     const int r_begin = g * per, r_end = min(m, r_begin + per);
-    double x[QR_B];
+    double x[QR_CPT][QR_RPT];
     for (int r0 = r_begin; r0 < r_end; r0 += QR_B) {
         const int nb = min(QR_B, r_end - r0);
         if (threadIdx.x < 32) {
-            int j0 = threadIdx.x < nb ? rj0[r0 + threadIdx.x] : k;
+            int j0 = k;
+            for (int i = threadIdx.x; i < nb; i += 32) j0 = min(j0, rj0[r0 + i]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) j0 = min(j0, __shfl_xor_sync(0xffffffffu, j0, o));
-            if (threadIdx.x == 0) sh.j0 = j0;
+            if (threadIdx.x == 0) {
+                sh.j0 = j0;
+                sh.nbe = nb;
+            }
         }
 #pragma unroll
-        for (int i = 0; i < QR_B; ++i) {
-            double v = 0.0;
-            if (has_col && i < nb) v = c < k ? Hst[(size_t)(r0 + i) * k + c] : rst[r0 + i];
-            x[i] = v;
+        for (int cc = 0; cc < QR_CPT; ++cc) {
+            // column c of [H | r]: element (row) at src[row * stride]
+            const int c = QR_CPT * cp + cc;
+            const double *src = c < k ? Hst + c : rst;
+            const size_t stride = c < k ? (size_t)k : 1;
+#pragma unroll
+            for (int i = 0; i < QR_RPT; ++i) {
+                const int row = q * QR_RPT + i;
+                x[cc][i] = (c < kw && row < nb) ? src[(size_t)(r0 + row) * stride] : 0.0;
+            }
         }
         __syncthreads();
-        qr_sweep(x, R, ldr, k, kw, c, sh.j0, sh);
+        qr_sweep(x, R, ldr, k, kw, cp, q, sh.j0, sh);
     }
     __syncthreads();
     if (ng == 1) {
         qr_extract(R, ldr, k, Tm, rt);
         if (threadIdx.x == 0) st.mt = k;
+    } else {
+        unsigned char *fl = bb.Rfill + ((size_t)s * QR_G + g) * ldr;
+        for (int j = threadIdx.x; j < k; j += QR_THREADS) fl[j] = sh.filled[j];
     }
 }
 
 // TSQR combine, a binary tree over the QR_G = 4 triangles: level 1 (grid (2, S)) folds triangle 1 into 0
 // and 3 into 2 in parallel, level 2 (grid (1, S)) folds 2 into 0 and extracts T.  Row i of a triangle is
-// zero left of column i, so the sweep of a 32-row block starts at its first row index.
+// zero left of column i, so the sweep of a row block starts at its first row index; rows of the source
+// that never received a reflector are zero and do not count.
 __global__ void __launch_bounds__(QR_THREADS) be_qr_combine_kernel(BeConst bc, BeBuf bb, int level) {
     const int s = blockIdx.y;
     const BeStep sp = bb.step[s];
@@ -2219,25 +2330,54 @@ __global__ void __launch_bounds__(QR_THREADS) be_qr_combine_kernel(BeConst bc, B
     const int dst_g = level == 1 ? 2 * blockIdx.x : 0, src_g = level == 1 ? 2 * blockIdx.x + 1 : 2;
     double *Rd = bb.Rq + ((size_t)s * QR_G + dst_g) * ldr * ldr;
     const double *Rs = bb.Rq + ((size_t)s * QR_G + src_g) * ldr * ldr;
+    unsigned char *fd = bb.Rfill + ((size_t)s * QR_G + dst_g) * ldr;
+    const unsigned char *fs = bb.Rfill + ((size_t)s * QR_G + src_g) * ldr;
     __shared__ QrShared sh;
-    const int c = threadIdx.x;
-    const bool has_col = c < kw;
-    double x[QR_B];
+    const int cp = threadIdx.x / QR_T, q = threadIdx.x % QR_T;
+    for (int j = threadIdx.x; j < QR_COLS; j += QR_THREADS) {
+        sh.filled[j] = j < k ? fd[j] : 0;
+        sh.diag[j] = j < k ? Rd[j * ldr + j] : 0.0;
+    }
+    double x[QR_CPT][QR_RPT];
     for (int r0 = 0; r0 < k; r0 += QR_B) {
         const int nb = min(QR_B, k - r0);
+        if (threadIdx.x < 32) {
+            int cnt = 0, first = k;
+            for (int i = threadIdx.x; i < nb; i += 32)
+                if (fs[r0 + i]) {
+                    ++cnt;
+                    first = min(first, r0 + i);
+                }
 #pragma unroll
-        for (int i = 0; i < QR_B; ++i) {
-            double v = 0.0;
-            if (has_col && i < nb && c >= r0 + i) v = Rs[(r0 + i) * ldr + c];
-            x[i] = v;
+            for (int o = 16; o > 0; o >>= 1) {
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+            }
+            if (threadIdx.x == 0) {
+                sh.nbe = cnt;
+                sh.j0 = first;
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < QR_CPT; ++cc) {
+            const int c = QR_CPT * cp + cc;
+#pragma unroll
+            for (int i = 0; i < QR_RPT; ++i) {
+                const int row = r0 + q * QR_RPT + i;
+                x[cc][i] = (c < kw && row < k && c >= row) ? Rs[row * ldr + c] : 0.0;
+            }
         }
         __syncthreads();
-        qr_sweep(x, Rd, ldr, k, kw, c, r0, sh);
+        if (sh.nbe > 0) qr_sweep(x, Rd, ldr, k, kw, cp, q, sh.j0, sh);
+        else __syncthreads();
     }
     if (level == 2) {
         __syncthreads();
         qr_extract(Rd, ldr, k, bb.Tm + (size_t)s * KC * KC, bb.rt + (size_t)s * KC);
         if (threadIdx.x == 0) st.mt = k;
+    } else {
+        __syncthreads();
+        for (int j = threadIdx.x; j < k; j += QR_THREADS) fd[j] = sh.filled[j];
     }
 }
 
@@ -2568,8 +2708,9 @@ struct BeBuffers {
 
 int be_create(mskf_handle *h) {
     const mskf_config &c = h->cfg;
-    if (c.max_cam_state_size < 5 || c.max_cam_state_size > NSM) {
-        h->err = "max_cam_state_size must be in [5, 32]";
+    // 31: the QR compression gives every column of [H | r] (6 N + 1 of them) a slot among QR_COLS = 192
+    if (c.max_cam_state_size < 5 || c.max_cam_state_size > NSM - 1 || 6 * c.max_cam_state_size + 1 > QR_COLS) {
+        h->err = "max_cam_state_size must be in [5, 31]";
         return MSKF_ERR_ARG;
     }
     BeBuffers *B = new BeBuffers;
@@ -2636,7 +2777,7 @@ int be_create(mskf_handle *h) {
     A(bb.l_slot, S * bc.ML); A(bb.l_ok, S * bc.ML); A(bb.l_pass, S * bc.ML); A(bb.l_M, S * bc.ML);
     A(bb.l_eoff, S * bc.ML); A(bb.l_roff, S * bc.ML); A(bb.l_soff, S * bc.ML); A(bb.l_oslots, S * bc.ML * NSM);
     A(bb.Hblk, S * bc.ecap); A(bb.rblk, S * bc.rcap);
-    A(bb.Hst, S * bc.hst_cap); A(bb.rst, S * bc.hst_rows); A(bb.rst_j0, S * bc.hst_rows); A(bb.Rq, S * QR_G * (bc.KC + 1) * (bc.KC + 1));
+    A(bb.Hst, S * bc.hst_cap); A(bb.rst, S * bc.hst_rows); A(bb.rst_j0, S * bc.hst_rows); A(bb.Rq, S * QR_G * (bc.KC + 1) * (bc.KC + 1)); A(bb.Rfill, S * QR_G * (bc.KC + 1));
     A(bb.Tm, S * bc.KC * bc.KC); A(bb.rt, S * bc.KC); A(bb.PHt, S * bc.LD * bc.KC); A(bb.Sm, S * bc.KC * bc.KC);
     A(bb.Linv, S * bc.KC * bc.KC); A(bb.W, S * bc.LD * bc.KC); A(bb.yv, S * bc.KC); A(bb.dxv, S * bc.LD);
 #undef A
@@ -2725,8 +2866,8 @@ static void launch_update(mskf_handle *h, int phase = 0) {
     const int S = h->S;
     const int tiles_ld = (bc.LD + GT - 1) / GT, tiles_kc = (bc.KC + GT - 1) / GT;
     MSKF_LAUNCH(h, phase == 0 ? PK_BE_QR : PK_BE_QR_PRUNE, (be_qr_kernel<<<dim3(QR_G, S), QR_THREADS, 0, q>>>(bc, bb, phase)));
-    MSKF_LAUNCH(h, phase == 0 ? PK_BE_QR : PK_BE_QR_PRUNE, (be_qr_combine_kernel<<<dim3(2, S), QR_THREADS, 0, q>>>(bc, bb, 1)));
-    MSKF_LAUNCH(h, phase == 0 ? PK_BE_QR : PK_BE_QR_PRUNE, (be_qr_combine_kernel<<<dim3(1, S), QR_THREADS, 0, q>>>(bc, bb, 2)));
+    MSKF_LAUNCH(h, PK_BE_QR_COMBINE, (be_qr_combine_kernel<<<dim3(2, S), QR_THREADS, 0, q>>>(bc, bb, 1)));
+    MSKF_LAUNCH(h, PK_BE_QR_COMBINE, (be_qr_combine_kernel<<<dim3(1, S), QR_THREADS, 0, q>>>(bc, bb, 2)));
     MSKF_LAUNCH(h, PK_BE_GEMM_PHT, (be_gemm_kernel<0><<<dim3(tiles_ld * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_GEMM_S, (be_gemm_kernel<1><<<dim3(tiles_kc * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_CHOL, (be_chol_kernel<<<S, BE_THREADS, B->smem_chol, q>>>(bc, bb)));
@@ -3011,6 +3152,14 @@ int be_op_update(mskf_handle *t, int n_cam, int m, const double *H, const double
     MSKF_CUDA_CHECK(t, cudaMemcpy(bb.P, Pl.data(), sizeof(double) * Pl.size(), cudaMemcpyHostToDevice));
     MSKF_CUDA_CHECK(t, cudaMemcpy(bb.Hst, Hc.data(), sizeof(double) * Hc.size(), cudaMemcpyHostToDevice));
     MSKF_CUDA_CHECK(t, cudaMemcpy(bb.rst, r, sizeof(double) * m, cudaMemcpyHostToDevice));
+    std::vector<int> j0v(m, k);
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < k; ++j)
+            if (Hc[(size_t)i * k + j] != 0.0) {
+                j0v[i] = j;
+                break;
+            }
+    MSKF_CUDA_CHECK(t, cudaMemcpy(bb.rst_j0, j0v.data(), sizeof(int) * m, cudaMemcpyHostToDevice));
     launch_update(t);
     MSKF_CUDA_CHECK(t, cudaGetLastError());
     MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->be_stream));

@@ -123,7 +123,7 @@ static const char *kProfNames[PK_COUNT] = {
     "pyr_down_l1", "pyr_down_ln", "klt_temporal", "klt_stereo", "klt_new", "detect", "fe_bookkeeping",
     "be_propagate", "be_augment", "be_add_obs", "be_select", "be_triangulate", "be_layout", "be_feature_jac",
     "be_stack", "be_qr", "be_gemm_pht", "be_gemm_s", "be_chol", "be_gemm_w", "be_apply", "be_gemm_pupd",
-    "be_prune_finish", "be_finish", "be_feature_jac_prune", "be_qr_prune"};
+    "be_prune_finish", "be_finish", "be_feature_jac_prune", "be_qr_prune", "be_qr_combine"};
 const char *mskf_prof_name(int tag) { return tag >= 0 && tag < PK_COUNT ? kProfNames[tag] : "?"; }
 void prof_begin(mskf_handle *h, int tag) {
     if (!h->prof_on) return;
@@ -765,7 +765,14 @@ int mskf_op_ekf_update(mskf_handle *h, int n_cam, int m, const double *H, const 
     if (n_cam > c.max_cam_state_size) c.max_cam_state_size = n_cam;
     if (m > c.max_jacobian_rows) c.max_jacobian_rows = m;
     int rc = mskf_create(&c, 1, h->device, &t);
-    if (rc == MSKF_OK) rc = be_op_update(t, n_cam, m, H, r, P, out_delta_x, out_P);
+    if (rc == MSKF_OK) {
+        t->prof_on = h->prof_on;  // per-kernel times of the operator are accounted to the caller's handle
+        rc = be_op_update(t, n_cam, m, H, r, P, out_delta_x, out_P);
+        if (t->prof_on) {
+            prof_collect(t);
+            for (int i = 0; i < PK_COUNT; ++i) { h->prof_ms[i] += t->prof_ms[i]; h->prof_n[i] += t->prof_n[i]; }
+        }
+    }
     if (rc != MSKF_OK && t) h->err = t->err;
     if (t) mskf_destroy(t);
     return rc;

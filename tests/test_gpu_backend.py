@@ -334,3 +334,33 @@ def test_op_ekf_update_rank_deficient_tail_group(eng, ob, synth):
     assert np.abs(P_g - P_o).max() <= UPDATE_TOL * np.abs(P_o).max()
     assert np.abs(dx_g - dx_o).max() <= UPDATE_TOL * max(np.abs(dx_o).max(), 1e-12)
     e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m_target", [150, 300, 700, 1200])
+def test_op_ekf_update_block_structured(eng, ob, synth, m_target):
+    """Stacked Jacobian shaped like removeLostFeatures' (msckf_vio.cpp:937-1024): each feature contributes
+    4M-3 rows that are non-zero only in the 6M columns of the camera states that observed it, so row
+    blocks start at different columns (the QR sweep skips the leading zeros and stops once a block's
+    rows are used up), whole column ranges are empty and the system is column-rank deficient."""
+    rng = np.random.default_rng(m_target)
+    n_cam = 28
+    n = 21 + 6 * n_cam
+    P = _spd(rng, n)
+    rows = []
+    while sum(b.shape[0] for b in rows) < m_target:
+        M = int(rng.integers(3, 20))
+        first = int(rng.integers(2, n_cam - M + 1))  # camera states 0 and 1 are never observed
+        blk = np.zeros((4 * M - 3, n))
+        blk[:, 21 + 6 * first:21 + 6 * (first + M)] = rng.standard_normal((4 * M - 3, 6 * M))
+        rows.append(blk)
+    H = np.vstack(rows)
+    r = rng.standard_normal(H.shape[0]) * 1e-2
+    cfg = copy_cfg(synth.default_config("bench"))
+    e = eng.Engine(cfg, 1)
+    dx_g, P_g = e.op_ekf_update(H, r, P)
+    dx_o, P_o = ob.update_math(H, r, P, cfg.noise_feature ** 2)
+    assert np.isfinite(P_g).all() and np.isfinite(dx_g).all()
+    assert np.abs(P_g - P_o).max() <= UPDATE_TOL * np.abs(P_o).max()
+    assert np.abs(dx_g - dx_o).max() <= UPDATE_TOL * max(np.abs(dx_o).max(), 1e-12)
+    e.close()
