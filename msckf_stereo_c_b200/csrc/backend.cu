@@ -2453,49 +2453,153 @@ __global__ void __launch_bounds__(BE_THREADS) be_gemm_kernel(BeConst bc, BeBuf b
 }
 
 // S = L L^T (packed lower in shared memory), Linv = L^-1, y = Linv r.  One CTA per stream.
-__global__ void __launch_bounds__(BE_THREADS) be_chol_kernel(BeConst bc, BeBuf bb) {
+// 1 / sqrt(a) for a > 0 from the RSQ64H seed and two Newton steps (fp64 round-off), as in the QR chain
+__device__ __forceinline__ double chol_rsqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    y = fma(y, fma(-h, y * y, 0.5), y);
+    y = fma(y, fma(-h, y * y, 0.5), y);
+    return y;
+}
+
+// S = L L^T and X = L^-1 in one pass, with the whole lower triangle in REGISTERS: thread t owns the 6x6
+// tile (ti, tj) of the 31x31 lower tile triangle (496 tiles <= 512 threads, 72 registers of data).  Step kk
+// of the right-looking factorization needs only the scaled column kk (c_i = L[i][kk]); the same column
+// drives the forward substitution L X = I (Gauss-Jordan on the identity), whose partial result for rows
+// i > kk lives in the columns j <= kk that the factorization no longer reads:
+//     G[i][j] -= c_i c_j            (j > kk: trailing Cholesky update)
+//     X[i][j] -= c_i X[kk][j]       (j < kk),      X[i][kk] = -c_i / L[kk][kk]
+// so each step is one "tile -= c_i (x) r_j" with r = [X[kk][0..kk) | 0 | c(kk..n)] broadcast through 1.5 KB
+// of shared memory: no shared-memory traffic for the matrix itself, two barriers per column.
+// (The earlier version kept the packed triangle in shared memory: 2.6k cycles per column for the factor
+// and 4.1k per row for the inverse, both latency-bound on LDS -> FMA -> STS chains.)
+#define CH_T 6
+#define CH_THREADS 512
+#define CH_NMAX (NSM * 6)
+
+#define CH_FOR_COL(ak, BODY)                                     \
+    switch (ak) {                                                \
+    case 0: { constexpr int B_ = 0; BODY } break;                \
+    case 1: { constexpr int B_ = 1; BODY } break;                \
+    case 2: { constexpr int B_ = 2; BODY } break;                \
+    case 3: { constexpr int B_ = 3; BODY } break;                \
+    case 4: { constexpr int B_ = 4; BODY } break;                \
+    default: { constexpr int B_ = 5; BODY } break;               \
+    }
+
+__global__ void __launch_bounds__(CH_THREADS) be_chol_kernel(BeConst bc, BeBuf bb) {
     const int s = blockIdx.x;
     const BeStep sp = bb.step[s];
     if (!sp.active) return;
     const BeState &st = bb.st[s];
     if (!st.do_update) return;
     const int KC = bc.KC, n = st.mt;
-    extern __shared__ unsigned char be_smem[];
-    double *L = (double *)be_smem;  // packed lower, row i at i(i+1)/2
-    double *colv = L + (size_t)KC * (KC + 1) / 2;  // [KC]
     const double *Sm = bb.Sm + (size_t)s * KC * KC;
     double *Linv = bb.Linv + (size_t)s * KC * KC;
-    auto ix = [](int i, int j) { return i * (i + 1) / 2 + j; };
-    for (int e = threadIdx.x; e < n * n; e += BE_THREADS) {
-        int i = e / n, j = e - i * n;
-        if (j <= i) L[ix(i, j)] = Sm[i * KC + j];
-    }
-    packed_cholesky(L, 0, n);
-    // in-place inverse of the lower-triangular factor, last column first (dtrti2 order)
-    __shared__ double s_dj;
-    for (int j = n - 1; j >= 0; --j) {
-        for (int i = j + 1 + threadIdx.x; i < n; i += BE_THREADS) colv[i] = L[ix(i, j)];
-        if (threadIdx.x == 0) s_dj = 1.0 / L[ix(j, j)];
-        __syncthreads();
-        const double dj = s_dj;
-        for (int i = j + 1 + threadIdx.x; i < n; i += BE_THREADS) {
-            double sacc = 0;
-            for (int l = j + 1; l <= i; ++l) sacc += L[ix(i, l)] * colv[l];  // X[i][l] (already inverse) * L[l][j]
-            L[ix(i, j)] = -sacc * dj;
+    __shared__ double vec[CH_NMAX + CH_T];
+    __shared__ double s_dinv;
+    // tile (ti, tj), tj <= ti, of thread t = ti (ti + 1) / 2 + tj
+    const int t = threadIdx.x;
+    int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    const int tj = t - ti * (ti + 1) / 2;
+    const int i0 = CH_T * ti, j0 = CH_T * tj;
+    const bool live = i0 < n;
+    double g[CH_T][CH_T];
+#pragma unroll
+    for (int a = 0; a < CH_T; ++a)
+#pragma unroll
+        for (int b = 0; b < CH_T; ++b) {
+            const int i = i0 + a, j = j0 + b;
+            g[a][b] = (i < n && j <= i) ? Sm[i * KC + j] : 0.0;
         }
-        if (threadIdx.x == 0) L[ix(j, j)] = dj;
+    // the strictly upper tiles of Linv are zero (be_gemm_kernel<2> reads full rows)
+    for (int e = threadIdx.x; e < n * n; e += CH_THREADS) {
+        const int i = e / n, j = e - i * n;
+        if (j / CH_T > i / CH_T) Linv[i * KC + j] = 0.0;
+    }
+    for (int kk = 0; kk < n; ++kk) {
+        const int tk = kk / CH_T, ak = kk - tk * CH_T;
+        if (ti == tk && tj == tk) {
+            double piv = 0.0;
+            CH_FOR_COL(ak, piv = g[B_][B_];)
+            // a non-positive pivot propagates NaN, as sqrt would
+            s_dinv = piv > 0.0 ? chol_rsqrt(piv) : __longlong_as_double(0x7ff8000000000000ll);
+        }
         __syncthreads();
+        const double dinv = s_dinv;
+        if (tj == tk && ti >= tk) {
+            // column kk: c_i = L[i][kk] for the rows below the diagonal; X[i][kk] takes its place
+            CH_FOR_COL(ak,
+#pragma unroll
+                       for (int a = 0; a < CH_T; ++a) {
+                           const int i = i0 + a;
+                           if (i > kk && i < n) {
+                               const double c = g[a][B_] * dinv;
+                               vec[i] = c;
+                               g[a][B_] = -c * dinv;
+                           } else if (i == kk) {
+                               vec[i] = 0.0;
+                               g[a][B_] = dinv;
+                           }
+                       })
+        }
+        if (ti == tk && tj <= tk) {
+            // row kk of X is final: X[kk][j] = Y[kk][j] / L[kk][kk]
+            CH_FOR_COL(ak,
+#pragma unroll
+                       for (int b = 0; b < CH_T; ++b) {
+                           const int j = j0 + b;
+                           if (j < kk) {
+                               const double xr = g[B_][b] * dinv;
+                               vec[j] = xr;
+                               g[B_][b] = xr;
+                           }
+                       })
+        }
+        __syncthreads();
+        if (live && i0 + CH_T - 1 > kk) {
+            double ci[CH_T], rj[CH_T];
+#pragma unroll
+            for (int a = 0; a < CH_T; ++a) ci[a] = (i0 + a > kk && i0 + a < n) ? vec[i0 + a] : 0.0;
+#pragma unroll
+            for (int b = 0; b < CH_T; ++b) rj[b] = (j0 + b < n) ? vec[j0 + b] : 0.0;
+#pragma unroll
+            for (int a = 0; a < CH_T; ++a)
+#pragma unroll
+                for (int b = 0; b < CH_T; ++b) g[a][b] = fma(-ci[a], rj[b], g[a][b]);
+        }
     }
-    for (int e = threadIdx.x; e < n * n; e += BE_THREADS) {
-        int i = e / n, j = e - i * n;
-        Linv[i * KC + j] = j <= i ? L[ix(i, j)] : 0.0;
+    // X = L^-1 out; y = X rt row by row in a fixed order (a stream's result must not depend on scheduling)
+    if (live) {
+#pragma unroll
+        for (int a = 0; a < CH_T; ++a) {
+            const int i = i0 + a;
+            if (i >= n) continue;
+#pragma unroll
+            for (int b = 0; b < CH_T; ++b) {
+                const int j = j0 + b;
+                if (j < n) Linv[i * KC + j] = j <= i ? g[a][b] : 0.0;
+            }
+        }
     }
+    __syncthreads();
     const double *rt = bb.rt + (size_t)s * KC;
     double *yv = bb.yv + (size_t)s * KC;
-    for (int i = threadIdx.x; i < n; i += BE_THREADS) {
-        double sacc = 0;
-        for (int l = 0; l <= i; ++l) sacc += L[ix(i, l)] * rt[l];
-        yv[i] = sacc;
+    for (int i = threadIdx.x; i < n; i += CH_THREADS) {
+        const double *row = Linv + (size_t)i * KC;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        int l = 0;
+        for (; l + 3 <= i; l += 4) {
+            a0 = fma(__ldcg(row + l), rt[l], a0);
+            a1 = fma(__ldcg(row + l + 1), rt[l + 1], a1);
+            a2 = fma(__ldcg(row + l + 2), rt[l + 2], a2);
+            a3 = fma(__ldcg(row + l + 3), rt[l + 3], a3);
+        }
+        for (; l <= i; ++l) a0 = fma(__ldcg(row + l), rt[l], a0);
+        yv[i] = (a0 + a1) + (a2 + a3);
     }
 }
 
@@ -2811,7 +2915,6 @@ int be_create(mskf_handle *h) {
     MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_add_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_add));
     MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_sel));
     MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_feature_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_jac[0]));
-    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_chol));
     for (int s = 0; s < h->S; ++s) be_reset_kernel<<<1, BE_THREADS, 0, h->be_stream>>>(bc, bb, s, 1, h->cfg);
     MSKF_CUDA_CHECK(h, cudaGetLastError());
     return MSKF_OK;
@@ -2870,7 +2973,7 @@ static void launch_update(mskf_handle *h, int phase = 0) {
     MSKF_LAUNCH(h, PK_BE_QR_COMBINE, (be_qr_combine_kernel<<<dim3(1, S), QR_THREADS, 0, q>>>(bc, bb, 2)));
     MSKF_LAUNCH(h, PK_BE_GEMM_PHT, (be_gemm_kernel<0><<<dim3(tiles_ld * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_GEMM_S, (be_gemm_kernel<1><<<dim3(tiles_kc * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
-    MSKF_LAUNCH(h, PK_BE_CHOL, (be_chol_kernel<<<S, BE_THREADS, B->smem_chol, q>>>(bc, bb)));
+    MSKF_LAUNCH(h, PK_BE_CHOL, (be_chol_kernel<<<S, CH_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_GEMM_W, (be_gemm_kernel<2><<<dim3(tiles_ld * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_APPLY, (be_apply_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_GEMM_PUPD, (be_gemm_kernel<3><<<dim3(tiles_ld * (tiles_ld + 1) / 2, S), BE_THREADS, 0, q>>>(bc, bb)));
