@@ -364,3 +364,38 @@ def test_op_ekf_update_block_structured(eng, ob, synth, m_target):
     assert np.abs(P_g - P_o).max() <= UPDATE_TOL * np.abs(P_o).max()
     assert np.abs(dx_g - dx_o).max() <= UPDATE_TOL * max(np.abs(dx_o).max(), 1e-12)
     e.close()
+
+
+@pytest.mark.gpu
+def test_full_pipeline_equidistant_model(eng, ob, synth):
+    """Images + IMU in, state out on equidistant (fisheye) cameras: same checks as the radtan run."""
+    cfg = copy_cfg(synth.default_config("ref"), cam0_model=1, cam1_model=1)
+    for i, v in enumerate([-0.0135, 0.021, -0.03, 0.012]):
+        cfg.cam0_distortion[i] = v
+    for i, v in enumerate([-0.0121, 0.018, -0.027, 0.011]):
+        cfg.cam1_distortion[i] = v
+    s = synth.Stream(cfg, seed=3)
+    e = eng.Engine(cfg, 1)
+    o = ob.Oracle(cfg)
+
+    class Both:
+        def imu(self, t, w, a):
+            o.imu(t, w, a)
+            e.imu_callback(t, w, a)
+
+        def stereo(self, t, i0, i1):
+            o.stereo(t, i0, i1)
+            e.push_stereo(t, i0, i1)
+
+        def backend(self):
+            o.backend()
+            e.step()
+
+    seen = False
+    for k, t in synth.feed(s, 80, Both()):
+        (to, fo, no), (tg, fg, ng) = o.features(), e.features()
+        assert to == tg and no == ng and fo.tobytes() == fg.tobytes(), k
+        _compare(o, e, k, seen)
+        seen = seen or o.state().n_updates > 0
+    assert o.state().n_updates >= 20
+    e.close()

@@ -203,3 +203,22 @@ def test_frontend_pipeline_with_two_point_ransac(eng, ob, synth, fix_alias):
         ti = o.tracking_info()
         dropped += ti.after_matching - ti.after_ransac
     assert dropped > 0
+
+
+def _equidistant(cfg):
+    """Both cameras on the equidistant (fisheye) model, image_processor.cpp:811-813, 838-841."""
+    c = copy_cfg(cfg, cam0_model=1, cam1_model=1)
+    for i, v in enumerate([-0.0135, 0.021, -0.03, 0.012]):
+        c.cam0_distortion[i] = v
+    for i, v in enumerate([-0.0121, 0.018, -0.027, 0.011]):
+        c.cam1_distortion[i] = v
+    return c
+
+
+@pytest.mark.gpu
+def test_frontend_pipeline_equidistant_model(eng, ob, synth):
+    """The whole front end on equidistant cameras (rendered with the same model): stereo guess through
+    undistort_points_fisheye / distort_points_fisheye, epipolar gate, published normalized coordinates;
+    also with the two-point RANSAC on, which undistorts both frames' points."""
+    _run_pipeline(eng, ob, synth, _equidistant(synth.default_config("ref")), 3, 40)
+    _run_pipeline(eng, ob, synth, copy_cfg(_equidistant(synth.default_config("ref")), use_ransac=1), 4, 30)
