@@ -49,16 +49,36 @@ def shard(n_total, world, rank):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons of one GPU, sampled while the timed region runs."""
+    """SM clock and clock-event (throttle) reasons of one GPU, sampled through NVML every 5 ms while the
+    timed region runs (the recipe's `nvidia-smi --query-gpu=clocks.sm,...` line reads the same NVML
+    fields; a subprocess takes longer to start than the timed region lasts).  Falls back to nvidia-smi."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.run = index, [], None, None, False
+        if os.environ.get("MSKF_BENCH_NO_CLOCKS"):
+            return
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def start(self):
         if os.environ.get("MSKF_BENCH_NO_CLOCKS"):
+            return
+        if self.nvml:
+            self.run = True
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
             return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -68,16 +88,33 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        flags = [("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap)]
+        while self.run:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.dev, n.NVML_CLOCK_SM))
+                r = n.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+                self.rows.append([sm, self.mx, 0.0] + [("Active" if r & f else "Not Active") for _, f in flags])
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        self.th.join(timeout=2)
+        if self.nvml and self.run:
+            self.run = False
+            self.th.join(timeout=2)
+        elif self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -85,11 +122,12 @@ class ClockSampler:
                 sm.append(float(r[0]))
                 mx = float(r[1])
                 for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
+                    if str(v).lower().startswith("active"):
                         reasons.add(n)
             except (ValueError, IndexError):
                 continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------
