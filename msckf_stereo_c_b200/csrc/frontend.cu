@@ -512,121 +512,179 @@ __device__ __forceinline__ bool has_arc9(unsigned m) {  // 9 contiguous set bits
     return (a & 0xffffu) != 0;
 }
 
+// Stages of one 64x16 tile (ncu source page of the first version: tile load 18 %, ring test 22 %, arc score
+// 22 % at 8 of 32 lanes, NMS 11 %, Shi-Tomasi 24 % of the issue slots):
+//  1. the tile with its halo comes in as aligned 32-bit words (the tile starts 8 columns left of the
+//     block, so image words map to tile words; images whose width is not a multiple of 4 take bytes);
+//  2. ring test for every pixel of the (64+2)x(16+2) score window; pixels that pass are COMPACTED into a
+//     list so that
+//  3. the arc score runs on full warps (on a corner-dense texture a quarter of the pixels pass, which
+//     kept every warp in the score code at a quarter of its lanes);
+//  4. strict 3x3 NMS, maxima compacted;
+//  5. Shi-Tomasi response, 8 lanes per maximum (one row of the 8x8 box each, integer sums: order-free).
+#define DT_X0 8
+#define DT_STRIDE 84  // bytes per tile row: 64 + 8 left + 8 right, + 4 so that rows start in different banks
+#define DT_SW (DT_W + 2)
+#define DT_SH (DT_H + 2)
 __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
     const int s = blockIdx.z;
     const FeStep st = fb.step[s];
     if (!st.active) return;
     const uint8_t *img = fb.pyr[st.slot] + (size_t)s * fc.pyr_bytes;  // level 0 of current cam0
     const int rows = fc.rows, cols = fc.cols;
-    __shared__ uint8_t tile[DT_H + 2 * DT_HALO][DT_W + 2 * DT_HALO + 2];
-    __shared__ uint8_t score[DT_H + 2][DT_W + 2];
+    __shared__ __align__(16) uint8_t tile[DT_H + 2 * DT_HALO][DT_STRIDE];
+    __shared__ uint8_t score[DT_SH][DT_SW + 2];
+    __shared__ unsigned short s_list[DT_SH * DT_SW];  // pixels that passed the ring test: index | side << 15
+    __shared__ int s_nlist, s_nmax;
+    __shared__ unsigned short s_max[DT_H * DT_W / 4];  // strict 3x3 maxima: at most one per 2x2 block
     const int x0 = blockIdx.x * DT_W, y0 = blockIdx.y * DT_H;
-    for (int idx = threadIdx.x; idx < (DT_H + 2 * DT_HALO) * (DT_W + 2 * DT_HALO); idx += 256) {
-        int r = idx / (DT_W + 2 * DT_HALO), c = idx - r * (DT_W + 2 * DT_HALO);
-        int gy = y0 - DT_HALO + r, gx = x0 - DT_HALO + c;
-        uint8_t v = 0;
-        if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) v = img[(size_t)gy * cols + gx];
-        tile[r][c] = v;
+    if (threadIdx.x == 0) {
+        s_nlist = 0;
+        s_nmax = 0;
+    }
+    if ((cols & 3) == 0 && (((size_t)img) & 3) == 0) {
+        constexpr int WPR = (DT_W + 2 * DT_X0) / 4;  // 20 words per tile row
+        for (int idx = threadIdx.x; idx < (DT_H + 2 * DT_HALO) * WPR; idx += 256) {
+            const int r = idx / WPR, w = idx - r * WPR;
+            const int gy = y0 - DT_HALO + r, gx = x0 - DT_X0 + 4 * w;
+            unsigned v = 0;
+            if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) v = *reinterpret_cast<const unsigned *>(img + (size_t)gy * cols + gx);
+            *reinterpret_cast<unsigned *>(&tile[r][4 * w]) = v;
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < (DT_H + 2 * DT_HALO) * (DT_W + 2 * DT_X0); idx += 256) {
+            const int r = idx / (DT_W + 2 * DT_X0), c = idx - r * (DT_W + 2 * DT_X0);
+            const int gy = y0 - DT_HALO + r, gx = x0 - DT_X0 + c;
+            uint8_t v = 0;
+            if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) v = img[(size_t)gy * cols + gx];
+            tile[r][c] = v;
+        }
     }
     __syncthreads();
     const int t = fc.fast_threshold;
+    const int lane = threadIdx.x & 31;
     // Ring offsets as immediates: one LDS per ring pixel.  Bresenham circle of radius 3, k = 0 at (0, +3).
-#define DT_STRIDE (DT_W + 2 * DT_HALO + 2)
 #define RING_PX(pc, dx, dy) ((int)(pc)[(dy) * DT_STRIDE + (dx)])
 #define RING_LIST(X) X(0, 0, 3) X(1, 1, 3) X(2, 2, 2) X(3, 3, 1) X(4, 3, 0) X(5, 3, -1) X(6, 2, -2) X(7, 1, -3) \
     X(8, 0, -3) X(9, -1, -3) X(10, -2, -2) X(11, -3, -1) X(12, -3, 0) X(13, -3, 1) X(14, -2, 2) X(15, -1, 3)
-    for (int idx = threadIdx.x; idx < (DT_H + 2) * (DT_W + 2); idx += 256) {
-        int r = idx / (DT_W + 2), c = idx - r * (DT_W + 2);
-        int gy = y0 - 1 + r, gx = x0 - 1 + c;
-        uint8_t sc = 0;
-        if (gy >= 3 && gy < rows - 3 && gx >= 3 && gx < cols - 3) {
-            const uint8_t *pc = &tile[r + DT_HALO - 1][c + DT_HALO - 1];
-            const int v = pc[0];
-            const int lo = v - t, hi = v + t;  // darker ring pixel: p < lo (d = v - p > t); brighter: p > hi
-            int p[16];
-            unsigned dark = 0, bright = 0;
-            // sign bit of (p - lo) / (hi - p) shifted into the masks (bit order reversed: irrelevant on a ring)
-#define RING_TEST(k, dx, dy)                                               \
-    p[k] = RING_PX(pc, dx, dy);                                            \
-    dark = __funnelshift_l((unsigned)(p[k] - lo), dark, 1);                \
-    bright = __funnelshift_l((unsigned)(hi - p[k]), bright, 1);
-            RING_LIST(RING_TEST)
+    for (int base = 0; base < DT_SH * DT_SW; base += 256) {
+        const int idx = base + threadIdx.x;
+        int pass = 0;  // 1: darker arc, 2: brighter arc
+        if (idx < DT_SH * DT_SW) {
+            const int r = idx / DT_SW, c = idx - r * DT_SW;
+            const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+            score[r][c] = 0;
+            if (gy >= 3 && gy < rows - 3 && gx >= 3 && gx < cols - 3) {
+                const uint8_t *pc = &tile[r + DT_HALO - 1][c + DT_X0 - 1];
+                const int v = pc[0];
+                const int lo = v - t, hi = v + t;  // darker ring pixel: p < lo (d = v - p > t); brighter: p > hi
+                unsigned dark = 0, bright = 0;
+                // sign bit of (p - lo) / (hi - p) shifted into the masks (bit order reversed: irrelevant on a ring)
+#define RING_TEST(k, dx, dy)                                             \
+    {                                                                    \
+        const int pk = RING_PX(pc, dx, dy);                              \
+        dark = __funnelshift_l((unsigned)(pk - lo), dark, 1);            \
+        bright = __funnelshift_l((unsigned)(hi - pk), bright, 1);        \
+    }
+                RING_LIST(RING_TEST)
 #undef RING_TEST
-            const bool is_dark = has_arc9(dark);
-            if (is_dark || has_arc9(bright)) {
-                // S = max over the 16 arcs of 9 contiguous ring pixels of min(d) (darker ring) or min(-d)
-                // (brighter ring), d = centre - ring.  A ring cannot hold a darker and a brighter 9-arc at
-                // once, and the side without an arc scores <= t, so only the side that passed is evaluated.
-                // Sliding minimum of width 9 by doubling (2, 4, 8, +1); only `min` chains on purpose: ptxas
-                // 12.9 for sm_100a miscompiles interleaved min/max chains fused into VIMNMX3
-                // (tools/scratch/t2.cu).
-                const int sg = is_dark ? 1 : -1;
-                int n[16], a2[16], a4[16];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) n[k] = (v - p[k]) * sg;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) a2[k] = min(n[k], n[(k + 1) & 15]);
-#pragma unroll
-                for (int k = 0; k < 16; ++k) a4[k] = min(a2[k], a2[(k + 2) & 15]);
-                int best = -255;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    int a9 = min(min(a4[k], a4[(k + 4) & 15]), n[(k + 8) & 15]);
-                    best = max(best, a9);
-                }
-                sc = (uint8_t)(best - 1);
+                pass = has_arc9(dark) ? 1 : (has_arc9(bright) ? 2 : 0);
             }
         }
-        score[r][c] = sc;
+        // ordered compaction within the warp, one atomic per warp
+        const unsigned bal = __ballot_sync(0xffffffffu, pass != 0);
+        int wbase = 0;
+        if (lane == 0 && bal) wbase = atomicAdd(&s_nlist, __popc(bal));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (pass) s_list[wbase + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(idx | ((pass - 1) << 15));
+    }
+    __syncthreads();
+    // S = max over the 16 arcs of 9 contiguous ring pixels of min(d) (darker ring) or min(-d) (brighter ring),
+    // d = centre - ring.  A ring cannot hold a darker and a brighter 9-arc at once, and the side without an arc
+    // scores <= t, so only the side that passed is evaluated.  Sliding minimum of width 9 by doubling
+    // (2, 4, 8, +1); only `min` chains on purpose: ptxas 12.9 for sm_100a miscompiles interleaved min/max
+    // chains fused into VIMNMX3 (tools/scratch/t2.cu).
+    const int nlist = s_nlist;
+    for (int e = threadIdx.x; e < nlist; e += 256) {
+        const int code = s_list[e];
+        const int idx = code & 0x7fff, sg = (code >> 15) ? -1 : 1;
+        const int r = idx / DT_SW, c = idx - r * DT_SW;
+        const uint8_t *pc = &tile[r + DT_HALO - 1][c + DT_X0 - 1];
+        const int v = pc[0];
+        int n[16], a2[16], a4[16];
+#define RING_DIFF(k, dx, dy) n[k] = (v - RING_PX(pc, dx, dy)) * sg;
+        RING_LIST(RING_DIFF)
+#undef RING_DIFF
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a2[k] = min(n[k], n[(k + 1) & 15]);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a4[k] = min(a2[k], a2[(k + 2) & 15]);
+        int best = -255;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            int a9 = min(min(a4[k], a4[(k + 4) & 15]), n[(k + 8) & 15]);
+            best = max(best, a9);
+        }
+        score[r][c] = (uint8_t)(best - 1);
     }
 #undef RING_LIST
 #undef RING_PX
     __syncthreads();
-    __shared__ int s_nmax;
-    __shared__ unsigned short s_max[DT_H * DT_W / 4];  // strict 3x3 maxima: at most one per 2x2 block
-    if (threadIdx.x == 0) s_nmax = 0;
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < DT_H * DT_W; idx += 256) {
-        int r = idx / DT_W, c = idx - r * DT_W;
-        int gy = y0 + r, gx = x0 + c;
-        int sc = score[r + 1][c + 1];
-        if (fb.dbg_score && s == 0 && gy < rows && gx < cols) fb.dbg_score[(size_t)gy * cols + gx] = (uint8_t)sc;
-        if (sc == 0) continue;
-        bool is_max = sc > score[r][c] && sc > score[r][c + 1] && sc > score[r][c + 2] && sc > score[r + 1][c] &&
-                      sc > score[r + 1][c + 2] && sc > score[r + 2][c] && sc > score[r + 2][c + 1] &&
-                      sc > score[r + 2][c + 2];
-        if (!is_max) continue;
-        int k = (gy / fc.det_cell_h) * fc.det_cols + (gx / fc.det_cell_w);
-        if (fb.det_occ[(size_t)s * fc.det_cells + k]) continue;
-        if (gx < 5 || gy < 5 || gx > cols - 6 || gy > rows - 6) continue;  // response 0: never a candidate
-        s_max[atomicAdd(&s_nmax, 1)] = (unsigned short)idx;
-    }
-    __syncthreads();
-    // Shi-Tomasi response over the 8x8 box, one warp per maximum (integer sums: order-free)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int e = warp; e < s_nmax; e += 8) {
-        const int idx = s_max[e];
+    for (int base = 0; base < DT_H * DT_W; base += 256) {
+        const int idx = base + threadIdx.x;
         const int r = idx / DT_W, c = idx - r * DT_W;
         const int gy = y0 + r, gx = x0 + c;
-        const int tr = r + DT_HALO, tc = c + DT_HALO;
-        int dXX = 0, dYY = 0, dXY = 0;
+        const int sc = score[r + 1][c + 1];
+        if (fb.dbg_score && s == 0 && gy < rows && gx < cols) fb.dbg_score[(size_t)gy * cols + gx] = (uint8_t)sc;
+        bool is_max = false;
+        if (sc != 0) {
+            is_max = sc > score[r][c] && sc > score[r][c + 1] && sc > score[r][c + 2] && sc > score[r + 1][c] &&
+                     sc > score[r + 1][c + 2] && sc > score[r + 2][c] && sc > score[r + 2][c + 1] && sc > score[r + 2][c + 2];
+            if (is_max) {
+                const int k = (gy / fc.det_cell_h) * fc.det_cols + (gx / fc.det_cell_w);
+                if (fb.det_occ[(size_t)s * fc.det_cells + k]) is_max = false;
+                if (gx < 5 || gy < 5 || gx > cols - 6 || gy > rows - 6) is_max = false;  // response 0: never a candidate
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, is_max);
+        int wbase = 0;
+        if (lane == 0 && bal) wbase = atomicAdd(&s_nmax, __popc(bal));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (is_max) s_max[wbase + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)idx;
+    }
+    __syncthreads();
+    // Shi-Tomasi response over the 8x8 box: 8 lanes per maximum, lane q sums row q - 4 of the box
+    const int nmax = s_nmax;
+    const int q = threadIdx.x & 7;
+    for (int base = 0; base < nmax; base += 32) {
+        const int e = base + (threadIdx.x >> 3);
+        int dXX = 0, dYY = 0, dXY = 0, gy = 0, gx = 0;
+        if (e < nmax) {
+            const int idx = s_max[e];
+            const int r = idx / DT_W, c = idx - r * DT_W;
+            gy = y0 + r;
+            gx = x0 + c;
+            const uint8_t *row = &tile[r + DT_HALO + q - 4][c + DT_X0 - 4];
+            int pm = row[-1], p0 = row[0];
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-            const int p = lane + 32 * h2;
-            const int yy = (p >> 3) - 4, xx = (p & 7) - 4;
-            int dx = (int)tile[tr + yy][tc + xx + 1] - (int)tile[tr + yy][tc + xx - 1];
-            int dy = (int)tile[tr + yy + 1][tc + xx] - (int)tile[tr + yy - 1][tc + xx];
-            dXX += dx * dx;
-            dYY += dy * dy;
-            dXY += dx * dy;
+            for (int xx = 0; xx < 8; ++xx) {
+                const int pp = row[xx + 1];
+                const int dx = pp - pm;
+                const int dy = (int)row[xx + DT_STRIDE] - (int)row[xx - DT_STRIDE];
+                dXX += dx * dx;
+                dYY += dy * dy;
+                dXY += dx * dy;
+                pm = p0;
+                p0 = pp;
+            }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = 1; o < 8; o <<= 1) {
             dXX += __shfl_xor_sync(0xffffffffu, dXX, o);
             dYY += __shfl_xor_sync(0xffffffffu, dYY, o);
             dXY += __shfl_xor_sync(0xffffffffu, dXY, o);
         }
-        if (lane == 0) {
+        if (q == 0 && e < nmax) {
             float fXX = (float)dXX / 128.0f, fYY = (float)dYY / 128.0f, fXY = (float)dXY / 128.0f;
             float trc = fXX + fYY;
             float d1 = fXX - fYY;
