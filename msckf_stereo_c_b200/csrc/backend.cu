@@ -2034,7 +2034,9 @@ __global__ void __launch_bounds__(BE_THREADS) be_scatter_kernel(BeConst bc, BeBu
 //  * a sweep stops as soon as its rows are used up: a reflector whose pivot row of R was empty
 //    moves one direction of the block's (<= 64-dimensional) row space into R and leaves the block
 //    orthogonal to it, so after nb such reflectors the block is zero and the remaining columns have
-//    nothing to do.  Folding the b-th block of a fresh triangle costs min(k, 64 (b + 1)) steps, not k.
+//    nothing to do.  Folding the b-th block of a fresh triangle costs about min(k, 64 (b + 1)) steps,
+//    not k.  The count only nominates the exit (near-dependent columns make it optimistic); it is taken
+//    when the block's remaining Frobenius norm is negligible, checked every 8 steps from then on.
 //
 // A fleet's step time is set by its slowest stream, and the row count m has a heavy tail (on the
 // synthetic fleet a lost-feature update stacks 40-800 rows, tools/fleet_nan_check.py prints the
@@ -2049,17 +2051,15 @@ __global__ void __launch_bounds__(BE_THREADS) be_scatter_kernel(BeConst bc, BeBu
 #define QR_THREADS 384  // 48 column quads = 192 column slots >= 6 * 31 + 1
 #define QR_COLS (QR_THREADS / QR_T * QR_CPT)
 #define QR_G 4
-#define QR_SPLIT_MIN 448
+#define QR_SPLIT_MIN 352
 #define QR_VS (QR_RPT + 2)  // chunk stride of the reflector buffer: the 8 lanes read 16-byte pieces in distinct banks
-// A column whose squared norm fell below this fraction of the block's largest column is rounding residue
-// of earlier annihilations: it gets no reflector (and does not count as a consumed row, see below).
-#define QR_RESIDUE 1e-22
+// A sweep may stop once what is left of its block is below this fraction of the block (squared Frobenius norms).
+#define QR_NEGLIGIBLE 1e-22
 
 struct QrShared {
     double vbuf[2][QR_T * QR_VS];
     double tau[2], w0[2];
-    double red[32];
-    double scale, floor2;
+    double red[QR_THREADS / 32];
     double diag[QR_COLS];
     int stop[2];
     int j0, nbe, nf;
@@ -2106,21 +2106,25 @@ __device__ __forceinline__ double qr_norm2(const double (&x)[QR_RPT]) {
     return qr_oct_sum(n0 + n1);
 }
 
-// largest squared column norm of the block held in x (all threads get it)
-__device__ __forceinline__ double qr_block_scale(const double (&x)[QR_CPT][QR_RPT], QrShared &sh) {
-    double v = fmax(fmax(qr_norm2(x[0]), qr_norm2(x[1])), fmax(qr_norm2(x[2]), qr_norm2(x[3])));
+// squared Frobenius norm of the H columns (c < k) of the block held in x (all threads get it; two barriers);
+// the residual column keeps whatever part of r the columns do not explain and is not part of the test
+__device__ __forceinline__ double qr_block_fro(const double (&x)[QR_CPT][QR_RPT], int c0, int k, QrShared &sh) {
+    double v = 0.0;
 #pragma unroll
-    for (int o = 16; o >= QR_T; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int i = 0; i < QR_CPT; ++i)
+        if (c0 + i < k) {
+#pragma unroll
+            for (int r = 0; r < QR_RPT; ++r) v = fma(x[i][r], x[i][r], v);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = v;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        double w = threadIdx.x < QR_THREADS / 32 ? sh.red[threadIdx.x] : 0.0;
+    double w = 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) w = fmax(w, __shfl_xor_sync(0xffffffffu, w, o));
-        if (threadIdx.x == 0) sh.scale = w;
-    }
+    for (int i = 0; i < QR_THREADS / 32; ++i) w += sh.red[i];
     __syncthreads();
-    return sh.scale;
+    return w;
 }
 
 // squared norm of column `which` (0..3) of the lane's four: a switch, so that x[][] stays in registers
@@ -2138,16 +2142,13 @@ __device__ __forceinline__ double qr_norm2_of(const double (&x)[QR_CPT][QR_RPT],
 // reflectors on empty pivot rows; sh.filled[] marks the pivot rows of R that hold a reflector result and
 // sh.diag[] mirrors the diagonal of R (the pivot the next reflector needs at once).
 __device__ __forceinline__ void qr_sweep(double (&x)[QR_CPT][QR_RPT], double *R, int ldr, int k, int kw, int cq, int q, int jb, QrShared &sh) {
-    const double sc = qr_block_scale(x, sh);
-    if (threadIdx.x == 0) {
-        sh.floor2 = fmax(1e-200, QR_RESIDUE * sc);
-        sh.nf = 0;
-    }
+    if (threadIdx.x == 0) sh.nf = 0;
+    const double f0 = qr_block_fro(x, QR_CPT * cq, k, sh);
+    int verify_in = 0;
     const int wc0 = (int)(threadIdx.x >> 5) * (32 / QR_T * QR_CPT), wc1 = wc0 + 32 / QR_T * QR_CPT - 1;  // this warp's columns
     const int c0 = QR_CPT * cq;
     double xn = 0.0;
     if (jb >= wc0 && jb <= wc1) xn = qr_norm2_of(x, jb & 3);
-    __syncthreads();
     double *Rc = R + (size_t)jb * ldr + c0;  // row j of R at this lane's columns
     const double4 *vs0 = reinterpret_cast<const double4 *>(&sh.vbuf[0][q * QR_VS]), *vs1 = reinterpret_cast<const double4 *>(&sh.vbuf[1][q * QR_VS]);
     for (int j = jb; j < k; ++j, Rc += ldr) {
@@ -2164,7 +2165,8 @@ __device__ __forceinline__ void qr_sweep(double (&x)[QR_CPT][QR_RPT], double *R,
             case 2: dst[0] = make_double4(x[2][0], x[2][1], x[2][2], x[2][3]); dst[1] = make_double4(x[2][4], x[2][5], x[2][6], x[2][7]); break;
             default: dst[0] = make_double4(x[3][0], x[3][1], x[3][2], x[3][3]); dst[1] = make_double4(x[3][4], x[3][5], x[3][6], x[3][7]); break;
             }
-            const bool gen = xn > sh.floor2;
+            // Once xn leaves the normal range the reflector scalars would overflow: no reflector.
+            const bool gen = xn > 1e-200;
             double t = 0.0, w0 = 0.0, beta = 0.0;
             if (gen) qr_reflector(sh.diag[j], xn, t, w0, beta);
             __syncwarp(0xffu << (threadIdx.x & 24));  // every lane has read the pivot before lane 0 replaces it
@@ -2217,7 +2219,14 @@ __device__ __forceinline__ void qr_sweep(double (&x)[QR_CPT][QR_RPT], double *R,
         }
         // the warp that owns the next reflector: squared norm of its (now final) column
         if (j + 1 >= wc0 && j + 1 <= wc1) xn = qr_norm2_of(x, (j + 1) & 3);
-        if (stop) break;
+        // The count says the block's rows are used up; near-dependent columns (each camera's 6 columns hold
+        // about two independent directions of one feature's rows) make it optimistic, so the exit is taken only
+        // when what is left of the block is negligible: dropping a remainder x perturbs H^T H by x^T x, the
+        // SQUARE of its size (1e-22 of the block's: below fp64 round-off of the information it joins).
+        if (stop && --verify_in <= 0) {
+            if (qr_block_fro(x, c0, k, sh) <= QR_NEGLIGIBLE * f0) break;
+            verify_in = 8;
+        }
     }
     __syncthreads();
 }

@@ -337,7 +337,7 @@ def test_op_ekf_update_rank_deficient_tail_group(eng, ob, synth):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("m_target", [150, 300, 700, 1200])
+@pytest.mark.parametrize("m_target", [150, 300, 360, 400, 440, 500, 700, 1200])
 def test_op_ekf_update_block_structured(eng, ob, synth, m_target):
     """Stacked Jacobian shaped like removeLostFeatures' (msckf_vio.cpp:937-1024): each feature contributes
     4M-3 rows that are non-zero only in the 6M columns of the camera states that observed it, so row
