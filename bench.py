@@ -186,14 +186,16 @@ def run_reference(args, rank):
     steps, warm = args.steps, args.warmup
     # bounded sample: every core runs one stream for `steps` frames at filter steady state
     prime = PRIME_FRAMES
+    from msckf_stereo_c_b200 import synth as _synth
+    _cfg = _synth.default_config(args.preset)
     t0 = time.time()
     value, res = cpu_leg(args.preset, procs, prime, warm, steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": 1e3 * procs / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"fleet: {procs} independent 752x480 stereo+IMU streams (one per host core), preset {args.preset} "
-                               f"(L=4, KLT 21x21, ~300 features, N=30), {prime} untimed priming frames per stream",
+        "config": {"workload": f"fleet: {procs} independent {_cfg.img_cols}x{_cfg.img_rows} stereo+IMU streams (one per host core), preset {args.preset} "
+                               f"({preset_text(_cfg)}), {prime} untimed priming frames per stream",
                    "streams": procs, "preset": args.preset},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
                          "sample": f"{procs} processes x 1 stream x {steps} frames after {prime}+{warm} untimed frames; oracle re-host of "
@@ -227,6 +229,12 @@ class Group:
     def push(self, k, base_ptr, device):
         self.tvec[:] = self.fleet.frame_time(k)
         self.e.push_stereo_batch(self.tvec, base_ptr, base_ptr + self.img, 2 * self.img, device=device)
+
+
+def preset_text(cfg):
+    """One line describing the preset actually run (the metric names the default, 752x480)."""
+    return (f"{cfg.img_cols}x{cfg.img_rows}, L={cfg.pyramid_levels}, KLT {cfg.klt_win}x{cfg.klt_win}, "
+            f"grid {cfg.grid_row}x{cfg.grid_col} x {cfg.grid_min_feature_num}..{cfg.grid_max_feature_num}, max_cam_state_size {cfg.max_cam_state_size}")
 
 
 def run_ours(args, rank, world, local_rank):
@@ -470,8 +478,8 @@ def run_ours(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"fleet (BASELINE.json config 4): {S} independent 752x480 stereo+IMU streams per GPU driven as {H} engine "
-                                   f"handles x {Sh} streams, preset {args.preset} (L=4, KLT 21x21, ~300 grid features, max_cam_state_size 30), "
+            "config": {"workload": f"fleet (BASELINE.json config {5 if args.preset == 'stress' else 4}): {S} independent {cfg.img_cols}x{cfg.img_rows} stereo+IMU "
+                                   f"streams per GPU driven as {H} engine handles x {Sh} streams, preset {args.preset} ({preset_text(cfg)}), "
                                    f"full track+EKF per frame, {PRIME_FRAMES} untimed priming frames",
                        "streams_per_gpu": S, "handles_per_gpu": H, "preset": args.preset, "features_stream0": n_feat,
                        "cam_states_stream0": st.n_cam_states, "ekf_updates_stream0": int(st.n_updates),
