@@ -578,16 +578,20 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
                 const uint8_t *pc = &tile[r + DT_HALO - 1][c + DT_X0 - 1];
                 const int v = pc[0];
                 const int lo = v - t, hi = v + t;  // darker ring pixel: p < lo (d = v - p > t); brighter: p > hi
-                unsigned dark = 0, bright = 0;
-                // sign bit of (p - lo) / (hi - p) shifted into the masks (bit order reversed: irrelevant on a ring)
-#define RING_TEST(k, dx, dy)                                             \
-    {                                                                    \
-        const int pk = RING_PX(pc, dx, dy);                              \
-        dark = __funnelshift_l((unsigned)(pk - lo), dark, 1);            \
-        bright = __funnelshift_l((unsigned)(hi - pk), bright, 1);        \
+                // Both tests of a ring pixel in one multiply-add: y = (p - lo) + 65536 (hi - p) has the sign of
+                // p - lo in bit 15 and the sign of hi - p in bit 31 (a borrow out of the low half only happens
+                // when p < lo, where hi - p > 2t >= 1 keeps the high half non-negative).  Bit 15 moves to bit k,
+                // bit 31 to bit 16 + k: the darker mask ends up in the low half of z, the brighter one in the high.
+                const unsigned cst = ((unsigned)hi << 16) - (unsigned)lo;
+                unsigned z = 0;
+#define RING_TEST(k, dx, dy)                                                                   \
+    {                                                                                          \
+        const unsigned y = (unsigned)RING_PX(pc, dx, dy) * 0xffff0001u + cst;                  \
+        z |= (y >> (15 - k)) & (0x00010001u << k);                                             \
     }
                 RING_LIST(RING_TEST)
 #undef RING_TEST
+                const unsigned dark = z & 0xffffu, bright = z >> 16;
                 pass = has_arc9(dark) ? 1 : (has_arc9(bright) ? 2 : 0);
             }
         }
@@ -630,20 +634,33 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
 #undef RING_LIST
 #undef RING_PX
     __syncthreads();
-    for (int base = 0; base < DT_H * DT_W; base += 256) {
-        const int idx = base + threadIdx.x;
-        const int r = idx / DT_W, c = idx - r * DT_W;
-        const int gy = y0 + r, gx = x0 + c;
-        const int sc = score[r + 1][c + 1];
-        if (fb.dbg_score && s == 0 && gy < rows && gx < cols) fb.dbg_score[(size_t)gy * cols + gx] = (uint8_t)sc;
+    if (fb.dbg_score && s == 0) {
+        for (int idx = threadIdx.x; idx < DT_H * DT_W; idx += 256) {
+            const int r = idx / DT_W, c = idx - r * DT_W;
+            if (y0 + r < rows && x0 + c < cols) fb.dbg_score[(size_t)(y0 + r) * cols + x0 + c] = score[r + 1][c + 1];
+        }
+    }
+    // strict 3x3 maxima among the pixels that have a score (the compacted list again: full warps)
+    for (int base = 0; base < nlist; base += 256) {
+        const int e = base + threadIdx.x;
         bool is_max = false;
-        if (sc != 0) {
-            is_max = sc > score[r][c] && sc > score[r][c + 1] && sc > score[r][c + 2] && sc > score[r + 1][c] &&
-                     sc > score[r + 1][c + 2] && sc > score[r + 2][c] && sc > score[r + 2][c + 1] && sc > score[r + 2][c + 2];
-            if (is_max) {
-                const int k = (gy / fc.det_cell_h) * fc.det_cols + (gx / fc.det_cell_w);
-                if (fb.det_occ[(size_t)s * fc.det_cells + k]) is_max = false;
-                if (gx < 5 || gy < 5 || gx > cols - 6 || gy > rows - 6) is_max = false;  // response 0: never a candidate
+        int idx = 0;
+        if (e < nlist) {
+            const int li = s_list[e] & 0x7fff;
+            const int r = li / DT_SW, c = li - r * DT_SW;  // score-window coordinates
+            if (r >= 1 && r <= DT_H && c >= 1 && c <= DT_W) {
+                const int sc = score[r][c];
+                const int gy = y0 + r - 1, gx = x0 + c - 1;
+                idx = (r - 1) * DT_W + (c - 1);
+                if (sc != 0) {
+                    is_max = sc > score[r - 1][c - 1] && sc > score[r - 1][c] && sc > score[r - 1][c + 1] && sc > score[r][c - 1] &&
+                             sc > score[r][c + 1] && sc > score[r + 1][c - 1] && sc > score[r + 1][c] && sc > score[r + 1][c + 1];
+                    if (is_max) {
+                        const int k = (gy / fc.det_cell_h) * fc.det_cols + (gx / fc.det_cell_w);
+                        if (fb.det_occ[(size_t)s * fc.det_cells + k]) is_max = false;
+                        if (gx < 5 || gy < 5 || gx > cols - 6 || gy > rows - 6) is_max = false;  // response 0: never a candidate
+                    }
+                }
             }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, is_max);
