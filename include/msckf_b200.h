@@ -69,7 +69,7 @@ typedef struct mskf_config {
     double  T_imu_body[16];
     /* back end (app_msckfvio.yaml) */
     double  frame_rate;
-    int32_t max_cam_state_size;
+    int32_t max_cam_state_size;   /* 5..31 (app_msckfvio.yaml: 20; BASELINE bench config: 30) */
     int32_t chi2_mode;
     double  position_std_threshold;
     double  rotation_threshold, translation_threshold, tracking_rate_threshold;

@@ -392,19 +392,22 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
             }
         }
         __syncwarp();
-        long long A11 = 0, A12 = 0, A22 = 0;
+        // A lane's partial sums fit 32 bits: |gx|, |gy|, |diff| <= 255 * 32 = 8160, so a column of win <= 29
+        // products stays below 29 * 8160^2 = 1.93e9 < 2^31 (one IMAD per term instead of a multiply and a
+        // 64-bit add); only the warp reduction needs 64 bits.
+        int a11i = 0, a12i = 0, a22i = 0;
         if (lane < win) {
 #pragma unroll
             for (int j = 0; j < win; ++j) {
                 const int gx = (int)T[(j + 1) * tw + lane + 2] - (int)T[(j + 1) * tw + lane];
                 const int gy = (int)T[(j + 2) * tw + lane + 1] - (int)T[j * tw + lane + 1];
                 Gr[j * win + lane] = make_short2((short)gx, (short)gy);
-                A11 += (long long)(gx * gx);
-                A12 += (long long)(gx * gy);
-                A22 += (long long)(gy * gy);
+                a11i += gx * gx;
+                a12i += gx * gy;
+                a22i += gy * gy;
             }
         }
-        A11 = warp_sum(A11); A12 = warp_sum(A12); A22 = warp_sum(A22);
+        long long A11 = warp_sum((long long)a11i), A12 = warp_sum((long long)a12i), A22 = warp_sum((long long)a22i);
         __syncwarp();
         const double a11 = (double)A11, a12 = (double)A12, a22 = (double)A22;
         const double m1 = a11 * a22, m2 = a12 * a12;
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
                     break;
                 }
                 const BilinW wb = bilin_weights(qx, qy);
-                long long b1 = 0, b2 = 0;
+                int b1i = 0, b2i = 0;
                 {
                     const int xc = min(max(wb.ix - half + lane, 0), cols - 1);
                     const int y0 = wb.iy - half;
@@ -445,8 +448,8 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
                                 const int val = (wb.w00 * px[j] + wb.w01 * nx[j] + wb.w10 * px[j + 1] + wb.w11 * nx[j + 1] + 256) >> 9;
                                 const int diff = val - (int)Trow[j * tw];
                                 const short2 g = Grow[j * win];
-                                b1 += (long long)(diff * (int)g.x);
-                                b2 += (long long)(diff * (int)g.y);
+                                b1i += diff * (int)g.x;
+                                b2i += diff * (int)g.y;
                             }
                         }
                     } else {
@@ -459,15 +462,15 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
                                 const int val = (wb.w00 * top + wb.w01 * rt + wb.w10 * bot + wb.w11 * rb + 256) >> 9;
                                 const int diff = val - (int)Trow[j * tw];
                                 const short2 g = Grow[j * win];
-                                b1 += (long long)(diff * (int)g.x);
-                                b2 += (long long)(diff * (int)g.y);
+                                b1i += diff * (int)g.x;
+                                b2i += diff * (int)g.y;
                             }
                             top = bot;
                             rt = rb;
                         }
                     }
                 }
-                b1 = warp_sum(b1); b2 = warp_sum(b2);
+                const long long b1 = warp_sum((long long)b1i), b2 = warp_sum((long long)b2i);
                 const double fb1 = (double)b1, fb2 = (double)b2;
                 const double dx = (a12 * fb2 - a22 * fb1) * Dinv * 2.0;
                 const double dy = (a12 * fb1 - a11 * fb2) * Dinv * 2.0;
