@@ -1290,21 +1290,39 @@ __device__ __forceinline__ void cta_gemm_tile_dmma(int M, int N, int K, int i0, 
     double acc[8][2];
 #pragma unroll
     for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = 0.0;
-    for (int k0 = 0; k0 < K; k0 += GKK) {
-        __syncthreads();
-        for (int e = tid; e < GT * GKK; e += BE_THREADS) {
+    // Software pipeline: the operands of chunk k0 + GKK travel from global memory to registers while the
+    // DMMAs of chunk k0 run (each thread stages GT * GKK / BE_THREADS = 4 elements of A and of B).
+    constexpr int PER = GT * GKK / BE_THREADS;
+    double ra[PER], rb[PER];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int e = tid + u * BE_THREADS;
             int i, l;
             if (A_KFAST) { i = e / GKK; l = e - i * GKK; } else { l = e / GT; i = e - l * GT; }
-            int gi = i0 + i, gl = k0 + l;
-            sm.a[l][i] = (gi < M && gl < K) ? fa(gi, gl) : 0.0;
+            const int gi = i0 + i, gl = k0 + l;
+            ra[u] = (gi < M && gl < K) ? fa(gi, gl) : 0.0;
+            int j, lb;
+            if (B_KFAST) { j = e / GKK; lb = e - j * GKK; } else { lb = e / GT; j = e - lb * GT; }
+            const int gj = j0 + j, glb = k0 + lb;
+            rb[u] = (gj < N && glb < K) ? fb(glb, gj) : 0.0;
         }
-        for (int e = tid; e < GT * GKK; e += BE_THREADS) {
-            int j, l;
-            if (B_KFAST) { j = e / GKK; l = e - j * GKK; } else { l = e / GT; j = e - l * GT; }
-            int gj = j0 + j, gl = k0 + l;
-            sm.b[l][j] = (gj < N && gl < K) ? fb(gl, gj) : 0.0;
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += GKK) {
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int e = tid + u * BE_THREADS;
+            int i, l;
+            if (A_KFAST) { i = e / GKK; l = e - i * GKK; } else { l = e / GT; i = e - l * GT; }
+            sm.a[l][i] = ra[u];
+            int j, lb;
+            if (B_KFAST) { j = e / GKK; lb = e - j * GKK; } else { lb = e / GT; j = e - lb * GT; }
+            sm.b[lb][j] = rb[u];
         }
         __syncthreads();
+        if (k0 + GKK < K) fetch(k0 + GKK);
 #pragma unroll
         for (int kk = 0; kk < GKK; kk += 4) {
             const double a = sm.a[kk + t4][warp * 8 + g];
