@@ -2060,7 +2060,11 @@ __global__ void __launch_bounds__(BE_THREADS) be_scatter_kernel(BeConst bc, BeBu
 // synthetic fleet a lost-feature update stacks 40-800 rows, tools/fleet_nan_check.py prints the
 // distribution; the reference's cap is 1500).  Streams with m > QR_SPLIT_MIN split their rows over
 // QR_G = 4 CTAs (TSQR): each folds its share into its own triangle, then a two-level tree of
-// be_qr_combine_kernel launches folds the triangles pairwise.
+// be_qr_combine_kernel launches folds the triangles pairwise.  The split pays for one stream from about
+// 330 rows on (the combine costs ~2 x 330 column steps at k = 174), but every split stream also puts six
+// more CTAs on the machine: on the 256-stream fleet the throughput peaks with the threshold at 640 rows
+// (352: 43.6k frames/s, 512: 44.7k, 640: 45.0k, 768: 44.8k, 1024: 44.3k), where the slowest stream's
+// chain is 1.6 ms instead of 1.2 ms.
 // ======================================================================================
 #define QR_T 8     // lanes per column pair
 #define QR_RPT 8   // rows per lane
@@ -2069,7 +2073,7 @@ __global__ void __launch_bounds__(BE_THREADS) be_scatter_kernel(BeConst bc, BeBu
 #define QR_THREADS 384  // 48 column quads = 192 column slots >= 6 * 31 + 1
 #define QR_COLS (QR_THREADS / QR_T * QR_CPT)
 #define QR_G 4
-#define QR_SPLIT_MIN 352
+#define QR_SPLIT_MIN 640
 #define QR_VS (QR_RPT + 2)  // chunk stride of the reflector buffer: the 8 lanes read 16-byte pieces in distinct banks
 // A sweep may stop once what is left of its block is below this fraction of the block (squared Frobenius norms).
 #define QR_NEGLIGIBLE 1e-22

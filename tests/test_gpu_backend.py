@@ -319,11 +319,11 @@ def test_reset_callback(eng, ob, synth):
 
 
 def test_op_ekf_update_rank_deficient_tail_group(eng, ob, synth):
-    """m = 385 rows splits into four row groups for the QR compression and the last group holds a single
-    row: after its one reflector every further column of that group is rounding residue shrinking towards
-    the denormal range (regression test: the reflector scalars must not overflow there)."""
+    """m = 769 rows splits into four row groups of 256, 256, 256 and 1 for the QR compression: after the one
+    reflector of the last group every further column of it is rounding residue shrinking towards the
+    denormal range (regression test: the reflector scalars must not overflow there)."""
     rng = np.random.default_rng(7)
-    n_cam, m = 20, 385
+    n_cam, m = 20, 769
     n = 21 + 6 * n_cam
     P = _spd(rng, n)
     H = np.zeros((m, n))
