@@ -1395,7 +1395,7 @@ __device__ void packed_cholesky(double *G, int lo, int hi) {
 // G / S live in shared memory as a packed lower triangle; H' is written to the scratch only
 // for features that pass the gate.
 // ======================================================================================
-__global__ void __launch_bounds__(BE_THREADS) be_feature_jac_kernel(BeConst bc, BeBuf bb, int phase, int maxM) {
+__global__ void __launch_bounds__(BE_THREADS, 2) be_feature_jac_kernel(BeConst bc, BeBuf bb, int phase, int maxM) {
     const int s = blockIdx.y;
     const BeStep sp = bb.step[s];
     if (!sp.active) return;
