@@ -1713,7 +1713,7 @@ __global__ void __launch_bounds__(BE_THREADS, 2) be_feature_jac_kernel(BeConst b
 // covariance block staged once per CTA.
 // ======================================================================================
 #define JS_WARPS 8
-__global__ void __launch_bounds__(JS_WARPS * 32) be_feature_jac_prune_kernel(BeConst bc, BeBuf bb) {
+__global__ void __launch_bounds__(JS_WARPS * 32, 2) be_feature_jac_prune_kernel(BeConst bc, BeBuf bb) {
     const int s = blockIdx.y;
     const BeStep sp = bb.step[s];
     if (!sp.active) return;
