@@ -6,7 +6,8 @@ stopped a few columns early (3e-7 at one update of the ref preset).
     python tools/upd_check.py [preset=bench] [seed=1] [frames=56]      (GPU)
 """
 import sys, numpy as np
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from msckf_stereo_c_b200 import engine as eng, synth, abi
 from oracle import binding as ob
 cfg = abi.Config.from_buffer_copy(bytes(synth.default_config(sys.argv[1] if len(sys.argv) > 1 else "bench")))
