@@ -135,7 +135,8 @@ class ClockSampler:
 # used here only as the measured CPU baseline)
 # ------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    seed, preset, prime, warm, steps, frames = args
+    seed, preset, prime, warm, steps, frames = args[:6]
+    imu_rows = args[6] if len(args) > 6 else None  # per frame [rows][7] (t, w, a): the rows the engine was fed
     from msckf_stereo_c_b200 import synth
     from oracle import binding as ob
 
@@ -148,12 +149,15 @@ def _cpu_worker(args):
     for k in range(prime + warm + steps):
         t_img = s.frame_time(k)
         rows = []
-        while True:
-            t, w, a = s.imu(j)
-            j += 1
-            rows.append((t, w, a))
-            if not (t <= t_img):
-                break
+        if imu_rows is not None:
+            rows = [(r[0], r[1:4].copy(), r[4:7].copy()) for r in imu_rows[k]]
+        else:
+            while True:
+                t, w, a = s.imu(j)
+                j += 1
+                rows.append((t, w, a))
+                if not (t <= t_img):
+                    break
         im0, im1 = frames[k]
         t0 = time.perf_counter()
         for t, w, a in rows:
@@ -163,12 +167,17 @@ def _cpu_worker(args):
         if k >= prime + warm:
             t_timed += time.perf_counter() - t0
     st = o.state()
-    return t_timed, st.n_cam_states, st.n_updates
+    snap = None
+    if imu_rows is not None:  # final state, for the parity spot-check of the timed fleet's stream 0
+        _, feats, n_pub = o.features()
+        snap = {"T_b_w": np.array(st.T_b_w[:]), "P": o.cov(), "features": feats.tobytes(), "n_published": n_pub,
+                "n_cam_states": st.n_cam_states, "n_updates": int(st.n_updates)}
+    return t_timed, st.n_cam_states, st.n_updates, snap
 
 
-def cpu_leg(preset, n_procs, prime, warm, steps, seeds=None):
+def cpu_leg(preset, n_procs, prime, warm, steps, seeds=None, frames=None, imu_rows=None):
     seeds = seeds or list(range(n_procs))
-    jobs = [(sd, preset, prime, warm, steps, None) for sd in seeds]
+    jobs = [(sd, preset, prime, warm, steps, frames, imu_rows) for sd in seeds]
     if n_procs == 1:
         res = [_cpu_worker(jobs[0])]
     else:
@@ -220,10 +229,13 @@ class Group:
         self.e = engine.Engine(cfg, self.S, device=local_rank, cuda_stream=self.stream.cuda_stream)
         self.tvec = np.zeros(self.S)
         self.img = cfg.img_rows * cfg.img_cols
+        self.rec = None  # list: the IMU rows of this group's first stream, frame by frame (parity spot-check)
 
     def feed_imu(self, k):
         rows = self.fleet.imu_rows_for_frame(k)
         self.e.push_imu_batch(rows)
+        if self.rec is not None:
+            self.rec.append(rows[0].copy())
         return rows.nbytes
 
     def push(self, k, base_ptr, device):
@@ -284,6 +296,16 @@ def run_ours(args, rank, world, local_rank):
                 groups[0].stream.wait_event(done)
         ev.record(groups[0].stream)
 
+    KH = 3  # steps of the host-enqueue measurement
+    n_dev = W + K + KH
+    n_e2e = W + K + 1  # the upload of frame i+1 is issued while frame i computes
+    n_total = PRIME_FRAMES + n_dev + W + K  # frames every stream steps through in this run
+    # rank 0 keeps every input of stream 0 (images as the engine saw them, IMU rows) so that the CPU oracle,
+    # which runs afterwards for cpu_baseline, replays exactly this stream and its final state can be compared
+    host0 = None
+    if rank == 0 and not args.no_check:
+        host0 = torch.empty((n_total, 2, img), dtype=torch.uint8).pin_memory()
+        groups[0].rec = []
     # ---- priming (untimed): frames rendered on the fly
     scratch = torch.empty((S, 2, img), dtype=torch.uint8, device=dev)
     k = 0
@@ -291,14 +313,14 @@ def run_ours(args, rank, world, local_rank):
         for h, g in enumerate(groups):
             g.feed_imu(k)
             g.fleet.render_device(k, scratch[h * Sh:(h + 1) * Sh], g.stream.cuda_stream)
+            if h == 0 and host0 is not None:
+                with torch.cuda.stream(g.stream):
+                    host0[k].copy_(scratch[0], non_blocking=True)
             g.push(k, slab(scratch, h), True)
             g.e.step()
         k += 1
     sync_all()
     # ---- pre-render the timed frames: device-resident set for `value`, pinned host set for `e2e`
-    KH = 3  # steps of the host-enqueue measurement
-    n_dev = W + K + KH
-    n_e2e = W + K + 1  # the upload of frame i+1 is issued while frame i computes
     frames_dev = torch.empty((n_dev, S, 2, img), dtype=torch.uint8, device=dev)
     frames_host = torch.empty((n_e2e, S, 2, img), dtype=torch.uint8).pin_memory()
     for h, g in enumerate(groups):
@@ -309,6 +331,12 @@ def run_ours(args, rank, world, local_rank):
                 g.fleet.render_device(k + n_dev + i, scratch[h * Sh:(h + 1) * Sh], g.stream.cuda_stream)
                 frames_host[i, h * Sh:(h + 1) * Sh].copy_(scratch[h * Sh:(h + 1) * Sh], non_blocking=True)
     torch.cuda.synchronize()
+    if host0 is not None:
+        for i in range(n_dev):
+            host0[PRIME_FRAMES + i].copy_(frames_dev[i, 0])
+        for i in range(W + K):
+            host0[PRIME_FRAMES + n_dev + i].copy_(frames_host[i, 0])
+        torch.cuda.synchronize()
 
     # ---- leg 1: device-resident inputs ("value")
     def step_dev(i, kk):
@@ -394,6 +422,12 @@ def run_ours(args, rank, world, local_rank):
     st = groups[0].e.state(0)
     n_feat = len(groups[0].e.grid(0))
     assert all(np.isfinite(p).all() for p in poses)
+    gpu_snap = None
+    if host0 is not None:
+        _, feats, n_pub = groups[0].e.features(0)
+        gpu_snap = {"T_b_w": np.array(st.T_b_w[:]), "P": groups[0].e.cov(0), "features": feats.tobytes(), "n_published": n_pub,
+                    "n_cam_states": st.n_cam_states, "n_updates": int(st.n_updates)}
+        imu0 = groups[0].rec
     for g in groups:
         g.e.close()
     del frames_host
@@ -471,10 +505,34 @@ def run_ours(args, rank, world, local_rank):
                         "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": traffic,
                         "peak_source": peak_src if top["bound"] == "hbm" else "cuBLAS DGEMM 4096^3 measured in this run (fp64 pipe incl. DMMA; "
                         "MEASURED_PEAKS.json has no fp64 figure)", "share_of_step": top["share"]}
-        # CPU baseline: the oracle on one host core, a bounded sample of the same workload
-        cpu_steps = args.cpu_frames
+        # CPU baseline: the oracle on one host core, a bounded sample of the same workload.  With the spot-check
+        # on it replays stream 0 of the timed fleet (same images, same IMU rows) from frame 0 and is timed on
+        # its last frames; its final state is then compared with the engine's.
         t0 = time.time()
-        cpu_value, _ = cpu_leg(args.preset, 1, PRIME_FRAMES, 2, cpu_steps)
+        parity = None
+        if gpu_snap is not None:
+            cpu_steps = min(args.cpu_frames, n_total - PRIME_FRAMES)
+            fr = [(host0[i, 0].numpy().reshape(cfg.img_rows, cfg.img_cols), host0[i, 1].numpy().reshape(cfg.img_rows, cfg.img_cols))
+                  for i in range(n_total)]
+            cpu_value, res = cpu_leg(args.preset, 1, n_total - cpu_steps, 0, cpu_steps, seeds=[seeds[0]], frames=fr, imu_rows=imu0)
+            osnap = res[0][3]
+            dT = float(np.abs(osnap["T_b_w"] - gpu_snap["T_b_w"]).max())
+            same_shape = osnap["P"].shape == gpu_snap["P"].shape
+            dP = float(np.abs(osnap["P"] - gpu_snap["P"]).max() / np.abs(osnap["P"]).max()) if same_shape else float("inf")
+            parity = {"stream": 0, "frames": n_total, "features_identical": osnap["features"] == gpu_snap["features"],
+                      "n_published": [osnap["n_published"], gpu_snap["n_published"]],
+                      "cam_states": [osnap["n_cam_states"], gpu_snap["n_cam_states"]],
+                      "ekf_updates": [osnap["n_updates"], gpu_snap["n_updates"]], "pose_abs_dev": dT, "cov_rel_dev": dP,
+                      "bar": "CameraMeasurement identical; pose and covariance within 1e-8 of the CPU oracle after the whole run "
+                             "(1e-9 per update plus the reference's own one-ulp sensitivity, tests/test_gpu_backend.py)"}
+            parity["ok"] = bool(parity["features_identical"] and osnap["n_cam_states"] == gpu_snap["n_cam_states"]
+                                and osnap["n_updates"] == gpu_snap["n_updates"] and dT <= 1e-8 and dP <= 1e-8)
+            sample = (f"stream 0 of the timed fleet replayed from frame 0 ({n_total} frames, the engine's own images and IMU rows), "
+                      f"timed on its last {cpu_steps} frames")
+        else:
+            cpu_steps = args.cpu_frames
+            cpu_value, _ = cpu_leg(args.preset, 1, PRIME_FRAMES, 2, cpu_steps)
+            sample = f"1 stream x {cpu_steps} frames after {PRIME_FRAMES}+2 untimed frames"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -493,13 +551,16 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roofline,
             "kernels": per_kernel,
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": f"1 stream x {cpu_steps} frames after {PRIME_FRAMES}+2 untimed frames, same preset; oracle re-host of "
-                                       "run_euroc_single_thread (reference not buildable here); rendering excluded",
+                             "sample": sample + ", same preset; oracle re-host of run_euroc_single_thread (reference not "
+                                       "buildable here); rendering excluded",
                              "wall_s": time.time() - t0},
             "wall_ms_per_step": wall_max / K,
             "host_enqueue_ms_per_step": host_ms,
+            "parity_check": parity,
         }
         print(json.dumps(line), flush=True)
+        if parity is not None and not parity["ok"]:
+            raise SystemExit("bench.py: stream 0 of the timed fleet does not match the CPU oracle: " + json.dumps(parity))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -515,6 +576,7 @@ def main():
     ap.add_argument("--handles", type=int, default=4, help="engine handles per GPU (the streams are split evenly)")
     ap.add_argument("--preset", default="bench")
     ap.add_argument("--cpu-frames", type=int, default=40, help="frames of the 1-core CPU baseline sample")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle spot-check of stream 0 of the timed fleet")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -158,6 +158,14 @@ int mskf_set_cuda_stream(mskf_handle *h, void *cuda_stream);
 /* Replaces: System::imu_callback (system.cpp:45-48) -> ImageProcessor::imuCallback
  * (image_processor.cpp:205-211) + MsckfVio::imuCallback (msckf_vio.cpp:190-207). */
 int mskf_push_imu(mskf_handle *h, int stream, double t, const double w[3], const double a[3]);
+/* One half only, for callers that drive the two classes separately as the reference allows:
+ * MSKF_IMU_FRONTEND = ImageProcessor::imuCallback (image_processor.cpp:205-211: buffered for
+ * integrateImuData, ignored before the first image), MSKF_IMU_BACKEND = MsckfVio::imuCallback
+ * (msckf_vio.cpp:190-207: buffered for batchImuProcessing; the 200th sample initialises gravity and the
+ * gyro bias, :198-204).  mskf_push_imu is both. */
+#define MSKF_IMU_FRONTEND 1
+#define MSKF_IMU_BACKEND 2
+int mskf_push_imu_to(mskf_handle *h, int stream, int halves, double t, const double w[3], const double a[3]);
 
 /* Stage one stereo pair for `stream` from HOST memory (copied before return; the caller
  * may free its buffers, as with the by-value copy at image_processor.cpp:144-145). */
@@ -194,6 +202,12 @@ int mskf_backend_step_features(mskf_handle *h, int stream, double t, const mskf_
  * message of the last front-end step for `stream`; in compat_stale_features mode the
  * message carries the stale tail exactly as the reference's never-cleared vector does. */
 int mskf_get_features(mskf_handle *h, int stream, mskf_feature *out, int cap, int *n, double *t);
+/* The same message without materialising its value-initialised tail: entries [0, *n_head) are every entry
+ * that is not {id 0, zeros} (this frame's measurements followed by stale leftovers of longer earlier
+ * frames); *n_total is the length of the reference's vector, which grows by the frame's feature count every
+ * frame (image_processor.cpp:1157-1164) and so needs 64 bits and O(run length) memory if copied out whole. */
+int mskf_get_features_head(mskf_handle *h, int stream, mskf_feature *out, int cap, int *n_head,
+                           long long *n_total, double *t);
 int mskf_get_tracking_info(mskf_handle *h, int stream, mskf_tracking_info *out);
 /* The front end's grid after the step (what became prev_features_ptr), publish order. */
 int mskf_get_grid(mskf_handle *h, int stream, mskf_grid_feature *out, int cap, int *n);
@@ -230,6 +244,17 @@ int mskf_op_klt(mskf_handle *h, const uint8_t *img_a, const uint8_t *img_b, int 
  * n x n; observation noise comes from the configuration.  Outputs delta_x (n) and the posterior P. */
 int mskf_op_ekf_update(mskf_handle *h, int n_cam, int m, const double *H, const double *r, const double *P,
                        double *out_delta_x, double *out_P);
+
+/* Feature::checkMotion + Feature::initializePosition (feature.hpp:257-287, 289-450) as a stand-alone
+ * operator: n_cam camera states in ascending state id (orientation JPL [x y z w], position), n_feat
+ * features, each observed by the camera states whose bit is set in obs_mask[f]; obs is
+ * [n_feat][n_cam][4] = (u0, v0, u1, v1), normalised coordinates.  out_ok[f] = 1 iff checkMotion passed
+ * and initializePosition returned true; out_position[f] is what initializePosition leaves in
+ * Feature::position (written whenever it ran, valid or not; 0 otherwise).  The arithmetic and the
+ * summation order are the reference's, so results are comparable bit for bit. */
+int mskf_op_triangulate(mskf_handle *h, int n_cam, const double *cam_orientation, const double *cam_position,
+                        int n_feat, const unsigned *obs_mask, const double *obs, double *out_position,
+                        int *out_ok);
 
 /* ---- instrumentation (bench.py / tests; no reference counterpart) ------------------------ */
 /* Kernels launched by this handle so far. */

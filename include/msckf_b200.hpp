@@ -102,21 +102,27 @@ public:
         e_->check(mskf_push_stereo(e_->handle(), s_, cam0_img.time_stamp, cam0_img.data, cam1_img.data, cam0_img.rows,
                                    cam0_img.cols, cam0_img.stride ? cam0_img.stride : cam0_img.cols));
     }
+    // image_processor.cpp:205-211: the front end's own IMU buffer only (System::imu_callback feeds both halves)
     void imuCallback(const ImuConstPtr &msg) {
-        e_->check(mskf_push_imu(e_->handle(), s_, msg->time_stamp, msg->angular_velocity, msg->linear_acceleration));
+        e_->check(mskf_push_imu_to(e_->handle(), s_, MSKF_IMU_FRONTEND, msg->time_stamp, msg->angular_velocity,
+                                   msg->linear_acceleration));
     }
-    // copies the device-side message into feature_msg_ptr_ (incl. the never-cleared tail)
+    // Copies the device-side message into feature_msg_ptr_.  Like the reference's vector it is never cleared
+    // (SURVEY F4): it grows to the reference's length, but only the head that can hold measurements is fetched
+    // and rewritten each frame - the tail beyond it is value-initialised once, when the vector grows.
     void fetchFeatures() {
-        int n = 0;
+        int n_head = 0;
+        long long n_total = 0;
         double t = 0;
-        e_->check(mskf_get_features(e_->handle(), s_, nullptr, 0, &n, &t));
-        std::vector<mskf_feature> buf(n);
-        if (n) e_->check(mskf_get_features(e_->handle(), s_, buf.data(), n, &n, &t));
+        e_->check(mskf_get_features_head(e_->handle(), s_, nullptr, 0, &n_head, &n_total, &t));
+        buf_.resize(n_head);
+        if (n_head) e_->check(mskf_get_features_head(e_->handle(), s_, buf_.data(), n_head, &n_head, &n_total, &t));
         feature_msg_ptr_->time_stamp = t;
-        feature_msg_ptr_->features.resize(n);
-        for (int i = 0; i < n; ++i) {
-            FeatureMeasurement &f = feature_msg_ptr_->features[i];
-            f.id = buf[i].id; f.u0 = buf[i].u0; f.v0 = buf[i].v0; f.u1 = buf[i].u1; f.v1 = buf[i].v1;
+        std::vector<FeatureMeasurement> &v = feature_msg_ptr_->features;
+        if ((long long)v.size() != n_total) v.resize((size_t)n_total);  // shrinks only in fixed mode (fresh message per frame)
+        for (int i = 0; i < n_head; ++i) {
+            FeatureMeasurement &f = v[i];
+            f.id = buf_[i].id; f.u0 = buf_[i].u0; f.v0 = buf_[i].v0; f.u1 = buf_[i].u1; f.v1 = buf_[i].v1;
         }
     }
     TrackingInfo trackingInfo() const {
@@ -129,6 +135,7 @@ public:
 private:
     EnginePtr e_;
     int s_;
+    std::vector<mskf_feature> buf_;
 };
 
 class MsckfVio {  // cg::MsckfVio, msckf_vio.h:39-80
@@ -139,9 +146,12 @@ public:
         e_->check(mskf_reset(e_->handle(), s_));
         return true;
     }
-    // The IMU buffers of both halves are fed by ImageProcessor::imuCallback / System::imu_callback
-    // (one mskf_push_imu serves image_processor.cpp:205-211 and msckf_vio.cpp:190-207).
-    void imuCallback(const ImuConstPtr &) {}
+    // msckf_vio.cpp:190-207: the filter's IMU buffer; the 200th sample initialises gravity and the gyro bias.
+    // A caller that drives MsckfVio alone (imuCallback + featureCallback(msg)) needs nothing else.
+    void imuCallback(const ImuConstPtr &msg) {
+        e_->check(mskf_push_imu_to(e_->handle(), s_, MSKF_IMU_BACKEND, msg->time_stamp, msg->angular_velocity,
+                                   msg->linear_acceleration));
+    }
     // The device-resident message of the front end is consumed directly ...
     void featureCallback() {
         e_->backend_step();
@@ -203,7 +213,10 @@ public:
     }
     void backend_callback() {
         msckfvio_ptr_->featureCallback();
-        path_to_draw_ = msckfvio_ptr_->get_path();
+        // system.cpp:52 copies the whole path every frame (O(frames^2) over a run); only the new poses are appended here
+        const std::vector<std::pair<double, Mat4>> &p = msckfvio_ptr_->get_path();
+        if (p.size() < path_to_draw_.size()) path_to_draw_.clear();
+        path_to_draw_.insert(path_to_draw_.end(), p.begin() + path_to_draw_.size(), p.end());
     }
     std::shared_ptr<ImageProcessor> imgproc_ptr_;
     std::shared_ptr<MsckfVio> msckfvio_ptr_;

@@ -40,6 +40,7 @@
 //   be_prune_finish_kernel   pruneCamStateBuffer :1161-1181
 //   be_finish_kernel         publish :1238-1254, onlineReset :1186-1236
 #include <math.h>
+#include <unordered_set>
 #include <stddef.h>
 #include <string.h>
 
@@ -739,10 +740,16 @@ __global__ void __launch_bounds__(BE_THREADS) be_add_obs_kernel(BeConst bc, BeBu
         unsigned id = i < n_real ? ent[i].id : 0u;
         unsigned key = id + 1u;
         unsigned c = hash_u32(id) & hmask;
-        while (true) {
+        int probes = 0;
+        for (; probes < bc.HASH; ++probes) {  // bounded: a full table must not spin (be_step also rejects such messages)
             unsigned old = atomicCAS(&h_key[c], 0u, key);
             if (old == 0u || old == key) break;
             c = (c + 1u) & hmask;
+        }
+        if (probes == bc.HASH) {
+            e_cell[i] = -1;  // no cell: the entry is dropped and counted as overflow
+            s_over = 1;
+            continue;
         }
         e_cell[i] = (int)c;
         if (h_slot[c] < 0) atomicMin(&h_owner[c], i);
@@ -753,7 +760,7 @@ __global__ void __launch_bounds__(BE_THREADS) be_add_obs_kernel(BeConst bc, BeBu
     for (int start = 0; start < n_ent; start += BE_THREADS) {
         int i = start + threadIdx.x;
         int own = 0, c = 0;
-        if (i < n_ent) {
+        if (i < n_ent && e_cell[i] >= 0) {
             c = e_cell[i];
             own = (h_slot[c] < 0 && h_owner[c] == i) ? 1 : 0;
         }
@@ -781,13 +788,13 @@ __global__ void __launch_bounds__(BE_THREADS) be_add_obs_kernel(BeConst bc, BeBu
         if (h_slot[c] < 0 && h_owner[c] < 0) h_slot[c] = -1 - h_owner[c];
     __syncthreads();
     for (int i = threadIdx.x; i < n_ent; i += BE_THREADS) {
-        int slot = h_slot[e_cell[i]];
+        int slot = e_cell[i] >= 0 ? h_slot[e_cell[i]] : -1;
         if (slot >= 0) atomicMax(&f_last[slot], i);
     }
     __syncthreads();
     const unsigned curbit = 1u << st.cur_slot;
     for (int i = threadIdx.x; i < n_ent; i += BE_THREADS) {
-        int slot = h_slot[e_cell[i]];
+        int slot = e_cell[i] >= 0 ? h_slot[e_cell[i]] : -1;
         if (slot < 0 || f_last[slot] != i) continue;
         double *o = bb.f_obs + (((size_t)s * bc.MF + slot) * bc.NS + st.cur_slot) * 4;
         if (i < n_real) {
@@ -925,89 +932,175 @@ __global__ void __launch_bounds__(BE_THREADS) be_select_kernel(BeConst bc, BeBuf
 }
 
 // ======================================================================================
-// Feature::checkMotion + initializePosition.  One warp per listed feature: lane l keeps the
-// poses (relative to the first observing camera) of stereo views l and l + 32 in registers;
-// cost / normal-equation sums are warp reductions; all lanes run the same LM control flow.
+// Feature::checkMotion + initializePosition (feature.hpp:257-450).  One warp per listed
+// feature: lane l keeps the poses (relative to the first observing camera) of stereo views l
+// and l + 32 in registers; all lanes run the same LM control flow.
+//
+// The LM step is accepted iff new_cost < total_cost (feature.hpp:417), and at convergence
+// that comparison is decided by the last bits of a 2M-term sum, so this kernel reproduces the
+// reference's arithmetic exactly: every operation is a separately rounded IEEE fp64 operation
+// (type `sd`: __dadd_rn / __dmul_rn / __ddiv_rn / __dsqrt_rn are never contracted into FMAs;
+// the rest of this file is compiled with contraction on), in the expression order of
+// feature.hpp / oracle/backend.h, and the cost and normal-equation sums run over the views in
+// the reference's sequential order (per-view terms go through shared memory; one lane per
+// matrix entry adds them up in view order).  Given the same camera states and observations the
+// triangulated position equals the oracle's bit for bit (tests/test_gpu_backend.py).
 // ======================================================================================
-struct Pose { double R[9], t[3]; };
+struct sd {
+    double v;
+    __device__ __forceinline__ sd() {}
+    __device__ __forceinline__ sd(double x) : v(x) {}
+};
+__device__ __forceinline__ sd operator+(sd a, sd b) { return sd(__dadd_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator-(sd a, sd b) { return sd(__dsub_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator*(sd a, sd b) { return sd(__dmul_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator/(sd a, sd b) { return sd(__ddiv_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator-(sd a) { return sd(-a.v); }
+__device__ __forceinline__ sd ssqrt(sd a) { return sd(__dsqrt_rn(a.v)); }
 
+struct Pose { sd R[9], t[3]; };
+
+// oracle/linalg.h operator*(M3, M3): s = 0; s += a(i,k) b(k,j)
+__device__ __forceinline__ void s_m3mul(const sd *a, const sd *b, sd *c) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) c[i * 3 + j] = ((sd(0.0) + a[i * 3] * b[j]) + a[i * 3 + 1] * b[3 + j]) + a[i * 3 + 2] * b[6 + j];
+}
+// operator*(M3, V3)
+__device__ __forceinline__ void s_m3v(const sd *a, const sd *x, sd *y) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) y[i] = (a[i * 3] * x[0] + a[i * 3 + 1] * x[1]) + a[i * 3 + 2] * x[2];
+}
+// quat_to_rot(q).t(): (2w^2-1) I - 2w [q]x + 2 q q^T, element by element as oracle/kin.h, transposed
+__device__ __forceinline__ void s_quat_to_rot_t(const double q[4], sd Rt[9]) {
+    const sd w = q[3];
+    const sd a = sd(2.0) * w * w - sd(1.0), b = sd(2.0) * w;
+    const double K[9] = {0.0, -q[2], q[1], q[2], 0.0, -q[0], -q[1], q[0], 0.0};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            sd e = (sd(i == j ? 1.0 : 0.0) * a - sd(K[i * 3 + j]) * b) + (sd(q[i]) * sd(q[j])) * sd(2.0);
+            Rt[j * 3 + i] = e;
+        }
+}
+// SE3::inv(): R^T, -(R^T t)
+__device__ __forceinline__ void s_pose_inv(const Pose &p, Pose &o) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o.R[i * 3 + j] = p.R[j * 3 + i];
+    sd tt[3];
+    s_m3v(o.R, p.t, tt);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o.t[i] = -tt[i];
+}
+// operator*(SE3, SE3): (a.R b.R, a.R b.t + a.t)
+__device__ __forceinline__ void s_pose_mul(const Pose &a, const Pose &b, Pose &o) {
+    s_m3mul(a.R, b.R, o.R);
+    sd tt[3];
+    s_m3v(a.R, b.t, tt);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o.t[i] = tt[i] + a.t[i];
+}
 __device__ __forceinline__ void cam_pose_world(const BeCam &c, int cam1, const BeConst &bc, Pose &o) {
     // cam0_pose = (R(q)^T, p); cam1_pose = cam0_pose * T_cam0_cam1.inv()  (feature.hpp:307-318)
-    double Rwc[9];
-    quat_to_rot(c.q, Rwc);
-    double R0[9];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) R0[i * 3 + j] = Rwc[j * 3 + i];
+    Pose p0;
+    s_quat_to_rot_t(c.q, p0.R);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p0.t[i] = c.p[i];
     if (!cam1) {
-        for (int i = 0; i < 9; ++i) o.R[i] = R0[i];
-        for (int i = 0; i < 3; ++i) o.t[i] = c.p[i];
+        o = p0;
     } else {
-        double Ri[9], ti[3], tt[3];
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) Ri[i * 3 + j] = bc.R01[j * 3 + i];
-        m3v(Ri, bc.t01, tt);
-        for (int i = 0; i < 3; ++i) ti[i] = -tt[i];
-        m3mul(R0, Ri, o.R);
-        m3v(R0, ti, tt);
-        for (int i = 0; i < 3; ++i) o.t[i] = tt[i] + c.p[i];
+        Pose T01, Ti;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) T01.R[i] = bc.R01[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) T01.t[i] = bc.t01[i];
+        s_pose_inv(T01, Ti);
+        s_pose_mul(p0, Ti, o);
     }
 }
 __device__ __forceinline__ void pose_rel(const Pose &pose, const Pose &Tc0w, Pose &o) {  // pose.inv() * T_c0_w
-    double Ri[9], ti[3], tt[3];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) Ri[i * 3 + j] = pose.R[j * 3 + i];
-    m3v(Ri, pose.t, tt);
-    for (int i = 0; i < 3; ++i) ti[i] = -tt[i];
-    m3mul(Ri, Tc0w.R, o.R);
-    m3v(Ri, Tc0w.t, tt);
-    for (int i = 0; i < 3; ++i) o.t[i] = tt[i] + ti[i];
+    Pose pi;
+    s_pose_inv(pose, pi);
+    s_pose_mul(pi, Tc0w, o);
 }
-__device__ __forceinline__ double lm_cost(const Pose &T, const double x[3], const double z[2]) {
-    double h0 = T.R[0] * x[0] + T.R[1] * x[1] + T.R[2] * 1.0 + x[2] * T.t[0];
-    double h1 = T.R[3] * x[0] + T.R[4] * x[1] + T.R[5] * 1.0 + x[2] * T.t[1];
-    double h2 = T.R[6] * x[0] + T.R[7] * x[1] + T.R[8] * 1.0 + x[2] * T.t[2];
-    double zx = h0 / h2 - z[0], zy = h1 / h2 - z[1];
+// Feature::cost (feature.hpp:171-190)
+__device__ __forceinline__ sd lm_cost(const Pose &T, const sd x[3], const sd z[2]) {
+    sd h0 = ((T.R[0] * x[0] + T.R[1] * x[1]) + T.R[2] * sd(1.0)) + T.t[0] * x[2];
+    sd h1 = ((T.R[3] * x[0] + T.R[4] * x[1]) + T.R[5] * sd(1.0)) + T.t[1] * x[2];
+    sd h2 = ((T.R[6] * x[0] + T.R[7] * x[1]) + T.R[8] * sd(1.0)) + T.t[2] * x[2];
+    sd zx = h0 / h2 - z[0], zy = h1 / h2 - z[1];
     return zx * zx + zy * zy;
 }
-__device__ __forceinline__ void lm_accumulate(const Pose &T, const double x[3], const double z[2], double huber,
-                                              double A[9], double b[3]) {
-    double h1 = T.R[0] * x[0] + T.R[1] * x[1] + T.R[2] * 1.0 + x[2] * T.t[0];
-    double h2 = T.R[3] * x[0] + T.R[4] * x[1] + T.R[5] * 1.0 + x[2] * T.t[1];
-    double h3 = T.R[6] * x[0] + T.R[7] * x[1] + T.R[8] * 1.0 + x[2] * T.t[2];
-    double W[9] = {T.R[0], T.R[1], T.t[0], T.R[3], T.R[4], T.t[1], T.R[6], T.R[7], T.t[2]};
-    double J[6], r[2];
+// Feature::jacobian (feature.hpp:192-229) and this view's terms of A = sum w^2 J^T J (lower triangle
+// first: 00 10 11 20 21 22) and b = sum w^2 J^T r (feature.hpp:372-386)
+__device__ __forceinline__ void lm_terms(const Pose &T, const sd x[3], const sd z[2], sd huber, double *out /* [9] */) {
+    sd h1 = ((T.R[0] * x[0] + T.R[1] * x[1]) + T.R[2] * sd(1.0)) + T.t[0] * x[2];
+    sd h2 = ((T.R[3] * x[0] + T.R[4] * x[1]) + T.R[5] * sd(1.0)) + T.t[1] * x[2];
+    sd h3 = ((T.R[6] * x[0] + T.R[7] * x[1]) + T.R[8] * sd(1.0)) + T.t[2] * x[2];
+    const sd W[9] = {T.R[0], T.R[1], T.t[0], T.R[3], T.R[4], T.t[1], T.R[6], T.R[7], T.t[2]};
+    sd J[6], r[2];
+    const sd ih3 = sd(1.0) / h3, a1 = h1 / (h3 * h3), a2 = h2 / (h3 * h3);
+#pragma unroll
     for (int j = 0; j < 3; ++j) {
-        J[j] = 1 / h3 * W[j] - h1 / (h3 * h3) * W[6 + j];
-        J[3 + j] = 1 / h3 * W[3 + j] - h2 / (h3 * h3) * W[6 + j];
+        J[j] = ih3 * W[j] - a1 * W[6 + j];
+        J[3 + j] = ih3 * W[3 + j] - a2 * W[6 + j];
     }
     r[0] = h1 / h3 - z[0];
     r[1] = h2 / h3 - z[1];
-    double e = sqrt(r[0] * r[0] + r[1] * r[1]);
-    double w = e <= huber ? 1.0 : sqrt(2.0 * huber / e);
-    double ws = (w == 1) ? 1.0 : w * w;
+    sd e = ssqrt(r[0] * r[0] + r[1] * r[1]);
+    const bool unit = e.v <= huber.v;
+    sd w = unit ? sd(1.0) : ssqrt((sd(2.0) * huber) / e);
+    const bool w1 = (w.v == 1.0);
+    sd ws = w * w;
+    int o = 0;
+#pragma unroll
     for (int a = 0; a < 3; ++a) {
-        for (int c = 0; c < 3; ++c) A[a * 3 + c] += ws * (J[a] * J[c] + J[3 + a] * J[3 + c]);
-        b[a] += ws * (J[a] * r[0] + J[3 + a] * r[1]);
+#pragma unroll
+        for (int c = 0; c <= a; ++c) {
+            sd jtj = J[a] * J[c] + J[3 + a] * J[3 + c];
+            out[o++] = (w1 ? jtj : ws * jtj).v;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        sd jtr = J[a] * r[0] + J[3 + a] * r[1];
+        out[6 + a] = (w1 ? jtr : ws * jtr).v;
     }
 }
-__device__ __forceinline__ void ldlt3_solve(const double S[9], const double b[3], double x[3]) {
-    double L10, L20, L21, D0, D1, D2;
-    D0 = S[0];
-    L10 = S[3] / D0;
-    L20 = S[6] / D0;
-    D1 = S[4] - L10 * L10 * D0;
-    L21 = (S[7] - L20 * L10 * D0) / D1;
-    D2 = S[8] - L20 * L20 * D0 - L21 * L21 * D1;
-    double y0 = b[0], y1 = b[1] - L10 * y0, y2 = b[2] - L20 * y0 - L21 * y1;
-    y0 /= D0; y1 /= D1; y2 /= D2;
+// Eigen Matrix3d::ldlt().solve (feature.hpp:395) as oracle/linalg.h ldlt_solve for n = 3;
+// S given by its lower triangle 00 10 11 20 21 22
+__device__ __forceinline__ void ldlt3_solve(const sd S[6], const sd b[3], sd x[3]) {
+    sd D0 = S[0];
+    sd L10 = S[1] / D0, L20 = S[3] / D0;
+    sd D1 = S[2] - L10 * L10 * D0;
+    sd L21 = (S[4] - L20 * L10 * D0) / D1;
+    sd D2 = (S[5] - L20 * L20 * D0) - L21 * L21 * D1;
+    sd y0 = b[0], y1 = b[1], y2 = b[2];
+    if (L10.v != 0.0) y1 = y1 - L10 * y0;
+    if (L20.v != 0.0) y2 = y2 - L20 * y0;
+    if (L21.v != 0.0) y2 = y2 - L21 * y1;
+    y0 = y0 / D0; y1 = y1 / D1; y2 = y2 / D2;
     x[2] = y2;
-    x[1] = y1 - L21 * x[2];
-    x[0] = y0 - L10 * x[1] - L20 * x[2];
+    x[1] = y1;
+    if (L21.v != 0.0) x[1] = x[1] - L21 * x[2];
+    x[0] = y0;
+    if (L10.v != 0.0) x[0] = x[0] - L10 * x[1];
+    if (L20.v != 0.0) x[0] = x[0] - L20 * x[2];
 }
 
 #define TRI_WARPS 4
-__device__ void triangulate_one(const BeConst &bc, const BeBuf &bb, const BeState &st, int s, int li, int lane, size_t fo);
+#define TRI_VIEWS 64  // 2 * NSM stereo views
+struct TriShared {
+    double term[TRI_VIEWS][9];  // per-view terms of A (lower triangle) and b
+    double cost[TRI_VIEWS];
+};
+__device__ void triangulate_one(const BeConst &bc, const BeBuf &bb, const BeState &st, int s, int li, int lane, size_t fo, TriShared &sh);
 __global__ void __launch_bounds__(TRI_WARPS * 32) be_triangulate_kernel(BeConst bc, BeBuf bb, int phase) {
+    __shared__ TriShared s_tri[TRI_WARPS];
     const int s = blockIdx.y;
     const BeStep sp = bb.step[s];
     if (!sp.active) return;
@@ -1016,10 +1109,22 @@ __global__ void __launch_bounds__(TRI_WARPS * 32) be_triangulate_kernel(BeConst 
     const size_t fo = (size_t)s * bc.MF;
     const int n_list = st.n_list;
     for (int li = blockIdx.x * TRI_WARPS + (threadIdx.x >> 5); li < n_list; li += gridDim.x * TRI_WARPS)
-        triangulate_one(bc, bb, st, s, li, lane, fo);
+        triangulate_one(bc, bb, st, s, li, lane, fo, s_tri[threadIdx.x >> 5]);
 }
 
-__device__ void triangulate_one(const BeConst &bc, const BeBuf &bb, const BeState &st, int s, int li, int lane, size_t fo) {
+// sum of the np per-view costs in view order, starting from 0.0 (feature.hpp:359-364, 402-407); every lane
+// computes the same value
+__device__ __forceinline__ sd tri_cost_sum(TriShared &sh, int np, int lane, const bool have[2], const sd c[2]) {
+    __syncwarp();
+    if (have[0]) sh.cost[lane] = c[0].v;
+    if (have[1]) sh.cost[lane + 32] = c[1].v;
+    __syncwarp();
+    sd t(0.0);
+    for (int i = 0; i < np; ++i) t = t + sd(sh.cost[i]);
+    return t;
+}
+
+__device__ void triangulate_one(const BeConst &bc, const BeBuf &bb, const BeState &st, int s, int li, int lane, size_t fo, TriShared &sh) {
     const int slot = bb.l_slot[(size_t)s * bc.ML + li];
     uint8_t *ok = bb.l_ok + (size_t)s * bc.ML + li;
     if (bb.f_init[fo + slot]) {
@@ -1043,19 +1148,19 @@ __device__ void triangulate_one(const BeConst &bc, const BeBuf &bb, const BeStat
     // ---- checkMotion (feature.hpp:257-287)
     {
         const BeCam &c0 = st.cam[first_slot], &c1 = st.cam[last_slot];
-        double R0w[9];
-        quat_to_rot(c0.q, R0w);
+        sd R0[9];  // first_pose.R = R(q)^T
+        s_quat_to_rot_t(c0.q, R0);
         const double *o0 = obs + first_slot * 4;
-        double dir[3] = {o0[0], o0[1], 1.0};
-        double dn = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
-        for (int i = 0; i < 3; ++i) dir[i] /= dn;
-        double dw[3];
-        m3Tv(R0w, dir, dw);
-        double tr[3] = {c1.p[0] - c0.p[0], c1.p[1] - c0.p[1], c1.p[2] - c0.p[2]};
-        double par = tr[0] * dw[0] + tr[1] * dw[1] + tr[2] * dw[2];
-        double orth[3] = {tr[0] - par * dw[0], tr[1] - par * dw[1], tr[2] - par * dw[2]};
-        double on = sqrt(orth[0] * orth[0] + orth[1] * orth[1] + orth[2] * orth[2]);
-        if (!(on > bc.feat_trans_thr)) {
+        sd dir[3] = {o0[0], o0[1], 1.0};
+        sd dn = ssqrt((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]);
+        for (int i = 0; i < 3; ++i) dir[i] = dir[i] / dn;
+        sd dw[3];
+        s_m3v(R0, dir, dw);
+        sd tr[3] = {sd(c1.p[0]) - sd(c0.p[0]), sd(c1.p[1]) - sd(c0.p[1]), sd(c1.p[2]) - sd(c0.p[2])};
+        sd par = (tr[0] * dw[0] + tr[1] * dw[1]) + tr[2] * dw[2];
+        sd orth[3] = {tr[0] - par * dw[0], tr[1] - par * dw[1], tr[2] - par * dw[2]};
+        sd on = ssqrt((orth[0] * orth[0] + orth[1] * orth[1]) + orth[2] * orth[2]);
+        if (!(on.v > bc.feat_trans_thr)) {
             if (lane == 0) *ok = 0;
             return;
         }
@@ -1065,8 +1170,8 @@ __device__ void triangulate_one(const BeConst &bc, const BeBuf &bb, const BeStat
     cam_pose_world(st.cam[first_slot], 0, bc, Tc0w);
     const int np = 2 * M;
     Pose my[2];
-    double mz[2][2];
-    bool have[2] = {lane < np, lane + 32 < np};
+    sd mz[2][2];
+    const bool have[2] = {lane < np, lane + 32 < np};
     for (int h = 0; h < 2; ++h) {
         if (!have[h]) continue;
         int j = lane + 32 * h;
@@ -1077,76 +1182,87 @@ __device__ void triangulate_one(const BeConst &bc, const BeBuf &bb, const BeStat
         mz[h][0] = o[0];
         mz[h][1] = o[1];
     }
-    double sol[3];
-    {
+    sd sol[3];
+    {   // generateInitialGuess (feature.hpp:231-255) from the first and the last view
         Pose wl, Tl;
         cam_pose_world(st.cam[last_slot], 1, bc, wl);
         pose_rel(wl, Tc0w, Tl);
         const double *z1 = obs + first_slot * 4, *z2 = obs + last_slot * 4 + 2;
-        double m[3], zz[3] = {z1[0], z1[1], 1.0};
-        m3v(Tl.R, zz, m);
-        double A0 = m[0] - z2[0] * m[2], A1 = m[1] - z2[1] * m[2];
-        double b0 = z2[0] * Tl.t[2] - Tl.t[0], b1 = z2[1] * Tl.t[2] - Tl.t[1];
-        double depth = (1.0 / (A0 * A0 + A1 * A1)) * (A0 * b0 + A1 * b1);
-        double ip[3] = {z1[0] * depth, z1[1] * depth, depth};
+        sd m[3], zz[3] = {z1[0], z1[1], 1.0};
+        s_m3v(Tl.R, zz, m);
+        sd A0 = m[0] - sd(z2[0]) * m[2], A1 = m[1] - sd(z2[1]) * m[2];
+        sd b0 = sd(z2[0]) * Tl.t[2] - Tl.t[0], b1 = sd(z2[1]) * Tl.t[2] - Tl.t[1];
+        sd depth = (sd(1.0) / (A0 * A0 + A1 * A1)) * (A0 * b0 + A1 * b1);
+        sd ip[3] = {sd(z1[0]) * depth, sd(z1[1]) * depth, depth};
         sol[0] = ip[0] / ip[2];
         sol[1] = ip[1] / ip[2];
-        sol[2] = 1.0 / ip[2];
+        sol[2] = sd(1.0) / ip[2];
     }
-    const double huber = 0.01, est_prec = 5e-7;
-    double lambda = 1e-3;
+    const sd huber(0.01);
+    const double est_prec = 5e-7;
+    sd lambda(1e-3);
     int inner = 0, outer = 0;
     bool reduced = false;
-    double delta_norm = 0;
-    double total_cost = 0;
+    sd delta_norm(0.0);
+    sd total_cost;
     {
-        double c = 0;
+        sd c[2];
         for (int h = 0; h < 2; ++h)
-            if (have[h]) c += lm_cost(my[h], sol, mz[h]);
-        total_cost = warp_sum_d(c);
+            if (have[h]) c[h] = lm_cost(my[h], sol, mz[h]);
+        total_cost = tri_cost_sum(sh, np, lane, have, c);
     }
     do {
-        double A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+        __syncwarp();
         for (int h = 0; h < 2; ++h)
-            if (have[h]) lm_accumulate(my[h], sol, mz[h], huber, A, b);
-        for (int i = 0; i < 9; ++i) A[i] = warp_sum_d(A[i]);
-        for (int i = 0; i < 3; ++i) b[i] = warp_sum_d(b[i]);
+            if (have[h]) lm_terms(my[h], sol, mz[h], huber, sh.term[lane + 32 * h]);
+        __syncwarp();
+        sd Ab[9];
+        {
+            sd acc(0.0);
+            if (lane < 9)
+                for (int i = 0; i < np; ++i) acc = acc + sd(sh.term[i][lane]);
+#pragma unroll
+            for (int e = 0; e < 9; ++e) Ab[e] = sd(__shfl_sync(0xffffffffu, acc.v, e));
+        }
         do {
-            double At[9];
-            for (int i = 0; i < 9; ++i) At[i] = A[i];
-            At[0] += lambda; At[4] += lambda; At[8] += lambda;
-            double delta[3], ns[3];
-            ldlt3_solve(At, b, delta);
+            sd At[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) At[i] = Ab[i];
+            At[0] = At[0] + lambda; At[2] = At[2] + lambda; At[5] = At[5] + lambda;
+            sd delta[3], ns[3];
+            ldlt3_solve(At, Ab + 6, delta);
             for (int i = 0; i < 3; ++i) ns[i] = sol[i] - delta[i];
-            delta_norm = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
-            double c = 0;
+            delta_norm = ssqrt((delta[0] * delta[0] + delta[1] * delta[1]) + delta[2] * delta[2]);
+            sd c[2];
             for (int h = 0; h < 2; ++h)
-                if (have[h]) c += lm_cost(my[h], ns, mz[h]);
-            double new_cost = warp_sum_d(c);
-            if (new_cost < total_cost) {
+                if (have[h]) c[h] = lm_cost(my[h], ns, mz[h]);
+            sd new_cost = tri_cost_sum(sh, np, lane, have, c);
+            if (new_cost.v < total_cost.v) {
                 reduced = true;
                 for (int i = 0; i < 3; ++i) sol[i] = ns[i];
                 total_cost = new_cost;
-                lambda = lambda / 10 > 1e-10 ? lambda / 10 : 1e-10;
+                sd l10 = lambda / sd(10.0);
+                lambda = l10.v > 1e-10 ? l10 : sd(1e-10);
             } else {
                 reduced = false;
-                lambda = lambda * 10 < 1e12 ? lambda * 10 : 1e12;
+                sd l10 = lambda * sd(10.0);
+                lambda = l10.v < 1e12 ? l10 : sd(1e12);
             }
         } while (inner++ < 10 && !reduced);
         inner = 0;
-    } while (outer++ < 10 && delta_norm > est_prec);
-    double fp[3] = {sol[0] / sol[2], sol[1] / sol[2], 1.0 / sol[2]};
+    } while (outer++ < 10 && delta_norm.v > est_prec);
+    sd fp[3] = {sol[0] / sol[2], sol[1] / sol[2], sd(1.0) / sol[2]};
     bool valid = true;
     for (int h = 0; h < 2; ++h)
         if (have[h]) {
-            double z = my[h].R[6] * fp[0] + my[h].R[7] * fp[1] + my[h].R[8] * fp[2] + my[h].t[2];
-            if (z <= 0) valid = false;
+            sd z = ((my[h].R[6] * fp[0] + my[h].R[7] * fp[1]) + my[h].R[8] * fp[2]) + my[h].t[2];
+            if (z.v <= 0) valid = false;
         }
     valid = __all_sync(0xffffffffu, valid);
     if (lane == 0) {
-        double pw[3];
-        m3v(Tc0w.R, fp, pw);
-        for (int i = 0; i < 3; ++i) bb.f_pos[(fo + slot) * 3 + i] = pw[i] + Tc0w.t[i];
+        sd pw[3];
+        s_m3v(Tc0w.R, fp, pw);
+        for (int i = 0; i < 3; ++i) bb.f_pos[(fo + slot) * 3 + i] = (pw[i] + Tc0w.t[i]).v;
         if (valid) bb.f_init[fo + slot] = 1;
         *ok = valid ? 1 : 0;
     }
@@ -2943,9 +3059,9 @@ int be_create(mskf_handle *h) {
     }
     B->smem_qr = sizeof(double) * ((size_t)(bc.KC + 1) * (bc.KC + 2) / 2 + (size_t)QR_B * (bc.KC + 1));
     B->smem_chol = sizeof(double) * ((size_t)bc.KC * (bc.KC + 1) / 2 + bc.KC);
-    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_add_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_add));
-    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_sel));
-    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(be_feature_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_jac[0]));
+    if ((rc = smem_optin(h, be_add_obs_kernel, B->smem_add)) != MSKF_OK) return rc;
+    if ((rc = smem_optin(h, be_select_kernel, B->smem_sel)) != MSKF_OK) return rc;
+    if ((rc = smem_optin(h, be_feature_jac_kernel, B->smem_jac[0])) != MSKF_OK) return rc;
     for (int s = 0; s < h->S; ++s) be_reset_kernel<<<1, BE_THREADS, 0, h->be_stream>>>(bc, bb, s, 1, h->cfg);
     MSKF_CUDA_CHECK(h, cudaGetLastError());
     return MSKF_OK;
@@ -3026,9 +3142,19 @@ int be_step(mskf_handle *h, const std::vector<int> &streams, const mskf_feature 
     } else {
         MSKF_CUDA_CHECK(h, cudaStreamWaitEvent(q, h->ev_msg_ready, 0));
     }
+    // the find-or-insert hash of be_add_obs_kernel has HASH cells for <= MF live features plus the
+    // message's ids: a message that could fill it is refused here (the kernel's probe is bounded as well)
     if (inject && n_inject > bc.ent_cap) {
         h->err = "too many injected measurements";
         return MSKF_ERR_CAPACITY;
+    }
+    if (inject && n_inject > bc.HASH - bc.MF) {  // only distinct ids take cells (a compat-mode message repeats id 0 in its tail)
+        std::unordered_set<unsigned> ids;
+        for (int i = 0; i < n_inject; ++i) ids.insert(inject[i].id);
+        if ((int)ids.size() > bc.HASH - bc.MF) {
+            h->err = "too many distinct feature ids in the injected message for the configured feature-map capacity";
+            return MSKF_ERR_CAPACITY;
+        }
     }
     const int slot = B->pos;
     B->pos = (B->pos + 1) % BE_RING;
@@ -3304,6 +3430,65 @@ int be_op_update(mskf_handle *t, int n_cam, int m, const double *H, const double
         dx[i] = dxl[i];
         for (int j = 0; j < n; ++j) Pn[(size_t)i * n + j] = Pl[(size_t)i * LD + j];
     }
+    return MSKF_OK;
+}
+
+// Stand-alone Feature::checkMotion + initializePosition (feature.hpp:257-450) on caller-supplied camera
+// states and observations, run by be_triangulate_kernel on stream 0 of a scratch handle.
+int be_op_triangulate(mskf_handle *t, int n_cam, const double *cam_q, const double *cam_p, int n_feat, const unsigned *mask,
+                      const double *obs, double *pos, int *ok) {
+    BeBuffers *B = t->bb;
+    const BeConst &bc = B->bc;
+    const BeBuf &bb = B->bb;
+    if (n_cam < 1 || n_cam > bc.NS || n_feat < 1 || n_feat > bc.MF || n_feat > bc.ML) {
+        t->err = "mskf_op_triangulate: dimensions exceed the configured capacity";
+        return MSKF_ERR_CAPACITY;
+    }
+    for (int f = 0; f < n_feat; ++f)
+        if (mask[f] == 0 || (n_cam < 32 && (mask[f] >> n_cam))) {
+            t->err = "mskf_op_triangulate: a feature needs at least one observation, all of them by the given camera states";
+            return MSKF_ERR_ARG;
+        }
+    MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->stream));
+    MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->be_stream));
+    t->cur = t->be_stream;
+    BeState st;
+    MSKF_CUDA_CHECK(t, cudaMemcpy(&st, bb.st, sizeof(BeState), cudaMemcpyDeviceToHost));
+    st.n_cam = n_cam;
+    st.cam_used = n_cam >= 32 ? 0xffffffffu : ((1u << n_cam) - 1u);
+    for (int i = 0; i < n_cam; ++i) {
+        st.order[i] = i;
+        st.cam[i].id = i;
+        for (int k = 0; k < 4; ++k) st.cam[i].q[k] = cam_q[i * 4 + k];
+        for (int k = 0; k < 3; ++k) st.cam[i].p[k] = cam_p[i * 3 + k];
+    }
+    st.n_list = n_feat;
+    MSKF_CUDA_CHECK(t, cudaMemcpy(bb.st, &st, sizeof(BeState), cudaMemcpyHostToDevice));
+    BeStep sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.active = 1;
+    MSKF_CUDA_CHECK(t, cudaMemcpy(bb.step, &sp, sizeof(sp), cudaMemcpyHostToDevice));
+    std::vector<double> o((size_t)n_feat * bc.NS * 4, 0.0);
+    std::vector<int> slots(n_feat);
+    for (int f = 0; f < n_feat; ++f) {
+        slots[f] = f;
+        for (int c = 0; c < n_cam; ++c)
+            for (int k = 0; k < 4; ++k) o[((size_t)f * bc.NS + c) * 4 + k] = obs[((size_t)f * n_cam + c) * 4 + k];
+    }
+    MSKF_CUDA_CHECK(t, cudaMemcpy(bb.f_obs, o.data(), sizeof(double) * o.size(), cudaMemcpyHostToDevice));
+    MSKF_CUDA_CHECK(t, cudaMemcpy(bb.f_mask, mask, sizeof(unsigned) * n_feat, cudaMemcpyHostToDevice));
+    MSKF_CUDA_CHECK(t, cudaMemcpy(bb.l_slot, slots.data(), sizeof(int) * n_feat, cudaMemcpyHostToDevice));
+    MSKF_CUDA_CHECK(t, cudaMemset(bb.f_init, 0, n_feat));
+    MSKF_CUDA_CHECK(t, cudaMemset(bb.f_pos, 0, sizeof(double) * 3 * n_feat));
+    MSKF_CUDA_CHECK(t, cudaMemset(bb.l_ok, 0, n_feat));
+    MSKF_CUDA_CHECK(t, cudaDeviceSynchronize());
+    MSKF_LAUNCH(t, PK_BE_TRIANGULATE, (be_triangulate_kernel<<<dim3(16, 1), TRI_WARPS * 32, 0, t->be_stream>>>(bc, bb, 0)));
+    MSKF_CUDA_CHECK(t, cudaGetLastError());
+    MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->be_stream));
+    std::vector<uint8_t> okb(n_feat);
+    MSKF_CUDA_CHECK(t, cudaMemcpy(okb.data(), bb.l_ok, n_feat, cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(t, cudaMemcpy(pos, bb.f_pos, sizeof(double) * 3 * n_feat, cudaMemcpyDeviceToHost));
+    for (int f = 0; f < n_feat; ++f) ok[f] = okb[f];
     return MSKF_OK;
 }
 

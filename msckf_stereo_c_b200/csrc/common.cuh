@@ -218,6 +218,8 @@ int be_get_cam_states(mskf_handle *h, int s, mskf_cam_state *out, int cap, int *
 int be_get_cov(mskf_handle *h, int s, double *out, int cap, int *dim);
 int be_reset(mskf_handle *h, int s);
 int be_get_map(mskf_handle *h, int s, long long *ids, int *init, double *pos, int *nobs, int cap, int *n);
+int be_op_triangulate(mskf_handle *t, int n_cam, const double *cam_q, const double *cam_p, int n_feat, const unsigned *mask,
+                      const double *obs, double *pos, int *ok);
 int be_op_update(mskf_handle *t, int n_cam, int m, const double *H, const double *r, const double *P, double *dx, double *Pn);
 int be_debug_update_dims(mskf_handle *h, int *out6);
 int be_get_poses(mskf_handle *h, double *out, int cap_streams, int lag);
@@ -230,8 +232,30 @@ int dev_alloc(mskf_handle *h, T **p, size_t n) {
         h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
         return MSKF_ERR_CUDA;
     }
+    // the engine's streams are non-blocking (not ordered against the legacy default stream the memset
+    // runs on), so the clear is completed here, before any kernel can touch the buffer
     cudaMemset(q, 0, n * sizeof(T));
+    cudaStreamSynchronize(cudaStreamLegacy);
     h->allocs.push_back(q);
     *p = (T *)q;
+    return MSKF_OK;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per kernel for the whole process, not per handle: every
+// kernel that needs more than 48 KB gets the device's opt-in maximum (only ever the same value), so a
+// handle with a smaller configuration cannot lower the limit under a live larger one.
+template <typename F>
+int smem_optin(mskf_handle *h, F *kernel, size_t need) {
+    int optin = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+    if (e == cudaSuccess && need > (size_t)optin) {
+        h->err = "configuration needs more shared memory per block than the device offers";
+        return MSKF_ERR_CAPACITY;
+    }
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e != cudaSuccess) {
+        h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+        return MSKF_ERR_CUDA;
+    }
     return MSKF_OK;
 }

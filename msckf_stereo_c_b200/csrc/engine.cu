@@ -310,20 +310,26 @@ int mskf_set_cuda_stream(mskf_handle *h, void *cuda_stream) {
 
 long long mskf_launch_count(const mskf_handle *h) { return h ? h->launches : 0; }
 
-int mskf_push_imu(mskf_handle *h, int s, double t, const double w[3], const double a[3]) {
-    if (!h || s < 0 || s >= h->S) return MSKF_ERR_ARG;
+int mskf_push_imu_to(mskf_handle *h, int s, int halves, double t, const double w[3], const double a[3]) {
+    if (!h || s < 0 || s >= h->S || !w || !a || !(halves & (MSKF_IMU_FRONTEND | MSKF_IMU_BACKEND))) return MSKF_ERR_ARG;
     HostStream &hs = h->hs[s];
     HostImu m;
     m.t = t;
     for (int i = 0; i < 3; ++i) { m.w[i] = w[i]; m.a[i] = a[i]; }
-    if (!hs.fe_first) hs.fe_imu.push_back(m);  // image_processor.cpp:205-211
-    hs.be_imu.push_back(m);                     // msckf_vio.cpp:190-207
-    if (!hs.gravity_set && hs.be_imu.size() >= 200) {
-        int rc = be_init_gravity(h, s);
-        if (rc != MSKF_OK) return rc;
-        hs.gravity_set = true;
+    if ((halves & MSKF_IMU_FRONTEND) && !hs.fe_first) hs.fe_imu.push_back(m);  // image_processor.cpp:205-211
+    if (halves & MSKF_IMU_BACKEND) {                                            // msckf_vio.cpp:190-207
+        hs.be_imu.push_back(m);
+        if (!hs.gravity_set && hs.be_imu.size() >= 200) {
+            int rc = be_init_gravity(h, s);
+            if (rc != MSKF_OK) return rc;
+            hs.gravity_set = true;
+        }
     }
     return MSKF_OK;
+}
+
+int mskf_push_imu(mskf_handle *h, int s, double t, const double w[3], const double a[3]) {
+    return mskf_push_imu_to(h, s, MSKF_IMU_FRONTEND | MSKF_IMU_BACKEND, t, w, a);
 }
 
 int mskf_push_imu_batch(mskf_handle *h, int stream, int n, const double *samples) {
@@ -348,8 +354,13 @@ int mskf_push_stereo_batch(mskf_handle *h, const double *t, const uint8_t *cam0,
     int rc = stage_prepare_write(h);
     if (rc != MSKF_OK) return rc;
     uint8_t *base = stage_slot_base(h);
-    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(base, 2 * img, cam0, stream_stride, img, h->S, cudaMemcpyHostToDevice, h->copy_stream));
-    MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(base + img, 2 * img, cam1, stream_stride, img, h->S, cudaMemcpyHostToDevice, h->copy_stream));
+    if (cam1 == cam0 + img && stream_stride == 2 * img) {
+        // the caller's frame set is laid out like the landing area ([stream][cam][pixels]): one contiguous copy
+        MSKF_CUDA_CHECK(h, cudaMemcpyAsync(base, cam0, 2 * img * (size_t)h->S, cudaMemcpyHostToDevice, h->copy_stream));
+    } else {
+        MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(base, 2 * img, cam0, stream_stride, img, h->S, cudaMemcpyHostToDevice, h->copy_stream));
+        MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(base + img, 2 * img, cam1, stream_stride, img, h->S, cudaMemcpyHostToDevice, h->copy_stream));
+    }
     for (int s = 0; s < h->S; ++s) {
         HostStream &hs = h->hs[s];
         hs.pending = true;
@@ -530,7 +541,7 @@ int mskf_get_features(mskf_handle *h, int s, mskf_feature *out, int cap, int *n,
     MSKF_CUDA_CHECK(h, cudaMemcpy(&cur, h->fb.msg_n + s, sizeof(int), cudaMemcpyDeviceToHost));
     MSKF_CUDA_CHECK(h, cudaMemcpy(&hw, h->fb.stale_hw + s, sizeof(int), cudaMemcpyDeviceToHost));
     MSKF_CUDA_CHECK(h, cudaMemcpy(&total, h->fb.msg_total + s, sizeof(long long), cudaMemcpyDeviceToHost));
-    *n = (int)total;
+    *n = total > 0x7fffffffLL ? 0x7fffffff : (int)total;  // the reference's vector grows without bound; see mskf_get_features_head
     if (t) *t = h->hs[s].msg_t;
     if (!out || cap <= 0) return MSKF_OK;
     std::vector<mskf_feature> buf(fc.max_f);
@@ -541,6 +552,25 @@ int mskf_get_features(mskf_handle *h, int s, mskf_feature *out, int cap, int *n,
         if (i < hw) out[i] = buf[(size_t)i];
         else memset(&out[i], 0, sizeof(mskf_feature));
     }
+    return MSKF_OK;
+}
+
+// The never-cleared message without its O(run length) value-initialised tail: entries [0, *n_head) are all that
+// is not {id 0, zeros}; *n_total is the length of the reference's vector (64-bit: it grows every frame).
+int mskf_get_features_head(mskf_handle *h, int s, mskf_feature *out, int cap, int *n_head, long long *n_total, double *t) {
+    if (!h || s < 0 || s >= h->S || !n_head) return MSKF_ERR_ARG;
+    int rc = mskf_sync(h);
+    if (rc != MSKF_OK) return rc;
+    int hw = 0;
+    long long total = 0;
+    MSKF_CUDA_CHECK(h, cudaMemcpy(&hw, h->fb.stale_hw + s, sizeof(int), cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(h, cudaMemcpy(&total, h->fb.msg_total + s, sizeof(long long), cudaMemcpyDeviceToHost));
+    *n_head = hw;
+    if (n_total) *n_total = total;
+    if (t) *t = h->hs[s].msg_t;
+    if (!out || cap <= 0 || hw == 0) return MSKF_OK;
+    const int k = hw < cap ? hw : cap;
+    MSKF_CUDA_CHECK(h, cudaMemcpy(out, h->fb.stale + (size_t)s * h->fc.max_f, sizeof(mskf_feature) * (size_t)k, cudaMemcpyDeviceToHost));
     return MSKF_OK;
 }
 
@@ -773,6 +803,20 @@ int mskf_op_ekf_update(mskf_handle *h, int n_cam, int m, const double *H, const 
             for (int i = 0; i < PK_COUNT; ++i) { h->prof_ms[i] += t->prof_ms[i]; h->prof_n[i] += t->prof_n[i]; }
         }
     }
+    if (rc != MSKF_OK && t) h->err = t->err;
+    if (t) mskf_destroy(t);
+    return rc;
+}
+
+// Feature::checkMotion + initializePosition as a stand-alone operator (feature.hpp:257-450)
+int mskf_op_triangulate(mskf_handle *h, int n_cam, const double *cam_orientation, const double *cam_position, int n_feat,
+                        const unsigned *obs_mask, const double *obs, double *out_position, int *out_ok) {
+    if (!h || !cam_orientation || !cam_position || !obs_mask || !obs || !out_position || !out_ok) return MSKF_ERR_ARG;
+    mskf_handle *t = nullptr;
+    mskf_config c = h->cfg;
+    if (n_cam > c.max_cam_state_size) c.max_cam_state_size = n_cam;
+    int rc = mskf_create(&c, 1, h->device, &t);
+    if (rc == MSKF_OK) rc = be_op_triangulate(t, n_cam, cam_orientation, cam_position, n_feat, obs_mask, obs, out_position, out_ok);
     if (rc != MSKF_OK && t) h->err = t->err;
     if (t) mskf_destroy(t);
     return rc;

@@ -1684,9 +1684,13 @@ int fe_create(mskf_handle *h) {
         h->err = "feature capacity too large for twoPointRansac's shared memory";
         return MSKF_ERR_ARG;
     }
-    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(fe_after_stereo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_after_stereo_smem(fc)));
-    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(fe_sieve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_sieve_smem(fc)));
-    MSKF_CUDA_CHECK(h, cudaFuncSetAttribute(fe_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_finish_smem(fc)));
+    if ((rc = smem_optin(h, fe_after_stereo, fe_after_stereo_smem(fc))) != MSKF_OK) return rc;
+    if ((rc = smem_optin(h, fe_sieve, fe_sieve_smem(fc))) != MSKF_OK) return rc;
+    if ((rc = smem_optin(h, fe_finish, fe_finish_smem(fc))) != MSKF_OK) return rc;
+    // pyramid strip kernels (launch_pyr_level): the widest strip is level 0's
+    if ((rc = smem_optin(h, pyr_down_bulk_kernel<true>, (size_t)PS_IN * fc.lvl_cols[0] + 32)) != MSKF_OK) return rc;
+    if ((rc = smem_optin(h, pyr_down_strip_kernel<true, 4>, 0)) != MSKF_OK) return rc;
+    if ((rc = smem_optin(h, pyr_down_strip_kernel<false, 4>, 0)) != MSKF_OK) return rc;
     return MSKF_OK;
 }
 
@@ -1710,18 +1714,12 @@ static void launch_pyr_level(mskf_handle *h, int l, int images) {
     const int tag = l == 1 ? PK_PYR_L1 : PK_PYR_LN;
     if (smem <= 200 * 1024 && (icols % 4) == 0 && icols >= 8) {
         dim3 g((fc.lvl_rows[l] + PS_ROWS - 1) / PS_ROWS, 1, images);
-        if (l == 1 && (icols % 16) == 0 && !getenv("MSKF_PYR_NO_TMA")) {
+        if (l == 1 && (icols % 16) == 0) {
             const size_t bsmem = (size_t)PS_IN * icols + 32;
-            cudaFuncSetAttribute(pyr_down_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
             MSKF_LAUNCH(h, tag, (pyr_down_bulk_kernel<true><<<g, 256, bsmem, q>>>(fc, fb, l)));
-        } else if (l == 1 && (icols % 16) == 0) {
-            cudaFuncSetAttribute(pyr_down_strip_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            MSKF_LAUNCH(h, tag, (pyr_down_strip_kernel<true, 16><<<g, 256, smem, q>>>(fc, fb, l, row_stride)));
         } else if (l == 1) {
-            cudaFuncSetAttribute(pyr_down_strip_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             MSKF_LAUNCH(h, tag, (pyr_down_strip_kernel<true, 4><<<g, 256, smem, q>>>(fc, fb, l, row_stride)));
         } else {
-            cudaFuncSetAttribute(pyr_down_strip_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             MSKF_LAUNCH(h, tag, (pyr_down_strip_kernel<false, 4><<<g, 256, smem, q>>>(fc, fb, l, row_stride)));
         }
     } else {

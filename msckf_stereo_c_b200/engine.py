@@ -30,7 +30,8 @@ ABI_SYMBOLS = [
     "mskf_launch_count", "mskf_get_n_published", "mskf_get_poses", "mskf_profile_enable", "mskf_profile_read",
     "mskf_debug_detect_scores", "mskf_debug_get_map", "mskf_op_ekf_update", "mskf_push_imu_batch",
     "mskf_push_stereo_batch", "mskf_push_stereo_device_batch", "mskf_get_work", "mskf_get_poses_prev", "mskf_join",
-    "mskf_set_overlap", "mskf_debug_update_dims",
+    "mskf_set_overlap", "mskf_debug_update_dims", "mskf_op_triangulate", "mskf_push_imu_to",
+    "mskf_get_features_head",
 ]
 
 
@@ -55,6 +56,8 @@ def lib():
         L.mskf_launch_count.argtypes = [P]
         L.mskf_launch_count.restype = C.c_longlong
         L.mskf_push_imu.argtypes = [P, I, D, P, P]
+        L.mskf_push_imu_to.argtypes = [P, I, I, D, P, P]
+        L.mskf_get_features_head.argtypes = [P, I, P, I, C.POINTER(I), C.POINTER(C.c_longlong), C.POINTER(D)]
         L.mskf_push_stereo.argtypes = [P, I, D, P, P, I, I, I]
         L.mskf_push_stereo_device.argtypes = [P, I, D, P, P]
         for n in ("mskf_frontend_step", "mskf_backend_step", "mskf_step", "mskf_sync"):
@@ -83,10 +86,10 @@ def lib():
         L.mskf_push_stereo_device_batch.argtypes = [P, P, P, P, C.c_size_t]
         L.mskf_get_work.argtypes = [P, I, C.POINTER(D)]
         L.mskf_op_ekf_update.argtypes = [P, I, I, P, P, P, P, P]
+        L.mskf_op_triangulate.argtypes = [P, I, P, P, I, P, P, P, P]
         L.mskf_debug_get_map.argtypes = [P, I, P, P, P, P, I, C.POINTER(I)]
         L.mskf_profile_enable.argtypes = [P, I]
         L.mskf_profile_read.argtypes = [P, I, C.POINTER(C.c_char_p), C.POINTER(D), C.POINTER(C.c_longlong)]
-        L.mskf_synth_render_device.argtypes = [P, P, P, P, P, P, I, I, I, P]
         _LIB = L
     return _LIB
 
@@ -119,7 +122,11 @@ class Engine:
             _LIB.mskf_destroy(self.h)
             self.h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: ctypes may already be torn down
+            pass
 
     def _ck(self, rc):
         if rc != 0:
@@ -130,6 +137,21 @@ class Engine:
         w = np.ascontiguousarray(w, np.float64)
         a = np.ascontiguousarray(a, np.float64)
         self._ck(lib().mskf_push_imu(self.h, stream, t, w.ctypes.data, a.ctypes.data))
+
+    def imu_callback_to(self, halves, t, w, a, stream=0):
+        """halves: 1 = ImageProcessor::imuCallback only, 2 = MsckfVio::imuCallback only, 3 = both."""
+        w = np.ascontiguousarray(w, np.float64)
+        a = np.ascontiguousarray(a, np.float64)
+        self._ck(lib().mskf_push_imu_to(self.h, stream, halves, t, w.ctypes.data, a.ctypes.data))
+
+    def features_head(self, stream=0):
+        """(t, entries that can hold measurements, length of the reference's never-cleared vector)."""
+        n, tot, t = C.c_int(), C.c_longlong(), C.c_double()
+        self._ck(lib().mskf_get_features_head(self.h, stream, None, 0, C.byref(n), C.byref(tot), C.byref(t)))
+        out = np.zeros(n.value, FEAT_DT)
+        if n.value:
+            self._ck(lib().mskf_get_features_head(self.h, stream, out.ctypes.data, n.value, C.byref(n), C.byref(tot), C.byref(t)))
+        return t.value, out, tot.value
 
     def push_stereo(self, t, cam0, cam1, stream=0):
         cam0 = np.ascontiguousarray(cam0, np.uint8)
@@ -332,6 +354,21 @@ class Engine:
         self._ck(lib().mskf_op_ekf_update(self.h, (n - 21) // 6, m, H.ctypes.data, r.ctypes.data, P.ctypes.data,
                                           dx.ctypes.data, Pn.ctypes.data))
         return dx, Pn
+
+    def op_triangulate(self, cam_q, cam_p, mask, obs):
+        """Feature::checkMotion + initializePosition on n_cam camera states (ascending id) and
+        obs[n_feat][n_cam][4]; mask bit c of feature f = camera state c observes f."""
+        cam_q = np.ascontiguousarray(cam_q, np.float64)
+        cam_p = np.ascontiguousarray(cam_p, np.float64)
+        mask = np.ascontiguousarray(mask, np.uint32)
+        obs = np.ascontiguousarray(obs, np.float64)
+        n_cam, n_feat = cam_q.shape[0], mask.shape[0]
+        assert obs.shape == (n_feat, n_cam, 4)
+        pos = np.zeros((n_feat, 3))
+        ok = np.zeros(n_feat, np.int32)
+        self._ck(lib().mskf_op_triangulate(self.h, n_cam, cam_q.ctypes.data, cam_p.ctypes.data, n_feat, mask.ctypes.data,
+                                           obs.ctypes.data, pos.ctypes.data, ok.ctypes.data))
+        return pos, ok
 
     def debug_detect_scores(self, img):
         img = np.ascontiguousarray(img, np.uint8)

@@ -18,7 +18,7 @@ _LIB = None
 def build(force=False):
     d = os.path.join(_HERE, "synth")
     so = os.path.join(d, "libmskf_synth.so")
-    if force or not os.path.exists(so):
+    if force or not os.path.exists(so) or not os.path.exists(os.path.join(d, "libmskf_synth_cuda.so")):
         subprocess.check_call(["make", "-s", "-C", d])
     return so
 
@@ -47,6 +47,21 @@ def lib():
     return _LIB
 
 
+_CUDA_LIB = None
+
+
+def cuda_lib():
+    """The device renderer (libmskf_synth_cuda.so, built from synth/synth_cuda.cu)."""
+    global _CUDA_LIB
+    if _CUDA_LIB is None:
+        build()
+        L = C.CDLL(os.path.join(_HERE, "synth", "libmskf_synth_cuda.so"))
+        P, I = C.c_void_p, C.c_int
+        L.mskf_synth_render_device.argtypes = [P, P, P, P, P, P, I, I, I, P]
+        _CUDA_LIB = L
+    return _CUDA_LIB
+
+
 def default_config(preset="ref"):
     cfg = abi.Config()
     rc = lib().synth_default_config(C.byref(cfg), preset.encode())
@@ -68,9 +83,12 @@ class Stream:
         self.na = cfg.noise_acc * np.sqrt(imu_rate) if imu_noise else 0.0
 
     def __del__(self):
-        if getattr(self, "h", None) and _LIB is not None:
-            _LIB.synth_destroy(self.h)
-            self.h = None
+        try:
+            if getattr(self, "h", None) and _LIB is not None:
+                _LIB.synth_destroy(self.h)
+                self.h = None
+        except Exception:  # interpreter shutdown
+            pass
 
     def frame_time(self, k):
         # images lag the IMU clock start by 1/4 IMU period so stamps never coincide exactly
@@ -171,8 +189,6 @@ class Fleet:
         """Render frame k of every stream into the CUDA uint8 tensor `out` [n][2][rows*cols]."""
         import torch
 
-        from . import engine
-
         if self._dev is None:
             L = lib()
             csz = L.synth_cam_size()
@@ -187,7 +203,7 @@ class Fleet:
         ctx = torch.cuda.stream(torch.cuda.ExternalStream(cuda_stream)) if cuda_stream else torch.cuda.stream(torch.cuda.current_stream())
         with ctx:
             d["t"].fill_(self.frame_time(k))
-        rc = engine.lib().mskf_synth_render_device(d["traj"].data_ptr(), d["cams"].data_ptr(), d["r0"].data_ptr(), d["r1"].data_ptr(),
+        rc = cuda_lib().mskf_synth_render_device(d["traj"].data_ptr(), d["cams"].data_ptr(), d["r0"].data_ptr(), d["r1"].data_ptr(),
                                                    d["t"].data_ptr(), out.data_ptr(), self.n, self.cfg.img_rows, self.cfg.img_cols,
                                                    C.c_void_p(cuda_stream))
         if rc != 0:

@@ -1,8 +1,8 @@
-// synth.cu — device build of the synthetic stereo generator (see ../synth/scene.h).
-// Input generation for bench.py only; not on the hot path.
+// synth_cuda.cu — device build of the synthetic stereo generator (scene.h), in its own library
+// (libmskf_synth_cuda.so): input generation for bench.py and the tests, not part of the engine.
 #include <cuda_runtime.h>
 
-#include "../synth/scene.h"
+#include "scene.h"
 
 __global__ void synth_render_kernel(const SynthTraj *traj, const SynthCam *cams, const float *rays0, const float *rays1,
                                     const double *times, uint8_t *out, int n_streams) {

@@ -262,5 +262,20 @@ def update_math(H, r, P, obs_noise):
     return dx, Pn
 
 
+def triangulate(cfg, cam_q, cam_p, mask, obs):
+    """Feature::checkMotion + initializePosition (feature.hpp:257-450); same layout as Engine.op_triangulate."""
+    cam_q, cam_p, obs = _f64(cam_q), _f64(cam_p), _f64(obs)
+    mask = np.ascontiguousarray(mask, np.uint32)
+    n_cam, n_feat = cam_q.shape[0], mask.shape[0]
+    pos = np.zeros((n_feat, 3))
+    ok = np.zeros(n_feat, np.int32)
+    f = lib().orc_triangulate
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    f.restype = None
+    f(C.byref(cfg), n_cam, cam_q.ctypes.data, cam_p.ctypes.data, n_feat, mask.ctypes.data, obs.ctypes.data,
+      pos.ctypes.data, ok.ctypes.data)
+    return pos, ok
+
+
 def chi2(cfg, dof):
     return lib().orc_chi2(C.byref(cfg), dof)

@@ -310,6 +310,33 @@ int orc_get_map(void *h, long long *ids, int *init, double *pos, int *nobs, int 
     }
     return n;
 }
+// Feature::checkMotion + initializePosition (feature.hpp:257-450) on caller-supplied camera states
+// (ascending state id 0..n_cam-1) and observations obs[n_feat][n_cam][4]; mask bit c = observed by c
+void orc_triangulate(const mskf_config *cfg, int n_cam, const double *cam_q, const double *cam_p, int n_feat,
+                     const unsigned *mask, const double *obs, double *pos, int *ok) {
+    MsckfVio v(*cfg);
+    CamStateServer cams;
+    for (int c = 0; c < n_cam; ++c) {
+        CAMState cs;
+        cs.id = c;
+        cs.orientation = Quat(cam_q[c * 4], cam_q[c * 4 + 1], cam_q[c * 4 + 2], cam_q[c * 4 + 3]);
+        cs.position = V3(cam_p[c * 3], cam_p[c * 3 + 1], cam_p[c * 3 + 2]);
+        cams[c] = cs;
+    }
+    for (int f = 0; f < n_feat; ++f) {
+        Feature ft;
+        ft.id = f;
+        for (int c = 0; c < n_cam; ++c)
+            if (mask[f] & (1u << c)) {
+                Obs4 o;
+                for (int k = 0; k < 4; ++k) o.v[k] = obs[((size_t)f * n_cam + c) * 4 + k];
+                ft.observations[c] = o;
+            }
+        ok[f] = 0;
+        if (ft.checkMotion(cams, v.opt_cfg)) ok[f] = ft.initializePosition(cams, v.T_cam0_cam1, v.opt_cfg) ? 1 : 0;
+        for (int k = 0; k < 3; ++k) pos[f * 3 + k] = ft.position[k];
+    }
+}
 double orc_chi2(const mskf_config *cfg, int dof) {
     MsckfVio v(*cfg);
     return v.chi2(dof);

@@ -79,3 +79,37 @@ def test_cpp_feed_loop_equals_python_engine(tmp_path, synth):
         assert int(v[8]) == st.n_cam_states and int(v[9]) == len(e.features()[1])
     assert e.state().n_cam_states > 10
     e.close()
+
+
+@pytest.mark.gpu
+def test_cpp_standalone_msckfvio_equals_system(tmp_path, synth):
+    """MsckfVio driven alone (imuCallback + featureCallback(msg), msckf_vio.cpp:190-207, 306-375) initialises
+    gravity from its own IMU buffer and ends in the same state as the one inside System."""
+    exe = _build()
+    cfg = synth.default_config("ref")
+    path = str(tmp_path / "dump.bin")
+    _dump(path, synth, cfg, 6, 45)
+    a = subprocess.run([exe, path, "ref"], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    b = subprocess.run([exe, path, "ref", "vio"], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert len(a) == len(b) == 45
+    assert a == b
+    assert int(a[-1].split()[8]) > 10
+
+
+@pytest.mark.gpu
+def test_features_head_equals_full_message(synth):
+    """mskf_get_features_head returns the part of the never-cleared message that can hold measurements;
+    the rest of the reference's vector is value-initialised."""
+    from msckf_stereo_c_b200 import engine
+
+    cfg = synth.default_config("ref")
+    s = synth.Stream(cfg, seed=2)
+    e = engine.Engine(cfg, 1)
+    for k, t in synth.feed(s, 12, e):
+        t_full, full, n_pub = e.features()
+        t_head, head, total = e.features_head()
+        assert t_full == t_head and total == len(full) and len(head) <= total and n_pub <= len(head)
+        assert full[:len(head)].tobytes() == head.tobytes()
+        assert not full[len(head):].tobytes().strip(b"\0")
+    assert total > len(head)
+    e.close()

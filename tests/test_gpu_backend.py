@@ -1,16 +1,24 @@
 """GPU: the CUDA MSCKF back end (through the C ABI) against the CPU oracle.
 
 Bars.  (1) With IDENTICAL inputs to an update (H, r, P) the posterior agrees to 1e-9 relative
-(measured ~1e-13): test_op_ekf_update_*.  (2) Frame by frame through the whole filter the
-discrete state (camera-state ids, map ids / observation counts / initialisation flags, update
-and reset counters) is identical and the continuous state agrees to PIPELINE_TOL.  The
-pipeline tolerance is looser than 1e-9 for a reason that is a property of the reference
-algorithm, not of the engine: Feature::initializePosition accepts an LM step iff
-new_cost < total_cost (feature.hpp:417), and at convergence that comparison is decided by the
-last bits of a 2M-term sum, so any change of summation order (another compiler, another
-thread count, a warp reduction) accepts or rejects a final ~1e-9 step, moving the triangulated
-point by ~1e-8 relative; DESIGN.md "EKF parity" shows the trace.  The oracle shows the same
-sensitivity when its own inputs are perturbed by one ulp."""
+(measured ~1e-13; asserted at 1e-12 on the filter's own data): test_op_ekf_update_*.  (2) With identical
+camera states and observations the triangulated feature positions are equal BIT FOR BIT:
+test_op_triangulate_bit_exact.  (3) Frame by frame through the whole filter the discrete state
+(camera-state ids, map ids / observation counts / initialisation flags, update and reset counters) is
+identical, the IMU and camera states agree to PIPELINE_TOL = 1e-9 absolute (measured <= 5e-11) and the
+covariance to PIPELINE_COV_TOL = 1e-8 of its largest entry (measured <= 5e-9, typically 1e-10).
+
+Why the whole-run covariance bar is 1e-8 and not 1e-9 - a property of the reference algorithm, shown by
+a CPU-only test (tests/test_oracle_backend.py::test_reference_is_not_1e9_reproducible_under_one_ulp):
+Feature::initializePosition accepts an LM step iff new_cost < total_cost (feature.hpp:417).  For the
+last steps of a run (|delta| ~ 1e-9 in inverse depth) that comparison is decided by the rounding of a
+2M-term sum, so ANY one-ulp change of an input re-rolls it and moves that feature by z^2 |delta|
+(<= 7e-8 m), the Jacobians by as much relative, and the posterior covariance by ~1e-9.  Two runs of the
+CPU oracle whose measurements differ by one ulp deviate by 1.5e-9 in P within 62 frames.  After the first
+update the engine's state differs from the oracle's in the last bits (equivalent but different
+factorizations: ~1e-13), so the same re-rolls happen between engine and oracle.  Round 1 measured 3e-8
+here because the kernel's warp-tree sums re-rolled nearly every feature; with the reference's summation
+order and no FMA contraction only the genuinely knife-edge decisions remain."""
 import numpy as np
 import pytest
 
@@ -20,7 +28,13 @@ pytestmark = pytest.mark.gpu
 
 UPDATE_TOL = 1e-9       # relative, identical inputs (north_star)
 PRE_UPDATE_TOL = 1e-12  # propagation + augmentation only
-PIPELINE_TOL = 1e-6     # relative covariance / absolute state, whole filter, see module docstring
+PIPELINE_TOL = 1e-9      # absolute, IMU and camera states, whole filter (north_star)
+PIPELINE_COV_TOL = 1e-8  # covariance relative to its largest entry, whole filter, see module docstring
+# Triangulated positions inside the running filter, metres.  With identical inputs they are bit-exact
+# (test_op_triangulate_bit_exact); inside the filter a re-rolled last LM step (module docstring) moves a
+# point by z^2 * |delta rho| (measured: <= 7e-8 m), which is far inside the LM's own termination
+# precision of 5e-7 in inverse depth (feature.hpp:52, ~2e-5 m at 6 m).
+POS_TOL = 1e-6
 
 
 @pytest.fixture(scope="module")
@@ -92,30 +106,55 @@ def test_op_ekf_update_on_filter_data(eng, ob, synth, preset, seed, frames):
     e.close()
 
 
-def _compare(o, e, k, first_update_seen):
-    so, sg = o.state(), e.state()
+@pytest.mark.parametrize("n_cam,n_feat,thr,seed", [(30, 300, -1.0, 0), (31, 120, 0.6, 1), (20, 200, -1.0, 2), (3, 40, -1.0, 3),
+                                                    (12, 160, 0.3, 4)])
+def test_op_triangulate_bit_exact(eng, ob, synth, n_cam, n_feat, thr, seed):
+    """a17: Feature::checkMotion + initializePosition (feature.hpp:257-450) with identical camera states and
+    observations.  The kernel evaluates the reference's expressions with separately rounded fp64
+    operations and adds the per-view cost / normal-equation terms in view order, so every LM accept
+    decision (feature.hpp:417) and therefore the position are equal to the oracle's bit for bit."""
+    from tri_scene import make_scene
+
+    cfg = copy_cfg(synth.default_config("bench"), feature_translation_threshold=thr, max_cam_state_size=max(n_cam, 5))
+    q, p, mask, obs, pts = make_scene(cfg, n_cam, n_feat, seed)
+    pos_o, ok_o = ob.triangulate(cfg, q, p, mask, obs)
+    e = eng.Engine(cfg, 1)
+    pos_g, ok_g = e.op_triangulate(q, p, mask, obs)
+    e.close()
+    assert np.array_equal(ok_o, ok_g)
+    assert ok_o.sum() > 0 and (thr < 0 or ok_o.sum() < n_feat)
+    assert pos_o.tobytes() == pos_g.tobytes(), np.abs(pos_o - pos_g).max()
+
+
+def _compare(o, e, k, first_update_seen, stream=0):
+    so, sg = o.state(), e.state(stream)
     assert (so.n_cam_states, so.is_gravity_set, so.n_updates, so.n_resets, so.n_map_features) == \
            (sg.n_cam_states, sg.is_gravity_set, sg.n_updates, sg.n_resets, sg.n_map_features), k
     if not so.is_gravity_set:
         return 0.0
     tol_rel = PIPELINE_TOL if first_update_seen or so.n_updates else PRE_UPDATE_TOL
+    tol_state = tol_rel
+    tol_P = PIPELINE_COV_TOL if first_update_seen or so.n_updates else PRE_UPDATE_TOL
     dev = 0.0
     for f in ("orientation", "position", "velocity", "gyro_bias", "acc_bias", "t_cam0_imu", "R_imu_cam0", "gravity", "T_b_w"):
         a, b = np.array(getattr(so, f)[:]), np.array(getattr(sg, f)[:])
         dev = max(dev, np.abs(a - b).max())
-    assert dev <= tol_rel, (k, dev)
+    assert dev <= tol_state, (k, dev)
     if so.n_cam_states:
-        co, cg = o.cam_states(), e.cam_states()
+        co, cg = o.cam_states(), e.cam_states(stream)
         assert np.array_equal(co["id"], cg["id"]) and np.array_equal(co["time"], cg["time"]), k
-        assert np.abs(co["position"] - cg["position"]).max() <= tol_rel and np.abs(co["orientation"] - cg["orientation"]).max() <= tol_rel, k
-    Po, Pg = o.cov(), e.cov()
+        assert np.abs(co["position"] - cg["position"]).max() <= tol_state and np.abs(co["orientation"] - cg["orientation"]).max() <= tol_state, k
+    Po, Pg = o.cov(), e.cov(stream)
     assert Po.shape == Pg.shape == (so.cov_dim, so.cov_dim), k
     dP = np.abs(Po - Pg).max() / np.abs(Po).max()
-    assert dP <= tol_rel, (k, dP)
+    assert dP <= tol_P, (k, dP, tol_P)
     assert np.array_equal(Pg, Pg.T), k
     io, no, po, oo = o.feature_map()
-    ig, ng, pg, og = e.feature_map()
+    ig, ng, pg, og = e.feature_map(stream)
     assert np.array_equal(io, ig) and np.array_equal(no, ng) and np.array_equal(oo, og), k
+    if no.any():  # triangulated positions of the features that stay in the map (a17), absolute, metres
+        dpos = np.abs(po[no == 1] - pg[no == 1]).max()
+        assert dpos <= POS_TOL, (k, dpos)
     assert (np.isnan(so.tracking_rate) and np.isnan(sg.tracking_rate)) or so.tracking_rate == sg.tracking_rate, k
     return max(dev, dP)
 
@@ -144,6 +183,7 @@ def _split_phase_run(eng, ob, synth, cfg, seed, n_frames):
         seen = seen or o.state().n_updates > 0
     st = o.state()
     e.close()
+    print(f"worst deviation {worst:.2e}")
     return worst, st
 
 
@@ -183,11 +223,10 @@ def _ate(est, gt):
     return np.sqrt((np.linalg.norm((R @ (est - ma).T).T + mb - gt, axis=1) ** 2).mean())
 
 
-def test_full_pipeline_and_ate(eng, ob, synth):
-    """Images + IMU in, pose out: CUDA front end feeding the CUDA EKF (mskf_step) against the
-    oracle run, plus the trajectory criterion (ATE within 5 % of the reference run)."""
-    cfg = synth.default_config("ref")
-    s = synth.Stream(cfg, seed=0)
+def _full_pipeline_run(eng, ob, synth, cfg, seed, n_frames):
+    """Images + IMU in, pose out: CUDA front end feeding the CUDA EKF (mskf_step) against the oracle run
+    frame by frame (CameraMeasurement bytes, filter state), plus both trajectories and the ground truth."""
+    s = synth.Stream(cfg, seed=seed)
     e = eng.Engine(cfg, 1)
     o = ob.Oracle(cfg)
 
@@ -206,7 +245,7 @@ def test_full_pipeline_and_ate(eng, ob, synth):
 
     p0 = s.pose(s.frame_time(0))[1]
     est_o, est_g, gt, seen = [], [], [], False
-    for k, t in synth.feed(s, 110, Both()):
+    for k, t in synth.feed(s, n_frames, Both()):
         (to, fo, no), (tg, fg, ng) = o.features(), e.features()
         assert to == tg and no == ng and fo.tobytes() == fg.tobytes(), k
         _compare(o, e, k, seen)
@@ -215,11 +254,78 @@ def test_full_pipeline_and_ate(eng, ob, synth):
             est_o.append(np.array(o.state().position[:]))
             est_g.append(np.array(e.state().position[:]))
             gt.append(s.pose(t)[1] - p0)
-    ate_o, ate_g = _ate(np.array(est_o), np.array(gt)), _ate(np.array(est_g), np.array(gt))
+    assert np.abs(e.poses()[0] - np.array(e.state().T_b_w[:]).reshape(4, 4)).max() == 0.0
+    st = o.state()
+    e.close()
+    return np.array(est_o), np.array(est_g), np.array(gt), st
+
+
+def test_full_pipeline_and_ate(eng, ob, synth):
+    """Preset ref (what the reference's code runs), plus the trajectory criterion (ATE within 5 % of the
+    reference run)."""
+    est_o, est_g, gt, st = _full_pipeline_run(eng, ob, synth, synth.default_config("ref"), 0, 110)
+    ate_o, ate_g = _ate(est_o, gt), _ate(est_g, gt)
     assert abs(ate_g - ate_o) <= 0.05 * ate_o
     assert ate_o < 0.15
-    assert np.abs(e.poses()[0] - np.array(e.state().T_b_w[:]).reshape(4, 4)).max() == 0.0
-    e.close()
+
+
+def test_full_pipeline_bench_preset(eng, ob, synth):
+    """The preset the headline number is quoted on (BASELINE.json config 3: 21x21 KLT, ~300 grid
+    features, max_cam_state_size 30) through mskf_step: static start, gravity initialisation, motion,
+    window fill and steady-state pruning (a prune update on every other frame from frame ~62 on)."""
+    est_o, est_g, gt, st = _full_pipeline_run(eng, ob, synth, synth.default_config("bench"), 1, 84)
+    assert st.n_cam_states >= 28 and st.n_updates >= 40
+    assert abs(_ate(est_g, gt) - _ate(est_o, gt)) <= 0.05 * _ate(est_o, gt)
+
+
+def test_fleet_two_handles_vs_oracle(eng, ob, synth):
+    """The configuration bench.py times, at a size the oracle can follow: 2 engine handles x 64 streams
+    (seed = global stream index), preset bench, device-rendered frames pushed as device pointers, the
+    handles' steps interleaved.  Four of the 128 streams (first/last of each handle) are checked frame by
+    frame against their own CPU oracle run on the same images and IMU rows."""
+    import torch
+
+    cfg = synth.default_config("bench")
+    H, Sh, n_frames = 2, 64, 56
+    img = cfg.img_rows * cfg.img_cols
+    dev = torch.device("cuda", 0)
+    groups = []
+    for h in range(H):
+        seeds = list(range(h * Sh, (h + 1) * Sh))
+        stream = torch.cuda.Stream(device=dev)
+        groups.append(dict(fleet=synth.Fleet(cfg, seeds), stream=stream, e=eng.Engine(cfg, Sh, cuda_stream=stream.cuda_stream),
+                           buf=torch.empty((Sh, 2, img), dtype=torch.uint8, device=dev), tvec=np.zeros(Sh)))
+    checked = [(0, 0), (0, Sh - 1), (1, 3), (1, Sh - 1)]
+    oracles = {c: ob.Oracle(cfg) for c in checked}
+    seen = {c: False for c in checked}
+    for k in range(n_frames):
+        rows = []
+        for g in groups:
+            r = g["fleet"].imu_rows_for_frame(k)
+            rows.append(r)
+            g["e"].push_imu_batch(r)
+            g["fleet"].render_device(k, g["buf"], g["stream"].cuda_stream)
+            g["tvec"][:] = g["fleet"].frame_time(k)
+            g["e"].push_stereo_batch(g["tvec"], g["buf"].data_ptr(), g["buf"].data_ptr() + img, 2 * img, device=True)
+            g["e"].step()
+        for g in groups:
+            g["e"].sync()
+        for (h, i) in checked:
+            o = oracles[(h, i)]
+            g = groups[h]
+            for row in rows[h][i]:
+                o.imu(row[0], row[1:4].copy(), row[4:7].copy())
+            im = g["buf"][i].cpu().numpy().reshape(2, cfg.img_rows, cfg.img_cols)
+            o.stereo(g["fleet"].frame_time(k), im[0], im[1])
+            o.backend()
+            (to, fo, no), (tg, fg, ng) = o.features(), g["e"].features(i)
+            assert to == tg and no == ng and fo.tobytes() == fg.tobytes(), (h, i, k)
+            _compare(o, g["e"], k, seen[(h, i)], stream=i)
+            seen[(h, i)] = seen[(h, i)] or o.state().n_updates > 0
+    for c in checked:
+        assert oracles[c].state().n_updates >= 5, c
+    for g in groups:
+        g["e"].close()
 
 
 def test_batched_backend_equals_single_stream(eng, ob, synth):
@@ -307,8 +413,6 @@ def test_reset_callback(eng, ob, synth):
     seen = False
     for k, t in synth.feed(s, 75, Both()):
         if k == 30:
-            import ctypes as C
-
             ob.lib().orc_reset(o.h)
             e.reset()
             assert e.state().n_cam_states == 0 and e.state().is_gravity_set == 0
@@ -377,28 +481,27 @@ def test_full_pipeline_equidistant_model(eng, ob, synth):
         cfg.cam0_distortion[i] = v
     for i, v in enumerate([-0.0121, 0.018, -0.027, 0.011]):
         cfg.cam1_distortion[i] = v
-    s = synth.Stream(cfg, seed=3)
+    est_o, est_g, gt, st = _full_pipeline_run(eng, ob, synth, cfg, 3, 80)
+    assert st.n_updates >= 20
+
+
+def test_injected_message_over_capacity_is_refused(eng, synth):
+    """A caller-supplied CameraMeasurement with more distinct ids than the find-or-insert table of
+    be_add_obs_kernel can hold is refused with MSKF_ERR_CAPACITY (it used to spin in the probe loop); a
+    message that only overflows the feature map's slots is processed and counted."""
+    cfg = synth.default_config("ref")
     e = eng.Engine(cfg, 1)
-    o = ob.Oracle(cfg)
-
-    class Both:
-        def imu(self, t, w, a):
-            o.imu(t, w, a)
-            e.imu_callback(t, w, a)
-
-        def stereo(self, t, i0, i1):
-            o.stereo(t, i0, i1)
-            e.push_stereo(t, i0, i1)
-
-        def backend(self):
-            o.backend()
-            e.step()
-
-    seen = False
-    for k, t in synth.feed(s, 80, Both()):
-        (to, fo, no), (tg, fg, ng) = o.features(), e.features()
-        assert to == tg and no == ng and fo.tobytes() == fg.tobytes(), k
-        _compare(o, e, k, seen)
-        seen = seen or o.state().n_updates > 0
-    assert o.state().n_updates >= 20
+    t = 100.0
+    for i in range(210):  # static start: gravity initialisation after 200 samples (msckf_vio.cpp:198)
+        e.imu_callback(t + 0.005 * i, np.zeros(3), np.array([0.0, 0.0, 9.81]))
+    assert e.state().is_gravity_set == 1
+    f = np.zeros(5000, eng.FEAT_DT)
+    f["id"] = np.arange(5000)
+    f["u0"], f["u1"] = 0.01, -0.02
+    with pytest.raises(eng.EngineError):
+        e.backend_features(t + 1.05, f)
+    e.backend_features(t + 1.05, f[:500])  # more than the map's free slots: the tail is dropped, nothing hangs
+    e.sync()
+    st = e.state()
+    assert st.n_cam_states == 1 and 0 < st.n_map_features <= 500
     e.close()

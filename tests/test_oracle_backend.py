@@ -115,3 +115,68 @@ def test_filter_tracks_ground_truth(ob, synth):
     est, gt = np.array(est), np.array(gt)
     assert abs(np.linalg.norm(est[-1]) - np.linalg.norm(gt[-1])) < 0.1
     assert abs(np.linalg.norm(np.array(st.gravity[:])) - 9.81) < 0.05
+
+
+def test_triangulation_recovers_scene_points(ob, synth):
+    """Feature::checkMotion / initializePosition (feature.hpp:257-450) on a seeded multi-view scene with
+    noise and 10 % outliers beyond the Huber radius: well-observed points are recovered, and a
+    positive translation threshold rejects features whose first and last views are too close."""
+    from tri_scene import make_scene
+
+    cfg = synth.default_config("bench")
+    q, p, mask, obs, pts = make_scene(cfg, 30, 200, 0)
+    pos, ok = ob.triangulate(cfg, q, p, mask, obs)
+    nobs = np.array([bin(int(m)).count("1") for m in mask])
+    err = np.linalg.norm(pos - pts, axis=1)
+    good = (ok == 1) & (nobs >= 8)
+    assert good.sum() > 100 and np.median(err[good]) < 0.05
+    cfg2 = copy_cfg(cfg, feature_translation_threshold=0.6)
+    pos2, ok2 = ob.triangulate(cfg2, q, p, mask, obs)
+    assert 0 < ok2.sum() < ok.sum()
+    assert np.all(pos2[ok2 == 1] == pos[ok2 == 1])
+
+
+def test_reference_is_not_1e9_reproducible_under_one_ulp(ob, synth):
+    """The noise floor of the reference algorithm itself, which bounds what a whole-run covariance
+    comparison can ask of ANY implementation: two CPU oracles on the same stream, the second one fed
+    the first one's CameraMeasurement with u0 moved by one ulp.  Feature::initializePosition's accept
+    rule (new_cost < total_cost, feature.hpp:417) is decided by rounding for the last LM steps, a
+    re-rolled step moves a triangulated point by z^2 |delta rho| and the covariance by ~1e-9: the two
+    oracles agree to 1e-9 in the IMU state but NOT in P (1.5e-9 by frame 60), while the discrete state
+    stays identical.  tests/test_gpu_backend.py holds the engine to 1e-9 (states) / 1e-8 (P)."""
+    cfg = synth.default_config("bench")
+    s = synth.Stream(cfg, seed=1)
+    a, b = ob.Oracle(cfg), ob.Oracle(cfg)
+
+    class Both:
+        def imu(self, t, w, acc):
+            a.imu(t, w, acc)
+            b.imu(t, w, acc)
+
+        def stereo(self, t, i0, i1):
+            a.stereo(t, i0, i1)
+
+        def backend(self):
+            a.backend()
+            t, f, _ = a.features()
+            g = f.copy()
+            g["u0"] = np.nextafter(g["u0"], np.inf)
+            b.backend_features(t, g)
+
+    dP = dp = dpos = 0.0
+    for k, t in synth.feed(s, 62, Both()):
+        sa, sb = a.state(), b.state()
+        assert (sa.n_cam_states, sa.n_updates, sa.n_map_features) == (sb.n_cam_states, sb.n_updates, sb.n_map_features)
+        if not sa.n_cam_states:
+            continue
+        Pa, Pb = a.cov(), b.cov()
+        dP = max(dP, np.abs(Pa - Pb).max() / np.abs(Pa).max())
+        dp = max(dp, np.abs(np.array(sa.position[:]) - np.array(sb.position[:])).max())
+        ia, na, pa, _ = a.feature_map()
+        ib, nb, pb, _ = b.feature_map()
+        assert np.array_equal(ia, ib) and np.array_equal(na, nb)
+        if na.any():
+            dpos = max(dpos, np.abs(pa - pb)[na == 1].max())
+    assert dp < 1e-9
+    assert 1e-9 < dP < 1e-8      # measured 1.47e-9
+    assert 1e-9 < dpos < 1e-6    # measured 4.1e-8 m: one re-rolled LM step
