@@ -248,6 +248,9 @@ template <typename F>
 int smem_optin(mskf_handle *h, F *kernel, size_t need) {
     int optin = 0;
     cudaError_t e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+    cudaFuncAttributes fa;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, kernel);
+    if (e == cudaSuccess) optin -= (int)fa.sharedSizeBytes;  // static + dynamic share the per-block limit
     if (e == cudaSuccess && need > (size_t)optin) {
         h->err = "configuration needs more shared memory per block than the device offers";
         return MSKF_ERR_CAPACITY;
