@@ -77,6 +77,7 @@ struct BeState {
     // per-step scratch
     int n_list;          // length of the current feature list
     int m, k, mt;        // stacked rows, compact columns, rows after compression
+    int t_upper;         // Tm is upper triangular (the QR compression ran)
     int u_nslots;
     int u_slots[NSM];
     int colpos[NSM];
@@ -1334,125 +1335,142 @@ __global__ void __launch_bounds__(BE_THREADS) be_layout_kernel(BeConst bc, BeBuf
 }
 
 // ======================================================================================
-// CTA-level fp64 GEMM tile: C[i0.., j0..] (64 x 64) = sum_l A(i, l) B(l, j), operands fetched
-// through functors (gathers by camera slot, transposes), staged in shared memory, 4x4
-// register micro-tiles.  256 threads.
+// CTA-level fp64 GEMM tile on the fp64 tensor pipe (mma.sync m8n8k4, SASS DMMA.8x8x4: one per 4
+// cycles per SM = 37 TFLOP/s, tools/micro/dmma_rate.cu):  C (<= 64 x 64) = sum_l A(i, l) B(j, l).
+//   * Operands go global -> shared with 8-byte cp.async (LDGSTS; rows of P start on odd multiples of
+//     8 bytes, so 16-byte copies are not possible), two stages of 16 k: the copies of chunk c + 1 are in
+//     flight while the DMMAs of chunk c run, and no register or thread is spent on staging.
+//   * Shared-memory layout [row][k] with a row stride of 20 doubles (B may also be [k][col] with a
+//     stride of 68): the 32 addresses of a fragment load (8 rows x 4 k) fall into 32 different 8-byte
+//     banks-pairs, i.e. every LDS.64 is conflict-free.
+//   * 8 warps as 2 x 4: a warp owns 32 rows x 16 columns = 4 x 2 DMMA tiles, so per k-step of 4 it
+//     loads 4 A and 2 B fragments for 8 DMMAs (the first version loaded 9 for 8).
+//   * Tiles are not a fixed 64: a dimension n is cut into ceil(n / 64) tiles of equal numbers of 8-row
+//     blocks (201 rows -> 56, 48, 48, 49 instead of 64, 64, 64, 9), and DMMA tiles outside the matrix
+//     are skipped (warp-uniform).
 // ======================================================================================
 #define GT 64
-#define GKK 16
-struct GemmSmem {
-    double a[GKK][GT + 1];
-    double b[GKK][GT + 1];
+#define UG_K 16
+#define UG_RS (UG_K + 4)
+#define UG_RSB (GT + 4)
+struct UpdGemmSmem {
+    double a[2][GT * UG_RS];
+    double b[2][GT * UG_RS];  // K-slow B needs UG_K * UG_RSB = 1088 <= 1280 doubles
 };
 
-template <bool A_KFAST, bool B_KFAST, class FA, class FB, class FC>
-__device__ __forceinline__ void cta_gemm_tile(int M, int N, int K, int i0, int j0, FA fa, FB fb, FC fc, GemmSmem &sm) {
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    double acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-    for (int k0 = 0; k0 < K; k0 += GKK) {
-        __syncthreads();
-        for (int e = tid; e < GT * GKK; e += BE_THREADS) {
-            int i, l;
-            if (A_KFAST) { i = e / GKK; l = e - i * GKK; } else { l = e / GT; i = e - l * GT; }
-            int gi = i0 + i, gl = k0 + l;
-            sm.a[l][i] = (gi < M && gl < K) ? fa(gi, gl) : 0.0;
-        }
-        for (int e = tid; e < GT * GKK; e += BE_THREADS) {
-            int j, l;
-            if (B_KFAST) { j = e / GKK; l = e - j * GKK; } else { l = e / GT; j = e - l * GT; }
-            int gj = j0 + j, gl = k0 + l;
-            sm.b[l][j] = (gj < N && gl < K) ? fb(gl, gj) : 0.0;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int l = 0; l < GKK; ++l) {
-            double av[4], bv[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) av[a] = sm.a[l][ty * 4 + a];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) bv[b] = sm.b[l][tx * 4 + b];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] += av[a] * bv[b];
-        }
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            int gi = i0 + ty * 4 + a, gj = j0 + tx * 4 + b;
-            if (gi < M && gj < N) fc(gi, gj, acc[a][b]);
-        }
-}
-
-// Same tile, inner product on the fp64 tensor pipe: mma.sync m8n8k4 (DMMA).  Warp w owns rows
-// [8w, 8w+8) of the 64 x 64 tile and all eight 8-column sub-tiles (16 accumulator doubles per thread);
-// per k-step of 4 it loads one A fragment and eight B fragments from the staged tiles.
 __device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+// 8-byte asynchronous copy global -> shared; !valid writes zeros (src-size 0: nothing is read)
+__device__ __forceinline__ void cp_async8(double *dst, const double *src, bool valid) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(src), "r"(sz) : "memory");
+}
+// tile t of a dimension of n elements: [start, start + count), count <= 64, a multiple of 8 except at the end
+__device__ __forceinline__ int ug_tiles(int n) { return ((n + 7) / 8 + 7) / 8; }
+__device__ __forceinline__ void ug_range(int n, int t, int &start, int &count) {
+    const int nb = (n + 7) / 8, nt = (nb + 7) / 8;
+    const int b0 = t * nb / nt, b1 = (t + 1) * nb / nt;
+    start = 8 * b0;
+    count = min(n, 8 * b1) - start;
+}
 
-template <bool A_KFAST, bool B_KFAST, class FA, class FB, class FC>
-__device__ __forceinline__ void cta_gemm_tile_dmma(int M, int N, int K, int i0, int j0, FA fa, FB fb, FC fc, GemmSmem &sm) {
+// acc += A B^T over k in [k_begin, k_end) for a tile of mr rows and nc columns.  pa(row, l) / pb(l, col) give
+// the address of an operand element (only called for elements inside the tile and the k range); `dummy` is
+// any valid address (used for the zero-filled copies).  B_KFAST: B's k index is the contiguous one.
+template <bool B_KFAST, class PA, class PB>
+__device__ __forceinline__ void upd_gemm_tile(int mr, int nc, int k_begin, int k_end, PA pa, PB pb, const double *dummy,
+                                              UpdGemmSmem &sm, double (&acc)[4][2][2]) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
-    double acc[8][2];
+    const int wr = warp >> 2, wc = warp & 3;
 #pragma unroll
-    for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = 0.0;
-    // Software pipeline: the operands of chunk k0 + GKK travel from global memory to registers while the
-    // DMMAs of chunk k0 run (each thread stages GT * GKK / BE_THREADS = 4 elements of A and of B).
-    constexpr int PER = GT * GKK / BE_THREADS;
-    double ra[PER], rb[PER];
-    auto fetch = [&](int k0) {
+    for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int u = 0; u < PER; ++u) {
-            const int e = tid + u * BE_THREADS;
-            int i, l;
-            if (A_KFAST) { i = e / GKK; l = e - i * GKK; } else { l = e / GT; i = e - l * GT; }
-            const int gi = i0 + i, gl = k0 + l;
-            ra[u] = (gi < M && gl < K) ? fa(gi, gl) : 0.0;
-            int j, lb;
-            if (B_KFAST) { j = e / GKK; lb = e - j * GKK; } else { lb = e / GT; j = e - lb * GT; }
-            const int gj = j0 + j, glb = k0 + lb;
-            rb[u] = (gj < N && glb < K) ? fb(glb, gj) : 0.0;
+        for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    k_begin &= ~(UG_K - 1);
+    const int nchunks = (k_end - k_begin + UG_K - 1) / UG_K;
+    if (nchunks <= 0) return;
+    auto stage = [&](int buf, int k0) {
+        // A (and a K-fast B): thread -> k offset tid & 15, rows (tid >> 4) + 16 u
+        const int l = k0 + (tid & 15);
+        const bool lv = l < k_end;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int row = (tid >> 4) + 16 * u;
+            const bool v = lv && row < mr;
+            cp_async8(&sm.a[buf][row * UG_RS + (tid & 15)], v ? pa(row, l) : dummy, v);
         }
+        if (B_KFAST) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int col = (tid >> 4) + 16 * u;
+                const bool v = lv && col < nc;
+                cp_async8(&sm.b[buf][col * UG_RS + (tid & 15)], v ? pb(l, col) : dummy, v);
+            }
+        } else {
+            // K-slow B: thread -> column tid & 63, k offsets (tid >> 6) + 4 u
+            const int col = tid & 63;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int lo = (tid >> 6) + 4 * u, lb = k0 + lo;
+                const bool v = lb < k_end && col < nc;
+                cp_async8(&sm.b[buf][lo * UG_RSB + col], v ? pb(lb, col) : dummy, v);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    fetch(0);
-    for (int k0 = 0; k0 < K; k0 += GKK) {
-        __syncthreads();
+    bool mv[4], nv[2];
 #pragma unroll
-        for (int u = 0; u < PER; ++u) {
-            const int e = tid + u * BE_THREADS;
-            int i, l;
-            if (A_KFAST) { i = e / GKK; l = e - i * GKK; } else { l = e / GT; i = e - l * GT; }
-            sm.a[l][i] = ra[u];
-            int j, lb;
-            if (B_KFAST) { j = e / GKK; lb = e - j * GKK; } else { lb = e / GT; j = e - lb * GT; }
-            sm.b[lb][j] = rb[u];
+    for (int mi = 0; mi < 4; ++mi) mv[mi] = wr * 32 + mi * 8 < mr;
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) nv[ni] = wc * 16 + ni * 8 < nc;
+    stage(0, k_begin);
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) {
+            stage((c + 1) & 1, k_begin + (c + 1) * UG_K);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        if (k0 + GKK < K) fetch(k0 + GKK);
+        if (mv[0] && nv[0]) {
+            const double *as = sm.a[c & 1] + (wr * 32 + g) * UG_RS + t4;
+            const double *bs = B_KFAST ? sm.b[c & 1] + (wc * 16 + g) * UG_RS + t4 : sm.b[c & 1] + t4 * UG_RSB + wc * 16 + g;
 #pragma unroll
-        for (int kk = 0; kk < GKK; kk += 4) {
-            const double a = sm.a[kk + t4][warp * 8 + g];
+            for (int kk = 0; kk < UG_K; kk += 4) {
+                double af[4], bf[2];
 #pragma unroll
-            for (int n = 0; n < 8; ++n) dmma_884(acc[n][0], acc[n][1], a, sm.b[kk + t4][n * 8 + g]);
+                for (int mi = 0; mi < 4; ++mi) af[mi] = as[mi * 8 * UG_RS + kk];
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) bf[ni] = B_KFAST ? bs[ni * 8 * UG_RS + kk] : bs[kk * UG_RSB + ni * 8];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ++ni)
+                        if (mv[mi] && nv[ni]) dmma_884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+            }
         }
+        __syncthreads();  // everyone is done with buffer c & 1 before chunk c + 2 lands in it
     }
+}
+// f(row, col, value) for every accumulator element of this thread inside the tile
+template <class F>
+__device__ __forceinline__ void upd_gemm_store(int mr, int nc, const double (&acc)[4][2][2], F f) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3, wr = warp >> 2, wc = warp & 3;
 #pragma unroll
-    for (int n = 0; n < 8; ++n)
+    for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-            int gi = i0 + warp * 8 + g, gj = j0 + n * 8 + 2 * t4 + h2;
-            if (gi < M && gj < N) fc(gi, gj, acc[n][h2]);
-        }
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int row = wr * 32 + mi * 8 + g, col = wc * 16 + ni * 8 + 2 * t4 + h2;
+                if (row < mr && col < nc) f(row, col, acc[mi][ni][h2]);
+            }
 }
 
 // In-place Cholesky of an n x n matrix in shared memory (row-major, leading dimension ld,
@@ -2405,7 +2423,10 @@ __global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb,
     if (m <= k) {
         for (int e = threadIdx.x; e < m * k; e += QR_THREADS) Tm[e] = Hst[e];
         for (int i = threadIdx.x; i < m; i += QR_THREADS) rt[i] = rst[i];
-        if (threadIdx.x == 0) st.mt = m;
+        if (threadIdx.x == 0) {
+            st.mt = m;
+            st.t_upper = 0;
+        }
         return;
     }
     const int kw = k + 1, ldr = KC + 1;
@@ -2454,7 +2475,10 @@ __global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb,
     __syncthreads();
     if (ng == 1) {
         qr_extract(R, ldr, k, Tm, rt);
-        if (threadIdx.x == 0) st.mt = k;
+        if (threadIdx.x == 0) {
+            st.mt = k;
+            st.t_upper = 1;
+        }
     } else {
         unsigned char *fl = bb.Rfill + ((size_t)s * QR_G + g) * ldr;
         for (int j = threadIdx.x; j < k; j += QR_THREADS) fl[j] = sh.filled[j];
@@ -2521,7 +2545,10 @@ __global__ void __launch_bounds__(QR_THREADS) be_qr_combine_kernel(BeConst bc, B
     if (level == 2) {
         __syncthreads();
         qr_extract(Rd, ldr, k, bb.Tm + (size_t)s * KC * KC, bb.rt + (size_t)s * KC);
-        if (threadIdx.x == 0) st.mt = k;
+        if (threadIdx.x == 0) {
+            st.mt = k;
+            st.t_upper = 1;
+        }
     } else {
         __syncthreads();
         for (int j = threadIdx.x; j < k; j += QR_THREADS) fd[j] = sh.filled[j];
@@ -2529,73 +2556,94 @@ __global__ void __launch_bounds__(QR_THREADS) be_qr_combine_kernel(BeConst bc, B
 }
 
 // ======================================================================================
-// Grouped GEMMs of the update, one 64x64 tile per CTA, grid (tiles, S).
-//   OP 0: PHt (LD x mt) = P[:, cols] T^T          OP 1: S (mt x mt) = T PHt[cols, :] + sigma^2 I
-//   OP 2: W (LD x mt)  = PHt Linv^T               OP 3: P <- P - W W^T (lower tiles, mirrored)
+// Grouped GEMMs of the update, one tile (<= 64 x 64) per CTA, grid (tiles, S).  T is the compressed
+// measurement matrix over the k active camera columns: upper triangular when the QR compression ran
+// (st.t_upper), which lets the k loop start at the tile's first row of T.
+//   OP 0: PHt (LD x mt) = P[:, cols] T^T          OP 1: S (mt x mt, lower tiles) = T PHt[cols, :] + sigma^2 I
+//   OP 2: W (LD x mt)  = PHt Linv^T (Linv lower triangular: k stops at the tile's last column)
+//   OP 3: P <- P - W W^T (lower tiles, mirrored through shared memory so both halves are written coalesced)
 // ======================================================================================
 template <int OP>
-__global__ void __launch_bounds__(BE_THREADS) be_gemm_kernel(BeConst bc, BeBuf bb) {
+__global__ void __launch_bounds__(BE_THREADS, 2) be_gemm_kernel(BeConst bc, BeBuf bb) {
     const int s = blockIdx.y;
     const BeStep sp = bb.step[s];
     if (!sp.active) return;
     const BeState &st = bb.st[s];
     if (!st.do_update) return;
     const int LD = bc.LD, KC = bc.KC, k = st.k, mt = st.mt;
-    __shared__ GemmSmem gs;
+    if (mt <= 0) return;
+    __shared__ __align__(16) UpdGemmSmem gs;
     __shared__ int cols[6 * NSM];
-    for (int l = threadIdx.x; l < k; l += BE_THREADS) cols[l] = N21 + 6 * st.u_slots[l / 6] + (l % 6);
-    __syncthreads();
     double *P = bb.P + (size_t)s * LD * LD;
     const double *Tm = bb.Tm + (size_t)s * KC * KC;
     double *PHt = bb.PHt + (size_t)s * LD * KC;
     double *Sm = bb.Sm + (size_t)s * KC * KC;
     const double *Linv = bb.Linv + (size_t)s * KC * KC;
     double *W = bb.W + (size_t)s * LD * KC;
-    if (OP == 0) {
-        const int tn = (mt + GT - 1) / GT;
+    double acc[4][2][2];
+    int i0, mr, j0, nc;
+    if (OP == 0 || OP == 2) {
+        const int tn = ug_tiles(mt);
         const int ti = blockIdx.x / tn, tj = blockIdx.x % tn;
-        if (ti * GT >= LD || tn == 0) return;
-        cta_gemm_tile_dmma<true, true>(
-            LD, mt, k, ti * GT, tj * GT, [&](int i, int l) { return P[(size_t)i * LD + cols[l]]; },
-            [&](int l, int j) { return Tm[j * k + l]; }, [&](int i, int j, double v) { PHt[(size_t)i * KC + j] = v; }, gs);
-    } else if (OP == 1) {
-        const int tn = (mt + GT - 1) / GT;
-        const int ti = blockIdx.x / tn, tj = blockIdx.x % tn;
-        if (ti >= tn) return;
-        cta_gemm_tile_dmma<true, false>(
-            mt, mt, k, ti * GT, tj * GT, [&](int i, int l) { return Tm[i * k + l]; },
-            [&](int l, int j) { return PHt[(size_t)cols[l] * KC + j]; },
-            [&](int i, int j, double v) { Sm[i * KC + j] = v + (i == j ? bc.obs_noise : 0.0); }, gs);
-    } else if (OP == 2) {
-        const int tn = (mt + GT - 1) / GT;
-        const int ti = blockIdx.x / tn, tj = blockIdx.x % tn;
-        if (ti * GT >= LD) return;
-        cta_gemm_tile_dmma<true, true>(
-            LD, mt, mt, ti * GT, tj * GT, [&](int i, int l) { return PHt[(size_t)i * KC + l]; },
-            [&](int l, int j) { return Linv[j * KC + l]; }, [&](int i, int j, double v) { W[(size_t)i * KC + j] = v; }, gs);
+        if (ti >= ug_tiles(LD)) return;
+        ug_range(LD, ti, i0, mr);
+        ug_range(mt, tj, j0, nc);
     } else {
         // lower-triangular tile pairs: blockIdx.x -> (ti >= tj)
         int t = blockIdx.x, ti = 0;
         while (t > ti) { t -= ti + 1; ++ti; }
-        const int tj = t;
-        if (ti * GT >= LD) return;
-        cta_gemm_tile_dmma<true, true>(
-            LD, LD, mt, ti * GT, tj * GT, [&](int i, int l) { return W[(size_t)i * KC + l]; },
-            [&](int l, int j) { return W[(size_t)j * KC + l]; },
-            [&](int i, int j, double v) {
-                if (ti != tj) {
-                    double x = P[(size_t)i * LD + j] - v;
-                    P[(size_t)i * LD + j] = x;
-                    P[(size_t)j * LD + i] = x;
-                } else if (j <= i) {
-                    // diagonal tile: (i, j) and (j, i) are computed from the same products in the
-                    // same order, so taking the lower one for both keeps P exactly symmetric
-                    double x = P[(size_t)i * LD + j] - v;
-                    P[(size_t)i * LD + j] = x;
-                    P[(size_t)j * LD + i] = x;
-                }
-            },
-            gs);
+        const int tj = t, n = OP == 1 ? mt : LD;
+        if (ti >= ug_tiles(n)) return;
+        ug_range(n, ti, i0, mr);
+        ug_range(n, tj, j0, nc);
+    }
+    if (OP == 0 || OP == 1) {
+        for (int l = threadIdx.x; l < k; l += BE_THREADS) cols[l] = N21 + 6 * st.u_slots[l / 6] + (l % 6);
+        __syncthreads();
+    }
+    if (OP == 0) {
+        upd_gemm_tile<true>(
+            mr, nc, st.t_upper ? j0 : 0, k, [&](int r, int l) { return P + (size_t)(i0 + r) * LD + cols[l]; },
+            [&](int l, int c) { return Tm + (size_t)(j0 + c) * k + l; }, P, gs, acc);
+        upd_gemm_store(mr, nc, acc, [&](int r, int c, double v) { PHt[(size_t)(i0 + r) * KC + j0 + c] = v; });
+    } else if (OP == 1) {
+        upd_gemm_tile<false>(
+            mr, nc, st.t_upper ? i0 : 0, k, [&](int r, int l) { return Tm + (size_t)(i0 + r) * k + l; },
+            [&](int l, int c) { return PHt + (size_t)cols[l] * KC + j0 + c; }, P, gs, acc);
+        upd_gemm_store(mr, nc, acc, [&](int r, int c, double v) {
+            const int i = i0 + r, j = j0 + c;
+            Sm[i * KC + j] = v + (i == j ? bc.obs_noise : 0.0);
+        });
+    } else if (OP == 2) {
+        upd_gemm_tile<true>(
+            mr, nc, 0, min(mt, j0 + nc), [&](int r, int l) { return PHt + (size_t)(i0 + r) * KC + l; },
+            [&](int l, int c) { return Linv + (size_t)(j0 + c) * KC + l; }, P, gs, acc);
+        upd_gemm_store(mr, nc, acc, [&](int r, int c, double v) { W[(size_t)(i0 + r) * KC + j0 + c] = v; });
+    } else {
+        upd_gemm_tile<true>(
+            mr, nc, 0, mt, [&](int r, int l) { return W + (size_t)(i0 + r) * KC + l; },
+            [&](int l, int c) { return W + (size_t)(j0 + c) * KC + l; }, P, gs, acc);
+        // P[i][j] and P[j][i] get the same value x = P[i][j] - (W W^T)[i][j], taken from the lower triangle (on a
+        // diagonal tile (i, j) and (j, i) are computed from the same products in the same order anyway), so P
+        // stays exactly symmetric.  The tile goes through shared memory so that the mirrored half is written
+        // in rows as well.
+        double *Ct = gs.a[0];  // [64][65], the staging buffers are free now (upd_gemm_tile ends with a barrier)
+        const bool diag = i0 == j0;
+        upd_gemm_store(mr, nc, acc, [&](int r, int c, double v) { Ct[r * 65 + c] = v; });
+        __syncthreads();
+        for (int e = threadIdx.x; e < mr * nc; e += BE_THREADS) {
+            const int r = e / nc, c = e - r * nc;
+            if (diag && c > r) continue;
+            const double x = P[(size_t)(i0 + r) * LD + j0 + c] - Ct[r * 65 + c];
+            P[(size_t)(i0 + r) * LD + j0 + c] = x;
+            Ct[r * 65 + c] = x;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < mr * nc; e += BE_THREADS) {
+            const int c = e / mr, r = e - c * mr;  // r fastest: row j0 + c of P, columns i0 + r
+            if (diag && c >= r) continue;
+            P[(size_t)(j0 + c) * LD + i0 + r] = Ct[r * 65 + c];
+        }
     }
 }
 
@@ -3119,7 +3167,7 @@ static void launch_update(mskf_handle *h, int phase = 0) {
     MSKF_LAUNCH(h, PK_BE_QR_COMBINE, (be_qr_combine_kernel<<<dim3(2, S), QR_THREADS, 0, q>>>(bc, bb, 1)));
     MSKF_LAUNCH(h, PK_BE_QR_COMBINE, (be_qr_combine_kernel<<<dim3(1, S), QR_THREADS, 0, q>>>(bc, bb, 2)));
     MSKF_LAUNCH(h, PK_BE_GEMM_PHT, (be_gemm_kernel<0><<<dim3(tiles_ld * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
-    MSKF_LAUNCH(h, PK_BE_GEMM_S, (be_gemm_kernel<1><<<dim3(tiles_kc * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
+    MSKF_LAUNCH(h, PK_BE_GEMM_S, (be_gemm_kernel<1><<<dim3(tiles_kc * (tiles_kc + 1) / 2, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_CHOL, (be_chol_kernel<<<S, CH_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_GEMM_W, (be_gemm_kernel<2><<<dim3(tiles_ld * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_APPLY, (be_apply_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb)));

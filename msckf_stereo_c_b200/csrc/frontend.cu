@@ -495,6 +495,173 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
     }
 }
 
+// --------------------------------------------------------------------------------------
+// Register version for compile-time windows (15, 21): no shared memory at all.
+//   * Lane l owns column l of the (WIN + 2)-wide template patch: it loads the WIN + 3 raw bytes of its
+//     column (independent loads, all in flight together), takes the right-hand neighbours by shuffle and
+//     keeps its column of T in registers.  The gradients of window column i = l - 1 need T of lanes
+//     l - 1 / l + 1 (two shuffles per row) and the lane's own column for the vertical difference; they stay
+//     in registers as one packed (gx, gy) word per row for all iterations of the level.
+//   * The mismatch vector is accumulated as sum(val * g) - sum(T * g): the second term is a per-level
+//     constant, so an iteration touches neither T nor shared memory (integers: the sums are exact, the
+//     result is identical to the oracle's sum((val - T) * g)).
+//   * Every warp sum is two REDUX.SUM (the 32-bit partial split into its low 16 bits and the rest: both
+//     halves of the 64-bit total fit 32 bits) instead of a 5-step 64-bit shuffle tree.
+// --------------------------------------------------------------------------------------
+// base + y * cols as ONE 32 x 32 + 64-bit multiply-add (the compiler otherwise folds the column offset into the
+// product and adds the 64-bit level pointer separately: three instructions per row instead of one)
+__device__ __forceinline__ const uint8_t *row_ptr(const uint8_t *base, int y, int cols) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"((unsigned)y), "r"((unsigned)cols), "l"((unsigned long long)base));
+    return (const uint8_t *)r;
+}
+__device__ __forceinline__ long long warp_sum_i32(int v) {
+    const int lo = v & 0xffff, hi = v >> 16;  // v = hi * 65536 + lo, 0 <= lo < 65536
+    return ((long long)__reduce_add_sync(0xffffffffu, hi) << 16) + (long long)__reduce_add_sync(0xffffffffu, lo);
+}
+
+template <int WIN>
+__global__ void __launch_bounds__(KLT_WARPS * 32) klt_reg_kernel(FeConst fc, FeBuffers fb, int mode) {
+    static_assert(WIN >= 3 && WIN + 3 <= 32 && (WIN & 1), "window");
+    const int s = blockIdx.y;
+    const FeStep st = fb.step[s];
+    if (!st.active) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * KLT_WARPS + warp;
+    if (f >= fb.k_n[s]) return;
+    if (mode == 2 && fb.k_skip[(size_t)s * fc.cap_k + f]) {
+        if (lane == 0) fb.k_status[(size_t)s * fc.cap_k + f] = 0;
+        return;
+    }
+    const uint8_t *pa = (mode == 0 ? fb.pyr[st.slot ^ 1] : fb.pyr[st.slot]) + (size_t)s * fc.pyr_bytes;
+    const uint8_t *pb = (mode == 0 ? fb.pyr[st.slot] : fb.pyr[2]) + (size_t)s * fc.pyr_bytes;
+    constexpr int half = WIN >> 1, tw = WIN + 2;
+    const bool act = lane >= 1 && lane <= WIN;  // lanes that own a window column (i = lane - 1)
+
+    const float2 p0 = fb.k_a[(size_t)s * fc.cap_k + f];
+    const float2 q0 = fb.k_b[(size_t)s * fc.cap_k + f];
+    int status = 1;
+    const int L = fc.levels;
+    const float top_scale = 1.0f / (float)(1 << (L - 1));
+    float qx = q0.x * top_scale, qy = q0.y * top_scale;
+    for (int l = L - 1; l >= 0; --l) {
+        const int rows = fc.lvl_rows[l], cols = fc.lvl_cols[l];
+        const uint8_t *A = pa + fc.lvl_off[l], *B = pb + fc.lvl_off[l];
+        const float sc = 1.0f / (float)(1 << l);
+        const float px = p0.x * sc, py = p0.y * sc;
+        const BilinW wa = bilin_weights(px, py);
+        int G[WIN];  // (gy << 16) | (gx & 0xffff) of window column lane - 1, rows 0 .. WIN - 1
+        int a11i = 0, a12i = 0, a22i = 0, c1i = 0, c2i = 0;
+        {
+            // template column T[j], j in [0, tw): A sampled at (px + lane - half - 1, py + j - half - 1)
+            const int xc = min(max(wa.ix - half - 1 + lane, 0), cols - 1);
+            const int y0 = wa.iy - half - 1;
+            const uint8_t *Ax = A + xc;  // one 32 x 32 + 64-bit multiply-add per row address
+            int raw[WIN + 3];
+#pragma unroll
+            if (y0 >= 0 && y0 + WIN + 2 <= rows - 1) {  // warp-uniform: no row of the patch needs clamping
+                const uint8_t *Ay = row_ptr(Ax, y0, cols);
+#pragma unroll
+                for (int j = 0; j <= WIN + 2; ++j) raw[j] = __ldg(row_ptr(Ay, j, cols));
+            } else {
+#pragma unroll
+                for (int j = 0; j <= WIN + 2; ++j) raw[j] = __ldg(row_ptr(Ax, min(max(y0 + j, 0), rows - 1), cols));
+            }
+            int T[WIN + 2];
+            int n0 = __shfl_down_sync(0xffffffffu, raw[0], 1);
+#pragma unroll
+            for (int j = 0; j < WIN + 2; ++j) {
+                const int n1 = __shfl_down_sync(0xffffffffu, raw[j + 1], 1);
+                T[j] = (((wa.w00 * raw[j] + 256) + wa.w01 * n0) + wa.w10 * raw[j + 1] + wa.w11 * n1) >> 9;
+                n0 = n1;
+            }
+#pragma unroll
+            for (int j = 0; j < WIN; ++j) {
+                const int tl = __shfl_up_sync(0xffffffffu, T[j + 1], 1), tr = __shfl_down_sync(0xffffffffu, T[j + 1], 1);
+                const int gx = tr - tl, gy = T[j + 2] - T[j];  // garbage on the lanes without a window column: masked below
+                G[j] = (int)__byte_perm((unsigned)gx, (unsigned)gy, 0x5410);
+                a11i += gx * gx;
+                a12i += gx * gy;
+                a22i += gy * gy;
+                c1i += T[j + 1] * gx;
+                c2i += T[j + 1] * gy;
+            }
+        }
+        // A lane's partial sums fit 32 bits: |gx|, |gy|, T, val <= 255 * 32 = 8160, so a column of WIN <= 29
+        // products stays below 29 * 8160^2 = 1.93e9 < 2^31; the warp totals need 64 bits.
+        if (!act) a11i = a12i = a22i = c1i = c2i = 0;
+        const long long A11 = warp_sum_i32(a11i), A12 = warp_sum_i32(a12i), A22 = warp_sum_i32(a22i);
+        const double a11 = (double)A11, a12 = (double)A12, a22 = (double)A22;
+        const double m1 = a11 * a22, m2 = a12 * a12;
+        const double D = m1 - m2;
+        const double df = a11 - a22;
+        const double disc = df * df + 4.0 * m2;
+        const double lam = (a11 + a22 - sqrt(disc)) * 0.5;
+        const double min_eig = lam / (4194304.0 * (double)(WIN * WIN));
+        const bool ok = !(min_eig < fc.klt_min_eig || D < 1.1920929e-07);
+        if (!ok) {
+            if (l == 0) status = 0;
+        } else {
+            const long long C1 = warp_sum_i32(c1i), C2 = warp_sum_i32(c2i);
+            const double Dinv = 1.0 / D;
+            double pdx = 0, pdy = 0;
+            for (int it = 0; it < fc.klt_max_iters; ++it) {
+                if (qx < 0.f || qy < 0.f || qx > (float)(cols - 1) || qy > (float)(rows - 1)) {
+                    if (l == 0) status = 0;
+                    break;
+                }
+                const BilinW wb = bilin_weights(qx, qy);
+                int b1i = 0, b2i = 0;
+                {
+                    const int xc = min(max(wb.ix - half - 1 + lane, 0), cols - 1);
+                    const int y0 = wb.iy - half;
+                    const uint8_t *Bx = B + xc;
+                    int pxv[WIN + 1];
+#pragma unroll
+                    if (y0 >= 0 && y0 + WIN <= rows - 1) {
+                        const uint8_t *By = row_ptr(Bx, y0, cols);
+#pragma unroll
+                        for (int j = 0; j <= WIN; ++j) pxv[j] = __ldg(row_ptr(By, j, cols));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j <= WIN; ++j) pxv[j] = __ldg(row_ptr(Bx, min(max(y0 + j, 0), rows - 1), cols));
+                    }
+                    int n0 = __shfl_down_sync(0xffffffffu, pxv[0], 1);
+#pragma unroll
+                    for (int j = 0; j < WIN; ++j) {
+                        const int n1 = __shfl_down_sync(0xffffffffu, pxv[j + 1], 1);
+                        const int val = (((wb.w00 * pxv[j] + 256) + wb.w01 * n0) + wb.w10 * pxv[j + 1] + wb.w11 * n1) >> 9;
+                        b1i += val * (int)(short)(G[j] & 0xffff);
+                        b2i += val * (G[j] >> 16);
+                        n0 = n1;
+                    }
+                }
+                if (!act) b1i = b2i = 0;
+                const long long b1 = warp_sum_i32(b1i) - C1, b2 = warp_sum_i32(b2i) - C2;
+                const double fb1 = (double)b1, fb2 = (double)b2;
+                const double dx = (a12 * fb2 - a22 * fb1) * Dinv * 2.0;
+                const double dy = (a12 * fb1 - a11 * fb2) * Dinv * 2.0;
+                const float fdx = (float)dx, fdy = (float)dy;
+                qx += fdx;
+                qy += fdy;
+                if (dx * dx + dy * dy <= fc.klt_eps2) break;
+                if (it > 0 && fabs(dx + pdx) < 0.01 && fabs(dy + pdy) < 0.01) {
+                    qx -= fdx * 0.5f;
+                    qy -= fdy * 0.5f;
+                    break;
+                }
+                pdx = dx;
+                pdy = dy;
+            }
+        }
+        if (l > 0) { qx *= 2.0f; qy *= 2.0f; }
+    }
+    if (lane == 0) {
+        fb.k_b[(size_t)s * fc.cap_k + f] = make_float2(qx, qy);
+        fb.k_status[(size_t)s * fc.cap_k + f] = (uint8_t)status;
+    }
+}
+
 // ======================================================================================
 // FAST-9/16 + score + 3x3 NMS + Shi-Tomasi response + best-per-fine-cell (atomicMax).
 // Shared-memory tile with a 5-pixel halo; the 16-bit brighter/darker ring masks decide
@@ -1411,64 +1578,106 @@ __global__ void __launch_bounds__(FE_THREADS) fe_finish(FeConst fc, FeBuffers fb
         s_glife[i] = fb.g_life[gc][go + i];
     }
     __syncthreads();
-    // one thread per cell: choose the new features to add (best responses, stable)
-    for (int c = threadIdx.x; c < fc.n_cells_all; c += FE_THREADS) {
-        int cur = 0;
-        for (int i = 0; i < ncur; ++i)
-            if (s_gcell[i] == c) ++cur;
-        int add = 0;
-        if (c < fc.n_cells && cur < fc.grid_min) {
-            int vacancy = fc.grid_min - cur;
-            float last_r = 3.0e38f;
-            int last_i = -1;
-            for (int k = 0; k < vacancy; ++k) {
-                int bi = -1;
-                float br = -1.0f;
-                for (int i = 0; i < m; ++i) {
-                    if (s_icode[i] != c) continue;
-                    float r = s_iresp[i];
-                    bool after_last = (r < last_r) || (r == last_r && i > last_i);
-                    if (!after_last) continue;
-                    if (bi < 0 || r > br) { bi = i; br = r; }
+    // one WARP per cell: choose the new features to add (best responses, stable), then the members that
+    // survive pruneGridFeatures.  Lanes scan the candidate / member lists 32 at a time; a selection round
+    // is a warp arg-max over a 64-bit key (value, reversed position), so ties keep list order.
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const unsigned lt_mask = (1u << lane) - 1u;
+        for (int c = warp; c < fc.n_cells_all; c += FE_THREADS / 32) {
+            int cur = 0;
+            for (int i0 = 0; i0 < ncur; i0 += 32) {
+                const int i = i0 + lane;
+                cur += __popc(__ballot_sync(0xffffffffu, i < ncur && s_gcell[i] == c));
+            }
+            int add = 0;
+            if (c < fc.n_cells && cur < fc.grid_min) {
+                const int vacancy = fc.grid_min - cur;
+                float last_r = 3.0e38f;
+                int last_i = -1;
+                for (int k = 0; k < vacancy; ++k) {
+                    // best (largest response, then smallest index) candidate of this cell after (last_r, last_i)
+                    unsigned long long best = 0ull;  // (response bits | 1 << 63 never set: responses are >= 0) << 32 | ~index
+                    bool have = false;
+                    for (int i = lane; i < m; i += 32) {
+                        if (s_icode[i] != c) continue;
+                        const float r = s_iresp[i];
+                        const bool after_last = (r < last_r) || (r == last_r && i > last_i);
+                        if (!after_last) continue;
+                        const unsigned long long key = ((unsigned long long)__float_as_uint(r) << 32) | (unsigned)(0x7fffffff - i);
+                        if (!have || key > best) { best = key; have = true; }
+                    }
+                    unsigned long long kb = have ? (best | (1ull << 63)) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const unsigned long long other = __shfl_xor_sync(0xffffffffu, kb, o);
+                        kb = other > kb ? other : kb;
+                    }
+                    if (!(kb >> 63)) break;
+                    const int bi = 0x7fffffff - (int)(unsigned)(kb & 0xffffffffu);
+                    const float br = __uint_as_float((unsigned)((kb >> 32) & 0x7fffffffu));
+                    if (lane == 0) s_addsel[c * fc.grid_min + add] = bi;
+                    ++add;
+                    last_r = br;
+                    last_i = bi;
                 }
-                if (bi < 0) break;
-                s_addsel[c * fc.grid_min + add++] = bi;
-                last_r = br;
-                last_i = bi;
+            }
+            // members after the additions: tracked entries (index i, lifetime from the grid) then
+            // new ones (lifetime 1); pruneGridFeatures keeps the grid_max longest-lived (stable)
+            const int total = cur + add;
+            int keep = 0;
+            int *fin = s_final + c * fc.grid_max;
+            if (total <= fc.grid_max) {
+                for (int i0 = 0; i0 < ncur; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool mine = i < ncur && s_gcell[i] == c;
+                    const unsigned bal = __ballot_sync(0xffffffffu, mine);
+                    if (mine) fin[keep + __popc(bal & lt_mask)] = i;
+                    keep += __popc(bal);
+                }
+                for (int a = lane; a < add; a += 32) fin[keep + a] = -1 - a;
+                keep += add;
+            } else {
+                int last_l = 0x7fffffff, last_o = -1;
+                for (int k = 0; k < fc.grid_max; ++k) {
+                    // key: (lifetime << 32 | ~order) with the member's encoding as payload
+                    long long best = -1;
+                    int benc = 0, o_base = 0;
+                    for (int i0 = 0; i0 < ncur; i0 += 32) {
+                        const int i = i0 + lane;
+                        const bool mine = i < ncur && s_gcell[i] == c;
+                        const unsigned bal = __ballot_sync(0xffffffffu, mine);
+                        if (mine) {
+                            const int o = o_base + __popc(bal & lt_mask), l = s_glife[i];
+                            const bool after_last = (l < last_l) || (l == last_l && o > last_o);
+                            const long long key = ((long long)l << 32) | (unsigned)(0x7fffffff - o);
+                            if (after_last && key > best) { best = key; benc = i; }
+                        }
+                        o_base += __popc(bal);
+                    }
+                    for (int a = lane; a < add; a += 32) {
+                        const int o = o_base + a, l = 1;
+                        const bool after_last = (l < last_l) || (l == last_l && o > last_o);
+                        const long long key = ((long long)l << 32) | (unsigned)(0x7fffffff - o);
+                        if (after_last && key > best) { best = key; benc = -1 - a; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oe = __shfl_xor_sync(0xffffffffu, benc, o);
+                        if (ob > best) { best = ob; benc = oe; }
+                    }
+                    if (lane == 0) fin[keep] = benc;
+                    ++keep;
+                    last_l = (int)(best >> 32);
+                    last_o = 0x7fffffff - (int)(unsigned)(best & 0xffffffffu);
+                }
+            }
+            if (lane == 0) {
+                s_add[c] = add;
+                s_keep[c] = keep;
             }
         }
-        s_add[c] = add;
-        // members after the additions: tracked entries (index i, lifetime from the grid) then
-        // new ones (lifetime 1); pruneGridFeatures keeps the grid_max longest-lived (stable)
-        int total = cur + add;
-        int keep = 0;
-        int *fin = s_final + c * fc.grid_max;
-        if (total <= fc.grid_max) {
-            for (int i = 0; i < ncur; ++i)
-                if (s_gcell[i] == c) fin[keep++] = i;
-            for (int k = 0; k < add; ++k) fin[keep++] = -1 - k;
-        } else {
-            int last_l = 0x7fffffff, last_o = -1;
-            for (int k = 0; k < fc.grid_max; ++k) {
-                int bo = -1, bl = -1, benc = 0, o = 0;
-                for (int i = 0; i < ncur; ++i) {
-                    if (s_gcell[i] != c) continue;
-                    int l = s_glife[i];
-                    bool after_last = (l < last_l) || (l == last_l && o > last_o);
-                    if (after_last && (bo < 0 || l > bl)) { bo = o; bl = l; benc = i; }
-                    ++o;
-                }
-                for (int a = 0; a < add; ++a, ++o) {
-                    int l = 1;
-                    bool after_last = (l < last_l) || (l == last_l && o > last_o);
-                    if (after_last && (bo < 0 || l > bl)) { bo = o; bl = l; benc = -1 - a; }
-                }
-                fin[keep++] = benc;
-                last_l = bl;
-                last_o = bo;
-            }
-        }
-        s_keep[c] = keep;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1698,8 +1907,8 @@ static void launch_klt(mskf_handle *h, int tag, dim3 g, size_t smem, int mode) {
     const FeConst &fc = h->fc;
     const FeBuffers &fb = h->fb;
     cudaStream_t q = h->stream;
-    if (fc.klt_win == 21) MSKF_LAUNCH(h, tag, (klt_kernel<21><<<g, KLT_WARPS * 32, smem, q>>>(fc, fb, mode)));
-    else if (fc.klt_win == 15) MSKF_LAUNCH(h, tag, (klt_kernel<15><<<g, KLT_WARPS * 32, smem, q>>>(fc, fb, mode)));
+    if (fc.klt_win == 21) MSKF_LAUNCH(h, tag, (klt_reg_kernel<21><<<g, KLT_WARPS * 32, 0, q>>>(fc, fb, mode)));
+    else if (fc.klt_win == 15) MSKF_LAUNCH(h, tag, (klt_reg_kernel<15><<<g, KLT_WARPS * 32, 0, q>>>(fc, fb, mode)));
     else MSKF_LAUNCH(h, tag, (klt_kernel<0><<<g, KLT_WARPS * 32, smem, q>>>(fc, fb, mode)));
 }
 
