@@ -68,6 +68,24 @@ def main():
                                          criteria=(cv2.TERM_CRITERIA_COUNT | cv2.TERM_CRITERIA_EPS, 30, 0.01),
                                          flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
     np.savez_compressed(os.path.join(HERE, "cv2_klt.npz"), a=A, b=B, p0=p0, p1=p1.reshape(-1, 2), st=st.ravel())
+    # --- KLT under real motion: temporal pair (frames 70 -> 72, flow ~5 px) and stereo pair (cam0 -> cam1,
+    # initial guess -20 px, flow ~13 px) on a 256 x 384 crop; cv2 with a tight termination so that the
+    # vectors are OpenCV's fixed points, not its 0.01 px stopping noise
+    _, m0, m1 = s.render(70)
+    _, m2, _ = s.render(72)
+    sl = (slice(100, 356), slice(180, 564))
+    A, Bt, Bs = (np.ascontiguousarray(x[sl]) for x in (m0, m2, m1))
+    p0 = cv2.goodFeaturesToTrack(A, 150, 0.01, 10).reshape(-1, 2).astype(np.float32)
+    crit = (cv2.TERM_CRITERIA_COUNT | cv2.TERM_CRITERIA_EPS, 100, 1e-4)
+    out = {"a": A, "b_temporal": Bt, "b_stereo": Bs, "p0": p0}
+    for name, B, shift in (("temporal", Bt, (0.0, 0.0)), ("stereo", Bs, (-20.0, 0.0))):
+        g0 = (p0 + np.array(shift, np.float32)).reshape(-1, 1, 2)
+        p1, st, _ = cv2.calcOpticalFlowPyrLK(A, B, p0.reshape(-1, 1, 2), g0.copy(), winSize=(15, 15), maxLevel=3, criteria=crit,
+                                             flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+        out[f"p1_{name}"] = p1.reshape(-1, 2)
+        out[f"st_{name}"] = st.ravel()
+        out[f"guess_{name}"] = g0.reshape(-1, 2)
+    np.savez_compressed(os.path.join(HERE, "cv2_klt_motion.npz"), **out)
     print("golden vectors written to", HERE)
 
 
