@@ -322,6 +322,7 @@ __device__ __forceinline__ long long warp_sum(long long v) {
 }
 
 #define KLT_WARPS 4
+#define KLT_REG_CTAS 5  // register version: <= 102 registers per thread -> 20 warps per SM
 // mode 0: temporal (A = previous cam0 pyramid, B = current cam0 pyramid)
 // mode 1: stereo   (A = current cam0 pyramid,  B = current cam1 pyramid)
 // mode 2: stereo of new candidates: entries flagged in k_skip are not matched (their cell has no
@@ -521,8 +522,12 @@ __device__ __forceinline__ long long warp_sum_i32(int v) {
 }
 
 template <int WIN>
-__global__ void __launch_bounds__(KLT_WARPS * 32) klt_reg_kernel(FeConst fc, FeBuffers fb, int mode) {
+__global__ void __launch_bounds__(KLT_WARPS * 32, KLT_REG_CTAS) klt_reg_kernel(FeConst fc, FeBuffers fb, int mode) {
     static_assert(WIN >= 3 && WIN + 3 <= 32 && (WIN & 1), "window");
+    // packed gradients of the level: [row][lane] per warp (a lane only ever reads its own words: no bank
+    // conflicts, no synchronisation); in registers they cost 2 x WIN live values across the iteration loop
+    // and capped the kernel at 16 warps per SM
+    __shared__ int s_G[KLT_WARPS][WIN][32];
     const int s = blockIdx.y;
     const FeStep st = fb.step[s];
     if (!st.active) return;
@@ -550,7 +555,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_reg_kernel(FeConst fc, FeB
         const float sc = 1.0f / (float)(1 << l);
         const float px = p0.x * sc, py = p0.y * sc;
         const BilinW wa = bilin_weights(px, py);
-        int G[WIN];  // (gy << 16) | (gx & 0xffff) of window column lane - 1, rows 0 .. WIN - 1
+        int *G = &s_G[warp][0][lane];  // G[32 j] = (gy << 16) | (gx & 0xffff) of window column lane - 1, row j
         int a11i = 0, a12i = 0, a22i = 0, c1i = 0, c2i = 0;
         {
             // template column T[j], j in [0, tw): A sampled at (px + lane - half - 1, py + j - half - 1)
@@ -579,7 +584,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_reg_kernel(FeConst fc, FeB
             for (int j = 0; j < WIN; ++j) {
                 const int tl = __shfl_up_sync(0xffffffffu, T[j + 1], 1), tr = __shfl_down_sync(0xffffffffu, T[j + 1], 1);
                 const int gx = tr - tl, gy = T[j + 2] - T[j];  // garbage on the lanes without a window column: masked below
-                G[j] = (int)__byte_perm((unsigned)gx, (unsigned)gy, 0x5410);
+                G[32 * j] = (int)__byte_perm((unsigned)gx, (unsigned)gy, 0x5410);
                 a11i += gx * gx;
                 a12i += gx * gy;
                 a22i += gy * gy;
@@ -631,8 +636,9 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_reg_kernel(FeConst fc, FeB
                     for (int j = 0; j < WIN; ++j) {
                         const int n1 = __shfl_down_sync(0xffffffffu, pxv[j + 1], 1);
                         const int val = (((wb.w00 * pxv[j] + 256) + wb.w01 * n0) + wb.w10 * pxv[j + 1] + wb.w11 * n1) >> 9;
-                        b1i += val * (int)(short)(G[j] & 0xffff);
-                        b2i += val * (G[j] >> 16);
+                        const int gj = G[32 * j];
+                        b1i += val * (int)(short)(gj & 0xffff);
+                        b2i += val * (gj >> 16);
                         n0 = n1;
                     }
                 }
@@ -703,7 +709,7 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
     const uint8_t *img = fb.pyr[st.slot] + (size_t)s * fc.pyr_bytes;  // level 0 of current cam0
     const int rows = fc.rows, cols = fc.cols;
     __shared__ __align__(16) uint8_t tile[DT_H + 2 * DT_HALO][DT_STRIDE];
-    __shared__ uint8_t score[DT_SH][DT_SW + 2];
+    __shared__ __align__(16) uint8_t score[DT_SH][DT_SW + 2];
     __shared__ unsigned short s_list[DT_SH * DT_SW];  // pixels that passed the ring test: index | side << 15
     __shared__ int s_nlist, s_nmax;
     __shared__ unsigned short s_max[DT_H * DT_W / 4];  // strict 3x3 maxima: at most one per 2x2 block
@@ -737,14 +743,25 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
 #define RING_PX(pc, dx, dy) ((int)(pc)[(dy) * DT_STRIDE + (dx)])
 #define RING_LIST(X) X(0, 0, 3) X(1, 1, 3) X(2, 2, 2) X(3, 3, 1) X(4, 3, 0) X(5, 3, -1) X(6, 2, -2) X(7, 1, -3) \
     X(8, 0, -3) X(9, -1, -3) X(10, -2, -2) X(11, -3, -1) X(12, -3, 0) X(13, -3, 1) X(14, -2, 2) X(15, -1, 3)
-    for (int base = 0; base < DT_SH * DT_SW; base += 256) {
-        const int idx = base + threadIdx.x;
+    // The score window is cleared with word stores, the ring test runs over it in DT_RT_ITERS passes of 256
+    // pixels, and the pixels that pass are compacted WITHOUT atomics: every pass keeps its warp ballot in a
+    // register, the eight warp totals are prefix-summed once, and each warp then writes its entries (list
+    // order is irrelevant: the score, the NMS and the per-cell arg-max below are order-free).  The first
+    // version did one shared-memory atomicAdd per warp and pass, which the compiler wrapped in a second
+    // warp-aggregation sequence: 40 of the 164 instructions per pixel (ncu source page).
+    constexpr int DT_RT_ITERS = (DT_SH * DT_SW + 255) / 256;
+    for (int w = threadIdx.x; w < (int)(sizeof(score) / 4); w += 256) reinterpret_cast<unsigned *>(&score[0][0])[w] = 0u;
+    const bool tile_inside = y0 - 1 >= 3 && y0 + DT_H < rows - 3 && x0 - 1 >= 3 && x0 + DT_W < cols - 3;  // no pixel of the window needs the border test
+    unsigned bal_it[DT_RT_ITERS];
+    int pass_it[DT_RT_ITERS];
+#pragma unroll
+    for (int it = 0; it < DT_RT_ITERS; ++it) {
+        const int idx = it * 256 + threadIdx.x;
         int pass = 0;  // 1: darker arc, 2: brighter arc
         if (idx < DT_SH * DT_SW) {
             const int r = idx / DT_SW, c = idx - r * DT_SW;
             const int gy = y0 - 1 + r, gx = x0 - 1 + c;
-            score[r][c] = 0;
-            if (gy >= 3 && gy < rows - 3 && gx >= 3 && gx < cols - 3) {
+            if (tile_inside || (gy >= 3 && gy < rows - 3 && gx >= 3 && gx < cols - 3)) {
                 const uint8_t *pc = &tile[r + DT_HALO - 1][c + DT_X0 - 1];
                 const int v = pc[0];
                 const int lo = v - t, hi = v + t;  // darker ring pixel: p < lo (d = v - p > t); brighter: p > hi
@@ -761,16 +778,36 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
     }
                 RING_LIST(RING_TEST)
 #undef RING_TEST
+                // an arc of 9 needs 9 set bits, and only one side can have them: one arc test instead of two
                 const unsigned dark = z & 0xffffu, bright = z >> 16;
-                pass = has_arc9(dark) ? 1 : (has_arc9(bright) ? 2 : 0);
+                const bool dside = __popc(dark) >= 9;
+                if (has_arc9(dside ? dark : bright)) pass = dside ? 1 : 2;
             }
         }
-        // ordered compaction within the warp, one atomic per warp
-        const unsigned bal = __ballot_sync(0xffffffffu, pass != 0);
-        int wbase = 0;
-        if (lane == 0 && bal) wbase = atomicAdd(&s_nlist, __popc(bal));
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (pass) s_list[wbase + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(idx | ((pass - 1) << 15));
+        bal_it[it] = __ballot_sync(0xffffffffu, pass != 0);
+        pass_it[it] = pass;
+    }
+    {
+        __shared__ int s_wcnt[8];
+        int wtot = 0;
+#pragma unroll
+        for (int it = 0; it < DT_RT_ITERS; ++it) wtot += __popc(bal_it[it]);
+        if (lane == 0) s_wcnt[threadIdx.x >> 5] = wtot;
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int cnt = s_wcnt[w];
+            if (w < (int)(threadIdx.x >> 5)) wbase += cnt;
+            total += cnt;
+        }
+        if (threadIdx.x == 0) s_nlist = total;
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int it = 0; it < DT_RT_ITERS; ++it) {
+            if (pass_it[it]) s_list[wbase + __popc(bal_it[it] & lt)] = (unsigned short)((it * 256 + threadIdx.x) | ((pass_it[it] - 1) << 15));
+            wbase += __popc(bal_it[it]);
+        }
     }
     __syncthreads();
     // S = max over the 16 arcs of 9 contiguous ring pixels of min(d) (darker ring) or min(-d) (brighter ring),
@@ -810,34 +847,57 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
             if (y0 + r < rows && x0 + c < cols) fb.dbg_score[(size_t)(y0 + r) * cols + x0 + c] = score[r + 1][c + 1];
         }
     }
-    // strict 3x3 maxima among the pixels that have a score (the compacted list again: full warps)
-    for (int base = 0; base < nlist; base += 256) {
-        const int e = base + threadIdx.x;
-        bool is_max = false;
-        int idx = 0;
-        if (e < nlist) {
-            const int li = s_list[e] & 0x7fff;
-            const int r = li / DT_SW, c = li - r * DT_SW;  // score-window coordinates
-            if (r >= 1 && r <= DT_H && c >= 1 && c <= DT_W) {
-                const int sc = score[r][c];
-                const int gy = y0 + r - 1, gx = x0 + c - 1;
-                idx = (r - 1) * DT_W + (c - 1);
-                if (sc != 0) {
-                    is_max = sc > score[r - 1][c - 1] && sc > score[r - 1][c] && sc > score[r - 1][c + 1] && sc > score[r][c - 1] &&
-                             sc > score[r][c + 1] && sc > score[r + 1][c - 1] && sc > score[r + 1][c] && sc > score[r + 1][c + 1];
-                    if (is_max) {
-                        const int k = (gy / fc.det_cell_h) * fc.det_cols + (gx / fc.det_cell_w);
-                        if (fb.det_occ[(size_t)s * fc.det_cells + k]) is_max = false;
-                        if (gx < 5 || gy < 5 || gx > cols - 6 || gy > rows - 6) is_max = false;  // response 0: never a candidate
+    // strict 3x3 maxima among the pixels that have a score (the compacted list again: full warps); the maxima
+    // are compacted like the list above (ballots in registers, one prefix sum, no atomics)
+    {
+        unsigned bal_it[DT_RT_ITERS];
+        int idx_it[DT_RT_ITERS];
+#pragma unroll
+        for (int it = 0; it < DT_RT_ITERS; ++it) {
+            const int e = it * 256 + threadIdx.x;
+            bool is_max = false;
+            int idx = 0;
+            if (e < nlist) {
+                const int li = s_list[e] & 0x7fff;
+                const int r = li / DT_SW, c = li - r * DT_SW;  // score-window coordinates
+                if (r >= 1 && r <= DT_H && c >= 1 && c <= DT_W) {
+                    const int sc = score[r][c];
+                    const int gy = y0 + r - 1, gx = x0 + c - 1;
+                    idx = (r - 1) * DT_W + (c - 1);
+                    if (sc != 0) {
+                        is_max = sc > score[r - 1][c - 1] && sc > score[r - 1][c] && sc > score[r - 1][c + 1] && sc > score[r][c - 1] &&
+                                 sc > score[r][c + 1] && sc > score[r + 1][c - 1] && sc > score[r + 1][c] && sc > score[r + 1][c + 1];
+                        if (is_max) {
+                            const int k = (gy / fc.det_cell_h) * fc.det_cols + (gx / fc.det_cell_w);
+                            if (fb.det_occ[(size_t)s * fc.det_cells + k]) is_max = false;
+                            if (gx < 5 || gy < 5 || gx > cols - 6 || gy > rows - 6) is_max = false;  // response 0: never a candidate
+                        }
                     }
                 }
             }
+            bal_it[it] = __ballot_sync(0xffffffffu, is_max);
+            idx_it[it] = is_max ? idx : -1;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, is_max);
-        int wbase = 0;
-        if (lane == 0 && bal) wbase = atomicAdd(&s_nmax, __popc(bal));
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (is_max) s_max[wbase + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)idx;
+        __shared__ int s_wcnt2[8];
+        int wtot = 0;
+#pragma unroll
+        for (int it = 0; it < DT_RT_ITERS; ++it) wtot += __popc(bal_it[it]);
+        if (lane == 0) s_wcnt2[threadIdx.x >> 5] = wtot;
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int cnt = s_wcnt2[w];
+            if (w < (int)(threadIdx.x >> 5)) wbase += cnt;
+            total += cnt;
+        }
+        if (threadIdx.x == 0) s_nmax = total;
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int it = 0; it < DT_RT_ITERS; ++it) {
+            if (idx_it[it] >= 0) s_max[wbase + __popc(bal_it[it] & lt)] = (unsigned short)idx_it[it];
+            wbase += __popc(bal_it[it]);
+        }
     }
     __syncthreads();
     // Shi-Tomasi response over the 8x8 box: 8 lanes per maximum, lane q sums row q - 4 of the box
