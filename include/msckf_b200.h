@@ -179,7 +179,17 @@ int mskf_push_stereo_device(mskf_handle *h, int stream, double t, const uint8_t 
  * {t, wx, wy, wz, ax, ay, az} for `stream`, or, with stream == -1, [n_streams][n][7]; the stereo batches
  * take one image per stream at cam0 + s * stream_stride (bytes), time stamps t[n_streams]. */
 int mskf_push_imu_batch(mskf_handle *h, int stream, int n, const double *samples);
+/* The host -> device copy of mskf_push_stereo_batch is ASYNCHRONOUS (the engine's copy stream; one
+ * contiguous copy when cam1 == cam0 + rows*cols and stream_stride == 2*rows*cols, the landing area's own
+ * layout): the images should be page-locked (mskf_host_alloc) and must stay unchanged until
+ * mskf_wait_uploads (or mskf_sync) returns. */
 int mskf_push_stereo_batch(mskf_handle *h, const double *t, const uint8_t *cam0, const uint8_t *cam1, size_t stream_stride);
+/* Blocks until every upload issued by mskf_push_stereo* on this handle has left the caller's buffers. */
+int mskf_wait_uploads(mskf_handle *h);
+/* Page-locked host memory for the image ring of a fleet loader (examples/run_euroc_fleet.cpp), so that a host
+ * application needs no CUDA headers; no handle: valid for every engine of the process. */
+int mskf_host_alloc(void **out, size_t bytes);
+void mskf_host_free(void *p);
 int mskf_push_stereo_device_batch(mskf_handle *h, const double *t, const uint8_t *d_cam0, const uint8_t *d_cam1,
                                   size_t stream_stride);
 

@@ -371,6 +371,23 @@ int mskf_push_stereo_batch(mskf_handle *h, const double *t, const uint8_t *cam0,
     return MSKF_OK;
 }
 
+int mskf_wait_uploads(mskf_handle *h) {
+    if (!h) return MSKF_ERR_ARG;
+    MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));
+    MSKF_CUDA_CHECK(h, cudaStreamSynchronize(h->copy_stream));
+    return MSKF_OK;
+}
+
+int mskf_host_alloc(void **out, size_t bytes) {
+    if (!out || bytes == 0) return MSKF_ERR_ARG;
+    *out = nullptr;
+    return cudaHostAlloc(out, bytes, cudaHostAllocPortable) == cudaSuccess ? MSKF_OK : MSKF_ERR_CUDA;
+}
+
+void mskf_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 int mskf_push_stereo_device_batch(mskf_handle *h, const double *t, const uint8_t *d_cam0, const uint8_t *d_cam1, size_t stream_stride) {
     if (!h || !t || !d_cam0 || !d_cam1) return MSKF_ERR_ARG;
     if ((((uintptr_t)d_cam0) | ((uintptr_t)d_cam1) | (uintptr_t)stream_stride) & 15) {

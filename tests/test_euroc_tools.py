@@ -88,3 +88,36 @@ def test_run_euroc_on_synthetic_mav0(tmp_path, synth):
     r = euroc.ate(est, euroc.read_tum(os.path.join(d, "groundtruth_tum.txt")))
     assert r["pairs"] == len(est) and r["rmse"] < 0.1
     e.close()
+
+
+@pytest.mark.gpu
+def test_run_euroc_fleet_equals_single_stream_runs(tmp_path, synth):
+    """several mav0 directories on disk -> decoder threads -> page-locked ring -> one
+    asynchronous upload per step -> one engine handle.  Every stream's trajectory file is byte-identical to
+    what the single-stream runner writes for the same directory (a stream's result does not depend on its
+    neighbours, on the ring depth or on the number of decoder threads)."""
+    import json
+
+    from msckf_stereo_c_b200 import euroc
+
+    exe = _exe()
+    fleet = os.path.join(ROOT, "examples", "run_euroc_fleet")
+    cfg = synth.default_config("ref")
+    nf = 60
+    dirs, single = [], []
+    for i, (seed, fmt) in enumerate(((6, "png"), (11, "pgm"))):
+        d = euroc.write_mav0(synth.Stream(cfg, seed=seed), nf, str(tmp_path / f"mav0_{i}"), image_format=fmt)
+        out = str(tmp_path / f"single_{i}.txt")
+        subprocess.run([exe, d, "ref", out, "9"], check=True, capture_output=True)
+        dirs.append(d)
+        single.append(open(out).read())
+        assert len(single[-1].splitlines()) > 10
+    for threads, ring in ((3, 2), (8, 4)):
+        od = tmp_path / f"fleet_{threads}_{ring}"
+        od.mkdir()
+        r = subprocess.run([fleet, "--threads", str(threads), "--ring", str(ring), "--repeat", "2", "--preset", "ref", "--decimals", "9",
+                            "--out", str(od)] + dirs, check=True, capture_output=True, text=True)
+        rep = json.loads(r.stdout.strip().splitlines()[-1])
+        assert rep["streams"] == 4 and rep["steps"] == nf and rep["disk_to_pose_frames_per_s"] > 0
+        for s in range(4):
+            assert open(od / f"pose_{s}.txt").read() == single[s // 2], (threads, ring, s)
