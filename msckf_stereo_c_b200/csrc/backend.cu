@@ -18,7 +18,7 @@
 //     algebra: H only ever touches camera columns (msckf_vio.cpp:709-712), so with T the
 //     (QR-compressed) measurement matrix over the k active camera columns,
 //         S = T P_cc T^T + sigma^2 I = L L^T,  W = (P_:c T^T) L^-T,
-//         delta_x = W (L^-1 r),  P <- P - W W^T
+//         P <- P - W W^T,  delta_x = P[:, c] (H^T r) / sigma^2   (K = P+ H^T / sigma^2)
 //     which equals K = P H^T S^-1, P <- (I - K H) P, (P + P^T)/2 of msckf_vio.cpp:833-904 in
 //     exact arithmetic and is symmetric by construction.  The posterior does not depend on
 //     the orthonormal basis chosen for the null-space projection or on the QR row signs
@@ -35,7 +35,7 @@
 //   be_layout_kernel         removeLostFeatures :965-990 bookkeeping
 //   be_feature_jac_kernel    measurementJacobian :610-677, featureJacobian :679-775, gatingTest :909-935
 //   be_stack_kernel          removeLostFeatures :992-1015 (stacking + row cap), pruneCamStateBuffer :1126-1150
-//   be_qr_kernel             measurementUpdate :795-810 (SPQR compression)
+//   be_gram_kernel, be_pchol_kernel   measurementUpdate :795-810 (SPQR compression, here via the Gram matrix)
 //   be_gemm_kernel<...>, be_chol_kernel, be_apply_kernel   measurementUpdate :833-904
 //   be_prune_finish_kernel   pruneCamStateBuffer :1161-1181
 //   be_finish_kernel         publish :1238-1254, onlineReset :1186-1236
@@ -135,16 +135,15 @@ struct BeBuf {
     double *rblk;      // [S][rcap]
     double *Hst;       // [S][hst_cap]
     double *rst;       // [S][hst_rows]
-    int *rst_j0;       // [S][hst_rows] first nonzero column of each stacked row
-    double *Rq;        // [S][QR_G][(KC+1)^2] triangular factors of the QR compression (row-major, column c owned by its lanes)
-    unsigned char *Rfill;  // [S][QR_G][KC+1] pivot rows of each triangle that hold a reflector result
+    double *Gm;        // [S][(KC+1)^2] Gram matrix of [H | r], lower 64-tiles (be_gram_kernel)
+    double *Rp;        // [S][KC*KC] rows of the pivoted Cholesky factor in the original column order
+    int *perm;         // [S][KC] column order of Tm: compact column perm[l] of the stacked H is column l of Tm
     double *Tm;        // [S][KC*KC]
-    double *rt;        // [S][KC]
+    double *gv;        // [S][KC] H^T r over the compact columns
     double *PHt;       // [S][LD*KC]
     double *Sm;        // [S][KC*KC]
     double *Linv;      // [S][KC*KC]
     double *W;         // [S][LD*KC]
-    double *yv;        // [S][KC]
     double *dxv;       // [S][LD] delta_x of the latest update
     double *work;      // [S][MSKF_PROF_TAGS] algorithmic flops done per kernel class (bench roofline)
     // front-end message (fb.stale / stale_hw / msg_total)
@@ -2157,263 +2156,59 @@ __global__ void __launch_bounds__(BE_THREADS) be_scatter_kernel(BeConst bc, BeBu
         for (int c = threadIdx.x; c < C6; c += BE_THREADS) s_col[c] = 6 * st.colpos[os[c / 6]] + (c % 6);
         for (int e = threadIdx.x; e < rows * k; e += BE_THREADS) Hst[(size_t)so * k + e] = 0.0;
         __syncthreads();
-        int j0 = k;
-        for (int a = 0; a < M; ++a) j0 = min(j0, 6 * st.colpos[os[a]]);
         for (int r = threadIdx.x / 32; r < rows; r += BE_THREADS / 32)
             for (int c = threadIdx.x & 31; c < C6; c += 32) Hst[(size_t)(so + r) * k + s_col[c]] = Hp[r * C6 + c];
-        for (int r = threadIdx.x; r < rows; r += BE_THREADS) {
-            rst[so + r] = rp[r];
-            bb.rst_j0[(size_t)s * bc.hst_rows + so + r] = j0;
-        }
+        for (int r = threadIdx.x; r < rows; r += BE_THREADS) rst[so + r] = rp[r];
     }
 }
 
 // ======================================================================================
-// QR compression of the stacked system (measurementUpdate :795-810): Householder reflectors fold
-// the rows, 64 at a time, into an upper-triangular factor R (with Q^T r as an extra column).  If
-// m <= k the system is used as it is.
+// QR compression of the stacked system (measurementUpdate :795-810) through its Gram matrix.
 //
-// The factorization is a serial chain of column steps, so everything here is about the latency of
-// one step (tools/micro/fp64_pipe.cu: DFMA 8.4 cycles dependent, 64 lanes/clk/SM; STS+BAR+LDS 72):
-//  * a 64-row block is held in registers as 8 x 4 tiles: QR_T = 8 adjacent lanes share four columns,
-//    8 rows each, so a step loads 8 reflector values per lane for 64 FMAs (shared-memory bandwidth, not
-//    the fp64 pipe, limited a one-column-per-lane layout), the dot products and the next column's norm
-//    are 8-long plus three shuffles, and a sweep folds 64 rows for the price of one chain;
-//  * unnormalised reflectors H_j = I - t w w^T, w = [alpha - beta; x], t = 1 / (beta (beta - alpha)):
-//    the owner publishes its column the moment it is up to date and only two scalars sit behind
-//    the rsqrt / rcp chain (MUFU.RSQ64H / RCP64H seeds + two Newton steps each, no branches);
-//  * column c of R lives in global memory (L2), read one step ahead; ONE barrier per step;
-//  * a sweep stops as soon as its rows are used up: a reflector whose pivot row of R was empty
-//    moves one direction of the block's (<= 64-dimensional) row space into R and leaves the block
-//    orthogonal to it, so after nb such reflectors the block is zero and the remaining columns have
-//    nothing to do.  Folding the b-th block of a fresh triangle costs about min(k, 64 (b + 1)) steps,
-//    not k.  The count only nominates the exit (near-dependent columns make it optimistic); it is taken
-//    when the block's remaining Frobenius norm is negligible, checked every 8 steps from then on.
-//
-// A fleet's step time is set by its slowest stream, and the row count m has a heavy tail (on the
-// synthetic fleet a lost-feature update stacks 40-800 rows, tools/fleet_nan_check.py prints the
-// distribution; the reference's cap is 1500).  Streams with m > QR_SPLIT_MIN split their rows over
-// QR_G = 4 CTAs (TSQR): each folds its share into its own triangle, then a two-level tree of
-// be_qr_combine_kernel launches folds the triangles pairwise.  The split pays for one stream from about
-// 330 rows on (the combine costs ~2 x 330 column steps at k = 174), but every split stream also puts six
-// more CTAs on the machine: on the 256-stream fleet the throughput peaks with the threshold at 640 rows
-// (352: 43.6k frames/s, 512: 44.7k, 640: 45.0k, 768: 44.8k, 1024: 44.3k), where the slowest stream's
-// chain is 1.6 ms instead of 1.2 ms.
+// The reference replaces (H, r), m x k with m > k, by (T, Q1^T r) from a thin QR H = Q1 T.  The
+// measurement noise is sigma^2 I (:833, :911), so the posterior is a function of H^T H and H^T r only:
+// ANY T with T^T T = H^T H, together with r_t = T^-T H^T r on T's row space, gives the same K r and the
+// same P - K S K^T.  Here T comes from the Gram matrix (CholeskyQR):
+//     G = [H r]^T [H r]                        be_gram_kernel, fp64 tensor pipe (DMMA), tiled over (k+1)^2
+//     G[:k,:k] = Pi R^T R Pi^T, r_t            be_pchol_kernel, Cholesky with diagonal pivoting
+// instead of a chain of m-row Householder reflectors (the first version of this file: 2 m k^2 flops on
+// a serial chain of k column steps per 64-row block, 1.6 + 0.8 ms per fleet launch at 3 % of the fp64
+// peak).  H always has a numerical null space (moving every camera state rigidly changes no residual, so
+// cond(H) ~ 1e16 on the filter's own updates): the pivoting moves those directions to the end, where the
+// factorization stops once the largest remaining diagonal is below PC_TOL of the largest initial one,
+// and mt = rank(H) < k rows go on.  Backward error: T^T T = H^T H + E with |E| of the order of the
+// rounding of the Gram sums, the same order as the backward error of Householder QR expressed in
+// H^T H; measured on the filter's own updates the posterior agrees with the oracle's Householder path
+// to ~1e-14 (tests/test_gpu_backend.py::test_op_ekf_update_*, tools/upd_check.py).  Without pivoting
+// (zero pivots skipped in place) the same updates show up to 2.5e-9.
+// If m <= k the system is used as it is (:795 runs the QR only for tall systems).
 // ======================================================================================
-#define QR_T 8     // lanes per column pair
-#define QR_RPT 8   // rows per lane
-#define QR_CPT 4   // columns per lane
-#define QR_B (QR_T * QR_RPT)
-#define QR_THREADS 384  // 48 column quads = 192 column slots >= 6 * 31 + 1
-#define QR_COLS (QR_THREADS / QR_T * QR_CPT)
-#define QR_G 4
-#define QR_SPLIT_MIN 640
-#define QR_VS (QR_RPT + 2)  // chunk stride of the reflector buffer: the 8 lanes read 16-byte pieces in distinct banks
-// A sweep may stop once what is left of its block is below this fraction of the block (squared Frobenius norms).
-#define QR_NEGLIGIBLE 1e-22
-
-struct QrShared {
-    double vbuf[2][QR_T * QR_VS];
-    double tau[2], w0[2];
-    double red[QR_THREADS / 32];
-    double diag[QR_COLS];
-    int stop[2];
-    int j0, nbe, nf;
-    unsigned char filled[QR_COLS];
+#define GR_K 16
+#define GR_RS (GT + 4)  // row stride of a staged [row of H][column] chunk: fragment loads hit 32 distinct bank pairs
+struct GramSmem {
+    double a[2][GR_K * GR_RS];
+    double b[2][GR_K * GR_RS];
 };
 
-// Reflector scalars for pivot alpha and squared column norm xn (> 0): beta = -sign(alpha) sqrt(alpha^2 + xn),
-// w0 = alpha - beta, t = 1 / (beta (beta - alpha)) = 1 / (a + |alpha| sqrt(a)).  The hardware seeds look at
-// the upper word only (relative error ~2^-22); two Newton steps take them to fp64 round-off.
-__device__ __forceinline__ void qr_reflector(double alpha, double xn, double &t, double &w0, double &beta) {
-    const double a = fma(alpha, alpha, xn);
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    const double h = 0.5 * a;
-    y = fma(y, fma(-h, y * y, 0.5), y);
-    y = fma(y, fma(-h, y * y, 0.5), y);
-    double sq = a * y;
-    sq = fma(fma(-sq, sq, a), 0.5 * y, sq);
-    const double den = fma(fabs(alpha), sq, a);
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
-    r = fma(r, fma(-den, r, 1.0), r);
-    r = fma(r, fma(-den, r, 1.0), r);
-    t = r;
-    beta = -copysign(sq, alpha);
-    w0 = alpha - beta;
-}
-
-// sum over the 8 lanes that share a column pair
-__device__ __forceinline__ double qr_oct_sum(double v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    return v;
-}
-
-__device__ __forceinline__ double qr_norm2(const double (&x)[QR_RPT]) {
-    double n0 = 0, n1 = 0;
-#pragma unroll
-    for (int i = 0; i < QR_RPT; i += 2) {
-        n0 = fma(x[i], x[i], n0);
-        n1 = fma(x[i + 1], x[i + 1], n1);
-    }
-    return qr_oct_sum(n0 + n1);
-}
-
-// squared Frobenius norm of the H columns (c < k) of the block held in x (all threads get it; two barriers);
-// the residual column keeps whatever part of r the columns do not explain and is not part of the test
-__device__ __forceinline__ double qr_block_fro(const double (&x)[QR_CPT][QR_RPT], int c0, int k, QrShared &sh) {
-    double v = 0.0;
-#pragma unroll
-    for (int i = 0; i < QR_CPT; ++i)
-        if (c0 + i < k) {
-#pragma unroll
-            for (int r = 0; r < QR_RPT; ++r) v = fma(x[i][r], x[i][r], v);
-        }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double w = 0.0;
-#pragma unroll
-    for (int i = 0; i < QR_THREADS / 32; ++i) w += sh.red[i];
-    __syncthreads();
-    return w;
-}
-
-// squared norm of column `which` (0..3) of the lane's four: a switch, so that x[][] stays in registers
-__device__ __forceinline__ double qr_norm2_of(const double (&x)[QR_CPT][QR_RPT], int which) {
-    switch (which) {
-    case 0: return qr_norm2(x[0]);
-    case 1: return qr_norm2(x[1]);
-    case 2: return qr_norm2(x[2]);
-    default: return qr_norm2(x[3]);
-    }
-}
-
-// One sweep: fold the QR_B rows held in x[][] (lane (cq, q) has rows 8q.. of columns 4cq .. 4cq+3) into R,
-// starting at column jb.  sh.nbe = number of non-zero rows in the block: the sweep ends after that many
-// reflectors on empty pivot rows; sh.filled[] marks the pivot rows of R that hold a reflector result and
-// sh.diag[] mirrors the diagonal of R (the pivot the next reflector needs at once).
-__device__ __forceinline__ void qr_sweep(double (&x)[QR_CPT][QR_RPT], double *R, int ldr, int k, int kw, int cq, int q, int jb, QrShared &sh) {
-    if (threadIdx.x == 0) sh.nf = 0;
-    const double f0 = qr_block_fro(x, QR_CPT * cq, k, sh);
-    int verify_in = 0;
-    const int wc0 = (int)(threadIdx.x >> 5) * (32 / QR_T * QR_CPT), wc1 = wc0 + 32 / QR_T * QR_CPT - 1;  // this warp's columns
-    const int c0 = QR_CPT * cq;
-    double xn = 0.0;
-    if (jb >= wc0 && jb <= wc1) xn = qr_norm2_of(x, jb & 3);
-    double *Rc = R + (size_t)jb * ldr + c0;  // row j of R at this lane's columns
-    const double4 *vs0 = reinterpret_cast<const double4 *>(&sh.vbuf[0][q * QR_VS]), *vs1 = reinterpret_cast<const double4 *>(&sh.vbuf[1][q * QR_VS]);
-    for (int j = jb; j < k; ++j, Rc += ldr) {
-        const int b = j & 1;
-        // row j of R for this lane's columns: needed after the barrier and the dot products, which hide the L2 latency
-        double rq[QR_CPT];
-#pragma unroll
-        for (int i = 0; i < QR_CPT; ++i) rq[i] = (c0 + i > j && c0 + i < kw) ? Rc[i] : 0.0;
-        if (cq == (j >> 2)) {
-            double4 *dst = const_cast<double4 *>(b ? vs1 : vs0);
-            switch (j & 3) {
-            case 0: dst[0] = make_double4(x[0][0], x[0][1], x[0][2], x[0][3]); dst[1] = make_double4(x[0][4], x[0][5], x[0][6], x[0][7]); break;
-            case 1: dst[0] = make_double4(x[1][0], x[1][1], x[1][2], x[1][3]); dst[1] = make_double4(x[1][4], x[1][5], x[1][6], x[1][7]); break;
-            case 2: dst[0] = make_double4(x[2][0], x[2][1], x[2][2], x[2][3]); dst[1] = make_double4(x[2][4], x[2][5], x[2][6], x[2][7]); break;
-            default: dst[0] = make_double4(x[3][0], x[3][1], x[3][2], x[3][3]); dst[1] = make_double4(x[3][4], x[3][5], x[3][6], x[3][7]); break;
-            }
-            // Once xn leaves the normal range the reflector scalars would overflow: no reflector.
-            const bool gen = xn > 1e-200;
-            double t = 0.0, w0 = 0.0, beta = 0.0;
-            if (gen) qr_reflector(sh.diag[j], xn, t, w0, beta);
-            __syncwarp(0xffu << (threadIdx.x & 24));  // every lane has read the pivot before lane 0 replaces it
-            if (q == 0) {
-                sh.tau[b] = t;
-                sh.w0[b] = w0;
-                int nf = sh.nf;
-                if (gen) {
-                    if (!sh.filled[j]) sh.nf = ++nf;
-                    sh.filled[j] = 1;
-                    sh.diag[j] = beta;
-                    Rc[j - c0] = beta;
-                }
-                sh.stop[b] = nf >= sh.nbe;
-            }
-        }
-        __syncthreads();
-        const double t = sh.tau[b];
-        const bool stop = sh.stop[b] != 0;
-        if (wc1 > j && t != 0.0) {
-            const double w0 = sh.w0[b];
-            const double4 *vs = b ? vs1 : vs0;
-            const double4 u0 = vs[0], u1 = vs[1];
-            const double v[QR_RPT] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-            double d[QR_CPT];
-#pragma unroll
-            for (int i = 0; i < QR_CPT; ++i) {
-                double e0 = v[0] * x[i][0], e1 = v[1] * x[i][1];
-#pragma unroll
-                for (int r = 2; r < QR_RPT; r += 2) {
-                    e0 = fma(v[r], x[i][r], e0);
-                    e1 = fma(v[r + 1], x[i][r + 1], e1);
-                }
-                d[i] = e0 + e1;
-            }
-#pragma unroll
-            for (int o = 1; o < QR_T; o <<= 1) {
-#pragma unroll
-                for (int i = 0; i < QR_CPT; ++i) d[i] += __shfl_xor_sync(0xffffffffu, d[i], o);
-            }
-#pragma unroll
-            for (int i = 0; i < QR_CPT; ++i) {
-                if (c0 + i > j && c0 + i < kw) {
-                    const double sacc = fma(w0, rq[i], d[i]) * t;
-                    if (q == 0) Rc[i] = fma(-sacc, w0, rq[i]);
-#pragma unroll
-                    for (int r = 0; r < QR_RPT; ++r) x[i][r] = fma(-sacc, v[r], x[i][r]);
-                }
-            }
-        }
-        // the warp that owns the next reflector: squared norm of its (now final) column
-        if (j + 1 >= wc0 && j + 1 <= wc1) xn = qr_norm2_of(x, (j + 1) & 3);
-        // The count says the block's rows are used up; near-dependent columns (each camera's 6 columns hold
-        // about two independent directions of one feature's rows) make it optimistic, so the exit is taken only
-        // when what is left of the block is negligible: dropping a remainder x perturbs H^T H by x^T x, the
-        // SQUARE of its size (1e-22 of the block's: below fp64 round-off of the information it joins).
-        if (stop && --verify_in <= 0) {
-            if (qr_block_fro(x, c0, k, sh) <= QR_NEGLIGIBLE * f0) break;
-            verify_in = 8;
-        }
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ int qr_groups(int m, int k) { return (m > k && m > QR_SPLIT_MIN) ? QR_G : 1; }
-
-__device__ __forceinline__ void qr_extract(const double *R, int ldr, int k, double *Tm, double *rt) {
-    for (int e = threadIdx.x; e < k * k; e += QR_THREADS) {
-        int i = e / k, cc = e - i * k;
-        Tm[e] = cc >= i ? R[i * ldr + cc] : 0.0;
-    }
-    for (int i = threadIdx.x; i < k; i += QR_THREADS) rt[i] = R[i * ldr + k];
-}
-
-__global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb, int phase) {
-    const int s = blockIdx.y, g = blockIdx.x;
+// Lower tile (ti >= tj) of G = [H r]^T [H r]: C(i, j) = sum over the rows l of H of Hr(l, i0 + i) Hr(l, j0 + j).
+// Both operands are rows of the same row-major matrix, staged as [l][column] with coalesced 8-byte
+// cp.async (column k is the residual, from rst), two stages of 16 rows.
+__global__ void __launch_bounds__(BE_THREADS, 2) be_gram_kernel(BeConst bc, BeBuf bb, int phase) {
+    const int s = blockIdx.y;
     const BeStep sp = bb.step[s];
     if (!sp.active) return;
     BeState &st = bb.st[s];
     if (!st.do_update) return;
     const int m = st.m, k = st.k, KC = bc.KC;
-    const int ng = qr_groups(m, k);
-    if (g >= ng) return;
     const double *Hst = bb.Hst + (size_t)s * bc.hst_cap, *rst = bb.rst + (size_t)s * bc.hst_rows;
-    const int *rj0 = bb.rst_j0 + (size_t)s * bc.hst_rows;
-    double *Tm = bb.Tm + (size_t)s * KC * KC, *rt = bb.rt + (size_t)s * KC;
-    if (threadIdx.x == 0 && g == 0) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
         // algorithmic flops of this stream's update (dense-equivalent over the active columns)
         const double dm = m, dk = k, dmt = m <= k ? m : k, dld = bc.LD;
         double *w = bb.work + (size_t)s * MSKF_PROF_TAGS;
-        if (m > k) w[phase == 0 ? PK_BE_QR : PK_BE_QR_PRUNE] += 2.0 * dm * dk * dk;
+        if (m > k) {
+            w[phase == 0 ? PK_BE_GRAM : PK_BE_GRAM_PRUNE] += dm * (dk + 1) * (dk + 2);  // lower triangle of (k+1)^2, 2 flops per product
+            w[PK_BE_PCHOL] += dk * dk * dk / 3.0;
+        }
         w[PK_BE_GEMM_PHT] += 2.0 * dld * dk * dmt;
         w[PK_BE_GEMM_S] += 2.0 * dmt * dk * dmt;
         w[PK_BE_CHOL] += 2.0 * dmt * dmt * dmt / 3.0;
@@ -2421,138 +2216,91 @@ __global__ void __launch_bounds__(QR_THREADS) be_qr_kernel(BeConst bc, BeBuf bb,
         w[PK_BE_GEMM_PUPD] += dld * dld * dmt;
     }
     if (m <= k) {
-        for (int e = threadIdx.x; e < m * k; e += QR_THREADS) Tm[e] = Hst[e];
-        for (int i = threadIdx.x; i < m; i += QR_THREADS) rt[i] = rst[i];
+        if (blockIdx.x != 0) return;
+        double *Tm = bb.Tm + (size_t)s * KC * KC;
+        int *perm = bb.perm + (size_t)s * KC;
+        double *gv = bb.gv + (size_t)s * KC;
+        for (int e = threadIdx.x; e < m * k; e += BE_THREADS) Tm[e] = Hst[e];
+        for (int i = threadIdx.x; i < k; i += BE_THREADS) {
+            perm[i] = i;
+            double a = 0.0;  // (H^T r)_i, rows in order
+            for (int l = 0; l < m; ++l) a = fma(Hst[(size_t)l * k + i], rst[l], a);
+            gv[i] = a;
+        }
         if (threadIdx.x == 0) {
             st.mt = m;
             st.t_upper = 0;
         }
         return;
     }
-    const int kw = k + 1, ldr = KC + 1;
-    double *R = bb.Rq + ((size_t)s * QR_G + g) * ldr * ldr;  // R[j][c] at j * ldr + c
-    __shared__ QrShared sh;
-    const int cp = threadIdx.x / QR_T, q = threadIdx.x % QR_T;
-    for (int cc = 0; cc < QR_CPT; ++cc) {
-        const int c = QR_CPT * cp + cc;
-        if (c < kw)
-            for (int j = q; j <= min(c, k - 1); j += QR_T) R[j * ldr + c] = 0.0;
-    }
-    for (int j = threadIdx.x; j < QR_COLS; j += QR_THREADS) {
-        sh.filled[j] = 0;
-        sh.diag[j] = 0.0;
-    }
-    const int per = ((m + ng - 1) / ng + QR_B - 1) / QR_B * QR_B;
-    const int r_begin = g * per, r_end = min(m, r_begin + per);
-    double x[QR_CPT][QR_RPT];
-    for (int r0 = r_begin; r0 < r_end; r0 += QR_B) {
-        const int nb = min(QR_B, r_end - r0);
-        if (threadIdx.x < 32) {
-            int j0 = k;
-            for (int i = threadIdx.x; i < nb; i += 32) j0 = min(j0, rj0[r0 + i]);
+    const int kw = k + 1, ldg = KC + 1;
+    int t = blockIdx.x, ti = 0;
+    while (t > ti) { t -= ti + 1; ++ti; }
+    const int tj = t;
+    if (ti >= ug_tiles(kw)) return;
+    int i0, mr, j0, nc;
+    ug_range(kw, ti, i0, mr);
+    ug_range(kw, tj, j0, nc);
+    __shared__ __align__(16) GramSmem gs;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3, wr = warp >> 2, wc = warp & 3;
+    const bool diag = ti == tj;
+    double acc[4][2][2];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) j0 = min(j0, __shfl_xor_sync(0xffffffffu, j0, o));
-            if (threadIdx.x == 0) {
-                sh.j0 = j0;
-                sh.nbe = nb;
-            }
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    const int col = tid & 63, ca = i0 + col, cb = j0 + col;
+    const bool va = col < mr, vb = !diag && col < nc;
+    // column c of [H | r] at row l
+    const double *pa = ca < k ? Hst + ca : rst, *pb = cb < k ? Hst + cb : rst;
+    const size_t sa = ca < k ? (size_t)k : 1, sb = cb < k ? (size_t)k : 1;
+    auto stage = [&](int buf, int l0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int lo = (tid >> 6) + 4 * u, l = l0 + lo;
+            const bool lv = l < m;
+            cp_async8(&gs.a[buf][lo * GR_RS + col], (lv && va) ? pa + (size_t)l * sa : Hst, lv && va);
+            if (!diag) cp_async8(&gs.b[buf][lo * GR_RS + col], (lv && vb) ? pb + (size_t)l * sb : Hst, lv && vb);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    bool mv[4], nv[2];
 #pragma unroll
-        for (int cc = 0; cc < QR_CPT; ++cc) {
-            // column c of [H | r]: element (row) at src[row * stride]
-            const int c = QR_CPT * cp + cc;
-            const double *src = c < k ? Hst + c : rst;
-            const size_t stride = c < k ? (size_t)k : 1;
+    for (int mi = 0; mi < 4; ++mi) mv[mi] = wr * 32 + mi * 8 < mr;
 #pragma unroll
-            for (int i = 0; i < QR_RPT; ++i) {
-                const int row = q * QR_RPT + i;
-                x[cc][i] = (c < kw && row < nb) ? src[(size_t)(r0 + row) * stride] : 0.0;
+    for (int ni = 0; ni < 2; ++ni) nv[ni] = wc * 16 + ni * 8 < nc;
+    const int nchunks = (m + GR_K - 1) / GR_K;
+    stage(0, 0);
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) {
+            stage((c + 1) & 1, (c + 1) * GR_K);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        if (mv[0] && nv[0]) {
+            const double *as = gs.a[c & 1] + t4 * GR_RS + wr * 32 + g;
+            const double *bs = (diag ? gs.a[c & 1] : gs.b[c & 1]) + t4 * GR_RS + wc * 16 + g;
+#pragma unroll
+            for (int kk = 0; kk < GR_K; kk += 4) {
+                double af[4], bf[2];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) af[mi] = as[kk * GR_RS + mi * 8];
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) bf[ni] = bs[kk * GR_RS + ni * 8];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ++ni)
+                        if (mv[mi] && nv[ni]) dmma_884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
             }
         }
         __syncthreads();
-        qr_sweep(x, R, ldr, k, kw, cp, q, sh.j0, sh);
     }
-    __syncthreads();
-    if (ng == 1) {
-        qr_extract(R, ldr, k, Tm, rt);
-        if (threadIdx.x == 0) {
-            st.mt = k;
-            st.t_upper = 1;
-        }
-    } else {
-        unsigned char *fl = bb.Rfill + ((size_t)s * QR_G + g) * ldr;
-        for (int j = threadIdx.x; j < k; j += QR_THREADS) fl[j] = sh.filled[j];
-    }
-}
-
-// TSQR combine, a binary tree over the QR_G = 4 triangles: level 1 (grid (2, S)) folds triangle 1 into 0
-// and 3 into 2 in parallel, level 2 (grid (1, S)) folds 2 into 0 and extracts T.  Row i of a triangle is
-// zero left of column i, so the sweep of a row block starts at its first row index; rows of the source
-// that never received a reflector are zero and do not count.
-__global__ void __launch_bounds__(QR_THREADS) be_qr_combine_kernel(BeConst bc, BeBuf bb, int level) {
-    const int s = blockIdx.y;
-    const BeStep sp = bb.step[s];
-    if (!sp.active) return;
-    BeState &st = bb.st[s];
-    if (!st.do_update) return;
-    const int m = st.m, k = st.k, KC = bc.KC;
-    if (qr_groups(m, k) == 1) return;
-    const int kw = k + 1, ldr = KC + 1;
-    const int dst_g = level == 1 ? 2 * blockIdx.x : 0, src_g = level == 1 ? 2 * blockIdx.x + 1 : 2;
-    double *Rd = bb.Rq + ((size_t)s * QR_G + dst_g) * ldr * ldr;
-    const double *Rs = bb.Rq + ((size_t)s * QR_G + src_g) * ldr * ldr;
-    unsigned char *fd = bb.Rfill + ((size_t)s * QR_G + dst_g) * ldr;
-    const unsigned char *fs = bb.Rfill + ((size_t)s * QR_G + src_g) * ldr;
-    __shared__ QrShared sh;
-    const int cp = threadIdx.x / QR_T, q = threadIdx.x % QR_T;
-    for (int j = threadIdx.x; j < QR_COLS; j += QR_THREADS) {
-        sh.filled[j] = j < k ? fd[j] : 0;
-        sh.diag[j] = j < k ? Rd[j * ldr + j] : 0.0;
-    }
-    double x[QR_CPT][QR_RPT];
-    for (int r0 = 0; r0 < k; r0 += QR_B) {
-        const int nb = min(QR_B, k - r0);
-        if (threadIdx.x < 32) {
-            int cnt = 0, first = k;
-            for (int i = threadIdx.x; i < nb; i += 32)
-                if (fs[r0 + i]) {
-                    ++cnt;
-                    first = min(first, r0 + i);
-                }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-                first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-            }
-            if (threadIdx.x == 0) {
-                sh.nbe = cnt;
-                sh.j0 = first;
-            }
-        }
-#pragma unroll
-        for (int cc = 0; cc < QR_CPT; ++cc) {
-            const int c = QR_CPT * cp + cc;
-#pragma unroll
-            for (int i = 0; i < QR_RPT; ++i) {
-                const int row = r0 + q * QR_RPT + i;
-                x[cc][i] = (c < kw && row < k && c >= row) ? Rs[row * ldr + c] : 0.0;
-            }
-        }
-        __syncthreads();
-        if (sh.nbe > 0) qr_sweep(x, Rd, ldr, k, kw, cp, q, sh.j0, sh);
-        else __syncthreads();
-    }
-    if (level == 2) {
-        __syncthreads();
-        qr_extract(Rd, ldr, k, bb.Tm + (size_t)s * KC * KC, bb.rt + (size_t)s * KC);
-        if (threadIdx.x == 0) {
-            st.mt = k;
-            st.t_upper = 1;
-        }
-    } else {
-        __syncthreads();
-        for (int j = threadIdx.x; j < k; j += QR_THREADS) fd[j] = sh.filled[j];
-    }
+    double *G = bb.Gm + (size_t)s * ldg * ldg;
+    upd_gemm_store(mr, nc, acc, [&](int r, int c, double v) { G[(size_t)(i0 + r) * ldg + j0 + c] = v; });
 }
 
 // ======================================================================================
@@ -2598,7 +2346,11 @@ __global__ void __launch_bounds__(BE_THREADS, 2) be_gemm_kernel(BeConst bc, BeBu
         ug_range(n, tj, j0, nc);
     }
     if (OP == 0 || OP == 1) {
-        for (int l = threadIdx.x; l < k; l += BE_THREADS) cols[l] = N21 + 6 * st.u_slots[l / 6] + (l % 6);
+        const int *perm = bb.perm + (size_t)s * KC;
+        for (int l = threadIdx.x; l < k; l += BE_THREADS) {
+            const int c = perm[l];
+            cols[l] = N21 + 6 * st.u_slots[c / 6] + (c % 6);
+        }
         __syncthreads();
     }
     if (OP == 0) {
@@ -2647,7 +2399,7 @@ __global__ void __launch_bounds__(BE_THREADS, 2) be_gemm_kernel(BeConst bc, BeBu
     }
 }
 
-// S = L L^T (packed lower in shared memory), Linv = L^-1, y = Linv r.  One CTA per stream.
+// S = L L^T, Linv = L^-1.  One CTA per stream.
 // 1 / sqrt(a) for a > 0 from the RSQ64H seed and two Newton steps (fp64 round-off), as in the QR chain
 __device__ __forceinline__ double chol_rsqrt(double a) {
     double y;
@@ -2767,7 +2519,7 @@ __global__ void __launch_bounds__(CH_THREADS) be_chol_kernel(BeConst bc, BeBuf b
                 for (int b = 0; b < CH_T; ++b) g[a][b] = fma(-ci[a], rj[b], g[a][b]);
         }
     }
-    // X = L^-1 out; y = X rt row by row in a fixed order (a stream's result must not depend on scheduling)
+    // X = L^-1 out
     if (live) {
 #pragma unroll
         for (int a = 0; a < CH_T; ++a) {
@@ -2780,39 +2532,215 @@ __global__ void __launch_bounds__(CH_THREADS) be_chol_kernel(BeConst bc, BeBuf b
             }
         }
     }
-    __syncthreads();
-    const double *rt = bb.rt + (size_t)s * KC;
-    double *yv = bb.yv + (size_t)s * KC;
-    for (int i = threadIdx.x; i < n; i += CH_THREADS) {
-        const double *row = Linv + (size_t)i * KC;
-        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        int l = 0;
-        for (; l + 3 <= i; l += 4) {
-            a0 = fma(__ldcg(row + l), rt[l], a0);
-            a1 = fma(__ldcg(row + l + 1), rt[l + 1], a1);
-            a2 = fma(__ldcg(row + l + 2), rt[l + 2], a2);
-            a3 = fma(__ldcg(row + l + 3), rt[l + 3], a3);
+}
+
+// Cholesky with diagonal pivoting of the Gram matrix of the stacked system (see be_gram_kernel), one CTA per
+// stream, same register layout as be_chol_kernel: thread t owns the 6x6 tile (ti, tj), tj <= ti, of G[:k,:k]
+// (diagonal tiles hold the full symmetric block).  Nothing is ever swapped: step t picks the largest
+// remaining diagonal entry p, broadcasts c_i = A_ip / sqrt(A_pp) (zero for earlier pivots) through shared
+// memory, every tile takes A_ij -= c_i c_j, and row t of R is c in the ORIGINAL column order; earlier pivots'
+// rows and columns are left as they fall (never read again: the `done` flags mask them).  Warp 0 keeps a
+// copy of the diagonal (same fma, so bit-identical to the tiles') and does the arg-max for the next pivot
+// while the other warps update their tiles: two barriers per step.  The compressed residual Q1^T r is never
+// formed (see be_apply_kernel: delta_x comes from H^T r, row k of the Gram matrix).  It stops at the numerical rank: largest remaining diagonal <= PC_TOL x the
+// largest initial one.  Output: mt = rank, perm = pivots in order followed by the unused columns, and
+// T[t][l] = R[t][perm[l]] (zero for l < t): upper trapezoidal in the permuted column order, which the
+// products fold into their column gather (cols[l] = camera column perm[l]).
+#define PC_TOL 1e-14
+
+__global__ void __launch_bounds__(CH_THREADS) be_pchol_kernel(BeConst bc, BeBuf bb) {
+    const int s = blockIdx.x;
+    const BeStep sp = bb.step[s];
+    if (!sp.active) return;
+    BeState &st = bb.st[s];
+    if (!st.do_update) return;
+    const int KC = bc.KC, k = st.k, ldg = KC + 1;
+    if (st.m <= k) return;
+    const double *G = bb.Gm + (size_t)s * ldg * ldg;
+    double *Rt = bb.Rp + (size_t)s * KC * KC;  // row t of R, original column order, row stride k
+    double *Tm = bb.Tm + (size_t)s * KC * KC;
+    int *perm = bb.perm + (size_t)s * KC;
+    __shared__ double vec[CH_NMAX + CH_T];
+    __shared__ double s_dinv;
+    __shared__ int s_p, s_stop, s_rank;
+    __shared__ unsigned char s_done[CH_NMAX + CH_T];
+    __shared__ int s_perm[CH_NMAX + CH_T];
+    const int t = threadIdx.x;
+    int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    const int tj = t - ti * (ti + 1) / 2;
+    const int i0 = CH_T * ti, j0 = CH_T * tj;
+    const bool live = i0 < k;
+    double g[CH_T][CH_T];
+#pragma unroll
+    for (int a = 0; a < CH_T; ++a)
+#pragma unroll
+        for (int b = 0; b < CH_T; ++b) {
+            const int i = i0 + a, j = j0 + b;
+            g[a][b] = (i < k && j < k) ? G[(size_t)max(i, j) * ldg + min(i, j)] : 0.0;
         }
-        for (; l <= i; ++l) a0 = fma(__ldcg(row + l), rt[l], a0);
-        yv[i] = (a0 + a1) + (a2 + a3);
+    for (int i = t; i < CH_NMAX + CH_T; i += CH_THREADS) {
+        vec[i] = 0.0;
+        s_done[i] = 0;
+    }
+    // warp 0: lane l mirrors the diagonal entries of columns 6 l .. 6 l + 5
+    double d[CH_T];
+    unsigned open = 0;  // bit a: column 6 lane + a has not been a pivot yet
+    double d0 = 0.0;
+    if (t < 32) {
+#pragma unroll
+        for (int a = 0; a < CH_T; ++a) {
+            const int i = CH_T * t + a;
+            d[a] = i < k ? G[(size_t)i * ldg + i] : 0.0;
+            if (i < k) open |= 1u << a;
+        }
+    }
+    // (value, index) arg-max over the open columns of warp 0; ties go to the smaller index
+    auto warp_argmax = [&](double &best, int &bi) {
+        best = -1.0;
+        bi = 0x7fffffff;
+#pragma unroll
+        for (int a = 0; a < CH_T; ++a)
+            if (((open >> a) & 1u) && d[a] > best) {
+                best = d[a];
+                bi = CH_T * t + a;
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) {
+                best = ob;
+                bi = oi;
+            }
+        }
+    };
+    if (t < 32) {
+        double best;
+        int bi;
+        warp_argmax(best, bi);
+        d0 = best;
+        if (t == 0) {
+            s_rank = 0;
+            s_stop = !(best > 0.0);
+            s_p = best > 0.0 ? bi : 0;
+            s_dinv = best > 0.0 ? chol_rsqrt(best) : 0.0;
+        }
+    }
+    for (int step = 0; step < k; ++step) {
+        __syncthreads();
+        if (s_stop) break;
+        const int p = s_p, tp = p / CH_T, ap = p - tp * CH_T;
+        const double dinv = s_dinv;
+        if (tj == tp && ti >= tp) {
+            // rows i0.. of column p (the diagonal tile holds the full block)
+            CH_FOR_COL(ap,
+#pragma unroll
+                       for (int a = 0; a < CH_T; ++a) {
+                           const int i = i0 + a;
+                           if (i < k) vec[i] = s_done[i] ? 0.0 : g[a][B_] * dinv;
+                       })
+        } else if (ti == tp && tj < tp) {
+            // columns j0.. of row p = rows j0.. of column p
+            CH_FOR_COL(ap,
+#pragma unroll
+                       for (int b = 0; b < CH_T; ++b) {
+                           const int j = j0 + b;
+                           vec[j] = s_done[j] ? 0.0 : g[B_][b] * dinv;
+                       })
+        }
+        __syncthreads();
+        if (live) {
+            double ci[CH_T], rj[CH_T];
+#pragma unroll
+            for (int a = 0; a < CH_T; ++a) ci[a] = vec[i0 + a];
+#pragma unroll
+            for (int b = 0; b < CH_T; ++b) rj[b] = vec[j0 + b];
+#pragma unroll
+            for (int a = 0; a < CH_T; ++a)
+#pragma unroll
+                for (int b = 0; b < CH_T; ++b) g[a][b] = fma(-ci[a], rj[b], g[a][b]);
+        }
+        if (t < k) Rt[(size_t)step * k + t] = vec[t];
+        if (t < 32) {
+            double c[CH_T];
+#pragma unroll
+            for (int a = 0; a < CH_T; ++a) c[a] = vec[CH_T * t + a];
+            if (t == tp) open &= ~(1u << ap);
+#pragma unroll
+            for (int a = 0; a < CH_T; ++a) d[a] = fma(-c[a], c[a], d[a]);
+            double best;
+            int bi;
+            warp_argmax(best, bi);
+            if (t == 0) {
+                s_perm[step] = p;
+                s_done[p] = 1;
+                s_rank = step + 1;
+                const bool go = step + 1 < k && best > PC_TOL * d0;
+                s_stop = !go;
+                s_p = go ? bi : 0;
+                s_dinv = go ? chol_rsqrt(best) : 0.0;
+            }
+        }
+    }
+    __syncthreads();
+    const int rank = s_rank;
+    if (t == 0) {
+        int n = rank;
+        for (int i = 0; i < k; ++i)
+            if (!s_done[i]) s_perm[n++] = i;
+        st.mt = rank;
+        st.t_upper = 1;
+    }
+    __syncthreads();
+    for (int i = t; i < k; i += CH_THREADS) {
+        perm[i] = s_perm[i];
+        bb.gv[(size_t)s * KC + i] = G[(size_t)k * ldg + i];  // H^T r: row k of the Gram matrix
+    }
+    for (int e = t; e < rank * k; e += CH_THREADS) {
+        const int i = e / k, l = e - i * k;
+        Tm[e] = l >= i ? __ldcg(Rt + (size_t)i * k + s_perm[l]) : 0.0;
     }
 }
 
-// delta_x = W y and the state correction (measurementUpdate :860-894).  One CTA per stream.
+// delta_x and the state correction (measurementUpdate :860-894).  One CTA per stream, AFTER the covariance
+// update: with R = sigma^2 I the gain is K = P+ H^T / sigma^2 (P+ the posterior covariance), so
+//     delta_x = K r = P+[:, cols] (H^T r) / sigma^2,
+// one product of the k active columns of the new covariance with g = H^T r taken straight from the stacked
+// system (row k of its Gram matrix).  This is the reference's K r in exact arithmetic, and it does not pass
+// through the compressed residual Q1^T r = T^-T g: directions of H with singular values near 1e-8 of the
+// largest carry no information but T^-T amplifies the rounding of g along them, which cost 3e-11 in delta_x
+// on the filter's own updates (tools/upd_check.py), whereas this form agrees with the oracle's Householder
+// path to ~1e-16 (errors of the order eps |P| |g| / sigma^2).
 __global__ void __launch_bounds__(BE_THREADS) be_apply_kernel(BeConst bc, BeBuf bb) {
     const int s = blockIdx.x;
     const BeStep sp = bb.step[s];
     if (!sp.active) return;
     BeState &st = bb.st[s];
     if (!st.do_update) return;
-    const int LD = bc.LD, KC = bc.KC, mt = st.mt;
+    const int LD = bc.LD, KC = bc.KC, k = st.k;
     __shared__ double dx[N21 + 6 * NSM];
-    const double *W = bb.W + (size_t)s * LD * KC, *yv = bb.yv + (size_t)s * KC;
+    __shared__ double s_g[6 * NSM];
+    __shared__ int s_cols[6 * NSM];
+    const double *P = bb.P + (size_t)s * LD * LD, *gv = bb.gv + (size_t)s * KC;
+    for (int l = threadIdx.x; l < k; l += BE_THREADS) {
+        s_cols[l] = N21 + 6 * st.u_slots[l / 6] + (l % 6);
+        s_g[l] = gv[l];
+    }
+    __syncthreads();
     for (int i = threadIdx.x; i < LD; i += BE_THREADS) {
-        double sacc = 0;
-        for (int l = 0; l < mt; ++l) sacc += W[(size_t)i * KC + l] * yv[l];
-        dx[i] = sacc;
-        bb.dxv[(size_t)s * LD + i] = sacc;
+        const double *row = P + (size_t)i * LD;
+        double a0 = 0, a1 = 0;
+        int l = 0;
+        for (; l + 1 < k; l += 2) {
+            a0 = fma(row[s_cols[l]], s_g[l], a0);
+            a1 = fma(row[s_cols[l + 1]], s_g[l + 1], a1);
+        }
+        if (l < k) a0 = fma(row[s_cols[l]], s_g[l], a0);
+        const double v = (a0 + a1) / bc.obs_noise;
+        dx[i] = v;
+        bb.dxv[(size_t)s * LD + i] = v;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -2999,7 +2927,7 @@ struct BeBuffers {
     double *h_poses[4];       // pinned [S][16], one slot per back-end step (ring)
     cudaEvent_t ev_poses[4];
     long long pose_seq = 0;   // back-end steps launched so far
-    size_t smem_add = 0, smem_sel = 0, smem_jac[2] = {0, 0}, smem_qr = 0, smem_chol = 0;
+    size_t smem_add = 0, smem_sel = 0, smem_jac[2] = {0, 0}, smem_chol = 0;
     int sort_n = 0;
 };
 
@@ -3007,8 +2935,8 @@ struct BeBuffers {
 
 int be_create(mskf_handle *h) {
     const mskf_config &c = h->cfg;
-    // 31: the QR compression gives every column of [H | r] (6 N + 1 of them) a slot among QR_COLS = 192
-    if (c.max_cam_state_size < 5 || c.max_cam_state_size > NSM - 1 || 6 * c.max_cam_state_size + 1 > QR_COLS) {
+    // 31: the factorization kernels keep one 6x6 tile of the lower tile triangle per thread (31 x 32 / 2 = 496 <= 512)
+    if (c.max_cam_state_size < 5 || c.max_cam_state_size > NSM - 1) {
         h->err = "max_cam_state_size must be in [5, 31]";
         return MSKF_ERR_ARG;
     }
@@ -3076,9 +3004,9 @@ int be_create(mskf_handle *h) {
     A(bb.l_slot, S * bc.ML); A(bb.l_ok, S * bc.ML); A(bb.l_pass, S * bc.ML); A(bb.l_M, S * bc.ML);
     A(bb.l_eoff, S * bc.ML); A(bb.l_roff, S * bc.ML); A(bb.l_soff, S * bc.ML); A(bb.l_oslots, S * bc.ML * NSM);
     A(bb.Hblk, S * bc.ecap); A(bb.rblk, S * bc.rcap);
-    A(bb.Hst, S * bc.hst_cap); A(bb.rst, S * bc.hst_rows); A(bb.rst_j0, S * bc.hst_rows); A(bb.Rq, S * QR_G * (bc.KC + 1) * (bc.KC + 1)); A(bb.Rfill, S * QR_G * (bc.KC + 1));
-    A(bb.Tm, S * bc.KC * bc.KC); A(bb.rt, S * bc.KC); A(bb.PHt, S * bc.LD * bc.KC); A(bb.Sm, S * bc.KC * bc.KC);
-    A(bb.Linv, S * bc.KC * bc.KC); A(bb.W, S * bc.LD * bc.KC); A(bb.yv, S * bc.KC); A(bb.dxv, S * bc.LD);
+    A(bb.Hst, S * bc.hst_cap); A(bb.rst, S * bc.hst_rows); A(bb.Gm, S * (bc.KC + 1) * (bc.KC + 1)); A(bb.Rp, S * bc.KC * bc.KC); A(bb.perm, S * bc.KC);
+    A(bb.Tm, S * bc.KC * bc.KC); A(bb.gv, S * bc.KC); A(bb.PHt, S * bc.LD * bc.KC); A(bb.Sm, S * bc.KC * bc.KC);
+    A(bb.Linv, S * bc.KC * bc.KC); A(bb.W, S * bc.LD * bc.KC); A(bb.dxv, S * bc.LD);
 #undef A
     bb.work = h->d_work;
     bb.fe_msg = h->fb.stale;
@@ -3105,7 +3033,6 @@ int be_create(mskf_handle *h) {
         int maxR4 = 4 * maxM;
         B->smem_jac[ph] = sizeof(double) * ((size_t)maxR4 * (maxR4 + 1) / 2 + (size_t)maxM * 24 + (size_t)maxR4 * 10 + (size_t)maxM * 18);
     }
-    B->smem_qr = sizeof(double) * ((size_t)(bc.KC + 1) * (bc.KC + 2) / 2 + (size_t)QR_B * (bc.KC + 1));
     B->smem_chol = sizeof(double) * ((size_t)bc.KC * (bc.KC + 1) / 2 + bc.KC);
     if ((rc = smem_optin(h, be_add_obs_kernel, B->smem_add)) != MSKF_OK) return rc;
     if ((rc = smem_optin(h, be_select_kernel, B->smem_sel)) != MSKF_OK) return rc;
@@ -3163,15 +3090,16 @@ static void launch_update(mskf_handle *h, int phase = 0) {
     cudaStream_t q = h->be_stream;
     const int S = h->S;
     const int tiles_ld = (bc.LD + GT - 1) / GT, tiles_kc = (bc.KC + GT - 1) / GT;
-    MSKF_LAUNCH(h, phase == 0 ? PK_BE_QR : PK_BE_QR_PRUNE, (be_qr_kernel<<<dim3(QR_G, S), QR_THREADS, 0, q>>>(bc, bb, phase)));
-    MSKF_LAUNCH(h, PK_BE_QR_COMBINE, (be_qr_combine_kernel<<<dim3(2, S), QR_THREADS, 0, q>>>(bc, bb, 1)));
-    MSKF_LAUNCH(h, PK_BE_QR_COMBINE, (be_qr_combine_kernel<<<dim3(1, S), QR_THREADS, 0, q>>>(bc, bb, 2)));
+    const int tiles_kw = (bc.KC + 1 + GT - 1) / GT;
+    MSKF_LAUNCH(h, phase == 0 ? PK_BE_GRAM : PK_BE_GRAM_PRUNE,
+                (be_gram_kernel<<<dim3(phase == 0 ? tiles_kw * (tiles_kw + 1) / 2 : 1, S), BE_THREADS, 0, q>>>(bc, bb, phase)));
+    MSKF_LAUNCH(h, PK_BE_PCHOL, (be_pchol_kernel<<<S, CH_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_GEMM_PHT, (be_gemm_kernel<0><<<dim3(tiles_ld * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_GEMM_S, (be_gemm_kernel<1><<<dim3(tiles_kc * (tiles_kc + 1) / 2, S), BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_CHOL, (be_chol_kernel<<<S, CH_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_GEMM_W, (be_gemm_kernel<2><<<dim3(tiles_ld * tiles_kc, S), BE_THREADS, 0, q>>>(bc, bb)));
-    MSKF_LAUNCH(h, PK_BE_APPLY, (be_apply_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb)));
     MSKF_LAUNCH(h, PK_BE_GEMM_PUPD, (be_gemm_kernel<3><<<dim3(tiles_ld * (tiles_ld + 1) / 2, S), BE_THREADS, 0, q>>>(bc, bb)));
+    MSKF_LAUNCH(h, PK_BE_APPLY, (be_apply_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb)));
 }
 
 int be_step(mskf_handle *h, const std::vector<int> &streams, const mskf_feature *inject, int n_inject, int inject_stream,
@@ -3460,14 +3388,6 @@ int be_op_update(mskf_handle *t, int n_cam, int m, const double *H, const double
     MSKF_CUDA_CHECK(t, cudaMemcpy(bb.P, Pl.data(), sizeof(double) * Pl.size(), cudaMemcpyHostToDevice));
     MSKF_CUDA_CHECK(t, cudaMemcpy(bb.Hst, Hc.data(), sizeof(double) * Hc.size(), cudaMemcpyHostToDevice));
     MSKF_CUDA_CHECK(t, cudaMemcpy(bb.rst, r, sizeof(double) * m, cudaMemcpyHostToDevice));
-    std::vector<int> j0v(m, k);
-    for (int i = 0; i < m; ++i)
-        for (int j = 0; j < k; ++j)
-            if (Hc[(size_t)i * k + j] != 0.0) {
-                j0v[i] = j;
-                break;
-            }
-    MSKF_CUDA_CHECK(t, cudaMemcpy(bb.rst_j0, j0v.data(), sizeof(int) * m, cudaMemcpyHostToDevice));
     launch_update(t);
     MSKF_CUDA_CHECK(t, cudaGetLastError());
     MSKF_CUDA_CHECK(t, cudaStreamSynchronize(t->be_stream));

@@ -182,8 +182,8 @@ struct mskf_handle {
 enum {
     PK_PYR_L1 = 0, PK_PYR_LN, PK_KLT_TEMPORAL, PK_KLT_STEREO, PK_KLT_NEW, PK_DETECT, PK_FE_BOOK,
     PK_BE_PROPAGATE, PK_BE_AUGMENT, PK_BE_ADD_OBS, PK_BE_SELECT, PK_BE_TRIANGULATE, PK_BE_LAYOUT, PK_BE_FEATURE_JAC,
-    PK_BE_STACK, PK_BE_QR, PK_BE_GEMM_PHT, PK_BE_GEMM_S, PK_BE_CHOL, PK_BE_GEMM_W, PK_BE_APPLY, PK_BE_GEMM_PUPD,
-    PK_BE_PRUNE_FINISH, PK_BE_FINISH, PK_BE_FEATURE_JAC_PRUNE, PK_BE_QR_PRUNE, PK_BE_QR_COMBINE, PK_COUNT
+    PK_BE_STACK, PK_BE_GRAM, PK_BE_GEMM_PHT, PK_BE_GEMM_S, PK_BE_CHOL, PK_BE_GEMM_W, PK_BE_APPLY, PK_BE_GEMM_PUPD,
+    PK_BE_PRUNE_FINISH, PK_BE_FINISH, PK_BE_FEATURE_JAC_PRUNE, PK_BE_GRAM_PRUNE, PK_BE_PCHOL, PK_COUNT
 };
 const char *mskf_prof_name(int tag);
 void prof_begin(mskf_handle *h, int tag);

@@ -122,8 +122,8 @@ static void host_predict_homography(mskf_handle *h, HostStream &hs, double H0[9]
 static const char *kProfNames[PK_COUNT] = {
     "pyr_down_l1", "pyr_down_ln", "klt_temporal", "klt_stereo", "klt_new", "detect", "fe_bookkeeping",
     "be_propagate", "be_augment", "be_add_obs", "be_select", "be_triangulate", "be_layout", "be_feature_jac",
-    "be_stack", "be_qr", "be_gemm_pht", "be_gemm_s", "be_chol", "be_gemm_w", "be_apply", "be_gemm_pupd",
-    "be_prune_finish", "be_finish", "be_feature_jac_prune", "be_qr_prune", "be_qr_combine"};
+    "be_stack", "be_gram", "be_gemm_pht", "be_gemm_s", "be_chol", "be_gemm_w", "be_apply", "be_gemm_pupd",
+    "be_prune_finish", "be_finish", "be_feature_jac_prune", "be_gram_prune", "be_pchol"};
 const char *mskf_prof_name(int tag) { return tag >= 0 && tag < PK_COUNT ? kProfNames[tag] : "?"; }
 void prof_begin(mskf_handle *h, int tag) {
     if (!h->prof_on) return;

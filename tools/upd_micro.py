@@ -1,5 +1,5 @@
 """Micro-benchmark of the update chain on one stream: per-kernel time for a dense m x k system.
-usage: python tools/qr_micro.py [m n_cam]   (GPU)"""
+usage: python tools/upd_micro.py [m n_cam]   (GPU)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
