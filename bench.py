@@ -249,11 +249,56 @@ def preset_text(cfg):
             f"grid {cfg.grid_row}x{cfg.grid_col} x {cfg.grid_min_feature_num}..{cfg.grid_max_feature_num}, max_cam_state_size {cfg.max_cam_state_size}")
 
 
+def bind_near_gpu(torch, local_rank):
+    """Pin this rank's threads to the CPUs of its GPU's NUMA node BEFORE any page-locked buffer is allocated, so
+    that the pinned frame sets are first-touched on the node the GPU hangs off (at N = 8 every rank otherwise
+    starts on node 0 and half of the uploads cross the socket link: SCALE_r01 e2e efficiency 0.72).  Falls back
+    to an even split of the allowed CPUs over the local ranks when sysfs has no NUMA information."""
+    info = {"numa_node": None, "cpus": None, "how": "unchanged"}
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        props = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        cpus = []
+        if node >= 0:
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus += list(range(int(lo), int(hi or lo) + 1))
+            cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            # the ranks that share a node split its CPUs
+            lw = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+            peers = [r for r in range(lw) if _gpu_node(torch, r) == node] or [local_rank]
+            i, n = peers.index(local_rank) if local_rank in peers else 0, len(peers)
+            mine = cpus[i * len(cpus) // n:(i + 1) * len(cpus) // n] or cpus
+            os.sched_setaffinity(0, mine)
+            info = {"numa_node": node, "cpus": len(mine), "how": "sysfs numa_node of the GPU"}
+        else:
+            lw = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+            if lw > 1 and len(allowed) >= lw:
+                mine = allowed[local_rank * len(allowed) // lw:(local_rank + 1) * len(allowed) // lw]
+                os.sched_setaffinity(0, mine)
+                info = {"numa_node": node, "cpus": len(mine), "how": "even split of the allowed CPUs (no NUMA information)"}
+    except (OSError, ValueError, AttributeError) as e:
+        info["how"] = f"unchanged ({type(e).__name__})"
+    return info
+
+
+def _gpu_node(torch, idx):
+    try:
+        p = torch.cuda.get_device_properties(idx)
+        return int(open(f"/sys/bus/pci/devices/{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0/numa_node").read())
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the engine; use --impl reference for the CPU leg)")
+    affinity = bind_near_gpu(torch, local_rank)
     from msckf_stereo_c_b200 import engine, synth
 
     dist = None
@@ -430,13 +475,29 @@ def run_ours(args, rank, world, local_rank):
         imu0 = groups[0].rec
     for g in groups:
         g.e.close()
+    # bare host->device ceiling: the same pinned frame sets copied back to back on one stream, all ranks at once
+    # (what the uploads of the e2e leg could reach at best on this box with N ranks sharing the host)
+    barrier()
+    hs = torch.cuda.Stream(device=dev)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = min(n_e2e, 8)
+    with torch.cuda.stream(hs):
+        scratch.copy_(frames_host[0], non_blocking=True)
+        c0.record(hs)
+        for i in range(reps):
+            scratch.copy_(frames_host[i], non_blocking=True)
+        c1.record(hs)
+    hs.synchronize()
+    h2d_gbs = reps * 2 * img * S / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    barrier()
     del frames_host
 
     # ---- max over ranks
-    times = torch.tensor([ms_dev, ms_e2e, 1e3 * t_wall], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_dev, ms_e2e, 1e3 * t_wall, -h2d_gbs], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_dev_max, ms_e2e_max, wall_max = [float(x) for x in times.tolist()]
+    ms_dev_max, ms_e2e_max, wall_max, neg_h2d = [float(x) for x in times.tolist()]
+    h2d_gbs_min = -neg_h2d  # the slowest rank's ceiling
     total_frames = world * S * K
     value = total_frames / (ms_dev_max * 1e-3)
     e2e_value = total_frames / (ms_e2e_max * 1e-3)
@@ -479,13 +540,27 @@ def run_ours(args, rank, world, local_rank):
             best = min(best, x0.elapsed_time(x1))
         fp64_peak = 2 * 4096 ** 3 / (best * 1e-3) / 1e12
         fe_classes = {"pyr_down_l1", "pyr_down_ln", "klt_temporal", "klt_stereo", "klt_new", "detect"}
+        issue_classes = {"klt_temporal", "klt_stereo", "klt_new", "detect"}
+        inst_per_stream = {}
+        try:
+            inst_per_stream = json.load(open(os.path.join(ROOT, "profiles", "inst.json")))
+        except (OSError, ValueError):
+            pass
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_mhz = clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0
+        issue_peak = n_sm * 4 * sm_mhz * 1e6 / 1e9  # one warp instruction per scheduler per clock, 4 schedulers per SM
         per_kernel = []
         tot_ms = sum(v[0] for v in prof.values())
         for name, (ms, n, work) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
             if n == 0:
                 continue
             ent = {"kernel": name, "launches": n, "ms_per_launch": ms / n, "share": ms / tot_ms}
-            if name in fe_classes:
+            if name in issue_classes and inst_per_stream.get(name):
+                # issue-bound kernels (ncu: 65-80 % of the issue slots busy, < 7 % of HBM): warp instructions per second
+                # against the SMs' issue rate; the HBM figure on the algorithmic bytes stays beside it
+                ent.update(bound="issue", achieved=inst_per_stream[name] * S / (ms / n * 1e-3) / 1e9, peak=issue_peak, unit="Gwarp-inst/s",
+                           hbm_gbs=work / (ms * 1e-3) / 1e9, hbm_frac=work / (ms * 1e-3) / 1e9 / hbm_peak)
+            elif name in fe_classes:
                 ent.update(bound="hbm", achieved=work / (ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s")
             elif work > 0:
                 ent.update(bound="fp64", achieved=work / (ms * 1e-3) / 1e12, peak=fp64_peak, unit="TFLOP/s")
@@ -501,10 +576,15 @@ def run_ours(args, rank, world, local_rank):
             pass
         roofline = None
         if top:
-            roofline = {"kernel": top["kernel"], "bound": "hbm" if top["bound"] == "hbm" else "tensor", "achieved": top["achieved"],
+            src = {"hbm": peak_src, "fp64": "cuBLAS DGEMM 4096^3 measured in this run (fp64 pipe incl. DMMA; MEASURED_PEAKS.json has no fp64 figure)",
+                   "issue": f"{n_sm} SMs x 4 schedulers x {sm_mhz:.0f} MHz (SM clock sampled in the timed region); warp instructions per launch from "
+                            "profiles/inst.json (ncu smsp__inst_executed.sum); the kernel is instruction-issue bound, not HBM bound: hbm_frac is its "
+                            "algorithmic bytes against the HBM peak"}[top["bound"]]
+            roofline = {"kernel": top["kernel"], "bound": {"hbm": "hbm", "fp64": "tensor", "issue": "issue"}[top["bound"]], "achieved": top["achieved"],
                         "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": traffic,
-                        "peak_source": peak_src if top["bound"] == "hbm" else "cuBLAS DGEMM 4096^3 measured in this run (fp64 pipe incl. DMMA; "
-                        "MEASURED_PEAKS.json has no fp64 figure)", "share_of_step": top["share"]}
+                        "peak_source": src, "share_of_step": top["share"]}
+            if "hbm_frac" in top:
+                roofline.update(hbm_gbs=top["hbm_gbs"], hbm_frac=top["hbm_frac"])
         # CPU baseline: the oracle on one host core, a bounded sample of the same workload.  With the spot-check
         # on it replays stream 0 of the timed fleet (same images, same IMU rows) from frame 0 and is timed on
         # its last frames; its final state is then compared with the engine's.
@@ -544,7 +624,11 @@ def run_ours(args, rank, world, local_rank):
                        "l2": f"inputs larger than L2: {2 * img * S / 1e6:.0f} MB of new images per step",
                        "front_end_dtype": "u8 / fixed point", "parallelism": f"stream-sharded x{world}, no collective on the data path"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e_max / K},
+                    "ms_per_step": ms_e2e_max / K,
+                    "h2d_ceiling_gbs": h2d_gbs_min, "h2d_ceiling_ms_per_step": 2 * img * S / (h2d_gbs_min * 1e9) * 1e3,
+                    "h2d_ceiling_note": "pinned frame sets copied back to back on one stream by all ranks at once, slowest rank: the "
+                                        "least an e2e step can take on this host when the upload is not hidden"},
+            "cpu_affinity": affinity,
             "gpu_launches": int(launches),
             "kernel_pass": {"steps": KP, "mode": f"one handle x {S} streams, front end and back end serialised (mskf_set_overlap 0)"},
             "clocks": clk,
