@@ -2435,6 +2435,12 @@ __device__ __forceinline__ double chol_rsqrt(double a) {
     default: { constexpr int B_ = 5; BODY } break;               \
     }
 
+__device__ __forceinline__ void chol_load6(const double *p, double (&v)[CH_T]) {  // p is 16-byte aligned (6-double chunks)
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = q[0], b = q[1], c = q[2];
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+}
+
 __global__ void __launch_bounds__(CH_THREADS) be_chol_kernel(BeConst bc, BeBuf bb) {
     const int s = blockIdx.x;
     const BeStep sp = bb.step[s];
@@ -2444,7 +2450,7 @@ __global__ void __launch_bounds__(CH_THREADS) be_chol_kernel(BeConst bc, BeBuf b
     const int KC = bc.KC, n = st.mt;
     const double *Sm = bb.Sm + (size_t)s * KC * KC;
     double *Linv = bb.Linv + (size_t)s * KC * KC;
-    __shared__ double vec[CH_NMAX + CH_T];
+    __shared__ __align__(16) double vec[CH_NMAX + CH_T];
     __shared__ double s_dinv;
     // tile (ti, tj), tj <= ti, of thread t = ti (ti + 1) / 2 + tj
     const int t = threadIdx.x;
@@ -2508,11 +2514,15 @@ __global__ void __launch_bounds__(CH_THREADS) be_chol_kernel(BeConst bc, BeBuf b
         }
         __syncthreads();
         if (live && i0 + CH_T - 1 > kk) {
+            // a tile's six c_i / r_j values are one 48-byte chunk: three LDS.128 each.  With 8-byte loads the r_j
+            // reads of a warp (consecutive tj: a stride of 48 bytes) hit every bank four times over
             double ci[CH_T], rj[CH_T];
+            chol_load6(vec + i0, ci);
+            chol_load6(vec + j0, rj);
 #pragma unroll
-            for (int a = 0; a < CH_T; ++a) ci[a] = (i0 + a > kk && i0 + a < n) ? vec[i0 + a] : 0.0;
+            for (int a = 0; a < CH_T; ++a) ci[a] = (i0 + a > kk && i0 + a < n) ? ci[a] : 0.0;
 #pragma unroll
-            for (int b = 0; b < CH_T; ++b) rj[b] = (j0 + b < n) ? vec[j0 + b] : 0.0;
+            for (int b = 0; b < CH_T; ++b) rj[b] = (j0 + b < n) ? rj[b] : 0.0;
 #pragma unroll
             for (int a = 0; a < CH_T; ++a)
 #pragma unroll
@@ -2560,7 +2570,7 @@ __global__ void __launch_bounds__(CH_THREADS) be_pchol_kernel(BeConst bc, BeBuf 
     double *Rt = bb.Rp + (size_t)s * KC * KC;  // row t of R, original column order, row stride k
     double *Tm = bb.Tm + (size_t)s * KC * KC;
     int *perm = bb.perm + (size_t)s * KC;
-    __shared__ double vec[CH_NMAX + CH_T];
+    __shared__ __align__(16) double vec[CH_NMAX + CH_T];
     __shared__ double s_dinv;
     __shared__ int s_p, s_stop, s_rank;
     __shared__ unsigned char s_done[CH_NMAX + CH_T];
@@ -2653,10 +2663,8 @@ __global__ void __launch_bounds__(CH_THREADS) be_pchol_kernel(BeConst bc, BeBuf 
         __syncthreads();
         if (live) {
             double ci[CH_T], rj[CH_T];
-#pragma unroll
-            for (int a = 0; a < CH_T; ++a) ci[a] = vec[i0 + a];
-#pragma unroll
-            for (int b = 0; b < CH_T; ++b) rj[b] = vec[j0 + b];
+            chol_load6(vec + i0, ci);
+            chol_load6(vec + j0, rj);
 #pragma unroll
             for (int a = 0; a < CH_T; ++a)
 #pragma unroll
@@ -2665,8 +2673,7 @@ __global__ void __launch_bounds__(CH_THREADS) be_pchol_kernel(BeConst bc, BeBuf 
         if (t < k) Rt[(size_t)step * k + t] = vec[t];
         if (t < 32) {
             double c[CH_T];
-#pragma unroll
-            for (int a = 0; a < CH_T; ++a) c[a] = vec[CH_T * t + a];
+            chol_load6(vec + CH_T * t, c);
             if (t == tp) open &= ~(1u << ap);
 #pragma unroll
             for (int a = 0; a < CH_T; ++a) d[a] = fma(-c[a], c[a], d[a]);

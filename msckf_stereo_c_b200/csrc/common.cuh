@@ -35,6 +35,8 @@ struct FeConst {
     int lvl_rows[MSKF_MAX_LEVELS], lvl_cols[MSKF_MAX_LEVELS];
     unsigned lvl_off[MSKF_MAX_LEVELS];
     unsigned pyr_bytes;  // per image, all levels
+    int pitch;           // row pitch of EVERY pyramid level = level-0 width (level l sits at rows sum(lvl_rows[<l]) of one
+                         // pitch-wide image), so that the KLT's row offsets are compile-time immediates for the standard widths
     int klt_win, klt_max_iters;
     double klt_eps2, klt_min_eig;
     int grid_row, grid_col, grid_min, grid_max, grid_h, grid_w, n_cells, n_cells_all;

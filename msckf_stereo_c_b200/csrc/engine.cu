@@ -648,7 +648,7 @@ int mskf_get_pyramid(mskf_handle *h, int s, int cam, int level, uint8_t *out, in
     if (!out) return MSKF_OK;
     if ((size_t)cap < bytes) return MSKF_ERR_CAPACITY;
     const uint8_t *p = (cam == 0 ? h->fb.pyr[h->hs[s].slot] : h->fb.pyr[2]) + (size_t)s * fc.pyr_bytes + fc.lvl_off[level];
-    MSKF_CUDA_CHECK(h, cudaMemcpy(out, p, bytes, cudaMemcpyDeviceToHost));
+    MSKF_CUDA_CHECK(h, cudaMemcpy2D(out, (size_t)*cols, p, (size_t)fc.pitch, (size_t)*cols, (size_t)*rows, cudaMemcpyDeviceToHost));
     return MSKF_OK;
 }
 

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(FeConst fc, FeBuffers fb,
     const int orows = fc.lvl_rows[level], ocols = fc.lvl_cols[level];
     const uint8_t *src = COPY_SRC ? (cam == 0 ? fb.src0[s] : fb.src1[s]) : pyr + fc.lvl_off[level - 1];
     uint8_t *dst = pyr + fc.lvl_off[level];
+    const int P = fc.pitch;  // row pitch of every level (the caller's level-0 image is tightly packed: the same value)
 
     __shared__ uint8_t tin[PD_IH][PD_IW + 4];
     __shared__ unsigned short hrow[PD_IH][PD_TW];
@@ -59,13 +60,13 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(FeConst fc, FeBuffers fb,
     for (int idx = threadIdx.x; idx < PD_IH * PD_IW; idx += 256) {
         int r = idx / PD_IW, c = idx - r * PD_IW;
         int gy = reflect101(iy0 + r, irows), gx = reflect101(ix0 + c, icols);
-        uint8_t v = src[(size_t)gy * icols + gx];
+        uint8_t v = src[(size_t)gy * P + gx];
         tin[r][c] = v;
         if (COPY_SRC) {
             // interior of the tile = this CTA's share of the level-0 landing copy
             int yy = iy0 + r, xx = ix0 + c;
             if (r >= 2 && r < PD_IH - 2 && c >= 2 && c < PD_IW - 2 && yy < irows && xx < icols)
-                pyr[(size_t)yy * icols + xx] = v;
+                pyr[(size_t)yy * P + xx] = v;
         }
     }
     __syncthreads();
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(FeConst fc, FeBuffers fb,
         if (oy < orows && ox < ocols) {
             int v = hrow[2 * r][c] + 4 * hrow[2 * r + 1][c] + 6 * hrow[2 * r + 2][c] + 4 * hrow[2 * r + 3][c] +
                     hrow[2 * r + 4][c];
-            dst[(size_t)oy * ocols + ox] = (uint8_t)((v + 128) >> 8);
+            dst[(size_t)oy * P + ox] = (uint8_t)((v + 128) >> 8);
         }
     }
 }
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(256) pyr_down_strip_kernel(FeConst fc, FeBuffe
     const int orows = fc.lvl_rows[level], ocols = fc.lvl_cols[level];
     const uint8_t *src = COPY_SRC ? (cam == 0 ? fb.src0[s] : fb.src1[s]) : pyr + fc.lvl_off[level - 1];
     uint8_t *dst = pyr + fc.lvl_off[level];
+    const int P = fc.pitch;  // row pitch of every level (the caller's level-0 image is tightly packed: the same value)
     extern __shared__ __align__(16) uint8_t ps_smem[];  // [PS_IN][row_stride]
     const int oy0 = blockIdx.x * PS_ROWS;
     const int iy0 = 2 * oy0 - 2;
@@ -127,11 +129,11 @@ __global__ void __launch_bounds__(256) pyr_down_strip_kernel(FeConst fc, FeBuffe
     for (int e = threadIdx.x; e < PS_IN * vpr; e += 256) {
         const int r = e / vpr, v = e - r * vpr;
         const int gy = reflect101(iy0 + r, irows);
-        const vec_t val = *(const vec_t *)(src + (size_t)gy * icols + (size_t)v * VEC);
+        const vec_t val = *(const vec_t *)(src + (size_t)gy * P + (size_t)v * VEC);
         *(vec_t *)(ps_smem + (size_t)r * row_stride + PS_PAD + v * VEC) = val;
         if (COPY_SRC) {
             const int yy = iy0 + r;  // interior rows of the strip = this CTA's share of the level-0 landing copy
-            if (r >= 2 && r < PS_IN - 2 && yy < irows) *(vec_t *)(pyr + (size_t)yy * icols + (size_t)v * VEC) = val;
+            if (r >= 2 && r < PS_IN - 2 && yy < irows) *(vec_t *)(pyr + (size_t)yy * P + (size_t)v * VEC) = val;
         }
     }
     __syncthreads();
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(256) pyr_down_strip_kernel(FeConst fc, FeBuffe
             const unsigned h3 = hfilt2(rp, q), h4 = hfilt2(rp + row_stride, q);
             const unsigned v = h0 + h4 + 6u * h2 + 4u * (h1 + h3);
             const unsigned o = ((v + 0x00800080u) >> 8) & 0x00FF00FFu;  // (sum + 128) >> 8 on both lanes
-            uint8_t *d = dst + (size_t)(oy0 + r) * ocols + 2 * q;
+            uint8_t *d = dst + (size_t)(oy0 + r) * P + 2 * q;
             if (!odd_w) {
                 *(unsigned short *)d = (unsigned short)((o & 0xFFu) | ((o >> 8) & 0xFF00u));
             } else {
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(256) pyr_down_bulk_kernel(FeConst fc, FeBuffer
     const int orows = fc.lvl_rows[level], ocols = fc.lvl_cols[level];
     const uint8_t *src = COPY_SRC ? (cam == 0 ? fb.src0[s] : fb.src1[s]) : pyr + fc.lvl_off[level - 1];
     uint8_t *dst = pyr + fc.lvl_off[level];
+    const int P = fc.pitch;  // row pitch of every level (the caller's level-0 image is tightly packed: the same value)
     extern __shared__ __align__(128) uint8_t ps_smem[];  // 16 B pad | PS_IN rows of icols bytes | 16 B pad
     __shared__ __align__(8) unsigned long long bar;
     uint8_t *tile = ps_smem + 16;
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(256) pyr_down_bulk_kernel(FeConst fc, FeBuffer
                 const unsigned h3 = hfilt2_packed(rp, q, first, last), h4 = hfilt2_packed(rp + icols, q, first, last);
                 const unsigned v = h0 + h4 + 6u * h2 + 4u * (h1 + h3);
                 const unsigned o = ((v + 0x00800080u) >> 8) & 0x00FF00FFu;
-                *(unsigned short *)(dst + (size_t)(oy0 + r) * ocols + 2 * q) = (unsigned short)((o & 0xFFu) | ((o >> 8) & 0xFF00u));
+                *(unsigned short *)(dst + (size_t)(oy0 + r) * P + 2 * q) = (unsigned short)((o & 0xFFu) | ((o >> 8) & 0xFF00u));
                 h0 = h2;
                 h1 = h3;
                 h2 = h4;
@@ -305,15 +308,6 @@ __device__ __forceinline__ BilinW bilin_weights(float x, float y) {
     b.w10 = __float2int_rn((1.f - a) * c * 16384.f);
     b.w11 = 16384 - b.w00 - b.w01 - b.w10;
     return b;
-}
-__device__ __forceinline__ int sample_fx(const uint8_t *__restrict__ im, int rows, int cols, const BilinW &b, int i, int j) {
-    int x0 = b.ix + i, y0 = b.iy + j;
-    int x1 = x0 + 1, y1 = y0 + 1;
-    x0 = min(max(x0, 0), cols - 1); x1 = min(max(x1, 0), cols - 1);
-    y0 = min(max(y0, 0), rows - 1); y1 = min(max(y1, 0), rows - 1);
-    const uint8_t *r0 = im + (size_t)y0 * cols, *r1 = im + (size_t)y1 * cols;
-    int sum = b.w00 * __ldg(r0 + x0) + b.w01 * __ldg(r0 + x1) + b.w10 * __ldg(r1 + x0) + b.w11 * __ldg(r1 + x1);
-    return (sum + 256) >> 9;
 }
 __device__ __forceinline__ long long warp_sum(long long v) {
 #pragma unroll
@@ -372,7 +366,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
             if (WIN) {
                 int px[(WIN ? WIN : 1) + 3], nx[(WIN ? WIN : 1) + 3];
 #pragma unroll
-                for (int j = 0; j <= WIN + 2; ++j) px[j] = __ldg(A + (size_t)min(max(y0 + j, 0), rows - 1) * cols + xc);
+                for (int j = 0; j <= WIN + 2; ++j) px[j] = __ldg(A + (size_t)min(max(y0 + j, 0), rows - 1) * fc.pitch + xc);
 #pragma unroll
                 for (int j = 0; j <= WIN + 2; ++j) nx[j] = __shfl_down_sync(0xffffffffu, px[j], 1);
                 if (lane < tw) {
@@ -381,10 +375,10 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
                         T[j * tw + lane] = (short)((wa.w00 * px[j] + wa.w01 * nx[j] + wa.w10 * px[j + 1] + wa.w11 * nx[j + 1] + 256) >> 9);
                 }
             } else {
-                int top = __ldg(A + (size_t)min(max(y0, 0), rows - 1) * cols + xc);
+                int top = __ldg(A + (size_t)min(max(y0, 0), rows - 1) * fc.pitch + xc);
                 int rt = __shfl_down_sync(0xffffffffu, top, 1);
                 for (int j = 0; j < tw; ++j) {
-                    const int bot = __ldg(A + (size_t)min(max(y0 + j + 1, 0), rows - 1) * cols + xc);
+                    const int bot = __ldg(A + (size_t)min(max(y0 + j + 1, 0), rows - 1) * fc.pitch + xc);
                     const int rb = __shfl_down_sync(0xffffffffu, bot, 1);
                     if (lane < tw) T[j * tw + lane] = (short)((wa.w00 * top + wa.w01 * rt + wa.w10 * bot + wa.w11 * rb + 256) >> 9);
                     top = bot;
@@ -440,7 +434,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
                         // neighbours by shuffle, then the arithmetic
                         int px[(WIN ? WIN : 1) + 1], nx[(WIN ? WIN : 1) + 1];
 #pragma unroll
-                        for (int j = 0; j <= WIN; ++j) px[j] = __ldg(B + (size_t)min(max(y0 + j, 0), rows - 1) * cols + xc);
+                        for (int j = 0; j <= WIN; ++j) px[j] = __ldg(B + (size_t)min(max(y0 + j, 0), rows - 1) * fc.pitch + xc);
 #pragma unroll
                         for (int j = 0; j <= WIN; ++j) nx[j] = __shfl_down_sync(0xffffffffu, px[j], 1);
                         if (lane < win) {
@@ -454,10 +448,10 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(FeConst fc, FeBuffe
                             }
                         }
                     } else {
-                        int top = __ldg(B + (size_t)min(max(y0, 0), rows - 1) * cols + xc);
+                        int top = __ldg(B + (size_t)min(max(y0, 0), rows - 1) * fc.pitch + xc);
                         int rt = __shfl_down_sync(0xffffffffu, top, 1);
                         for (int j = 0; j < win; ++j) {
-                            const int bot = __ldg(B + (size_t)min(max(y0 + j + 1, 0), rows - 1) * cols + xc);
+                            const int bot = __ldg(B + (size_t)min(max(y0 + j + 1, 0), rows - 1) * fc.pitch + xc);
                             const int rb = __shfl_down_sync(0xffffffffu, bot, 1);
                             if (lane < win) {
                                 const int val = (wb.w00 * top + wb.w01 * rt + wb.w10 * bot + wb.w11 * rb + 256) >> 9;
@@ -521,13 +515,17 @@ __device__ __forceinline__ long long warp_sum_i32(int v) {
     return ((long long)__reduce_add_sync(0xffffffffu, hi) << 16) + (long long)__reduce_add_sync(0xffffffffu, lo);
 }
 
-template <int WIN>
+//   * PITCH > 0: the row pitch of the pyramid is a compile-time constant (every level keeps the pitch of level
+//     0), so the rows of a patch are IMMEDIATE offsets of one 64-bit base address: one LDG per row instead of a
+//     multiply, a 64-bit add and the LDG (3 of the 12 instructions a window row costs per iteration).
+template <int WIN, int PITCH>
 __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_REG_CTAS) klt_reg_kernel(FeConst fc, FeBuffers fb, int mode) {
     static_assert(WIN >= 3 && WIN + 3 <= 32 && (WIN & 1), "window");
+    const int pitch = PITCH ? PITCH : fc.pitch;
     // packed gradients of the level: [row][lane] per warp (a lane only ever reads its own words: no bank
     // conflicts, no synchronisation); in registers they cost 2 x WIN live values across the iteration loop
     // and capped the kernel at 16 warps per SM
-    __shared__ int s_G[KLT_WARPS][WIN][32];
+    __shared__ int2 s_G[KLT_WARPS][WIN][32];
     const int s = blockIdx.y;
     const FeStep st = fb.step[s];
     if (!st.active) return;
@@ -555,7 +553,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_REG_CTAS) klt_reg_kernel(F
         const float sc = 1.0f / (float)(1 << l);
         const float px = p0.x * sc, py = p0.y * sc;
         const BilinW wa = bilin_weights(px, py);
-        int *G = &s_G[warp][0][lane];  // G[32 j] = (gy << 16) | (gx & 0xffff) of window column lane - 1, row j
+        int2 *G = &s_G[warp][0][lane];  // G[32 j] = (gx, gy) of window column lane - 1, row j: one LDS.64, no unpacking
         int a11i = 0, a12i = 0, a22i = 0, c1i = 0, c2i = 0;
         {
             // template column T[j], j in [0, tw): A sampled at (px + lane - half - 1, py + j - half - 1)
@@ -565,12 +563,12 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_REG_CTAS) klt_reg_kernel(F
             int raw[WIN + 3];
 #pragma unroll
             if (y0 >= 0 && y0 + WIN + 2 <= rows - 1) {  // warp-uniform: no row of the patch needs clamping
-                const uint8_t *Ay = row_ptr(Ax, y0, cols);
+                const uint8_t *Ay = row_ptr(Ax, y0, pitch);
 #pragma unroll
-                for (int j = 0; j <= WIN + 2; ++j) raw[j] = __ldg(row_ptr(Ay, j, cols));
+                for (int j = 0; j <= WIN + 2; ++j) raw[j] = __ldg(PITCH ? Ay + j * PITCH : row_ptr(Ay, j, pitch));
             } else {
 #pragma unroll
-                for (int j = 0; j <= WIN + 2; ++j) raw[j] = __ldg(row_ptr(Ax, min(max(y0 + j, 0), rows - 1), cols));
+                for (int j = 0; j <= WIN + 2; ++j) raw[j] = __ldg(row_ptr(Ax, min(max(y0 + j, 0), rows - 1), pitch));
             }
             int T[WIN + 2];
             int n0 = __shfl_down_sync(0xffffffffu, raw[0], 1);
@@ -584,7 +582,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_REG_CTAS) klt_reg_kernel(F
             for (int j = 0; j < WIN; ++j) {
                 const int tl = __shfl_up_sync(0xffffffffu, T[j + 1], 1), tr = __shfl_down_sync(0xffffffffu, T[j + 1], 1);
                 const int gx = tr - tl, gy = T[j + 2] - T[j];  // garbage on the lanes without a window column: masked below
-                G[32 * j] = (int)__byte_perm((unsigned)gx, (unsigned)gy, 0x5410);
+                G[32 * j] = make_int2(gx, gy);
                 a11i += gx * gx;
                 a12i += gx * gy;
                 a22i += gy * gy;
@@ -624,21 +622,21 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_REG_CTAS) klt_reg_kernel(F
                     int pxv[WIN + 1];
 #pragma unroll
                     if (y0 >= 0 && y0 + WIN <= rows - 1) {
-                        const uint8_t *By = row_ptr(Bx, y0, cols);
+                        const uint8_t *By = row_ptr(Bx, y0, pitch);
 #pragma unroll
-                        for (int j = 0; j <= WIN; ++j) pxv[j] = __ldg(row_ptr(By, j, cols));
+                        for (int j = 0; j <= WIN; ++j) pxv[j] = __ldg(PITCH ? By + j * PITCH : row_ptr(By, j, pitch));
                     } else {
 #pragma unroll
-                        for (int j = 0; j <= WIN; ++j) pxv[j] = __ldg(row_ptr(Bx, min(max(y0 + j, 0), rows - 1), cols));
+                        for (int j = 0; j <= WIN; ++j) pxv[j] = __ldg(row_ptr(Bx, min(max(y0 + j, 0), rows - 1), pitch));
                     }
                     int n0 = __shfl_down_sync(0xffffffffu, pxv[0], 1);
 #pragma unroll
                     for (int j = 0; j < WIN; ++j) {
                         const int n1 = __shfl_down_sync(0xffffffffu, pxv[j + 1], 1);
                         const int val = (((wb.w00 * pxv[j] + 256) + wb.w01 * n0) + wb.w10 * pxv[j + 1] + wb.w11 * n1) >> 9;
-                        const int gj = G[32 * j];
-                        b1i += val * (int)(short)(gj & 0xffff);
-                        b2i += val * (gj >> 16);
+                        const int2 gj = G[32 * j];
+                        b1i += val * gj.x;
+                        b2i += val * gj.y;
                         n0 = n1;
                     }
                 }
@@ -1844,11 +1842,11 @@ int fe_create(mskf_handle *h) {
     int r = c.img_rows, q = c.img_cols;
     for (int l = 0; l < fc.levels; ++l) {
         fc.lvl_rows[l] = r; fc.lvl_cols[l] = q; fc.lvl_off[l] = off;
-        off += (unsigned)(r * q);
-        off = (off + 255u) & ~255u;
+        off += (unsigned)(r * c.img_cols);  // every level keeps the pitch of level 0
         r = (r + 1) / 2; q = (q + 1) / 2;
     }
-    fc.pyr_bytes = off;
+    fc.pitch = c.img_cols;
+    fc.pyr_bytes = (off + 255u) & ~255u;
     fc.klt_win = c.klt_win; fc.klt_max_iters = c.klt_max_iters;
     fc.klt_eps2 = c.klt_eps * c.klt_eps; fc.klt_min_eig = c.klt_min_eig;
     fc.grid_row = c.grid_row; fc.grid_col = c.grid_col; fc.grid_min = c.grid_min_feature_num;
@@ -1967,8 +1965,12 @@ static void launch_klt(mskf_handle *h, int tag, dim3 g, size_t smem, int mode) {
     const FeConst &fc = h->fc;
     const FeBuffers &fb = h->fb;
     cudaStream_t q = h->stream;
-    if (fc.klt_win == 21) MSKF_LAUNCH(h, tag, (klt_reg_kernel<21><<<g, KLT_WARPS * 32, 0, q>>>(fc, fb, mode)));
-    else if (fc.klt_win == 15) MSKF_LAUNCH(h, tag, (klt_reg_kernel<15><<<g, KLT_WARPS * 32, 0, q>>>(fc, fb, mode)));
+    // standard geometries (EuRoC 752 wide, the stress preset's 1280) get their pitch as a compile-time constant
+    if (fc.klt_win == 21 && fc.pitch == 752) MSKF_LAUNCH(h, tag, (klt_reg_kernel<21, 752><<<g, KLT_WARPS * 32, 0, q>>>(fc, fb, mode)));
+    else if (fc.klt_win == 15 && fc.pitch == 752) MSKF_LAUNCH(h, tag, (klt_reg_kernel<15, 752><<<g, KLT_WARPS * 32, 0, q>>>(fc, fb, mode)));
+    else if (fc.klt_win == 21 && fc.pitch == 1280) MSKF_LAUNCH(h, tag, (klt_reg_kernel<21, 1280><<<g, KLT_WARPS * 32, 0, q>>>(fc, fb, mode)));
+    else if (fc.klt_win == 21) MSKF_LAUNCH(h, tag, (klt_reg_kernel<21, 0><<<g, KLT_WARPS * 32, 0, q>>>(fc, fb, mode)));
+    else if (fc.klt_win == 15) MSKF_LAUNCH(h, tag, (klt_reg_kernel<15, 0><<<g, KLT_WARPS * 32, 0, q>>>(fc, fb, mode)));
     else MSKF_LAUNCH(h, tag, (klt_kernel<0><<<g, KLT_WARPS * 32, smem, q>>>(fc, fb, mode)));
 }
 
@@ -1981,7 +1983,7 @@ static void launch_pyr_level(mskf_handle *h, int l, int images) {
     const int row_stride = (PS_PAD + icols + 8 + 15) & ~15;
     const size_t smem = (size_t)PS_IN * row_stride;
     const int tag = l == 1 ? PK_PYR_L1 : PK_PYR_LN;
-    if (smem <= 200 * 1024 && (icols % 4) == 0 && icols >= 8) {
+    if (smem <= 200 * 1024 && (icols % 4) == 0 && icols >= 8 && (fc.pitch % 4) == 0) {
         dim3 g((fc.lvl_rows[l] + PS_ROWS - 1) / PS_ROWS, 1, images);
         if (l == 1 && (icols % 16) == 0) {
             const size_t bsmem = (size_t)PS_IN * icols + 32;

@@ -104,7 +104,7 @@ def main():
     classes = classify(names)
     table = []
     for r, (n, _), c in zip(data, names, classes):
-        ent = {"class": c, "kernel": n.split("(")[0].replace("void ", "")}
+        ent = {"class": c, "kernel": n.split("(")[0].replace("void ", "").replace(", ", " ")}
         for i, short, m in idx:
             if i < 0:
                 ent[short] = None
