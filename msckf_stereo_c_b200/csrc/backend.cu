@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(BE_THREADS) be_add_obs_kernel(BeConst bc, BeBu
     const BeStep sp = bb.step[s];
     if (!sp.active) return;
     BeState &st = bb.st[s];
-    extern __shared__ unsigned char be_smem[];
+    extern __shared__ __align__(16) unsigned char be_smem[];
     unsigned *h_key = (unsigned *)be_smem;           // [HASH] id + 1, 0 = empty
     int *h_slot = (int *)(h_key + bc.HASH);          // [HASH]
     int *h_owner = h_slot + bc.HASH;                 // [HASH]
@@ -859,7 +859,7 @@ __global__ void __launch_bounds__(BE_THREADS) be_select_kernel(BeConst bc, BeBuf
     const BeStep sp = bb.step[s];
     if (!sp.active) return;
     BeState &st = bb.st[s];
-    extern __shared__ unsigned char be_smem[];
+    extern __shared__ __align__(16) unsigned char be_smem[];
     unsigned long long *keys = (unsigned long long *)be_smem;  // [sort_n]
     __shared__ int s_n, s_erased;
     const size_t fo = (size_t)s * bc.MF;
@@ -1493,26 +1493,162 @@ __device__ void cta_cholesky(double *S, int n, int ld) {
     __syncthreads();
 }
 
-// In-place Cholesky of the sub-matrix [lo, hi) x [lo, hi) of a packed lower triangle in shared
-// memory (entry (i, j), j <= i, at i (i + 1) / 2 + j).  256 threads as a 16 x 16 tile grid.
-__device__ void packed_cholesky(double *G, int lo, int hi) {
-    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-    for (int kk = lo; kk < hi; ++kk) {
-        const int kb = kk * (kk + 1) / 2;
+// 1 / sqrt(a) for a > 0 from the RSQ64H seed and two Newton steps (fp64 round-off)
+__device__ __forceinline__ double chol_rsqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    y = fma(y, fma(-h, y * y, 0.5), y);
+    y = fma(y, fma(-h, y * y, 0.5), y);
+    return y;
+}
+
+#define CH_T 6
+__device__ __forceinline__ void chol_load6(const double *p, double (&v)[CH_T]) {  // p is 16-byte aligned (6-double chunks)
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = q[0], b = q[1], c = q[2];
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+}
+__device__ __forceinline__ void chol_store6(double *p, const double (&v)[CH_T]) {
+    double2 *q = reinterpret_cast<double2 *>(p);
+    q[0] = make_double2(v[0], v[1]);
+    q[1] = make_double2(v[2], v[3]);
+    q[2] = make_double2(v[4], v[5]);
+}
+
+// Tile (ti, tj), tj <= ti, of thread t = ti (ti + 1) / 2 + tj of a lower tile triangle
+__device__ __forceinline__ void chol_tile_of_thread(int t, int &ti, int &tj) {
+    ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    tj = t - ti * (ti + 1) / 2;
+}
+
+// One 6x6 diagonal tile in registers: D = L L^T (lower triangle of g on entry), then g = X = L^-1 (lower; the upper
+// part is set to zero).  A non-positive pivot propagates NaN, as sqrt would.  Serial: ~6 rsqrt chains.
+__device__ __forceinline__ void chol_diag_tile_inverse(double (&g)[CH_T][CH_T]) {
+    double inv[CH_T];
+#pragma unroll
+    for (int c = 0; c < CH_T; ++c) {
+        const double piv = g[c][c];
+        inv[c] = piv > 0.0 ? chol_rsqrt(piv) : __longlong_as_double(0x7ff8000000000000ll);
+#pragma unroll
+        for (int a = c + 1; a < CH_T; ++a) g[a][c] *= inv[c];
+#pragma unroll
+        for (int b = c + 1; b < CH_T; ++b)
+#pragma unroll
+            for (int a = b; a < CH_T; ++a) g[a][b] = fma(-g[a][c], g[b][c], g[a][b]);
+    }
+    // X = L^-1 by forward substitution on the identity, column by column; L[i][i] = 1 / inv[i]
+    double x[CH_T][CH_T];
+#pragma unroll
+    for (int j = 0; j < CH_T; ++j) {
+        x[j][j] = inv[j];
+#pragma unroll
+        for (int i = j + 1; i < CH_T; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int m = j; m < i; ++m) acc = fma(g[i][m], x[m][j], acc);
+            x[i][j] = -acc * inv[i];
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < CH_T; ++a)
+#pragma unroll
+        for (int b = 0; b < CH_T; ++b) g[a][b] = b <= a ? x[a][b] : 0.0;
+}
+
+// gamma = r^T S^-1 r for the n x n SPD matrix S held as rows/columns [off, off + n) of a packed lower triangle in
+// shared memory (entry (i, j), j <= i, at i (i + 1) / 2 + j), by a BLOCKED right-looking Cholesky with the whole
+// triangle in REGISTERS: thread t owns the 6x6 tile (ti, tj) (231 tiles for n <= 126 on 256 threads).  Block step k:
+//   1. the owner of the diagonal tile factors it and inverts the 6x6 factor in registers (X = L_kk^-1), takes
+//      y_k = X r_k (forward substitution of the right-hand side) and publishes X and y_k;          -- barrier
+//   2. the tiles below it become the panel C_i = G_ik X^T = L_ik, published column-major, and fold their share
+//      into the right-hand side, r_i -= C_i y_k;                                                     -- barrier
+//   3. every trailing tile takes G_ij -= C_i C_j^T (216 FMAs from two 36-double panel pieces).
+// Two barriers per SIX columns; the column-by-column version on the packed triangle in shared memory took three
+// barriers per column plus a warp-serial forward substitution afterwards (85 of the kernel's 120 us per 30-view
+// feature).  The packed triangle is dead once the tiles are loaded; its storage holds the panel, r and X.
+// All BE_THREADS threads must call it; the result is returned to every thread.
+__device__ double tile_cholesky_gamma(double *G, int off, int n, const double *r, int ti, int tj) {
+    const int nt = (n + CH_T - 1) / CH_T, NP = nt * CH_T;
+    const int i0 = CH_T * ti, j0 = CH_T * tj;
+    const bool live = ti < nt;
+    double g[CH_T][CH_T];
+#pragma unroll
+    for (int a = 0; a < CH_T; ++a)
+#pragma unroll
+        for (int b = 0; b < CH_T; ++b) {
+            const int i = i0 + a, j = j0 + b;
+            // rows past n: identity, so that the padding factors to itself and adds nothing to gamma
+            g[a][b] = (live && i < n && j <= i) ? G[(i + off) * (i + off + 1) / 2 + j + off] : ((i == j) ? 1.0 : 0.0);
+        }
+    __syncthreads();
+    double *panel = G;                      // [6][NP]: column c of the current panel at panel + c NP
+    double *rs = panel + CH_T * NP;         // [NP]
+    double *s_X = rs + NP;                  // [6][6]
+    double *s_y = s_X + CH_T * CH_T;        // [6]
+    double *s_gamma = s_y + CH_T;           // [1]
+    for (int i = threadIdx.x; i < NP; i += BE_THREADS) rs[i] = i < n ? r[i] : 0.0;
+    if (threadIdx.x == 0) *s_gamma = 0.0;
+    __syncthreads();
+    for (int k = 0; k < nt; ++k) {
+        if (ti == k && tj == k) {
+            chol_diag_tile_inverse(g);
+            double rk[CH_T], y[CH_T];
+            chol_load6(rs + i0, rk);
+            double gsum = 0.0;
+#pragma unroll
+            for (int a = 0; a < CH_T; ++a) {
+                double acc = 0.0;
+#pragma unroll
+                for (int b = 0; b <= a; ++b) acc = fma(g[a][b], rk[b], acc);
+                y[a] = acc;
+                gsum = fma(acc, acc, gsum);
+            }
+            chol_store6(s_y, y);
+#pragma unroll
+            for (int a = 0; a < CH_T; ++a) chol_store6(s_X + CH_T * a, g[a]);
+            *s_gamma += gsum;
+        }
+        if (k == nt - 1) break;
         __syncthreads();
-        const double d = sqrt(G[kb + kk]);
+        if (live && tj == k && ti > k) {
+            double y[CH_T], ri[CH_T];
+            chol_load6(s_y, y);
+            chol_load6(rs + i0, ri);
+#pragma unroll
+            for (int cc = 0; cc < CH_T; ++cc) {
+                double xr[CH_T], col[CH_T];
+                chol_load6(s_X + CH_T * cc, xr);  // row cc of X: X[cc][b], b <= cc
+#pragma unroll
+                for (int a = 0; a < CH_T; ++a) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int b = 0; b <= cc; ++b) acc = fma(g[a][b], xr[b], acc);
+                    col[a] = acc;
+                    ri[a] = fma(-acc, y[cc], ri[a]);
+                }
+                chol_store6(panel + cc * NP + i0, col);
+            }
+            chol_store6(rs + i0, ri);
+        }
         __syncthreads();
-        if (threadIdx.x == 0) G[kb + kk] = d;
-        const double inv = 1.0 / d;
-        for (int i = kk + 1 + threadIdx.x; i < hi; i += BE_THREADS) G[i * (i + 1) / 2 + kk] *= inv;
-        __syncthreads();
-        for (int i = kk + 1 + ty; i < hi; i += 16) {
-            const int ib = i * (i + 1) / 2;
-            const double lik = G[ib + kk];
-            for (int j = kk + 1 + tx; j <= i; j += 16) G[ib + j] -= lik * G[j * (j + 1) / 2 + kk];
+        if (live && tj > k) {
+#pragma unroll
+            for (int cc = 0; cc < CH_T; ++cc) {
+                double ci[CH_T], cj[CH_T];
+                chol_load6(panel + cc * NP + i0, ci);
+                chol_load6(panel + cc * NP + j0, cj);
+#pragma unroll
+                for (int a = 0; a < CH_T; ++a)
+#pragma unroll
+                    for (int b = 0; b < CH_T; ++b) g[a][b] = fma(-ci[a], cj[b], g[a][b]);
+            }
         }
     }
     __syncthreads();
+    return *s_gamma;
 }
 
 // ======================================================================================
@@ -1538,7 +1674,7 @@ __global__ void __launch_bounds__(BE_THREADS, 2) be_feature_jac_kernel(BeConst b
     const double *P = bb.P + (size_t)s * bc.LD * bc.LD;
     const int LD = bc.LD;
 
-    extern __shared__ unsigned char be_smem[];
+    extern __shared__ __align__(16) unsigned char be_smem[];
     const int maxR4 = 4 * maxM;
     double *G = (double *)be_smem;                       // packed lower [maxR4 (maxR4 + 1) / 2]
     double *Hx = G + (size_t)maxR4 * (maxR4 + 1) / 2;    // [maxM][4][6]
@@ -1553,6 +1689,8 @@ __global__ void __launch_bounds__(BE_THREADS, 2) be_feature_jac_kernel(BeConst b
     __shared__ int s_pass;
     auto gix = [](int i, int j) { return i * (i + 1) / 2 + j; };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int ch_ti, ch_tj;
+    chol_tile_of_thread(threadIdx.x, ch_ti, ch_tj);
 
     for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
         __syncthreads();
@@ -1793,22 +1931,11 @@ __global__ void __launch_bounds__(BE_THREADS, 2) be_feature_jac_kernel(BeConst b
                 }
             }
         }
-        // Cholesky of S (rows 3..R4-1 of the packed triangle)
-        packed_cholesky(G, 3, R4);
         __syncthreads();
+        // gamma = r'^T S^-1 r' (gatingTest, msckf_vio.cpp:909-935): blocked Cholesky of S in registers with the
+        // forward substitution of r' folded in
+        const double g = tile_cholesky_gamma(G, 3, rows, rv + 3, ch_ti, ch_tj);
         if (warp == 0) {
-            // y = L^-1 r', gamma = y^T y (gatingTest, msckf_vio.cpp:909-935)
-            double g = 0;
-            for (int i = 3; i < R4; ++i) {
-                double sacc = 0;
-                for (int k = 3 + lane; k < i; k += 32) sacc += G[gix(i, k)] * Y[k];  // Y reused as the solution vector
-                sacc = warp_sum_d(sacc);
-                const double y = (rv[i] - sacc) / G[gix(i, i)];
-                __syncwarp();
-                if (lane == 0) Y[i] = y;
-                __syncwarp();
-                g += y * y;
-            }
             if (lane == 0) {
                 const int dof = phase == 0 ? M - 1 : M;  // msckf_vio.cpp:1001, :1145
                 const double thr = (dof >= 1 && dof <= 99) ? c_chi2[bc.chi2_mode][dof - 1] : 0.0;
@@ -2060,7 +2187,7 @@ __global__ void __launch_bounds__(BE_THREADS) be_stack_kernel(BeConst bc, BeBuf 
     BeState &st = bb.st[s];
     const int n = st.n_list;
     const size_t fo = (size_t)s * bc.MF, lo = (size_t)s * bc.ML;
-    extern __shared__ unsigned char be_smem[];
+    extern __shared__ __align__(16) unsigned char be_smem[];
     int *s_soff = (int *)be_smem;                  // [ML]
     unsigned *s_mask = (unsigned *)(s_soff + bc.ML);  // [ML]
     uint8_t *s_M = (uint8_t *)(s_mask + bc.ML);    // [ML]
@@ -2399,47 +2526,20 @@ __global__ void __launch_bounds__(BE_THREADS, 2) be_gemm_kernel(BeConst bc, BeBu
     }
 }
 
-// S = L L^T, Linv = L^-1.  One CTA per stream.
-// 1 / sqrt(a) for a > 0 from the RSQ64H seed and two Newton steps (fp64 round-off), as in the QR chain
-__device__ __forceinline__ double chol_rsqrt(double a) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    const double h = 0.5 * a;
-    y = fma(y, fma(-h, y * y, 0.5), y);
-    y = fma(y, fma(-h, y * y, 0.5), y);
-    return y;
-}
-
 // S = L L^T and X = L^-1 in one pass, with the whole lower triangle in REGISTERS: thread t owns the 6x6
-// tile (ti, tj) of the 31x31 lower tile triangle (496 tiles <= 512 threads, 72 registers of data).  Step kk
-// of the right-looking factorization needs only the scaled column kk (c_i = L[i][kk]); the same column
-// drives the forward substitution L X = I (Gauss-Jordan on the identity), whose partial result for rows
-// i > kk lives in the columns j <= kk that the factorization no longer reads:
-//     G[i][j] -= c_i c_j            (j > kk: trailing Cholesky update)
-//     X[i][j] -= c_i X[kk][j]       (j < kk),      X[i][kk] = -c_i / L[kk][kk]
-// so each step is one "tile -= c_i (x) r_j" with r = [X[kk][0..kk) | 0 | c(kk..n)] broadcast through 1.5 KB
-// of shared memory: no shared-memory traffic for the matrix itself, two barriers per column.
-// (The earlier version kept the packed triangle in shared memory: 2.6k cycles per column for the factor
-// and 4.1k per row for the inverse, both latency-bound on LDS -> FMA -> STS chains.)
-#define CH_T 6
+// tile (ti, tj) of the 31x31 lower tile triangle (496 tiles <= 512 threads, 72 registers of data), and the
+// factorization is BLOCKED by tile columns.  Block step k of the right-looking scheme:
+//   1. the owner of the diagonal tile factors it and inverts the 6x6 factor in registers: X_kk = L_kk^-1;  -- barrier
+//   2. the tiles below it become the panel C_i = G_ik X_kk^T = L_ik; the tiles left of it (row block k of the
+//      forward substitution L X = I, whose partial sums live in the columns the factorization has finished with)
+//      become final, X_kj = X_kk R_kj; both are published row-major per block row (6 x n);                 -- barrier
+//   3. every tile below block row k takes ONE "tile -= C_i B_j" with B = C^T (j > k: trailing Cholesky update
+//      G_ij -= C_i C_j^T) or B = X_k (j <= k: R_ij -= L_ik X_kj, where tile (i, k) starts from zero).
+// Two barriers and one serial 6x6 factor per SIX columns.  The column-by-column version of this layout took two
+// barriers per column (1.6k cycles, against 290 cycles of DFMA issue); the version before that kept the packed
+// triangle in shared memory (2.6k cycles per column for the factor and 4.1k per row for the inverse).
 #define CH_THREADS 512
 #define CH_NMAX (NSM * 6)
-
-#define CH_FOR_COL(ak, BODY)                                     \
-    switch (ak) {                                                \
-    case 0: { constexpr int B_ = 0; BODY } break;                \
-    case 1: { constexpr int B_ = 1; BODY } break;                \
-    case 2: { constexpr int B_ = 2; BODY } break;                \
-    case 3: { constexpr int B_ = 3; BODY } break;                \
-    case 4: { constexpr int B_ = 4; BODY } break;                \
-    default: { constexpr int B_ = 5; BODY } break;               \
-    }
-
-__device__ __forceinline__ void chol_load6(const double *p, double (&v)[CH_T]) {  // p is 16-byte aligned (6-double chunks)
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-    const double2 a = q[0], b = q[1], c = q[2];
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
-}
 
 __global__ void __launch_bounds__(CH_THREADS) be_chol_kernel(BeConst bc, BeBuf bb) {
     const int s = blockIdx.x;
@@ -2450,83 +2550,89 @@ __global__ void __launch_bounds__(CH_THREADS) be_chol_kernel(BeConst bc, BeBuf b
     const int KC = bc.KC, n = st.mt;
     const double *Sm = bb.Sm + (size_t)s * KC * KC;
     double *Linv = bb.Linv + (size_t)s * KC * KC;
-    __shared__ __align__(16) double vec[CH_NMAX + CH_T];
-    __shared__ double s_dinv;
-    // tile (ti, tj), tj <= ti, of thread t = ti (ti + 1) / 2 + tj
-    const int t = threadIdx.x;
-    int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    while (ti * (ti + 1) / 2 > t) --ti;
-    const int tj = t - ti * (ti + 1) / 2;
+    constexpr int NP = CH_NMAX + CH_T;
+    __shared__ __align__(16) double panel[CH_T][NP];   // panel[c][i] = L[i][6 k + c], i below block row k
+    __shared__ __align__(16) double xpanel[CH_T][NP];  // xpanel[c][j] = X[6 k + c][j], j < 6 k + 6
+    __shared__ __align__(16) double s_X[CH_T][CH_T];
+    int ti, tj;
+    chol_tile_of_thread(threadIdx.x, ti, tj);
     const int i0 = CH_T * ti, j0 = CH_T * tj;
-    const bool live = i0 < n;
+    const int nt = (n + CH_T - 1) / CH_T;
+    const bool live = ti < nt;
     double g[CH_T][CH_T];
 #pragma unroll
     for (int a = 0; a < CH_T; ++a)
 #pragma unroll
         for (int b = 0; b < CH_T; ++b) {
             const int i = i0 + a, j = j0 + b;
-            g[a][b] = (i < n && j <= i) ? Sm[i * KC + j] : 0.0;
+            // rows past n: identity (factors to itself, never written out)
+            g[a][b] = (i < n && j <= i) ? Sm[i * KC + j] : ((i == j) ? 1.0 : 0.0);
         }
     // the strictly upper tiles of Linv are zero (be_gemm_kernel<2> reads full rows)
     for (int e = threadIdx.x; e < n * n; e += CH_THREADS) {
         const int i = e / n, j = e - i * n;
         if (j / CH_T > i / CH_T) Linv[i * KC + j] = 0.0;
     }
-    for (int kk = 0; kk < n; ++kk) {
-        const int tk = kk / CH_T, ak = kk - tk * CH_T;
-        if (ti == tk && tj == tk) {
-            double piv = 0.0;
-            CH_FOR_COL(ak, piv = g[B_][B_];)
-            // a non-positive pivot propagates NaN, as sqrt would
-            s_dinv = piv > 0.0 ? chol_rsqrt(piv) : __longlong_as_double(0x7ff8000000000000ll);
+    for (int k = 0; k < nt; ++k) {
+        if (ti == k && tj == k) {
+            chol_diag_tile_inverse(g);
+#pragma unroll
+            for (int a = 0; a < CH_T; ++a) {
+                chol_store6(&s_X[a][0], g[a]);
+                chol_store6(&xpanel[a][j0], g[a]);
+            }
         }
         __syncthreads();
-        const double dinv = s_dinv;
-        if (tj == tk && ti >= tk) {
-            // column kk: c_i = L[i][kk] for the rows below the diagonal; X[i][kk] takes its place
-            CH_FOR_COL(ak,
+        if (live && ti == k && tj < k) {
+            // X_kj = X_kk R_kj, in place from the last row up (row a needs rows <= a of R)
 #pragma unroll
-                       for (int a = 0; a < CH_T; ++a) {
-                           const int i = i0 + a;
-                           if (i > kk && i < n) {
-                               const double c = g[a][B_] * dinv;
-                               vec[i] = c;
-                               g[a][B_] = -c * dinv;
-                           } else if (i == kk) {
-                               vec[i] = 0.0;
-                               g[a][B_] = dinv;
-                           }
-                       })
+            for (int a = CH_T - 1; a >= 0; --a) {
+                double xr[CH_T];
+                chol_load6(&s_X[a][0], xr);
+#pragma unroll
+                for (int b = 0; b < CH_T; ++b) {
+                    double acc = xr[a] * g[a][b];
+#pragma unroll
+                    for (int m = 0; m < a; ++m) acc = fma(xr[m], g[m][b], acc);
+                    g[a][b] = acc;
+                }
+                chol_store6(&xpanel[a][j0], g[a]);
+            }
         }
-        if (ti == tk && tj <= tk) {
-            // row kk of X is final: X[kk][j] = Y[kk][j] / L[kk][kk]
-            CH_FOR_COL(ak,
+        if (live && tj == k && ti > k) {
+            // C_i = G_ik X_kk^T, column by column; the tile itself restarts from zero as R_ik
 #pragma unroll
-                       for (int b = 0; b < CH_T; ++b) {
-                           const int j = j0 + b;
-                           if (j < kk) {
-                               const double xr = g[B_][b] * dinv;
-                               vec[j] = xr;
-                               g[B_][b] = xr;
-                           }
-                       })
-        }
-        __syncthreads();
-        if (live && i0 + CH_T - 1 > kk) {
-            // a tile's six c_i / r_j values are one 48-byte chunk: three LDS.128 each.  With 8-byte loads the r_j
-            // reads of a warp (consecutive tj: a stride of 48 bytes) hit every bank four times over
-            double ci[CH_T], rj[CH_T];
-            chol_load6(vec + i0, ci);
-            chol_load6(vec + j0, rj);
+            for (int cc = 0; cc < CH_T; ++cc) {
+                double xr[CH_T], col[CH_T];
+                chol_load6(&s_X[cc][0], xr);
 #pragma unroll
-            for (int a = 0; a < CH_T; ++a) ci[a] = (i0 + a > kk && i0 + a < n) ? ci[a] : 0.0;
+                for (int a = 0; a < CH_T; ++a) {
+                    double acc = 0.0;
 #pragma unroll
-            for (int b = 0; b < CH_T; ++b) rj[b] = (j0 + b < n) ? rj[b] : 0.0;
+                    for (int b = 0; b <= cc; ++b) acc = fma(g[a][b], xr[b], acc);
+                    col[a] = acc;
+                }
+                chol_store6(&panel[cc][i0], col);
+            }
 #pragma unroll
             for (int a = 0; a < CH_T; ++a)
 #pragma unroll
-                for (int b = 0; b < CH_T; ++b) g[a][b] = fma(-ci[a], rj[b], g[a][b]);
+                for (int b = 0; b < CH_T; ++b) g[a][b] = 0.0;
+        }
+        if (k == nt - 1) break;
+        __syncthreads();
+        if (live && ti > k) {
+            const double(*src)[NP] = tj > k ? panel : xpanel;
+#pragma unroll
+            for (int cc = 0; cc < CH_T; ++cc) {
+                double ci[CH_T], bj[CH_T];
+                chol_load6(&panel[cc][i0], ci);
+                chol_load6(&src[cc][j0], bj);
+#pragma unroll
+                for (int a = 0; a < CH_T; ++a)
+#pragma unroll
+                    for (int b = 0; b < CH_T; ++b) g[a][b] = fma(-ci[a], bj[b], g[a][b]);
+            }
         }
     }
     // X = L^-1 out
@@ -2543,6 +2649,16 @@ __global__ void __launch_bounds__(CH_THREADS) be_chol_kernel(BeConst bc, BeBuf b
         }
     }
 }
+
+#define CH_FOR_COL(ak, BODY)                                     \
+    switch (ak) {                                                \
+    case 0: { constexpr int B_ = 0; BODY } break;                \
+    case 1: { constexpr int B_ = 1; BODY } break;                \
+    case 2: { constexpr int B_ = 2; BODY } break;                \
+    case 3: { constexpr int B_ = 3; BODY } break;                \
+    case 4: { constexpr int B_ = 4; BODY } break;                \
+    default: { constexpr int B_ = 5; BODY } break;               \
+    }
 
 // Cholesky with diagonal pivoting of the Gram matrix of the stacked system (see be_gram_kernel), one CTA per
 // stream, same register layout as be_chol_kernel: thread t owns the 6x6 tile (ti, tj), tj <= ti, of G[:k,:k]

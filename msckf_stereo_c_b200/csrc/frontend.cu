@@ -708,14 +708,19 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
     const int rows = fc.rows, cols = fc.cols;
     __shared__ __align__(16) uint8_t tile[DT_H + 2 * DT_HALO][DT_STRIDE];
     __shared__ __align__(16) uint8_t score[DT_SH][DT_SW + 2];
-    __shared__ unsigned short s_list[DT_SH * DT_SW];  // pixels that passed the ring test: index | side << 15
+    __shared__ unsigned short s_list[DT_SH * DT_SW];  // pixels that passed the ring test: row << 7 | column | side << 15
     __shared__ int s_nlist, s_nmax;
     __shared__ unsigned short s_max[DT_H * DT_W / 4];  // strict 3x3 maxima: at most one per 2x2 block
+    // fine-cell column / row of every pixel column / row of the tile (two runtime divisions per candidate otherwise:
+    // 7 % of the kernel's instructions at 4 of 32 lanes, ncu source page)
+    __shared__ unsigned short s_cx[DT_W], s_cy[DT_H];
     const int x0 = blockIdx.x * DT_W, y0 = blockIdx.y * DT_H;
     if (threadIdx.x == 0) {
         s_nlist = 0;
         s_nmax = 0;
     }
+    if (threadIdx.x < DT_W) s_cx[threadIdx.x] = (unsigned short)((x0 + threadIdx.x) / fc.det_cell_w);
+    else if (threadIdx.x < DT_W + DT_H) s_cy[threadIdx.x - DT_W] = (unsigned short)((y0 + threadIdx.x - DT_W) / fc.det_cell_h);
     if ((cols & 3) == 0 && (((size_t)img) & 3) == 0) {
         constexpr int WPR = (DT_W + 2 * DT_X0) / 4;  // 20 words per tile row
         for (int idx = threadIdx.x; idx < (DT_H + 2 * DT_HALO) * WPR; idx += 256) {
@@ -751,13 +756,22 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
     for (int w = threadIdx.x; w < (int)(sizeof(score) / 4); w += 256) reinterpret_cast<unsigned *>(&score[0][0])[w] = 0u;
     const bool tile_inside = y0 - 1 >= 3 && y0 + DT_H < rows - 3 && x0 - 1 >= 3 && x0 + DT_W < cols - 3;  // no pixel of the window needs the border test
     unsigned bal_it[DT_RT_ITERS];
-    int pass_it[DT_RT_ITERS];
+    int pass_it[DT_RT_ITERS], code_it[DT_RT_ITERS];  // list entry: window row << 7 | window column | side << 15
+    static_assert(DT_W == 64 && DT_H == 16 && DT_RT_ITERS == 5, "window-to-thread mapping below");
 #pragma unroll
     for (int it = 0; it < DT_RT_ITERS; ++it) {
-        const int idx = it * 256 + threadIdx.x;
+        // Window pixel (r, c) of this thread in pass `it`, without a division: the 64 inner columns go four rows
+        // per pass (18 rows: four and a half passes), the two edge columns fill the idle half of the last pass.
+        int r = it * 4 + (threadIdx.x >> 6), c = 1 + (threadIdx.x & 63);
+        bool valid = true;
+        if (it == DT_RT_ITERS - 1 && threadIdx.x >= 128) {
+            const int e = threadIdx.x - 128;
+            r = e >> 1;
+            c = (e & 1) * (DT_SW - 1);
+            valid = e < 2 * DT_SH;
+        }
         int pass = 0;  // 1: darker arc, 2: brighter arc
-        if (idx < DT_SH * DT_SW) {
-            const int r = idx / DT_SW, c = idx - r * DT_SW;
+        if (valid) {
             const int gy = y0 - 1 + r, gx = x0 - 1 + c;
             if (tile_inside || (gy >= 3 && gy < rows - 3 && gx >= 3 && gx < cols - 3)) {
                 const uint8_t *pc = &tile[r + DT_HALO - 1][c + DT_X0 - 1];
@@ -784,6 +798,7 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
         }
         bal_it[it] = __ballot_sync(0xffffffffu, pass != 0);
         pass_it[it] = pass;
+        code_it[it] = (r << 7) | c;
     }
     {
         __shared__ int s_wcnt[8];
@@ -803,7 +818,7 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
         const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
         for (int it = 0; it < DT_RT_ITERS; ++it) {
-            if (pass_it[it]) s_list[wbase + __popc(bal_it[it] & lt)] = (unsigned short)((it * 256 + threadIdx.x) | ((pass_it[it] - 1) << 15));
+            if (pass_it[it]) s_list[wbase + __popc(bal_it[it] & lt)] = (unsigned short)(code_it[it] | ((pass_it[it] - 1) << 15));
             wbase += __popc(bal_it[it]);
         }
     }
@@ -816,8 +831,8 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
     const int nlist = s_nlist;
     for (int e = threadIdx.x; e < nlist; e += 256) {
         const int code = s_list[e];
-        const int idx = code & 0x7fff, sg = (code >> 15) ? -1 : 1;
-        const int r = idx / DT_SW, c = idx - r * DT_SW;
+        const int sg = (code >> 15) ? -1 : 1;
+        const int r = (code >> 7) & 31, c = code & 127;
         const uint8_t *pc = &tile[r + DT_HALO - 1][c + DT_X0 - 1];
         const int v = pc[0];
         int n[16], a2[16], a4[16];
@@ -856,8 +871,8 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
             bool is_max = false;
             int idx = 0;
             if (e < nlist) {
-                const int li = s_list[e] & 0x7fff;
-                const int r = li / DT_SW, c = li - r * DT_SW;  // score-window coordinates
+                const int li = s_list[e];
+                const int r = (li >> 7) & 31, c = li & 127;  // score-window coordinates
                 if (r >= 1 && r <= DT_H && c >= 1 && c <= DT_W) {
                     const int sc = score[r][c];
                     const int gy = y0 + r - 1, gx = x0 + c - 1;
@@ -866,7 +881,7 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
                         is_max = sc > score[r - 1][c - 1] && sc > score[r - 1][c] && sc > score[r - 1][c + 1] && sc > score[r][c - 1] &&
                                  sc > score[r][c + 1] && sc > score[r + 1][c - 1] && sc > score[r + 1][c] && sc > score[r + 1][c + 1];
                         if (is_max) {
-                            const int k = (gy / fc.det_cell_h) * fc.det_cols + (gx / fc.det_cell_w);
+                            const int k = s_cy[r - 1] * fc.det_cols + s_cx[c - 1];
                             if (fb.det_occ[(size_t)s * fc.det_cells + k]) is_max = false;
                             if (gx < 5 || gy < 5 || gx > cols - 6 || gy > rows - 6) is_max = false;  // response 0: never a candidate
                         }
@@ -937,7 +952,7 @@ __global__ void __launch_bounds__(256) detect_kernel(FeConst fc, FeBuffers fb) {
             float disc = d1 * d1 + 4.0f * xy2;
             float resp = 0.5f * (trc - sqrtf(disc));
             if (resp > 0.0f) {
-                int k = (gy / fc.det_cell_h) * fc.det_cols + (gx / fc.det_cell_w);
+                const int k = s_cy[gy - y0] * fc.det_cols + s_cx[gx - x0];
                 unsigned long long key = ((unsigned long long)__float_as_uint(resp) << 32) |
                                          (unsigned long long)(0xffffffffu - (unsigned)(gy * cols + gx));
                 atomicMax(&fb.det_best[(size_t)s * fc.det_cells + k], key);
