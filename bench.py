@@ -423,6 +423,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- leg 2: host buffers through the C ABI ("e2e")
     poses = [None] * H
     h2d = d2h = 0
+    e2e_wait = 0.0  # host time spent waiting for the previous step's poses: ~0 means the host loop is the limit
 
     def push_host(i, kk):
         for h, g in enumerate(groups):
@@ -432,14 +433,16 @@ def run_ours(args, rank, world, local_rank):
         """One e2e step: IMU rows + step of frame i, upload of frame i+1 (overlaps the kernels of frame i
         on the copy streams), poses of the previous step read back (already on the host: the pipeline
         stays full; every step's poses are copied to pinned memory by the step itself)."""
-        nonlocal h2d, d2h
+        nonlocal h2d, d2h, e2e_wait
         nb = 0
         for g in groups:
             nb += g.feed_imu(kk)
             g.e.step()
         push_host(i + 1, kk + 1)
+        t_w = time.perf_counter()
         for h, g in enumerate(groups):
             poses[h] = g.e.poses(prev=True)
+        e2e_wait += time.perf_counter() - t_w
         h2d = 2 * img * S + nb
         d2h = sum(p.nbytes for p in poses)
 
@@ -451,10 +454,12 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_e0 = time.perf_counter()
+    e2e_wait = 0.0
     ev2.record(groups[0].stream)
     for i in range(W, W + K):
         step_e2e(i, k)
         k += 1
+    e2e_wait_ms = 1e3 * e2e_wait / K
     for h, g in enumerate(groups):
         poses[h] = g.e.poses()  # the last step's result (blocks until it is on the host)
     close_region(ev3)
@@ -624,7 +629,7 @@ def run_ours(args, rank, world, local_rank):
                        "l2": f"inputs larger than L2: {2 * img * S / 1e6:.0f} MB of new images per step",
                        "front_end_dtype": "u8 / fixed point", "parallelism": f"stream-sharded x{world}, no collective on the data path"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e_max / K,
+                    "ms_per_step": ms_e2e_max / K, "host_wait_ms_per_step": e2e_wait_ms,
                     "h2d_ceiling_gbs": h2d_gbs_min, "h2d_ceiling_ms_per_step": 2 * img * S / (h2d_gbs_min * 1e9) * 1e3,
                     "h2d_ceiling_note": "pinned frame sets copied back to back on one stream by all ranks at once, slowest rank: the "
                                         "least an e2e step can take on this host when the upload is not hidden"},

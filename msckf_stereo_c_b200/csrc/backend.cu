@@ -2686,16 +2686,12 @@ __global__ void __launch_bounds__(CH_THREADS) be_pchol_kernel(BeConst bc, BeBuf 
     double *Rt = bb.Rp + (size_t)s * KC * KC;  // row t of R, original column order, row stride k
     double *Tm = bb.Tm + (size_t)s * KC * KC;
     int *perm = bb.perm + (size_t)s * KC;
-    __shared__ __align__(16) double vec[CH_NMAX + CH_T];
-    __shared__ double s_dinv;
-    __shared__ int s_p, s_stop, s_rank;
-    __shared__ unsigned char s_done[CH_NMAX + CH_T];
+    __shared__ __align__(16) double vec[2][CH_NMAX + CH_T];  // column of the step, double-buffered: ONE barrier per step
+    __shared__ unsigned s_open[32];
     __shared__ int s_perm[CH_NMAX + CH_T];
-    const int t = threadIdx.x;
-    int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    while (ti * (ti + 1) / 2 > t) --ti;
-    const int tj = t - ti * (ti + 1) / 2;
+    const int t = threadIdx.x, lane = t & 31;
+    int ti, tj;
+    chol_tile_of_thread(t, ti, tj);
     const int i0 = CH_T * ti, j0 = CH_T * tj;
     const bool live = i0 < k;
     double g[CH_T][CH_T];
@@ -2706,66 +2702,60 @@ __global__ void __launch_bounds__(CH_THREADS) be_pchol_kernel(BeConst bc, BeBuf 
             const int i = i0 + a, j = j0 + b;
             g[a][b] = (i < k && j < k) ? G[(size_t)max(i, j) * ldg + min(i, j)] : 0.0;
         }
-    for (int i = t; i < CH_NMAX + CH_T; i += CH_THREADS) {
-        vec[i] = 0.0;
-        s_done[i] = 0;
-    }
-    // warp 0: lane l mirrors the diagonal entries of columns 6 l .. 6 l + 5
+    for (int i = t; i < 2 * (CH_NMAX + CH_T); i += CH_THREADS) (&vec[0][0])[i] = 0.0;
+    __syncthreads();  // the first column is published before the first barrier of the loop
+    // EVERY warp mirrors the diagonal (lane l: columns 6 l .. 6 l + 5, same fma as the tiles: bit-identical) and
+    // repeats the pivot search, so the pivot, its scale and the stop decision are known to all threads without
+    // passing through shared memory: that, and the double-buffered column, leave one barrier per step
     double d[CH_T];
     unsigned open = 0;  // bit a: column 6 lane + a has not been a pivot yet
-    double d0 = 0.0;
-    if (t < 32) {
 #pragma unroll
-        for (int a = 0; a < CH_T; ++a) {
-            const int i = CH_T * t + a;
-            d[a] = i < k ? G[(size_t)i * ldg + i] : 0.0;
-            if (i < k) open |= 1u << a;
-        }
+    for (int a = 0; a < CH_T; ++a) {
+        const int i = CH_T * lane + a;
+        d[a] = i < k ? G[(size_t)i * ldg + i] : 0.0;
+        if (i < k) open |= 1u << a;
     }
-    // (value, index) arg-max over the open columns of warp 0; ties go to the smaller index
+    // (value, index) arg-max over the open columns; ties go to the smaller index.  Open entries are positive
+    // doubles when they matter, so their bit patterns order like integers: three warp reductions.
     auto warp_argmax = [&](double &best, int &bi) {
-        best = -1.0;
-        bi = 0x7fffffff;
+        double lb = -1.0;
+        int li = 0x7fffffff;
 #pragma unroll
         for (int a = 0; a < CH_T; ++a)
-            if (((open >> a) & 1u) && d[a] > best) {
-                best = d[a];
-                bi = CH_T * t + a;
+            if (((open >> a) & 1u) && d[a] > lb) {
+                lb = d[a];
+                li = CH_T * lane + a;
             }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) {
-                best = ob;
-                bi = oi;
-            }
-        }
+        // negative or zero candidates never become pivots: treat them as "none"
+        const unsigned long long key = lb > 0.0 ? (unsigned long long)__double_as_longlong(lb) : 0ull;
+        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+        const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+        const bool mine = hi == mhi && lo == mlo && key != 0ull;
+        const unsigned mi = __reduce_min_sync(0xffffffffu, mine ? (unsigned)li : 0x7fffffffu);
+        best = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+        if (mhi == 0u && mlo == 0u) best = -1.0;
+        bi = (int)mi;
     };
-    if (t < 32) {
-        double best;
-        int bi;
-        warp_argmax(best, bi);
-        d0 = best;
-        if (t == 0) {
-            s_rank = 0;
-            s_stop = !(best > 0.0);
-            s_p = best > 0.0 ? bi : 0;
-            s_dinv = best > 0.0 ? chol_rsqrt(best) : 0.0;
-        }
-    }
-    for (int step = 0; step < k; ++step) {
-        __syncthreads();
-        if (s_stop) break;
-        const int p = s_p, tp = p / CH_T, ap = p - tp * CH_T;
-        const double dinv = s_dinv;
+    double best;
+    int p;
+    warp_argmax(best, p);
+    const double d0 = best;
+    bool stop = !(best > 0.0);
+    double dinv = stop ? 0.0 : chol_rsqrt(best);
+    int rank = 0, buf = 0;
+    for (int step = 0; step < k && !stop; ++step) {
+        const int tp = p / CH_T, ap = p - tp * CH_T;
+        // the six "still open" flags of this thread's tile rows / tile columns (before the pivot itself closes)
+        const unsigned open_i = __shfl_sync(0xffffffffu, open, ti & 31), open_j = __shfl_sync(0xffffffffu, open, tj & 31);
+        double *v = vec[buf];
         if (tj == tp && ti >= tp) {
             // rows i0.. of column p (the diagonal tile holds the full block)
             CH_FOR_COL(ap,
 #pragma unroll
                        for (int a = 0; a < CH_T; ++a) {
                            const int i = i0 + a;
-                           if (i < k) vec[i] = s_done[i] ? 0.0 : g[a][B_] * dinv;
+                           if (i < k) v[i] = ((open_i >> a) & 1u) ? g[a][B_] * dinv : 0.0;
                        })
         } else if (ti == tp && tj < tp) {
             // columns j0.. of row p = rows j0.. of column p
@@ -2773,46 +2763,41 @@ __global__ void __launch_bounds__(CH_THREADS) be_pchol_kernel(BeConst bc, BeBuf 
 #pragma unroll
                        for (int b = 0; b < CH_T; ++b) {
                            const int j = j0 + b;
-                           vec[j] = s_done[j] ? 0.0 : g[B_][b] * dinv;
+                           v[j] = ((open_j >> b) & 1u) ? g[B_][b] * dinv : 0.0;
                        })
         }
+        if (lane == tp) open &= ~(1u << ap);
+        if (t == 0) s_perm[step] = p;
+        rank = step + 1;
         __syncthreads();
+        // next pivot first (the chain every thread waits for), then the tiles
+        {
+            double c[CH_T];
+            chol_load6(v + CH_T * lane, c);
+#pragma unroll
+            for (int a = 0; a < CH_T; ++a) d[a] = fma(-c[a], c[a], d[a]);
+            warp_argmax(best, p);
+            stop = !(step + 1 < k && best > PC_TOL * d0);
+            dinv = stop ? 0.0 : chol_rsqrt(best);
+        }
         if (live) {
             double ci[CH_T], rj[CH_T];
-            chol_load6(vec + i0, ci);
-            chol_load6(vec + j0, rj);
+            chol_load6(v + i0, ci);
+            chol_load6(v + j0, rj);
 #pragma unroll
             for (int a = 0; a < CH_T; ++a)
 #pragma unroll
                 for (int b = 0; b < CH_T; ++b) g[a][b] = fma(-ci[a], rj[b], g[a][b]);
         }
-        if (t < k) Rt[(size_t)step * k + t] = vec[t];
-        if (t < 32) {
-            double c[CH_T];
-            chol_load6(vec + CH_T * t, c);
-            if (t == tp) open &= ~(1u << ap);
-#pragma unroll
-            for (int a = 0; a < CH_T; ++a) d[a] = fma(-c[a], c[a], d[a]);
-            double best;
-            int bi;
-            warp_argmax(best, bi);
-            if (t == 0) {
-                s_perm[step] = p;
-                s_done[p] = 1;
-                s_rank = step + 1;
-                const bool go = step + 1 < k && best > PC_TOL * d0;
-                s_stop = !go;
-                s_p = go ? bi : 0;
-                s_dinv = go ? chol_rsqrt(best) : 0.0;
-            }
-        }
+        if (t < k) Rt[(size_t)step * k + t] = v[t];
+        buf ^= 1;
     }
+    if (t < 32) s_open[t] = open;
     __syncthreads();
-    const int rank = s_rank;
     if (t == 0) {
         int n = rank;
         for (int i = 0; i < k; ++i)
-            if (!s_done[i]) s_perm[n++] = i;
+            if ((s_open[i / CH_T] >> (i % CH_T)) & 1u) s_perm[n++] = i;
         st.mt = rank;
         st.t_upper = 1;
     }
@@ -3298,11 +3283,20 @@ int be_step(mskf_handle *h, const std::vector<int> &streams, const mskf_feature 
         sp.n_imu = n;
         if (n > max_imu) max_imu = n;
     }
-    MSKF_CUDA_CHECK(h, cudaMemcpyAsync(bb.step, hstep, sizeof(BeStep) * S, cudaMemcpyHostToDevice, q));
-    if (max_imu > 0) {
-        // one strided copy: the first max_imu samples of every stream
-        MSKF_CUDA_CHECK(h, cudaMemcpy2DAsync(bb.imu, sizeof(double) * BE_IMU_CAP * 7, himu, sizeof(double) * BE_IMU_CAP * 7,
-                                             sizeof(double) * 7 * max_imu, S, cudaMemcpyHostToDevice, q));
+    {
+        // descriptors and the first max_imu samples of every stream: fetched by a kernel, not by the copy engine
+        // (common.cuh, desc_fetch_kernel)
+        static_assert(sizeof(BeStep) % 8 == 0, "descriptor fetch moves 8-byte words");
+        FetchArgs fa;
+        fa.n = 1;
+        fa.seg[0] = fetch_seg(bb.step, hstep, sizeof(BeStep) * S);
+        if (max_imu > 0) {
+            fa.seg[1] = FetchSeg{bb.imu, himu, (unsigned)(7 * max_imu), (unsigned)(BE_IMU_CAP * 7), (unsigned)S};
+            fa.n = 2;
+        }
+        desc_fetch_kernel<<<4, 256, 0, q>>>(fa);
+        h->launches++;
+        MSKF_CUDA_CHECK(h, cudaGetLastError());
     }
     if (inject && n_inject > 0)
         MSKF_CUDA_CHECK(h, cudaMemcpyAsync(bb.inject, inject, sizeof(mskf_feature) * n_inject, cudaMemcpyHostToDevice, q));

@@ -193,6 +193,37 @@ void prof_end(mskf_handle *h);
 void prof_collect(mskf_handle *h);
 
 // launch + count + optional event bracket
+// Per-step descriptors (FeStep / BeStep arrays, image pointers, IMU rows: a few KB per handle) are FETCHED by a
+// small kernel from the page-locked host ring (device-visible through UVA) instead of copied by cudaMemcpyAsync:
+// a copy-engine transfer queues behind the 46 MB frame-set uploads of the other handles (up to 3 ms at 256
+// streams), which stalled every handle's step behind the fleet's uploads; SM loads over PCIe do not.
+struct FetchSeg {
+    void *dst;
+    const void *src;
+    unsigned width8;  // 8-byte words per row
+    unsigned pitch8;  // row pitch of dst and src in 8-byte words
+    unsigned rows;
+};
+struct FetchArgs {
+    FetchSeg seg[4];
+    int n;
+};
+static __global__ void __launch_bounds__(256) desc_fetch_kernel(FetchArgs a) {
+    for (int k = 0; k < a.n; ++k) {
+        const FetchSeg sg = a.seg[k];
+        const unsigned long long *src = (const unsigned long long *)sg.src;
+        unsigned long long *dst = (unsigned long long *)sg.dst;
+        const unsigned total = sg.width8 * sg.rows;
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+            const unsigned r = i / sg.width8, c = i - r * sg.width8;
+            dst[(size_t)r * sg.pitch8 + c] = src[(size_t)r * sg.pitch8 + c];
+        }
+    }
+}
+static inline FetchSeg fetch_seg(void *dst, const void *src, size_t bytes) {
+    return FetchSeg{dst, src, (unsigned)(bytes / 8), (unsigned)(bytes / 8), 1u};
+}
+
 #define MSKF_LAUNCH(h, tag, ...)        \
     do {                                \
         prof_begin((h), (tag));         \

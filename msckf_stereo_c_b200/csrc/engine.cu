@@ -499,9 +499,17 @@ int mskf_frontend_step(mskf_handle *h) {
         int rc = stage_begin_consume(h);
         if (rc != MSKF_OK) return rc;
     }
-    MSKF_CUDA_CHECK(h, cudaMemcpyAsync(h->fb.step, hstep, sizeof(FeStep) * S, cudaMemcpyHostToDevice, h->stream));
-    MSKF_CUDA_CHECK(h, cudaMemcpyAsync(h->fb.src0, hsrc, sizeof(uint8_t *) * S, cudaMemcpyHostToDevice, h->stream));
-    MSKF_CUDA_CHECK(h, cudaMemcpyAsync(h->fb.src1, hsrc + S, sizeof(uint8_t *) * S, cudaMemcpyHostToDevice, h->stream));
+    {
+        static_assert(sizeof(FeStep) % 8 == 0 && sizeof(uint8_t *) == 8, "descriptor fetch moves 8-byte words");
+        FetchArgs fa;
+        fa.n = 3;
+        fa.seg[0] = fetch_seg(h->fb.step, hstep, sizeof(FeStep) * S);
+        fa.seg[1] = fetch_seg(h->fb.src0, hsrc, sizeof(uint8_t *) * S);
+        fa.seg[2] = fetch_seg(h->fb.src1, hsrc + S, sizeof(uint8_t *) * S);
+        desc_fetch_kernel<<<4, 256, 0, h->stream>>>(fa);
+        h->launches++;
+        MSKF_CUDA_CHECK(h, cudaGetLastError());
+    }
     MSKF_CUDA_CHECK(h, cudaEventRecord(ex->ring_ev[slot], h->stream));
     ex->ring_used[slot] = true;
     return fe_step(h, any_first, max_prev, n_active);

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Warp instructions per CUDA source line of one kernel of an ncu report (needs -lineinfo and --import-source on).
 
-    python tools/ncu_lines.py report.ncu-rep kernel_name [launch_index=0] [min_share=0.003]
+    python tools/ncu_lines.py report.ncu-rep kernel_name [launch_index=0] [min_share=0.003] [function_substring]
+
+kernel_name is ncu's base name ("be_gemm_kernel"); function_substring picks a template instance ("<(int)3>").
 """
 import csv
 import io
@@ -18,6 +20,9 @@ def main():
     rows = list(csv.reader(io.StringIO(out)))
     # every launch of the kernel is one block that starts with a "File Path" row
     starts = [i for i, r in enumerate(rows) if r and r[0] == 'File Path']
+    if len(sys.argv) > 5:
+        starts = [i for i in starts if sys.argv[5] in rows[i + 1][1]]
+    starts = [i for i in starts if len(rows) > i + 3 and len(rows[i + 2]) > 5]  # blocks that carry metrics
     if not starts:
         print('no source page for', kern)
         return
