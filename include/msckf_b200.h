@@ -296,6 +296,13 @@ int mskf_debug_get_map(mskf_handle *h, int stream, long long *ids, int *is_initi
 /* Per stream {rows m, active columns k, listed features} of the lost-feature update and of the prune
  * update of the last back-end step: out[n_streams][2][3]. */
 int mskf_debug_update_dims(mskf_handle *h, int *out);
+/* The stacked system of the latest measurementUpdate of a stream (msckf_vio.cpp:778), i.e. the output of
+ * measurementJacobian + featureJacobian (null-space projection) + gatingTest + stacking (:610-775, :909-1024),
+ * in the basis-independent form the engine keeps: G = [H r]^T [H r] over the k active camera columns
+ * ((k+1) x (k+1), row-major, symmetric), m = stacked rows, cam_ids[g] = id of the camera state behind columns
+ * 6g .. 6g+5 (at most 32 groups).  *valid = 0 when m <= k (no compression ran: G is not formed). */
+int mskf_debug_last_gram(mskf_handle *h, int stream, double *G, int cap, int *m, int *k, long long *cam_ids,
+                         int *valid);
 /* mskf_op_detect that also returns the per-pixel FAST score map (0 = not a corner). */
 int mskf_debug_detect_scores(mskf_handle *h, const uint8_t *img, int rows, int cols, float *out_xy,
                              double *out_response, int cap, int *n, uint8_t *score_map);

@@ -86,6 +86,10 @@ struct BeState {
     unsigned rm_bits;
     int do_update;
     int dbg_m[2], dbg_k[2], dbg_nlist[2];  // per phase: stacked rows, active columns, listed features (last step)
+    // the latest measurementUpdate: stacked rows, active columns, whether its Gram matrix was formed (m > k) and
+    // the camera-state id behind every group of six active columns (mskf_debug_last_gram)
+    int gram_m, gram_k, gram_valid, gram_pad;
+    long long gram_ids[NSM];
     BeCam cam[NSM];
 };
 
@@ -2341,7 +2345,11 @@ __global__ void __launch_bounds__(BE_THREADS, 2) be_gram_kernel(BeConst bc, BeBu
         w[PK_BE_CHOL] += 2.0 * dmt * dmt * dmt / 3.0;
         w[PK_BE_GEMM_W] += dld * dmt * dmt;
         w[PK_BE_GEMM_PUPD] += dld * dld * dmt;
+        st.gram_m = m;
+        st.gram_k = k;
+        st.gram_valid = m > k ? 1 : 0;
     }
+    if (blockIdx.x == 0 && (int)threadIdx.x < k / 6) st.gram_ids[threadIdx.x] = st.cam[st.u_slots[threadIdx.x]].id;  // mskf_debug_last_gram
     if (m <= k) {
         if (blockIdx.x != 0) return;
         double *Tm = bb.Tm + (size_t)s * KC * KC;
@@ -2436,7 +2444,7 @@ __global__ void __launch_bounds__(BE_THREADS, 2) be_gram_kernel(BeConst bc, BeBu
 // (st.t_upper), which lets the k loop start at the tile's first row of T.
 //   OP 0: PHt (LD x mt) = P[:, cols] T^T          OP 1: S (mt x mt, lower tiles) = T PHt[cols, :] + sigma^2 I
 //   OP 2: W (LD x mt)  = PHt Linv^T (Linv lower triangular: k stops at the tile's last column)
-//   OP 3: P <- P - W W^T (lower tiles, mirrored through shared memory so both halves are written coalesced)
+//   OP 3: P <- P - W W^T (lower tiles; both halves written straight from the accumulators)
 // ======================================================================================
 template <int OP>
 __global__ void __launch_bounds__(BE_THREADS, 2) be_gemm_kernel(BeConst bc, BeBuf bb) {
@@ -2499,30 +2507,49 @@ __global__ void __launch_bounds__(BE_THREADS, 2) be_gemm_kernel(BeConst bc, BeBu
             [&](int l, int c) { return Linv + (size_t)(j0 + c) * KC + l; }, P, gs, acc);
         upd_gemm_store(mr, nc, acc, [&](int r, int c, double v) { W[(size_t)(i0 + r) * KC + j0 + c] = v; });
     } else {
+        {
+            // the tile of P this CTA updates is read only after the K loop: start it towards L2 now
+            const int r = threadIdx.x >> 2, q = threadIdx.x & 3;  // 64 rows x 4 quarters of <= 16 doubles
+            if (r < mr)
+                for (int c = 4 * q * 4; c < nc && c < 4 * (q + 1) * 4; c += 4)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(P + (size_t)(i0 + r) * LD + j0 + c));
+        }
         upd_gemm_tile<true>(
             mr, nc, 0, mt, [&](int r, int l) { return W + (size_t)(i0 + r) * KC + l; },
             [&](int l, int c) { return W + (size_t)(j0 + c) * KC + l; }, P, gs, acc);
         // P[i][j] and P[j][i] get the same value x = P[i][j] - (W W^T)[i][j], taken from the lower triangle (on a
         // diagonal tile (i, j) and (j, i) are computed from the same products in the same order anyway), so P
-        // stays exactly symmetric.  The tile goes through shared memory so that the mirrored half is written
-        // in rows as well.
-        double *Ct = gs.a[0];  // [64][65], the staging buffers are free now (upd_gemm_tile ends with a barrier)
+        // stays exactly symmetric.  Straight from the accumulators: a thread's two adjacent columns of eight rows
+        // per DMMA tile make full 64-byte row segments per warp in P, and its mirror writes (one column, eight
+        // consecutive rows of the tile = eight consecutive doubles of a row of P) do too.  All loads first, then
+        // all stores (the compiler must otherwise order every load behind the previous store to P).  The first
+        // version staged the tile in shared memory and walked it twice with a division per element: 28 % of the
+        // kernel's instructions and, with the unprefetched P reads, 43 % of its stall samples (ncu source page).
         const bool diag = i0 == j0;
-        upd_gemm_store(mr, nc, acc, [&](int r, int c, double v) { Ct[r * 65 + c] = v; });
-        __syncthreads();
-        for (int e = threadIdx.x; e < mr * nc; e += BE_THREADS) {
-            const int r = e / nc, c = e - r * nc;
-            if (diag && c > r) continue;
-            const double x = P[(size_t)(i0 + r) * LD + j0 + c] - Ct[r * 65 + c];
-            P[(size_t)(i0 + r) * LD + j0 + c] = x;
-            Ct[r * 65 + c] = x;
-        }
-        __syncthreads();
-        for (int e = threadIdx.x; e < mr * nc; e += BE_THREADS) {
-            const int c = e / mr, r = e - c * mr;  // r fastest: row j0 + c of P, columns i0 + r
-            if (diag && c >= r) continue;
-            P[(size_t)(j0 + c) * LD + i0 + r] = Ct[r * 65 + c];
-        }
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int g = lane >> 2, t4 = lane & 3, wr = warp >> 2, wc = warp & 3;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int r = wr * 32 + mi * 8 + g, c = wc * 16 + ni * 8 + 2 * t4 + h2;
+                    if (r < mr && c < nc && !(diag && c > r)) acc[mi][ni][h2] = P[(size_t)(i0 + r) * LD + j0 + c] - acc[mi][ni][h2];
+                }
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int r = wr * 32 + mi * 8 + g, c = wc * 16 + ni * 8 + 2 * t4 + h2;
+                    if (r < mr && c < nc && !(diag && c > r)) {
+                        const double x = acc[mi][ni][h2];
+                        P[(size_t)(i0 + r) * LD + j0 + c] = x;
+                        if (!(diag && c == r)) P[(size_t)(j0 + c) * LD + i0 + r] = x;
+                    }
+                }
     }
 }
 
@@ -3578,6 +3605,23 @@ int be_op_triangulate(mskf_handle *t, int n_cam, const double *cam_q, const doub
 }
 
 // bring-up / analysis: per stream {m, k, listed features} of the lost-feature and the prune update of the last step
+int be_debug_last_gram(mskf_handle *h, int s, double *G, int cap, int *m, int *k, long long *cam_ids, int *valid) {
+    BeState st;
+    MSKF_CUDA_CHECK(h, cudaMemcpy(&st, h->bb->bb.st + s, sizeof(BeState), cudaMemcpyDeviceToHost));
+    *m = st.gram_m;
+    *k = st.gram_k;
+    *valid = st.gram_valid;
+    for (int g = 0; g < st.gram_k / 6; ++g) cam_ids[g] = st.gram_ids[g];
+    if (!st.gram_valid || !G) return MSKF_OK;
+    const int kw = st.gram_k + 1, ldg = h->bb->bc.KC + 1;
+    if (cap < kw * kw) return MSKF_ERR_CAPACITY;
+    std::vector<double> buf((size_t)kw * ldg);
+    MSKF_CUDA_CHECK(h, cudaMemcpy(buf.data(), h->bb->bb.Gm + (size_t)s * ldg * ldg, sizeof(double) * buf.size(), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < kw; ++i)
+        for (int j = 0; j <= i; ++j) G[i * kw + j] = G[j * kw + i] = buf[(size_t)i * ldg + j];  // the kernel fills the lower triangle
+    return MSKF_OK;
+}
+
 int be_debug_update_dims(mskf_handle *h, int *out6) {
     std::vector<BeState> st(h->S);
     MSKF_CUDA_CHECK(h, cudaMemcpy(st.data(), h->bb->bb.st, sizeof(BeState) * h->S, cudaMemcpyDeviceToHost));

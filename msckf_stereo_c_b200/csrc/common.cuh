@@ -255,6 +255,7 @@ int be_op_triangulate(mskf_handle *t, int n_cam, const double *cam_q, const doub
                       const double *obs, double *pos, int *ok);
 int be_op_update(mskf_handle *t, int n_cam, int m, const double *H, const double *r, const double *P, double *dx, double *Pn);
 int be_debug_update_dims(mskf_handle *h, int *out6);
+int be_debug_last_gram(mskf_handle *h, int s, double *G, int cap, int *m, int *k, long long *cam_ids, int *valid);
 int be_get_poses(mskf_handle *h, double *out, int cap_streams, int lag);
 
 template <typename T>

@@ -690,6 +690,12 @@ int mskf_debug_update_dims(mskf_handle *h, int *out6) {
     if (rc != MSKF_OK) return rc;
     return be_debug_update_dims(h, out6);
 }
+int mskf_debug_last_gram(mskf_handle *h, int stream, double *G, int cap, int *m, int *k, long long *cam_ids, int *valid) {
+    if (!h || stream < 0 || stream >= h->S || !m || !k || !cam_ids || !valid) return MSKF_ERR_ARG;
+    int rc = mskf_sync(h);
+    if (rc != MSKF_OK) return rc;
+    return be_debug_last_gram(h, stream, G, cap, m, k, cam_ids, valid);
+}
 int mskf_get_poses(mskf_handle *h, double *out, int cap_streams) {
     if (!h || !out) return MSKF_ERR_ARG;
     MSKF_CUDA_CHECK(h, cudaSetDevice(h->device));

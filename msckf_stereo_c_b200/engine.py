@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "mskf_get_grid", "mskf_get_pyramid", "mskf_get_state", "mskf_get_cam_states", "mskf_get_covariance",
     "mskf_reset", "mskf_op_pyramid", "mskf_op_detect", "mskf_op_klt",
     "mskf_launch_count", "mskf_get_n_published", "mskf_get_poses", "mskf_profile_enable", "mskf_profile_read",
-    "mskf_debug_detect_scores", "mskf_debug_get_map", "mskf_op_ekf_update", "mskf_push_imu_batch",
+    "mskf_debug_detect_scores", "mskf_debug_get_map", "mskf_debug_last_gram", "mskf_op_ekf_update", "mskf_push_imu_batch",
     "mskf_push_stereo_batch", "mskf_push_stereo_device_batch", "mskf_get_work", "mskf_get_poses_prev", "mskf_join",
     "mskf_set_overlap", "mskf_debug_update_dims", "mskf_op_triangulate", "mskf_push_imu_to",
     "mskf_get_features_head", "mskf_wait_uploads", "mskf_host_alloc", "mskf_host_free",
@@ -80,6 +80,7 @@ def lib():
         L.mskf_get_poses_prev.argtypes = [P, P, I]
         L.mskf_join.argtypes = [P]
         L.mskf_debug_update_dims.argtypes = [P, P]
+        L.mskf_debug_last_gram.argtypes = [P, I, P, I, C.POINTER(I), C.POINTER(I), P, C.POINTER(I)]
         L.mskf_set_overlap.argtypes = [P, I]
         L.mskf_push_imu_batch.argtypes = [P, I, I, P]
         L.mskf_push_stereo_batch.argtypes = [P, P, P, P, C.c_size_t]
@@ -245,6 +246,17 @@ class Engine:
         f = lib().mskf_get_poses_prev if prev else lib().mskf_get_poses
         self._ck(f(self.h, out.ctypes.data, self.n_streams))
         return out
+
+    def last_gram(self, stream=0):
+        """(G, m, k, cam_ids) of the latest measurementUpdate of a stream: G = [H r]^T [H r] over the k active
+        camera columns, or G = None when m <= k (mskf_debug_last_gram)."""
+        m, k, valid = C.c_int(), C.c_int(), C.c_int()
+        ids = np.zeros(32, np.int64)
+        G = np.zeros((6 * 32 + 1) ** 2)
+        self._ck(lib().mskf_debug_last_gram(self.h, stream, G.ctypes.data, G.size, C.byref(m), C.byref(k), ids.ctypes.data,
+                                            C.byref(valid)))
+        kw = k.value + 1
+        return (G[:kw * kw].reshape(kw, kw).copy() if valid.value else None), m.value, k.value, ids[:k.value // 6].copy()
 
     def update_dims(self):
         out = np.zeros((self.n_streams, 2, 3), np.int32)

@@ -578,6 +578,8 @@ public:
             last_H = H;
             last_r = r;
             last_P_prior = state_cov;
+            last_cam_ids.clear();
+            for (const auto &kv : cam_states) last_cam_ids.push_back((long long)kv.first);
         }
         Mat delta_x, P_new;
         update_math(H, r, state_cov, observation_noise, delta_x, P_new);
@@ -785,6 +787,7 @@ public:
     double last_gamma = 0;
     bool keep_last_update = false;  // test hook: keep (H, r, P-) of the latest measurementUpdate
     Mat last_H, last_r, last_P_prior;
+    std::vector<long long> last_cam_ids;  // camera-state ids behind the column groups of last_H
 };
 
 }  // namespace orc

@@ -57,6 +57,7 @@ def lib():
         L.orc_keep_last_update.argtypes = [C.c_void_p, C.c_int]
         L.orc_last_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.orc_get_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_last_update_cam_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_chi2.argtypes = [C.POINTER(abi.Config), C.c_int]
         L.orc_chi2.restype = C.c_double
         _LIB = L
@@ -156,6 +157,12 @@ class Oracle:
         P = np.zeros((n.value, n.value))
         lib().orc_last_update(self.h, H.ctypes.data, r.ctypes.data, P.ctypes.data, max(H.size, P.size), C.byref(n))
         return H, r, P
+
+    def last_update_cam_ids(self):
+        """Camera-state ids behind the column groups 21 + 6 i of last_update()'s H."""
+        ids = np.zeros(64, np.int64)
+        n = lib().orc_last_update_cam_ids(self.h, ids.ctypes.data, 64)
+        return ids[:n].copy()
 
     def cov(self):
         n = lib().orc_get_cov(self.h, None, 0)

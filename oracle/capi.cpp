@@ -295,6 +295,13 @@ int orc_last_update(void *h, double *H, double *r, double *P, int cap, int *n) {
     if (P && (int)b.last_P_prior.d.size() <= cap) std::memcpy(P, b.last_P_prior.d.data(), sizeof(double) * b.last_P_prior.d.size());
     return b.last_H.r;
 }
+// test hook: ids of the camera states behind the column groups 21 + 6 i of the latest measurementUpdate's H
+int orc_last_update_cam_ids(void *h, long long *ids, int cap) {
+    const MsckfVio &b = ((Oracle *)h)->be;
+    const int n = (int)b.last_cam_ids.size();
+    for (int i = 0; i < n && i < cap; ++i) ids[i] = b.last_cam_ids[i];
+    return n;
+}
 // test hook: the feature map (ascending id): id, is_initialized, position, observation count
 int orc_get_map(void *h, long long *ids, int *init, double *pos, int *nobs, int cap) {
     Oracle *o = (Oracle *)h;

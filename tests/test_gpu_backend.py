@@ -187,6 +187,65 @@ def _split_phase_run(eng, ob, synth, cfg, seed, n_frames):
     return worst, st
 
 
+GRAM_TOL = 1e-9  # stacked system [H r]^T [H r], relative to its largest entry (measured ~1e-12)
+
+
+@pytest.mark.parametrize("preset,seed,frames", [("ref", 0, 80), ("bench", 1, 62)])
+def test_op_jacobian_gating_stacking_vs_oracle(eng, ob, synth, preset, seed, frames):
+    """a18-a21 at operator level: measurementJacobian (msckf_vio.cpp:610-677), featureJacobian with the null-space
+    projection (:679-775), gatingTest (:909-935) and the stacking of removeLostFeatures / pruneCamStateBuffer
+    (:937-1024, :1126-1150), compared at EVERY update of a split-phase run (identical feature inputs) through
+    the quantities the update depends on: G = H^T H, H^T r and r^T r of the stacked system over the active camera
+    columns.  These do not depend on the orthonormal null-space basis (H' = A^T H_x with A any basis of the left
+    null space of H_f gives H'^T H' = H_x^T (I - U U^T) H_x), so the oracle's Householder basis and the kernel's
+    compact-WY reflectors must agree; the stacked row count pins the gating decisions and the per-feature view
+    counts, the camera ids pin the column layout."""
+    cfg = copy_cfg(synth.default_config(preset), compat_stale_features=0)
+    s = synth.Stream(cfg, seed=seed)
+    e = eng.Engine(cfg, 1)
+    o = ob.Oracle(cfg)
+    o.keep_last_update()
+
+    class Both:
+        def imu(self, t, w, a):
+            o.imu(t, w, a)
+            e.imu_callback(t, w, a)
+
+        def stereo(self, t, i0, i1):
+            o.stereo(t, i0, i1)
+
+        def backend(self):
+            o.backend()
+            t, f, _ = o.features()
+            e.backend_features(t, f)
+
+    last, checked, tall, worst = 0, 0, 0, 0.0
+    for k, t in synth.feed(s, frames, Both()):
+        n_upd = o.state().n_updates
+        if n_upd == last:
+            continue
+        last = n_upd
+        H, r, _ = o.last_update()
+        ids_o = list(o.last_update_cam_ids())
+        G_e, m_e, k_e, ids_e = e.last_gram()
+        assert m_e == H.shape[0], (k, m_e, H.shape)  # same features pass the gate with the same view counts
+        assert set(ids_e) <= set(ids_o)
+        cols = np.concatenate([21 + 6 * ids_o.index(i) + np.arange(6) for i in ids_e])
+        rest = np.setdiff1d(np.arange(H.shape[1]), cols)
+        assert np.abs(H[:, rest]).max() == 0.0  # every column the oracle touches is an active column of the engine
+        checked += 1
+        if G_e is None:
+            continue  # m <= k: no compression, the Gram matrix is not formed
+        tall += 1
+        Hr = np.concatenate([H[:, cols], r[:, None]], axis=1)
+        G_o = Hr.T @ Hr
+        worst = max(worst, np.abs(G_e - G_o).max() / np.abs(G_o).max())
+    e.close()
+    print(f"updates {checked}, with Gram matrix {tall}, worst relative deviation {worst:.2e}")
+    assert checked >= 5 and tall >= 3
+    assert worst <= GRAM_TOL
+
+
 def test_backend_split_phase_ref(eng, ob, synth):
     """featureCallback frame by frame (msckf_vio.cpp:306-375) with the oracle's CameraMeasurement
     injected: gravity initialisation, propagation, augmentation, lost-feature updates, pruning."""

@@ -70,6 +70,26 @@ def test_detect_bit_exact(eng, ob, synth, preset, seed):
     e.close()
 
 
+def test_detect_bit_exact_realistic_corner_density(eng, ob, synth):
+    """The synthetic texture is corner-dense (26 % of the pixels are FAST corners); real imagery has 2-5 %.  A
+    low-pass filtered frame puts the detector in that regime (short candidate lists, mostly-empty tiles): the
+    score map, the keypoint set, its order and the responses must still be bit-exact."""
+    from scipy.ndimage import gaussian_filter
+
+    cfg = synth.default_config("bench")
+    (_, a, _), = _frames(synth, cfg, 3, [40])
+    a = np.clip(np.rint(gaussian_filter(a.astype(np.float32), 2.0)), 0, 255).astype(np.uint8)
+    e = eng.Engine(cfg, 1)
+    xy_o, r_o, sm_o = ob.detect(cfg, a, want_scores=True)
+    density = (sm_o > 0).mean()
+    assert 0.01 <= density <= 0.06, density
+    xy_g, r_g, sm_g = e.debug_detect_scores(a)
+    assert np.array_equal(sm_o, sm_g)
+    assert len(xy_o) > 50
+    assert np.array_equal(xy_o, xy_g) and np.array_equal(r_o, r_g)
+    e.close()
+
+
 @pytest.mark.parametrize("preset", ["ref", "bench"])
 def test_klt_parity(eng, ob, synth, preset):
     cfg = synth.default_config(preset)
