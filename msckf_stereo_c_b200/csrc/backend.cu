@@ -1971,13 +1971,18 @@ __global__ void __launch_bounds__(BE_THREADS, 2) be_feature_jac_kernel(BeConst b
 // ======================================================================================
 // Prune-phase variant of the kernel above (pruneCamStateBuffer :1126-1150): every involved feature
 // has exactly the two camera states being removed (M = 2: an 8 x 12 Jacobian, 5 projected rows), and
-// there are hundreds of them per stream, so one WARP handles a feature: lanes 0 and 1 evaluate the
-// two measurementJacobians, lane c < 12 owns column c of H_xj (lane 12 the residual), applies the
-// three reflectors to it privately, and S = H' P_sub H'^T is formed with shuffles against the 12 x 12
-// covariance block staged once per CTA.
+// there are hundreds of them per stream, so one THREAD handles a feature from the measurementJacobians to the
+// gate: the whole problem is ~3k flops of fixed-size dense algebra that unrolls into straight-line register
+// code (H' 5 x 13 lives in registers), where the warp-per-feature version spent ~1100 warp instructions per
+// feature with 2 of 32 lanes in the Jacobians, 13 in the column work and two SHFLs per double in the products
+// (0.17 ms per fleet launch).  What depends on the two cameras only (rotations, cam1 pose, the rotated gravity of
+// the observability projection, the 12 x 12 covariance block) is evaluated once per CTA.
 // ======================================================================================
-#define JS_WARPS 8
-__global__ void __launch_bounds__(JS_WARPS * 32, 2) be_feature_jac_prune_kernel(BeConst bc, BeBuf bb) {
+#define JP_THREADS 64
+struct JpCam {
+    double Rw0[9], Rw1[9], p[3], t1w[3], ug[3], pn[3];
+};
+__global__ void __launch_bounds__(JP_THREADS) be_feature_jac_prune_kernel(BeConst bc, BeBuf bb) {
     const int s = blockIdx.y;
     const BeStep sp = bb.step[s];
     if (!sp.active) return;
@@ -1988,42 +1993,65 @@ __global__ void __launch_bounds__(JS_WARPS * 32, 2) be_feature_jac_prune_kernel(
     const double *P = bb.P + (size_t)s * bc.LD * bc.LD;
     const int LD = bc.LD;
     __shared__ double Ps[12][12];
-    __shared__ double sHx[JS_WARPS][2][4][6], sHf[JS_WARPS][8][3], sr[JS_WARPS][8];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ JpCam cams[2];
+    __shared__ double sHx[48][JP_THREADS], sHf[24][JP_THREADS], sr[8][JP_THREADS];  // per-thread columns
     const int os[2] = {st.rm_slot[0], st.rm_slot[1]};
-    for (int e = threadIdx.x; e < 144; e += JS_WARPS * 32) {
+    for (int e = threadIdx.x; e < 144; e += JP_THREADS) {
         const int i = e / 12, j = e - i * 12;
         Ps[i][j] = P[(size_t)(N21 + 6 * os[i / 6] + i % 6) * LD + N21 + 6 * os[j / 6] + j % 6];
     }
+    if (threadIdx.x < 2) {
+        const BeCam &c = st.cam[os[threadIdx.x]];
+        JpCam &jc = cams[threadIdx.x];
+        double tmp[3], Rn[9];
+        quat_to_rot(c.q, jc.Rw0);
+        m3mul(bc.R01, jc.Rw0, jc.Rw1);
+        m3Tv(jc.Rw1, bc.t01, tmp);
+        for (int i = 0; i < 3; ++i) {
+            jc.p[i] = c.p[i];
+            jc.t1w[i] = c.p[i] - tmp[i];
+            jc.pn[i] = c.pn[i];
+        }
+        quat_to_rot(c.qn, Rn);
+        m3v(Rn, st.g, jc.ug);
+    }
     __syncthreads();
-    for (int li = blockIdx.x * JS_WARPS + warp; li < n_list; li += gridDim.x * JS_WARPS) {
+    const double gv[3] = {st.g[0], st.g[1], st.g[2]};
+    const double thr = c_chi2[bc.chi2_mode][1];  // dof = involved.size() = 2, msckf_vio.cpp:1145
+    for (int li = blockIdx.x * JP_THREADS + threadIdx.x; li < n_list; li += gridDim.x * JP_THREADS) {
         const int slot = bb.l_slot[lo + li];
-        __syncwarp();
-        if (lane < 2) {
+        const double *pw = bb.f_pos + (fo + slot) * 3;
+        const double pwv[3] = {pw[0], pw[1], pw[2]};
+        // the two measurementJacobians run one after the other (not interleaved: their temporaries would not fit the
+        // register file) and leave H_x, H_f and r in this thread's columns of shared memory
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
             // measurementJacobian, msckf_vio.cpp:610-677
-            const int t = lane, cs = os[t];
-            const BeCam &c = st.cam[cs];
-            const double *z = bb.f_obs + (((size_t)s * bc.MF + slot) * bc.NS + cs) * 4;
-            const double *pw = bb.f_pos + (fo + slot) * 3;
-            double Rw0[9], Rw1[9], t1w[3], tmp[3];
-            quat_to_rot(c.q, Rw0);
-            m3mul(bc.R01, Rw0, Rw1);
-            m3Tv(Rw1, bc.t01, tmp);
-            for (int i = 0; i < 3; ++i) t1w[i] = c.p[i] - tmp[i];
-            double d0[3] = {pw[0] - c.p[0], pw[1] - c.p[1], pw[2] - c.p[2]};
-            double d1[3] = {pw[0] - t1w[0], pw[1] - t1w[1], pw[2] - t1w[2]};
+            const JpCam &jc = cams[t];
+            const double *z = bb.f_obs + (((size_t)s * bc.MF + slot) * bc.NS + os[t]) * 4;
+            double Rw0[9], Rw1[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                Rw0[i] = jc.Rw0[i];
+                Rw1[i] = jc.Rw1[i];
+            }
+            const double d0[3] = {pwv[0] - jc.p[0], pwv[1] - jc.p[1], pwv[2] - jc.p[2]};
+            const double d1[3] = {pwv[0] - jc.t1w[0], pwv[1] - jc.t1w[1], pwv[2] - jc.t1w[2]};
             double p0[3], p1[3];
             m3v(Rw0, d0, p0);
             m3v(Rw1, d1, p1);
-            double dz0[4][3] = {{1 / p0[2], 0, -p0[0] / (p0[2] * p0[2])}, {0, 1 / p0[2], -p0[1] / (p0[2] * p0[2])}, {0, 0, 0}, {0, 0, 0}};
-            double dz1[4][3] = {{0, 0, 0}, {0, 0, 0}, {1 / p1[2], 0, -p1[0] / (p1[2] * p1[2])}, {0, 1 / p1[2], -p1[1] / (p1[2] * p1[2])}};
+            const double dz0[4][3] = {{1 / p0[2], 0, -p0[0] / (p0[2] * p0[2])}, {0, 1 / p0[2], -p0[1] / (p0[2] * p0[2])}, {0, 0, 0}, {0, 0, 0}};
+            const double dz1[4][3] = {{0, 0, 0}, {0, 0, 0}, {1 / p1[2], 0, -p1[0] / (p1[2] * p1[2])}, {0, 1 / p1[2], -p1[1] / (p1[2] * p1[2])}};
             double sk0[9], R01sk[9];
             skew3(p0, sk0);
             m3mul(bc.R01, sk0, R01sk);
             double Hxl[4][6];
+#pragma unroll
             for (int i = 0; i < 4; ++i)
+#pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     double a = 0, b = 0;
+#pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         a += dz0[i][k] * sk0[k * 3 + j] + dz1[i][k] * R01sk[k * 3 + j];
                         b += dz0[i][k] * (-Rw0[k * 3 + j]) + dz1[i][k] * (-Rw1[k * 3 + j]);
@@ -2031,32 +2059,39 @@ __global__ void __launch_bounds__(JS_WARPS * 32, 2) be_feature_jac_prune_kernel(
                     Hxl[i][j] = a;
                     Hxl[i][3 + j] = b;
                 }
-            double u[6], Rn[9], dn[3] = {pw[0] - c.pn[0], pw[1] - c.pn[1], pw[2] - c.pn[2]}, K[9];
-            quat_to_rot(c.qn, Rn);
-            m3v(Rn, st.g, u);
+            // observability projection: H_x <- A - A u (u^T u)^-1 u^T, H_f <- -H_x[:, 3:6]
+            double u[6], K[9];
+            const double dn[3] = {pwv[0] - jc.pn[0], pwv[1] - jc.pn[1], pwv[2] - jc.pn[2]};
+            u[0] = jc.ug[0]; u[1] = jc.ug[1]; u[2] = jc.ug[2];
             skew3(dn, K);
-            m3v(K, st.g, u + 3);
+            m3v(K, gv, u + 3);
             double utu = 0;
+#pragma unroll
             for (int i = 0; i < 6; ++i) utu += u[i] * u[i];
+#pragma unroll
             for (int i = 0; i < 4; ++i) {
                 double au = 0;
+#pragma unroll
                 for (int k = 0; k < 6; ++k) au += Hxl[i][k] * u[k];
                 au *= (1.0 / utu);
-                for (int k = 0; k < 6; ++k) sHx[warp][t][i][k] = Hxl[i][k] - au * u[k];
-                for (int k = 0; k < 3; ++k) sHf[warp][4 * t + i][k] = -(Hxl[i][3 + k] - au * u[3 + k]);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) sHx[t * 24 + i * 6 + k][threadIdx.x] = Hxl[i][k] - au * u[k];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) sHf[(4 * t + i) * 3 + k][threadIdx.x] = -(Hxl[i][3 + k] - au * u[3 + k]);
             }
-            sr[warp][4 * t + 0] = z[0] - p0[0] / p0[2];
-            sr[warp][4 * t + 1] = z[1] - p0[1] / p0[2];
-            sr[warp][4 * t + 2] = z[2] - p1[0] / p1[2];
-            sr[warp][4 * t + 3] = z[3] - p1[1] / p1[2];
+            sr[4 * t + 0][threadIdx.x] = z[0] - p0[0] / p0[2];
+            sr[4 * t + 1][threadIdx.x] = z[1] - p0[1] / p0[2];
+            sr[4 * t + 2][threadIdx.x] = z[2] - p1[0] / p1[2];
+            sr[4 * t + 3][threadIdx.x] = z[3] - p1[1] / p1[2];
         }
-        __syncwarp();
-        // every lane: Householder QR of H_f (8 x 3), redundantly (it is tiny and needs no traffic)
-        double V[8][3], tau[3];
+        // Householder QR of H_f (8 x 3): V below the diagonal, tau
+        double V[8][3], rv[8], tau[3];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 8; ++i) {
+            rv[i] = sr[i][threadIdx.x];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) V[i][k] = sHf[warp][i][k];
+            for (int k = 0; k < 3; ++k) V[i][k] = sHf[i * 3 + k][threadIdx.x];
+        }
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             double xn = 0;
@@ -2086,54 +2121,46 @@ __global__ void __launch_bounds__(JS_WARPS * 32, 2) be_feature_jac_prune_kernel(
             }
             tau[j] = tj;
         }
-        // my column of [H_xj | r]: lane c < 12 -> camera block c / 6, column c % 6; lane 12 -> r
-        double col[8];
+        // H' = (Q^T [H_xj | r])[3:, :]: column c < 12 -> camera block c / 6, column c % 6; column 12 -> r
+        double Hp[5][13];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            double v = 0.0;
-            if (lane < 12) {
-                if ((i >> 2) == lane / 6) v = sHx[warp][lane / 6][i & 3][lane % 6];
-            } else if (lane == 12) {
-                v = sr[warp][i];
+        for (int c = 0; c < 13; ++c) {
+            double col[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) col[i] = c == 12 ? rv[i] : (((i >> 2) == c / 6) ? sHx[(c / 6) * 24 + (i & 3) * 6 + c % 6][threadIdx.x] : 0.0);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                double sacc = col[j];
+#pragma unroll
+                for (int i = j + 1; i < 8; ++i) sacc += V[i][j] * col[i];
+                sacc *= tau[j];
+                col[j] -= sacc;
+#pragma unroll
+                for (int i = j + 1; i < 8; ++i) col[i] -= sacc * V[i][j];
             }
-            col[i] = v;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) Hp[i][c] = col[3 + i];
         }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            double sacc = col[j];
-#pragma unroll
-            for (int i = j + 1; i < 8; ++i) sacc += V[i][j] * col[i];
-            sacc *= tau[j];
-            col[j] -= sacc;
-#pragma unroll
-            for (int i = j + 1; i < 8; ++i) col[i] -= sacc * V[i][j];
-        }
-        // HP[:, d] for my column d (lanes < 12): sum_c H'[:, c] P[c][d]
-        double hp[5] = {0, 0, 0, 0, 0};
-#pragma unroll
-        for (int cc = 0; cc < 12; ++cc) {
-            const double pcd = lane < 12 ? Ps[cc][lane] : 0.0;
-#pragma unroll
-            for (int i = 0; i < 5; ++i) hp[i] += __shfl_sync(0xffffffffu, col[3 + i], cc) * pcd;
-        }
-        // S = HP H'^T (lower triangle), summed over the 12 column lanes
+        // S = H' P_sub H'^T + sigma^2 I (lower triangle)
         double S[15];
-        {
+#pragma unroll
+        for (int q = 0; q < 15; ++q) S[q] = 0.0;
+#pragma unroll
+        for (int d = 0; d < 12; ++d) {
+            double hp[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+            for (int cc = 0; cc < 12; ++cc) {
+                const double pcd = Ps[cc][d];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) hp[i] += Hp[i][cc] * pcd;
+            }
             int q = 0;
 #pragma unroll
             for (int i = 0; i < 5; ++i)
 #pragma unroll
-                for (int j = 0; j <= i; ++j) {
-                    double v = lane < 12 ? hp[i] * col[3 + j] : 0.0;
-#pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    S[q++] = v + (i == j ? bc.obs_noise : 0.0);
-                }
+                for (int j = 0; j <= i; ++j) S[q++] += hp[i] * Hp[j][d];
         }
-        double rp[5];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) rp[i] = __shfl_sync(0xffffffffu, col[3 + i], 12);
-        // Cholesky 5 x 5 + forward substitution (every lane of the first half-warp holds the same values)
+        // Cholesky 5 x 5 + forward substitution: gamma = r'^T S^-1 r' (gatingTest, msckf_vio.cpp:909-935)
         double g = 0;
         {
             double L[15];
@@ -2142,7 +2169,7 @@ __global__ void __launch_bounds__(JS_WARPS * 32, 2) be_feature_jac_prune_kernel(
             for (int i = 0; i < 5; ++i)
 #pragma unroll
                 for (int j = 0; j <= i; ++j) {
-                    double v = S[q];
+                    double v = S[q] + (i == j ? bc.obs_noise : 0.0);
 #pragma unroll
                     for (int k = 0; k < j; ++k) v -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
                     L[q] = (i == j) ? sqrt(v) : v / L[j * (j + 1) / 2 + j];
@@ -2151,31 +2178,27 @@ __global__ void __launch_bounds__(JS_WARPS * 32, 2) be_feature_jac_prune_kernel(
             double y[5];
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
-                double v = rp[i];
+                double v = Hp[i][12];
 #pragma unroll
                 for (int k = 0; k < i; ++k) v -= L[i * (i + 1) / 2 + k] * y[k];
                 y[i] = v / L[i * (i + 1) / 2 + i];
                 g += y[i] * y[i];
             }
         }
-        const double thr = c_chi2[bc.chi2_mode][1];  // dof = involved.size() = 2, msckf_vio.cpp:1145
         const int pass = g < thr ? 1 : 0;
-        double *H = bb.Hblk + (size_t)s * bc.ecap + bb.l_eoff[lo + li];   // [8][12], rows 3.. used
-        double *rg = bb.rblk + (size_t)s * bc.rcap + bb.l_roff[lo + li];  // [8]
         if (pass) {
-            if (lane < 12) {
+            double *H = bb.Hblk + (size_t)s * bc.ecap + bb.l_eoff[lo + li];   // [8][12], rows 3.. used
+            double *rg = bb.rblk + (size_t)s * bc.rcap + bb.l_roff[lo + li];  // [8]
 #pragma unroll
-                for (int i = 3; i < 8; ++i) H[i * 12 + lane] = col[i];
-            } else if (lane == 12) {
+            for (int i = 0; i < 5; ++i) {
 #pragma unroll
-                for (int i = 3; i < 8; ++i) rg[i] = col[i];
+                for (int c = 0; c < 12; ++c) H[(3 + i) * 12 + c] = Hp[i][c];
+                rg[3 + i] = Hp[i][12];
             }
         }
-        if (lane == 0) {
-            bb.l_pass[lo + li] = (uint8_t)pass;
-            bb.l_oslots[(lo + li) * NSM + 0] = (uint8_t)os[0];
-            bb.l_oslots[(lo + li) * NSM + 1] = (uint8_t)os[1];
-        }
+        bb.l_pass[lo + li] = (uint8_t)pass;
+        bb.l_oslots[(lo + li) * NSM + 0] = (uint8_t)os[0];
+        bb.l_oslots[(lo + li) * NSM + 1] = (uint8_t)os[1];
     }
     if (threadIdx.x == 0 && blockIdx.x == 0)
         bb.work[(size_t)s * MSKF_PROF_TAGS + PK_BE_FEATURE_JAC_PRUNE] += (double)n_list * (2.0 * 480.0 + 3.0 * 13.0 * 32.0 + 2.0 * 5.0 * 144.0 + 2.0 * 15.0 * 12.0 + 60.0);
@@ -3349,7 +3372,7 @@ int be_step(mskf_handle *h, const std::vector<int> &streams, const mskf_feature 
             MSKF_LAUNCH(h, PK_BE_FEATURE_JAC, (be_feature_jac_kernel<<<g, BE_THREADS, B->smem_jac[0], q>>>(bc, bb, 0, maxM)));
         } else {
             dim3 g(8, S);
-            MSKF_LAUNCH(h, PK_BE_FEATURE_JAC_PRUNE, (be_feature_jac_prune_kernel<<<g, JS_WARPS * 32, 0, q>>>(bc, bb)));
+            MSKF_LAUNCH(h, PK_BE_FEATURE_JAC_PRUNE, (be_feature_jac_prune_kernel<<<g, JP_THREADS, 0, q>>>(bc, bb)));
         }
         MSKF_LAUNCH(h, PK_BE_STACK, (be_stack_kernel<<<S, BE_THREADS, (size_t)bc.ML * 10, q>>>(bc, bb, phase)));
         MSKF_LAUNCH(h, PK_BE_STACK, (be_scatter_kernel<<<dim3(16, S), BE_THREADS, 0, q>>>(bc, bb)));
