@@ -2347,7 +2347,7 @@ struct GramSmem {
 // Lower tile (ti >= tj) of G = [H r]^T [H r]: C(i, j) = sum over the rows l of H of Hr(l, i0 + i) Hr(l, j0 + j).
 // Both operands are rows of the same row-major matrix, staged as [l][column] with coalesced 8-byte
 // cp.async (column k is the residual, from rst), two stages of 16 rows.
-__global__ void __launch_bounds__(BE_THREADS, 2) be_gram_kernel(BeConst bc, BeBuf bb, int phase) {
+__global__ void __launch_bounds__(BE_THREADS, 3) be_gram_kernel(BeConst bc, BeBuf bb, int phase) {
     const int s = blockIdx.y;
     const BeStep sp = bb.step[s];
     if (!sp.active) return;
@@ -2470,7 +2470,7 @@ __global__ void __launch_bounds__(BE_THREADS, 2) be_gram_kernel(BeConst bc, BeBu
 //   OP 3: P <- P - W W^T (lower tiles; both halves written straight from the accumulators)
 // ======================================================================================
 template <int OP>
-__global__ void __launch_bounds__(BE_THREADS, 2) be_gemm_kernel(BeConst bc, BeBuf bb) {
+__global__ void __launch_bounds__(BE_THREADS, 3) be_gemm_kernel(BeConst bc, BeBuf bb) {
     const int s = blockIdx.y;
     const BeStep sp = bb.step[s];
     if (!sp.active) return;

@@ -181,13 +181,168 @@ __global__ void __launch_bounds__(256) pyr_down_strip_kernel(FeConst fc, FeBuffe
     }
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+// Levels l0 .. L-1 of one image in ONE launch, one CTA per image (level 1 of a 752 x 480 frame is 90 KB: the
+// rest of the pyramid fits in shared memory).  Level l0 - 1 comes from global memory in chunks of rows (with
+// their two halo rows on either side), level l0 is filtered from the chunks into a resident shared-memory copy
+// and into the pyramid, and every further level is filtered from shared memory into shared memory and the
+// pyramid, alternating between the chunk area and the resident area.  Same arithmetic as the strip kernel
+// (hfilt2, a 5-row register window per column pair walking down); rows are mirrored (BORDER_REFLECT_101) at
+// access.  Replaces one launch per level >= 2 of pyr_down_strip_kernel<false, 4>, which at these sizes keeps
+// 94 resp. 47 of 256 threads busy per 16-row strip (0.9 TB/s: 14 % of the HBM peak, 75 us for two levels).
+#define PT_THREADS 256
+__device__ __forceinline__ void pt_patch_borders(uint8_t *buf, int rows, int cols, int rs) {
+    for (int r = threadIdx.x; r < rows; r += PT_THREADS) {
+        uint8_t *row = buf + (size_t)r * rs + PS_PAD;
+        row[-2] = row[reflect101(-2, cols)];
+        row[-1] = row[reflect101(-1, cols)];
+        row[cols] = row[reflect101(cols, cols)];
+        row[cols + 1] = row[reflect101(cols + 1, cols)];
+        row[cols + 2] = 0;
+        row[cols + 3] = 0;
+        row[cols + 4] = 0;
+        row[cols + 5] = 0;
+    }
+}
+// Output rows [o_begin, o_end) of a level (ocols wide) from the source rows held in `in`: source row y of the
+// level sits at in + (y - in_y0) * rs_in for y in [in_y0, in_y0 + in_rows); rows outside [0, irows) are mirrored
+// first.  Results go to the pyramid (dst, pitch P) and, when out != nullptr, to out + oy * rs_out + PS_PAD.
+__device__ __forceinline__ void pt_filter_rows(const uint8_t *in, int in_y0, int rs_in, int irows, int o_begin, int o_end, int ocols,
+                                               uint8_t *dst, int P, uint8_t *out, int rs_out) {
+    const int ncp = (ocols + 1) >> 1;                      // column pairs
+    const int cp = min(PT_THREADS, (ncp + 31) & ~31);      // threads per row group
+    const int groups = PT_THREADS / cp;                    // row groups working on disjoint output rows
+    const int g = threadIdx.x / cp, t = threadIdx.x - g * cp;
+    if (g >= groups) return;
+    const int n_rows = o_end - o_begin;
+    const int rpg = (n_rows + groups - 1) / groups;
+    const int r_begin = o_begin + g * rpg, r_end = min(o_end, r_begin + rpg);
+    if (r_begin >= r_end) return;
+    const bool odd_w = (ocols & 1) != 0;
+    auto rowp = [&](int y) { return in + (size_t)(reflect101(y, irows) - in_y0) * rs_in; };
+    for (int q = t; q < ncp; q += cp) {
+        unsigned h0 = hfilt2(rowp(2 * r_begin - 2), q), h1 = hfilt2(rowp(2 * r_begin - 1), q), h2 = hfilt2(rowp(2 * r_begin), q);
+        for (int r = r_begin; r < r_end; ++r) {
+            const unsigned h3 = hfilt2(rowp(2 * r + 1), q), h4 = hfilt2(rowp(2 * r + 2), q);
+            const unsigned v = h0 + h4 + 6u * h2 + 4u * (h1 + h3);
+            const unsigned o = ((v + 0x00800080u) >> 8) & 0x00FF00FFu;  // (sum + 128) >> 8 on both lanes
+            uint8_t *d = dst + (size_t)r * P + 2 * q;
+            const uint8_t b0 = (uint8_t)(o & 0xFFu), b1 = (uint8_t)(o >> 16);
+            if (!odd_w) {
+                *(unsigned short *)d = (unsigned short)(b0 | (b1 << 8));
+            } else {
+                d[0] = b0;
+                if (2 * q + 1 < ocols) d[1] = b1;
+            }
+            if (out) {
+                uint8_t *so = out + (size_t)r * rs_out + PS_PAD + 2 * q;
+                so[0] = b0;
+                if (2 * q + 1 < ocols) so[1] = b1;
+            }
+            h0 = h2;
+            h1 = h3;
+            h2 = h4;
+        }
+    }
+}
+__device__ __forceinline__ int pt_stride(int cols) { return (PS_PAD + cols + 8 + 15) & ~15; }
+
+__global__ void __launch_bounds__(PT_THREADS) pyr_tail_kernel(FeConst fc, FeBuffers fb, int l0, int chunk_out_rows, unsigned area_b_off) {
+    const int s = blockIdx.x >> 1, cam = blockIdx.x & 1;
+    const FeStep st = fb.step[s];
+    if (!st.active) return;
+    uint8_t *pyr = (cam == 0 ? fb.pyr[st.slot] : fb.pyr[2]) + (size_t)s * fc.pyr_bytes;
+    const int P = fc.pitch;
+    extern __shared__ __align__(16) uint8_t ps_smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    uint8_t *area_a = ps_smem, *area_b = ps_smem + area_b_off;  // chunk of level l0 - 1 | resident level l0
+    const unsigned bar_a = smem_u32(&bar);
+    const bool bulk = (P % 16) == 0;
+    unsigned phase = 0;
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    // ---- level l0 from global memory, chunk by chunk
+    {
+        const int irows = fc.lvl_rows[l0 - 1], icols = fc.lvl_cols[l0 - 1];
+        const int orows = fc.lvl_rows[l0], ocols = fc.lvl_cols[l0];
+        const uint8_t *src = pyr + fc.lvl_off[l0 - 1];
+        uint8_t *dst = pyr + fc.lvl_off[l0];
+        const int rs_in = pt_stride(icols), rs_out = pt_stride(ocols);
+        const bool resident = l0 + 1 < fc.levels;
+        const int wpr = icols / 4;  // launch condition: icols % 4 == 0, pitch % 4 == 0
+        for (int o_begin = 0; o_begin < orows; o_begin += chunk_out_rows) {
+            const int o_end = min(orows, o_begin + chunk_out_rows);
+            // source rows the chunk reads, after mirroring: [y_lo, y_hi]
+            int y_lo = max(0, 2 * o_begin - 2), y_hi = min(irows - 1, 2 * (o_end - 1) + 2);
+            if (2 * o_begin - 2 < 0) y_hi = max(y_hi, min(irows - 1, 2));        // rows -2, -1 mirror to 2, 1
+            if (2 * (o_end - 1) + 2 > irows - 1) y_lo = min(y_lo, max(0, irows - 3));  // rows past the end mirror back
+            const int n_in = y_hi - y_lo + 1;
+            __syncthreads();  // the previous chunk has been consumed
+            if (bulk) {
+                // one bulk copy (TMA engine) per source row, issued by the lanes of warp 0, all signalling one mbarrier;
+                // a row is copied in whole 16-byte units (the bytes past its end lie inside the pitch and are
+                // overwritten by the border patch or never read)
+                if (threadIdx.x < 32) {
+                    // the border bytes of the previous chunk were written through the generic proxy
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    const unsigned row_bytes = (unsigned)((icols + 15) & ~15);
+                    if (threadIdx.x == 0)
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(row_bytes * (unsigned)n_in) : "memory");
+                    __syncwarp();
+                    for (int r = threadIdx.x; r < n_in; r += 32)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                         smem_u32(area_a + (size_t)r * rs_in + PS_PAD)),
+                                     "l"(src + (size_t)(y_lo + r) * P), "r"(row_bytes), "r"(bar_a)
+                                     : "memory");
+                }
+                unsigned done = 0;
+                while (!done) {
+                    asm volatile(
+                        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                        : "=r"(done)
+                        : "r"(bar_a), "r"(phase)
+                        : "memory");
+                }
+                phase ^= 1u;
+            } else {
+                for (int e = threadIdx.x; e < n_in * wpr; e += PT_THREADS) {
+                    const int r = e / wpr, w = e - r * wpr;
+                    *(unsigned *)(area_a + (size_t)r * rs_in + PS_PAD + 4 * w) = *(const unsigned *)(src + (size_t)(y_lo + r) * P + 4 * w);
+                }
+                __syncthreads();
+            }
+            pt_patch_borders(area_a, n_in, icols, rs_in);
+            __syncthreads();
+            pt_filter_rows(area_a, y_lo, rs_in, irows, o_begin, o_end, ocols, dst, P, resident ? area_b : nullptr, rs_out);
+        }
+    }
+    // ---- further levels from shared memory
+    uint8_t *in = area_b, *out = area_a;
+    for (int l = l0 + 1; l < fc.levels; ++l) {
+        const int irows = fc.lvl_rows[l - 1], icols = fc.lvl_cols[l - 1];
+        const int orows = fc.lvl_rows[l], ocols = fc.lvl_cols[l];
+        const int rs_in = pt_stride(icols), rs_out = pt_stride(ocols);
+        __syncthreads();
+        pt_patch_borders(in, irows, icols, rs_in);
+        __syncthreads();
+        pt_filter_rows(in, 0, rs_in, irows, 0, orows, ocols, pyr + fc.lvl_off[l], P, l + 1 < fc.levels ? out : nullptr, rs_out);
+        uint8_t *t = in;
+        in = out;
+        out = t;
+    }
+}
+
 // Level 0 -> 1 with the strip staged by the TMA engine: when a strip's 36 input rows are one
 // contiguous span of the image (every strip except the top and bottom ones, whose reflected rows are
 // fetched row by row) ONE cp.async.bulk moves 27 KB global -> shared and signals an mbarrier, and the
 // level-0 landing copy is ONE cp.async.bulk shared -> global of the 32 interior rows: no thread touches
 // the staging.  Rows are packed (stride = icols, no halo columns); the two edge column pairs patch
 // their BORDER_REFLECT_101 bytes in registers.  Needs icols % 16 == 0.
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ unsigned hfilt2_packed(const uint8_t *row, int q, bool first, bool last) {
     const unsigned *w = (const unsigned *)(row - 4) + q;
@@ -1828,6 +1983,43 @@ __global__ void __launch_bounds__(FE_THREADS) fe_finish(FeConst fc, FeBuffers fb
 
 using namespace mskf;
 
+// Plan of pyr_tail_kernel for a geometry: first level it produces (0: not applicable), output rows per chunk of that
+// level, offset of the resident area, dynamic shared memory.
+struct PyrTailPlan {
+    int l0, chunk_out_rows;
+    unsigned area_b_off;
+    size_t smem;
+};
+static PyrTailPlan pyr_tail_plan(const FeConst &fc) {
+    PyrTailPlan pl = {0, 0, 0, 0};
+    auto stride = [](int cols) { return (PS_PAD + cols + 8 + 15) & ~15; };
+    if (fc.levels < 3 || (fc.pitch % 4) != 0) return pl;
+    if (fc.lvl_rows[fc.levels - 1] < 4 || fc.lvl_cols[fc.levels - 1] < 4) return pl;
+    for (int l0 = 2; l0 < fc.levels; ++l0) {
+        if (fc.levels - l0 < 2 && l0 > 2) break;  // a single remaining level gains nothing over the strip kernel
+        const int icols = fc.lvl_cols[l0 - 1];
+        if ((icols % 4) != 0) continue;
+        const size_t resident = (size_t)fc.lvl_rows[l0] * stride(fc.lvl_cols[l0]);
+        if (resident > 64 * 1024) continue;
+        const int rs_in = stride(icols), orows = fc.lvl_rows[l0];
+        int nchunks = 1;
+        while (nchunks < orows && (size_t)(2 * ((orows + nchunks - 1) / nchunks) + 6) * rs_in > 48 * 1024) ++nchunks;
+        const int c = (orows + nchunks - 1) / nchunks;
+        size_t area_a = (size_t)(2 * c + 6) * rs_in;
+        for (int l = l0 + 1; l < fc.levels; l += 2)  // levels l0 + 1, l0 + 3, ... live in the chunk area
+            area_a = std::max(area_a, (size_t)fc.lvl_rows[l] * stride(fc.lvl_cols[l]));
+        size_t area_b = resident;
+        for (int l = l0 + 2; l < fc.levels; l += 2) area_b = std::max(area_b, (size_t)fc.lvl_rows[l] * stride(fc.lvl_cols[l]));
+        area_a = (area_a + 15) & ~(size_t)15;
+        pl.l0 = l0;
+        pl.chunk_out_rows = c;
+        pl.area_b_off = (unsigned)area_a;
+        pl.smem = area_a + area_b;
+        return pl;
+    }
+    return pl;
+}
+
 static int fe_members_cap(const FeConst &fc) { return (fc.grid_w / fc.det_cell_w + 2) * (fc.grid_h / fc.det_cell_h + 2); }
 static size_t fe_sieve_smem(const FeConst &fc) {
     return (size_t)fc.det_cells * 9 + 16 + sizeof(int) * ((size_t)fc.n_cells * fc.grid_max + (FE_THREADS / 32) * fe_members_cap(fc));
@@ -1973,6 +2165,7 @@ int fe_create(mskf_handle *h) {
     if ((rc = smem_optin(h, pyr_down_bulk_kernel<true>, (size_t)PS_IN * fc.lvl_cols[0] + 32)) != MSKF_OK) return rc;
     if ((rc = smem_optin(h, pyr_down_strip_kernel<true, 4>, 0)) != MSKF_OK) return rc;
     if ((rc = smem_optin(h, pyr_down_strip_kernel<false, 4>, 0)) != MSKF_OK) return rc;
+    if ((rc = smem_optin(h, pyr_tail_kernel, pyr_tail_plan(fc).smem)) != MSKF_OK) return rc;
     return MSKF_OK;
 }
 
@@ -2026,8 +2219,13 @@ int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active) {
         return MSKF_ERR_ARG;
     }
     // pyramids
+    const PyrTailPlan tail = pyr_tail_plan(fc);
     for (int l = 1; l < fc.levels; ++l) {
-        launch_pyr_level(h, l, S * 2);
+        if (tail.l0 && l == tail.l0) {
+            MSKF_LAUNCH(h, PK_PYR_LN, (pyr_tail_kernel<<<S * 2, PT_THREADS, tail.smem, q>>>(fc, fb, tail.l0, tail.chunk_out_rows, tail.area_b_off)));
+        } else if (!tail.l0 || l < tail.l0) {
+            launch_pyr_level(h, l, S * 2);
+        }
         if (l == 1) {
             int rc = stage_end_consume(h);
             if (rc != MSKF_OK) return rc;
