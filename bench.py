@@ -280,7 +280,7 @@ def bind_near_gpu(torch, local_rank):
                 mine = allowed[local_rank * len(allowed) // lw:(local_rank + 1) * len(allowed) // lw]
                 os.sched_setaffinity(0, mine)
                 info = {"numa_node": node, "cpus": len(mine), "how": "even split of the allowed CPUs (no NUMA information)"}
-    except (OSError, ValueError, AttributeError) as e:
+    except (OSError, ValueError, AttributeError, RuntimeError, AssertionError) as e:
         info["how"] = f"unchanged ({type(e).__name__})"
     return info
 

@@ -1693,6 +1693,7 @@ __global__ void __launch_bounds__(BE_THREADS, 2) be_feature_jac_kernel(BeConst b
     __shared__ int s_pass;
     auto gix = [](int i, int j) { return i * (i + 1) / 2 + j; };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if ((int)blockIdx.x >= n_list) return;
     int ch_ti, ch_tj;
     chol_tile_of_thread(threadIdx.x, ch_ti, ch_tj);
 
@@ -3368,7 +3369,10 @@ int be_step(mskf_handle *h, const std::vector<int> &streams, const mskf_feature 
         }
         MSKF_LAUNCH(h, PK_BE_LAYOUT, (be_layout_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb, phase)));
         if (phase == 0) {
-            dim3 g(32, S);
+            // one CTA per lost feature (p99 of a stream's list is 10 in the fleet bench; longer lists loop).  The CTAs
+            // without a feature only read two descriptors, but at 73 KB of shared memory each they still cost a
+            // launch slot: 32 per stream made 28 waves, 30 us per launch before any work
+            dim3 g(16, S);
             MSKF_LAUNCH(h, PK_BE_FEATURE_JAC, (be_feature_jac_kernel<<<g, BE_THREADS, B->smem_jac[0], q>>>(bc, bb, 0, maxM)));
         } else {
             dim3 g(8, S);
@@ -3627,7 +3631,7 @@ int be_op_triangulate(mskf_handle *t, int n_cam, const double *cam_q, const doub
     return MSKF_OK;
 }
 
-// bring-up / analysis: per stream {m, k, listed features} of the lost-feature and the prune update of the last step
+// test hook (mskf_debug_last_gram): Gram matrix of the stacked system of the latest measurementUpdate of a stream
 int be_debug_last_gram(mskf_handle *h, int s, double *G, int cap, int *m, int *k, long long *cam_ids, int *valid) {
     BeState st;
     MSKF_CUDA_CHECK(h, cudaMemcpy(&st, h->bb->bb.st + s, sizeof(BeState), cudaMemcpyDeviceToHost));
@@ -3645,6 +3649,7 @@ int be_debug_last_gram(mskf_handle *h, int s, double *G, int cap, int *m, int *k
     return MSKF_OK;
 }
 
+// bring-up / analysis: per stream {m, k, listed features} of the lost-feature and the prune update of the last step
 int be_debug_update_dims(mskf_handle *h, int *out6) {
     std::vector<BeState> st(h->S);
     MSKF_CUDA_CHECK(h, cudaMemcpy(st.data(), h->bb->bb.st, sizeof(BeState) * h->S, cudaMemcpyDeviceToHost));

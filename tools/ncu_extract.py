@@ -67,7 +67,7 @@ def classify(names):
         c = base
         if "pyr_down_bulk" in base:
             c = "pyr_down_l1"
-        elif "pyr_down" in base:
+        elif "pyr_down" in base or "pyr_tail" in base:
             c = "pyr_down_ln"
         elif "klt" in base:
             c = ("klt_temporal", "klt_stereo", "klt_new")[klt_i % 3]
