@@ -76,6 +76,7 @@ struct BeState {
     int gravity_set;
     // per-step scratch
     int n_list;          // length of the current feature list
+    int n_todo;          // how many of them are not initialised yet (l_todo)
     int m, k, mt;        // stacked rows, compact columns, rows after compression
     int t_upper;         // Tm is upper triangular (the QR compression ran)
     int u_nslots;
@@ -133,6 +134,7 @@ struct BeBuf {
     // feature lists of the current phase
     int *l_slot;       // [S][ML]
     uint8_t *l_ok, *l_pass;  // [S][ML]
+    int *l_todo;             // [S][ML] list indices of the features that still need a position (be_select -> be_triangulate)
     int *l_M, *l_eoff, *l_roff, *l_soff;  // [S][ML]
     uint8_t *l_oslots; // [S][ML][NSM]
     double *Hblk;      // [S][ecap] projected per-feature Jacobians (features that pass the gate)
@@ -928,9 +930,23 @@ __global__ void __launch_bounds__(BE_THREADS) be_select_kernel(BeConst bc, BeBuf
         }
     const int n = min(s_n, min(sort_n, bc.ML));
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += BE_THREADS) bb.l_slot[(size_t)s * bc.ML + i] = (int)(keys[i] & 0xffffffffu);
+    // Most listed features are initialised already (the prune phase lists ~260 per stream, a handful of which
+    // still need their position): the ones that do are compacted HERE, from flags that be_triangulate_kernel does
+    // not write while it reads them, so that its warps take one each instead of queueing behind each other in
+    // list order (a triangulation is a serial Levenberg-Marquardt chain of ~50 us)
+    __shared__ int s_ntodo;
+    if (threadIdx.x == 0) s_ntodo = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += BE_THREADS) {
+        const int slot = (int)(keys[i] & 0xffffffffu);
+        bb.l_slot[(size_t)s * bc.ML + i] = slot;
+        if (bb.f_init[fo + slot]) bb.l_ok[(size_t)s * bc.ML + i] = 1;
+        else bb.l_todo[(size_t)s * bc.ML + atomicAdd(&s_ntodo, 1)] = i;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         st.n_list = n;
+        st.n_todo = s_ntodo;
         st.n_feat -= s_erased;
     }
 }
@@ -1111,9 +1127,11 @@ __global__ void __launch_bounds__(TRI_WARPS * 32) be_triangulate_kernel(BeConst 
     const BeState &st = bb.st[s];
     const int lane = threadIdx.x & 31;
     const size_t fo = (size_t)s * bc.MF;
-    const int n_list = st.n_list;
-    for (int li = blockIdx.x * TRI_WARPS + (threadIdx.x >> 5); li < n_list; li += gridDim.x * TRI_WARPS)
-        triangulate_one(bc, bb, st, s, li, lane, fo, s_tri[threadIdx.x >> 5]);
+    // the features that still need a position, compacted by be_select_kernel: one per warp
+    const int n_todo = st.n_todo;
+    const int *todo = bb.l_todo + (size_t)s * bc.ML;
+    for (int j = blockIdx.x * TRI_WARPS + (threadIdx.x >> 5); j < n_todo; j += gridDim.x * TRI_WARPS)
+        triangulate_one(bc, bb, st, s, todo[j], lane, fo, s_tri[threadIdx.x >> 5]);
 }
 
 // sum of the np per-view costs in view order, starting from 0.0 (feature.hpp:359-364, 402-407); every lane
@@ -2288,8 +2306,11 @@ __global__ void __launch_bounds__(BE_THREADS) be_stack_kernel(BeConst bc, BeBuf 
 }
 
 // Copies the gated per-feature blocks into the stacked system (rows from be_stack_kernel, columns
-// compacted to the active camera slots).  grid (G, S): CTA g takes features g, g + G, ...; every
-// feature owns its rows of H, so the CTA also zero-fills them.
+// compacted to the active camera slots).  A group of WG threads takes a feature (every feature owns its rows
+// of H, so the group also zero-fills them): the whole CTA for the lost-feature update (blocks of up to
+// 121 x 186), ONE WARP for the prune update, whose ~260 blocks per stream are 5 x 12 (a CTA per block spent
+// its time in barriers: 132 us per fleet launch for 125 KB per stream).
+template <int WG>
 __global__ void __launch_bounds__(BE_THREADS) be_scatter_kernel(BeConst bc, BeBuf bb) {
     const int s = blockIdx.y;
     const BeStep sp = bb.step[s];
@@ -2299,21 +2320,35 @@ __global__ void __launch_bounds__(BE_THREADS) be_scatter_kernel(BeConst bc, BeBu
     const int n = st.n_list, k = st.k;
     const size_t lo = (size_t)s * bc.ML;
     double *Hst = bb.Hst + (size_t)s * bc.hst_cap, *rst = bb.rst + (size_t)s * bc.hst_rows;
-    __shared__ int s_col[6 * NSM];
-    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    constexpr int GPC = BE_THREADS / WG;  // groups per CTA
+    __shared__ int s_col_all[GPC][WG == 32 ? 32 : 6 * NSM];
+    const int grp = threadIdx.x / WG, t = threadIdx.x % WG;
+    int *s_col = s_col_all[grp];
+    auto group_sync = [&]() {
+        if (WG == 32) __syncwarp();
+        else __syncthreads();
+    };
+    for (int i = blockIdx.x * GPC + grp; i < n; i += gridDim.x * GPC) {
         const int so = bb.l_soff[lo + i];
-        if (so < 0) continue;
+        if (so < 0) continue;  // (uniform over the group)
         const int M = bb.l_M[lo + i], C6 = 6 * M, rows = 4 * M - 3;
         const double *Hp = bb.Hblk + (size_t)s * bc.ecap + bb.l_eoff[lo + i] + 3 * C6;
         const double *rp = bb.rblk + (size_t)s * bc.rcap + bb.l_roff[lo + i] + 3;
         const uint8_t *os = bb.l_oslots + (lo + i) * NSM;
-        __syncthreads();
-        for (int c = threadIdx.x; c < C6; c += BE_THREADS) s_col[c] = 6 * st.colpos[os[c / 6]] + (c % 6);
-        for (int e = threadIdx.x; e < rows * k; e += BE_THREADS) Hst[(size_t)so * k + e] = 0.0;
-        __syncthreads();
-        for (int r = threadIdx.x / 32; r < rows; r += BE_THREADS / 32)
-            for (int c = threadIdx.x & 31; c < C6; c += 32) Hst[(size_t)(so + r) * k + s_col[c]] = Hp[r * C6 + c];
-        for (int r = threadIdx.x; r < rows; r += BE_THREADS) rst[so + r] = rp[r];
+        group_sync();
+        for (int c = t; c < C6; c += WG) s_col[c] = 6 * st.colpos[os[c / 6]] + (c % 6);
+        for (int e = t; e < rows * k; e += WG) Hst[(size_t)so * k + e] = 0.0;
+        group_sync();
+        if (WG == 32) {
+            for (int e = t; e < rows * C6; e += WG) {
+                const int r = e / C6, c = e - r * C6;
+                Hst[(size_t)(so + r) * k + s_col[c]] = Hp[e];
+            }
+        } else {
+            for (int r = t / 32; r < rows; r += WG / 32)
+                for (int c = t & 31; c < C6; c += 32) Hst[(size_t)(so + r) * k + s_col[c]] = Hp[r * C6 + c];
+        }
+        for (int r = t; r < rows; r += WG) rst[so + r] = rp[r];
     }
 }
 
@@ -3160,7 +3195,7 @@ int be_create(mskf_handle *h) {
     A(bb.f_id, S * bc.MF); A(bb.f_mask, S * bc.MF); A(bb.f_live, S * bc.MF); A(bb.f_init, S * bc.MF);
     A(bb.f_pos, S * bc.MF * 3); A(bb.f_obs, S * bc.MF * bc.NS * 4); A(bb.f_last, S * bc.MF); A(bb.freelist, S * bc.MF);
     A(bb.e_cell, S * (bc.ent_cap + 1)); A(bb.inject, bc.ent_cap);
-    A(bb.l_slot, S * bc.ML); A(bb.l_ok, S * bc.ML); A(bb.l_pass, S * bc.ML); A(bb.l_M, S * bc.ML);
+    A(bb.l_slot, S * bc.ML); A(bb.l_ok, S * bc.ML); A(bb.l_todo, S * bc.ML); A(bb.l_pass, S * bc.ML); A(bb.l_M, S * bc.ML);
     A(bb.l_eoff, S * bc.ML); A(bb.l_roff, S * bc.ML); A(bb.l_soff, S * bc.ML); A(bb.l_oslots, S * bc.ML * NSM);
     A(bb.Hblk, S * bc.ecap); A(bb.rblk, S * bc.rcap);
     A(bb.Hst, S * bc.hst_cap); A(bb.rst, S * bc.hst_rows); A(bb.Gm, S * (bc.KC + 1) * (bc.KC + 1)); A(bb.Rp, S * bc.KC * bc.KC); A(bb.perm, S * bc.KC);
@@ -3345,7 +3380,7 @@ int be_step(mskf_handle *h, const std::vector<int> &streams, const mskf_feature 
             fa.seg[1] = FetchSeg{bb.imu, himu, (unsigned)(7 * max_imu), (unsigned)(BE_IMU_CAP * 7), (unsigned)S};
             fa.n = 2;
         }
-        desc_fetch_kernel<<<4, 256, 0, q>>>(fa);
+        desc_fetch_kernel<<<fetch_grid(fa), 256, 0, q>>>(fa);
         h->launches++;
         MSKF_CUDA_CHECK(h, cudaGetLastError());
     }
@@ -3379,7 +3414,9 @@ int be_step(mskf_handle *h, const std::vector<int> &streams, const mskf_feature 
             MSKF_LAUNCH(h, PK_BE_FEATURE_JAC_PRUNE, (be_feature_jac_prune_kernel<<<g, JP_THREADS, 0, q>>>(bc, bb)));
         }
         MSKF_LAUNCH(h, PK_BE_STACK, (be_stack_kernel<<<S, BE_THREADS, (size_t)bc.ML * 10, q>>>(bc, bb, phase)));
-        MSKF_LAUNCH(h, PK_BE_STACK, (be_scatter_kernel<<<dim3(16, S), BE_THREADS, 0, q>>>(bc, bb)));
+        // the prune update's blocks are 5 x 12 (M = 2 <= 5 views: 30 columns fit a warp's table): one warp per block
+        if (phase == 0) MSKF_LAUNCH(h, PK_BE_STACK, (be_scatter_kernel<BE_THREADS><<<dim3(16, S), BE_THREADS, 0, q>>>(bc, bb)));
+        else MSKF_LAUNCH(h, PK_BE_STACK, (be_scatter_kernel<32><<<dim3(8, S), BE_THREADS, 0, q>>>(bc, bb)));
         launch_update(h, phase);
     }
     MSKF_LAUNCH(h, PK_BE_PRUNE_FINISH, (be_prune_finish_kernel<<<S, BE_THREADS, 0, q>>>(bc, bb)));
@@ -3602,6 +3639,7 @@ int be_op_triangulate(mskf_handle *t, int n_cam, const double *cam_q, const doub
         for (int k = 0; k < 3; ++k) st.cam[i].p[k] = cam_p[i * 3 + k];
     }
     st.n_list = n_feat;
+    st.n_todo = n_feat;
     MSKF_CUDA_CHECK(t, cudaMemcpy(bb.st, &st, sizeof(BeState), cudaMemcpyHostToDevice));
     BeStep sp;
     memset(&sp, 0, sizeof(sp));
@@ -3617,6 +3655,7 @@ int be_op_triangulate(mskf_handle *t, int n_cam, const double *cam_q, const doub
     MSKF_CUDA_CHECK(t, cudaMemcpy(bb.f_obs, o.data(), sizeof(double) * o.size(), cudaMemcpyHostToDevice));
     MSKF_CUDA_CHECK(t, cudaMemcpy(bb.f_mask, mask, sizeof(unsigned) * n_feat, cudaMemcpyHostToDevice));
     MSKF_CUDA_CHECK(t, cudaMemcpy(bb.l_slot, slots.data(), sizeof(int) * n_feat, cudaMemcpyHostToDevice));
+    MSKF_CUDA_CHECK(t, cudaMemcpy(bb.l_todo, slots.data(), sizeof(int) * n_feat, cudaMemcpyHostToDevice));  // identity: every feature
     MSKF_CUDA_CHECK(t, cudaMemset(bb.f_init, 0, n_feat));
     MSKF_CUDA_CHECK(t, cudaMemset(bb.f_pos, 0, sizeof(double) * 3 * n_feat));
     MSKF_CUDA_CHECK(t, cudaMemset(bb.l_ok, 0, n_feat));

@@ -220,6 +220,13 @@ static __global__ void __launch_bounds__(256) desc_fetch_kernel(FetchArgs a) {
         }
     }
 }
+// one pass over the largest segment (a load over PCIe costs ~1.5 us: a thread should issue one, not eight in a row)
+static inline int fetch_grid(const FetchArgs &a) {
+    unsigned most = 1;
+    for (int k = 0; k < a.n; ++k) most = a.seg[k].width8 * a.seg[k].rows > most ? a.seg[k].width8 * a.seg[k].rows : most;
+    const unsigned g = (most + 255) / 256;
+    return (int)(g < 1 ? 1 : g > 64 ? 64 : g);
+}
 static inline FetchSeg fetch_seg(void *dst, const void *src, size_t bytes) {
     return FetchSeg{dst, src, (unsigned)(bytes / 8), (unsigned)(bytes / 8), 1u};
 }

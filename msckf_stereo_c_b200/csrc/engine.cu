@@ -506,7 +506,7 @@ int mskf_frontend_step(mskf_handle *h) {
         fa.seg[0] = fetch_seg(h->fb.step, hstep, sizeof(FeStep) * S);
         fa.seg[1] = fetch_seg(h->fb.src0, hsrc, sizeof(uint8_t *) * S);
         fa.seg[2] = fetch_seg(h->fb.src1, hsrc + S, sizeof(uint8_t *) * S);
-        desc_fetch_kernel<<<4, 256, 0, h->stream>>>(fa);
+        desc_fetch_kernel<<<fetch_grid(fa), 256, 0, h->stream>>>(fa);
         h->launches++;
         MSKF_CUDA_CHECK(h, cudaGetLastError());
     }

@@ -4,7 +4,7 @@
     python tools/sass_summary.py [tag=r02]
 
 DMMA proves the fp64 tensor pipe, UBLKCP the 1-D bulk TMA copies, LDGSTS the cp.async staging, SYNCS the
-mbarriers, REDUX the warp reductions (names: /opt/skills/guides/B200_PROFILING.md).
+mbarriers, REDUX / CREDUX the warp reductions (names: /opt/skills/guides/B200_PROFILING.md).
 """
 import collections
 import os
@@ -13,7 +13,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OPS = ['DMMA', 'DFMA', 'DADD', 'DMUL', 'UBLKCP', 'UTMALDG', 'UTMASTG', 'LDGSTS', 'SYNCS', 'REDUX', 'IMAD', 'LDG', 'STG',
+OPS = ['DMMA', 'DFMA', 'DADD', 'DMUL', 'UBLKCP', 'UTMALDG', 'UTMASTG', 'LDGSTS', 'SYNCS', 'REDUX', 'CREDUX', 'IMAD', 'LDG', 'STG',
        'LDS', 'STS', 'SHFL', 'BAR', 'MUFU']
 
 
@@ -40,7 +40,7 @@ def main():
     with open(path, 'w') as f:
         f.write('# cuobjdump -sass msckf_stereo_c_b200/libmsckf_b200.so (sm_100a): static instruction counts per kernel\n')
         f.write('# DMMA = fp64 tensor pipe (mma.sync.m8n8k4.f64); UBLKCP = 1-D bulk TMA (cp.async.bulk); LDGSTS = cp.async;\n')
-        f.write('# SYNCS = mbarrier; REDUX = warp reduce.  No UTMALDG/UTMASTG: no tensor-map TMA; no tcgen05: the path has no\n')
+        f.write('# SYNCS = mbarrier; REDUX / CREDUX = warp reduce (add / min-max).  No UTMALDG/UTMASTG: no tensor-map TMA; no tcgen05: the path has no\n')
         f.write('# low-precision GEMM (fp64 has no tcgen05 form).\n')
         f.write('kernel,total,' + ','.join(OPS) + '\n')
         for k, c in counts.items():
