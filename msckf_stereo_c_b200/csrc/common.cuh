@@ -90,6 +90,8 @@ struct FeBuffers {
     uint8_t *k_status;      // [S][cap_k]
     uint8_t *k_skip;        // [S][cap_k] new-feature candidates whose cell has no vacancy (not matched)
     int *k_n;               // [S]
+    int *k_idx;             // [S][cap_k] new-feature candidates that ARE matched (cell with a vacancy), compacted by fe_sieve
+    int *k_nm;              // [S] their number
     // tracked meta carried through the temporal track
     unsigned long long *t_id;  // [S][max_f]
     int *t_life;               // [S][max_f]

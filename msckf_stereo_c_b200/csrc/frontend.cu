@@ -685,12 +685,13 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_REG_CTAS) klt_reg_kernel(F
     const FeStep st = fb.step[s];
     if (!st.active) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int f = blockIdx.x * KLT_WARPS + warp;
-    if (f >= fb.k_n[s]) return;
-    if (mode == 2 && fb.k_skip[(size_t)s * fc.cap_k + f]) {
-        if (lane == 0) fb.k_status[(size_t)s * fc.cap_k + f] = 0;
-        return;
-    }
+    // modes 0 / 1: the grid covers the list, one feature per warp.  Mode 2 (stereo match of the new candidates): a
+    // small grid strides over the candidates fe_sieve compacted (the ones whose cell has a vacancy: ~15 % of the
+    // list; a warp per list entry spent half of the launch on CTAs that had nothing to match)
+    const int n_items = mode == 2 ? fb.k_nm[s] : fb.k_n[s];
+    for (int item = blockIdx.x * KLT_WARPS + warp; item < n_items; item += gridDim.x * KLT_WARPS) {
+    const int f = mode == 2 ? fb.k_idx[(size_t)s * fc.cap_k + item] : item;
+    __syncwarp();
     const uint8_t *pa = (mode == 0 ? fb.pyr[st.slot ^ 1] : fb.pyr[st.slot]) + (size_t)s * fc.pyr_bytes;
     const uint8_t *pb = (mode == 0 ? fb.pyr[st.slot] : fb.pyr[2]) + (size_t)s * fc.pyr_bytes;
     constexpr int half = WIN >> 1, tw = WIN + 2;
@@ -819,6 +820,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_REG_CTAS) klt_reg_kernel(F
         fb.k_b[(size_t)s * fc.cap_k + f] = make_float2(qx, qy);
         fb.k_status[(size_t)s * fc.cap_k + f] = (uint8_t)status;
     }
+    }  // item loop
 }
 
 // ======================================================================================
@@ -1652,9 +1654,11 @@ __global__ void __launch_bounds__(FE_THREADS) fe_sieve(FeConst fc, FeBuffers fb,
             fb.k_a[ko + i] = p;
             fb.k_b[ko + i] = distort_pt(fc, 1, undistort_pt(fc, 0, p, fc.R01));
             fb.k_skip[ko + i] = 0;
+            fb.k_idx[ko + i] = i;
         }
         if (threadIdx.x == 0) {
             fb.k_n[s] = n;
+            fb.k_nm[s] = n;
             fb.work[(size_t)s * MSKF_PROF_TAGS + PK_KLT_NEW] += (double)n * klt_bytes_per_feature(fc);
         }
         return;
@@ -1725,7 +1729,9 @@ __global__ void __launch_bounds__(FE_THREADS) fe_sieve(FeConst fc, FeBuffers fb,
         }
     }
     __syncthreads();
+    __shared__ int s_nm;
     if (threadIdx.x == 0) {
+        s_nm = 0;
         int acc = 0, matched = 0;
         for (int c = 0; c < fc.n_cells; ++c) {
             s_cell_off[c] = acc;
@@ -1745,7 +1751,13 @@ __global__ void __launch_bounds__(FE_THREADS) fe_sieve(FeConst fc, FeBuffers fb,
         fb.k_a[ko + d] = p;
         fb.k_b[ko + d] = distort_pt(fc, 1, undistort_pt(fc, 0, p, fc.R01));
         fb.k_skip[ko + d] = s_vac[c] ? 0 : 1;
+        // the stereo match of the new candidates runs over the compacted list of the ones in cells with a
+        // vacancy (order irrelevant: results are written by list index); the others are settled here
+        if (s_vac[c]) fb.k_idx[ko + atomicAdd(&s_nm, 1)] = d;
+        else fb.k_status[ko + d] = 0;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) fb.k_nm[s] = s_nm;
 }
 
 // stereo-matched new features -> grid, prune, publish, rotate prev/curr
@@ -2142,7 +2154,7 @@ int fe_create(mskf_handle *h) {
         A(fb.g_n[g], S);
     }
     A(fb.gslot, S); A(fb.next_id, S);
-    A(fb.k_a, S * fc.cap_k); A(fb.k_b, S * fc.cap_k); A(fb.k_status, S * fc.cap_k); A(fb.k_skip, S * fc.cap_k); A(fb.k_n, S);
+    A(fb.k_a, S * fc.cap_k); A(fb.k_b, S * fc.cap_k); A(fb.k_status, S * fc.cap_k); A(fb.k_skip, S * fc.cap_k); A(fb.k_n, S); A(fb.k_idx, S * fc.cap_k); A(fb.k_nm, S);
     A(fb.t_id, S * fc.max_f); A(fb.t_life, S * fc.max_f); A(fb.t_p0, S * fc.max_f); A(fb.t_p1, S * fc.max_f); A(fb.track_calls, S);
     A(fb.det_best, S * fc.det_cells); A(fb.det_occ, S * fc.det_cells);
     A(fb.nf_resp, S * fc.det_cells); A(fb.nf_n, S); A(fb.in_resp, S * fc.cap_k);
@@ -2253,6 +2265,9 @@ int fe_step(mskf_handle *h, bool any_first, int max_prev, int n_active) {
     {
         int cap = any_first ? fc.det_cells : fc.n_cells * fc.grid_max;
         dim3 g((cap + KLT_WARPS - 1) / KLT_WARPS, S);
+        // the register kernels stride over the compacted candidates: a quarter of the list's warps is enough in
+        // steady state (the first frame matches every detection and keeps the full grid)
+        if (!any_first && (fc.klt_win == 21 || fc.klt_win == 15)) g.x = (g.x + 3) / 4;
         launch_klt(h, PK_KLT_NEW, g, klt_smem, 2);
     }
     const size_t fin_smem = fe_finish_smem(fc);
