@@ -507,6 +507,7 @@ def run_ours(args, rank, world, local_rank):
     value = total_frames / (ms_dev_max * 1e-3)
     e2e_value = total_frames / (ms_e2e_max * 1e-3)
 
+    failed = None
     if rank == 0:
         # ---- per-kernel pass: ONE handle with all S streams, front end and back end serialised, CUDA events
         # around every kernel class (the timed legs interleave H handles and overlap the two halves)
@@ -649,10 +650,12 @@ def run_ours(args, rank, world, local_rank):
         }
         print(json.dumps(line), flush=True)
         if parity is not None and not parity["ok"]:
-            raise SystemExit("bench.py: stream 0 of the timed fleet does not match the CPU oracle: " + json.dumps(parity))
+            failed = "bench.py: stream 0 of the timed fleet does not match the CPU oracle: " + json.dumps(parity)
     if dist is not None:
-        dist.barrier()
+        dist.barrier()  # (the other ranks wait here: leave the group in order before reporting a mismatch)
         dist.destroy_process_group()
+    if failed:
+        raise SystemExit(failed)
 
 
 def main():
