@@ -282,7 +282,7 @@ def _ate(est, gt):
     return np.sqrt((np.linalg.norm((R @ (est - ma).T).T + mb - gt, axis=1) ** 2).mean())
 
 
-def _full_pipeline_run(eng, ob, synth, cfg, seed, n_frames):
+def _full_pipeline_run(eng, ob, synth, cfg, seed, n_frames, blank=()):
     """Images + IMU in, pose out: CUDA front end feeding the CUDA EKF (mskf_step) against the oracle run
     frame by frame (CameraMeasurement bytes, filter state), plus both trajectories and the ground truth."""
     s = synth.Stream(cfg, seed=seed)
@@ -294,7 +294,12 @@ def _full_pipeline_run(eng, ob, synth, cfg, seed, n_frames):
             o.imu(t, w, a)
             e.imu_callback(t, w, a)
 
+        n_pushed = 0
+
         def stereo(self, t, i0, i1):
+            if Both.n_pushed in blank:  # a frame without any texture: every track fails, the grid empties
+                i0, i1 = np.full_like(i0, 100), np.full_like(i1, 100)
+            Both.n_pushed += 1
             o.stereo(t, i0, i1)
             e.push_stereo(t, i0, i1)
 
@@ -326,6 +331,15 @@ def test_full_pipeline_and_ate(eng, ob, synth):
     ate_o, ate_g = _ate(est_o, gt), _ate(est_g, gt)
     assert abs(ate_g - ate_o) <= 0.05 * ate_o
     assert ate_o < 0.15
+
+
+def test_full_pipeline_blank_frames(eng, ob, synth):
+    """Edge case: frames without any texture in the middle of a run (a covered lens).  Every track fails, the
+    grids and the CameraMeasurement become empty, all features are lost at once (one large lost-feature update)
+    and the front end has to re-detect from nothing; engine and oracle must stay identical through it."""
+    cfg = copy_cfg(synth.default_config("ref"), compat_stale_features=0)
+    est_o, est_g, gt, st = _full_pipeline_run(eng, ob, synth, cfg, 5, 70, blank={40, 41, 42, 55})
+    assert st.n_updates >= 2 and st.n_cam_states >= 15
 
 
 def test_full_pipeline_bench_preset(eng, ob, synth):
