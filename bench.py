@@ -435,10 +435,12 @@ def run_ours(args, rank, world, local_rank):
         stays full; every step's poses are copied to pinned memory by the step itself)."""
         nonlocal h2d, d2h, e2e_wait
         nb = 0
-        for g in groups:
+        for h, g in enumerate(groups):
             nb += g.feed_imu(kk)
             g.e.step()
-        push_host(i + 1, kk + 1)
+            # this handle's next frame set goes out as soon as its step is enqueued (not after all handles' steps):
+            # the copy engine then works through the enqueue time of the other handles as well
+            g.push(kk + 1, slab(frames_host[i + 1], h), False)
         t_w = time.perf_counter()
         for h, g in enumerate(groups):
             poses[h] = g.e.poses(prev=True)
