@@ -2321,7 +2321,7 @@ __global__ void __launch_bounds__(BE_THREADS) be_scatter_kernel(BeConst bc, BeBu
     const size_t lo = (size_t)s * bc.ML;
     double *Hst = bb.Hst + (size_t)s * bc.hst_cap, *rst = bb.rst + (size_t)s * bc.hst_rows;
     constexpr int GPC = BE_THREADS / WG;  // groups per CTA
-    __shared__ int s_col_all[GPC][WG == 32 ? 32 : 6 * NSM];
+    __shared__ int s_col_all[GPC][6 * NSM];  // any view count fits either variant (the prune update has M = 2)
     const int grp = threadIdx.x / WG, t = threadIdx.x % WG;
     int *s_col = s_col_all[grp];
     auto group_sync = [&]() {
