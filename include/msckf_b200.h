@@ -189,6 +189,10 @@ int mskf_wait_uploads(mskf_handle *h);
 /* Page-locked host memory for the image ring of a fleet loader (examples/run_euroc_fleet.cpp), so that a host
  * application needs no CUDA headers; no handle: valid for every engine of the process. */
 int mskf_host_alloc(void **out, size_t bytes);
+/* Same, write-combined (cudaHostAllocWriteCombined): for buffers the host only WRITES and the GPU's copy engine
+ * reads (frame rings).  The DMA reads do not snoop the CPU caches, which raises the upload rate when several GPUs
+ * pull from the same host at once; CPU reads of such memory are slow. */
+int mskf_host_alloc_wc(void **out, size_t bytes);
 void mskf_host_free(void *p);
 int mskf_push_stereo_device_batch(mskf_handle *h, const double *t, const uint8_t *d_cam0, const uint8_t *d_cam1,
                                   size_t stream_stride);

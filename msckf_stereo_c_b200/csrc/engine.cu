@@ -384,6 +384,12 @@ int mskf_host_alloc(void **out, size_t bytes) {
     return cudaHostAlloc(out, bytes, cudaHostAllocPortable) == cudaSuccess ? MSKF_OK : MSKF_ERR_CUDA;
 }
 
+int mskf_host_alloc_wc(void **out, size_t bytes) {
+    if (!out || bytes == 0) return MSKF_ERR_ARG;
+    *out = nullptr;
+    return cudaHostAlloc(out, bytes, cudaHostAllocPortable | cudaHostAllocWriteCombined) == cudaSuccess ? MSKF_OK : MSKF_ERR_CUDA;
+}
+
 void mskf_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }

@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "mskf_debug_detect_scores", "mskf_debug_get_map", "mskf_debug_last_gram", "mskf_op_ekf_update", "mskf_push_imu_batch",
     "mskf_push_stereo_batch", "mskf_push_stereo_device_batch", "mskf_get_work", "mskf_get_poses_prev", "mskf_join",
     "mskf_set_overlap", "mskf_debug_update_dims", "mskf_op_triangulate", "mskf_push_imu_to",
-    "mskf_get_features_head", "mskf_wait_uploads", "mskf_host_alloc", "mskf_host_free",
+    "mskf_get_features_head", "mskf_wait_uploads", "mskf_host_alloc", "mskf_host_alloc_wc", "mskf_host_free",
 ]
 
 
